@@ -1,0 +1,232 @@
+/*
+ * szb200.h -- C ABI of the B200-native zstd decode engine (libszb200.so).
+ *
+ * This is the drop-in boundary for the hot path of KillingSpark/sparkzstd.  The reference
+ * has no FFI: its surface is the Go package API.  Each entry point
+ * below names the reference interface it replaces (file:line under /root/reference) and is
+ * what the Go side binds through cgo (go/).
+ *
+ * Conventions: int return, 0 = OK, negative = error (codes map 1:1 onto the reference's
+ * Err* values); caller-owned buffers; the library never retains a caller pointer after a
+ * call returns (cgo rule); one szb_ctx per host thread; no global mutable state; plain
+ * pointers and sizes only -- no torch / C++ types in any signature.
+ */
+#ifndef SZB200_H
+#define SZB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes (shared numbering with oracle/szo.h) -------------------------------- */
+enum {
+    SZB_OK = 0,
+    SZB_ERR_WRONG_MAGICNUMBER = -1,          /* decompression/framedecompressor.go:128 ErrWrongMagicnumber */
+    SZB_ERR_CORRUPT_SIZES = -2,              /* framedecompressor.go:90 */
+    SZB_ERR_OUT_OF_BLOCKS = -3,              /* framedecompressor.go:196 */
+    SZB_ERR_ILLEGAL_CONTENT_SIZE_FLAG = -4,  /* structure/frame.go:76 */
+    SZB_ERR_ILLEGAL_DICTIONARY_ID_FLAG = -5, /* frame.go:110 */
+    SZB_ERR_NOT_ENOUGH_BYTES_FOR_BLOCK_HEADER = -6, /* structure/block.go:28 */
+    SZB_ERR_ILLEGAL_BLOCK_TYPE = -7,         /* block.go:29 */
+    SZB_ERR_ILLEGAL_BLOCK_SIZE = -8,         /* block.go:30 */
+    SZB_ERR_WRONG_JUMPTABLE_BYTES = -9,      /* structure/literals.go:43 */
+    SZB_ERR_CORRUPTED_JUMPTABLE = -10,       /* literals.go:44 */
+    SZB_ERR_ILLEGAL_LITERAL_SECTION_TYPE = -11,
+    SZB_ERR_ILLEGAL_LITERAL_SECTION_SIZE_FORMAT = -12,
+    SZB_ERR_WRONG_SIZES_BYTES = -13,
+    SZB_ERR_NO_HUFF_TABLE_TO_CARRY_OVER = -14,         /* literals.go:206 */
+    SZB_ERR_STREAM_DIDNT_DECODE_TO_RIGHT_LENGTH = -15, /* literals.go:207 */
+    SZB_ERR_WRONG_SUM_OF_WEIGHTS = -16,      /* structure/huffman.go:109 */
+    SZB_ERR_CORRUPTED_HUFF_TREE = -17,       /* huffman.go:110 */
+    SZB_ERR_BAD_PADDING = -18,               /* huffman.go:218, fse/fse.go:303 */
+    SZB_ERR_DIDNT_USE_ALL_BITS_TO_DECODE_HUFFMAN = -19, /* huffman.go:219 */
+    SZB_ERR_NOT_ALL_BITS_USED = -20,         /* structure/sequences.go:208 */
+    SZB_ERR_NO_LL_TABLE_TO_CARRY_OVER = -21, /* sequences.go:271 */
+    SZB_ERR_NO_ML_TABLE_TO_CARRY_OVER = -22, /* sequences.go:272 */
+    SZB_ERR_NO_OF_TABLE_TO_CARRY_OVER = -23, /* sequences.go:273 */
+    SZB_ERR_NOT_ALL_BYTES_USED_WHILE_SEQUENCE_DECODING = -24, /* sequences.go:452 */
+    SZB_ERR_DIDNT_READ_ALL_PROBABILITIES = -25, /* fse/fse.go:132 */
+    SZB_ERR_NO_SYMBOL_FOR_STATE = -26,       /* fse.go:259 */
+    SZB_ERR_CANT_UNWIND = -27,               /* bitstream/bitstream.go:18 */
+    SZB_ERR_DIDNT_COPY_ALL_LITERAL_BYTES = -28, /* decompression/sequence_execution.go:11 */
+    SZB_ERR_IDX_OUT_OF_BOUNDS = -29,         /* decompression/ringbuffer.go:52 */
+    SZB_ERR_CANT_REPEAT_BYTES = -30,         /* ringbuffer.go:189 */
+    SZB_ERR_DIDNT_DUMP_ALL = -31,            /* ringbuffer.go:303 */
+    SZB_ERR_UNEXPECTED_EOF = -32,            /* io.EOF / io.ErrUnexpectedEOF on truncated input */
+    SZB_ERR_PANIC = -33,                     /* input on which the Go reference panics */
+    SZB_ERR_NOMEM = -34,
+    SZB_ERR_UNSUPPORTED = -35,  /* beyond the engine's limits: FSE accuracy log > 9 (LL/ML/weights) or > 8 (OF),
+                                   > 64 FSE symbols, Huffman maxBits > 11, offset code > 31 (zstd spec limits;
+                                   the reference does not enforce them) */
+    /* engine-only codes */
+    SZB_ERR_DST_TOO_SMALL = -64,
+    SZB_ERR_CUDA = -65,
+    SZB_ERR_INVALID_ARGUMENT = -66,
+    SZB_ERR_NO_DEVICE = -67,
+    SZB_ERR_CHECKSUM_MISMATCH = -68 /* only when SZB_FLAG_VERIFY_CHECKSUM is set (not a reference behaviour) */
+};
+
+/* replaces: the Go `error` values' Error() strings */
+const char *szb_strerror(int code);
+
+/* ---- descriptor tables: the output of the header walk -------------------------------- */
+/* The reference walks headers inside FrameDecompressor (framedecompressor.go:130-150 magic,
+ * :306-374 frame header via structure/frame.go:23-127, :270-303 block headers via
+ * structure/block.go:33-55) and inside the literal / sequence section parsers
+ * (structure/literals.go:67-204, structure/sequences.go:228-269).  The Go host keeps that
+ * walk and emits these two tables; szb_walk_* is the C++ twin of that walker. */
+
+#define SZB_NONE 0xFFFFFFFFu
+#define SZB_CONTENT_SIZE_UNKNOWN 0xFFFFFFFFFFFFFFFFull
+
+typedef struct szb_frame_desc {
+    uint64_t src_off;       /* offset of the frame's magic number inside src */
+    uint64_t src_len;       /* bytes from the magic to the end of the last block (the reference
+                               leaves the optional 4-byte checksum unread: SURVEY A.1) */
+    uint64_t window_size;   /* frame.go:28-36; = content size for single-segment frames */
+    uint64_t content_size;  /* frame.go:49-61 (+256 rule applied) or SZB_CONTENT_SIZE_UNKNOWN */
+    uint64_t dictionary_id; /* frame.go:38-47; parsed and ignored, like the reference */
+    uint32_t first_block;   /* index of the frame's first row in the block table */
+    uint32_t nblocks;
+    uint32_t checksum;      /* the 4 bytes after the last block when has_checksum (never verified by the reference) */
+    int32_t status;         /* 0, or the error the header walk hit (frame is then skipped by the device) */
+    uint8_t descriptor;     /* Frame_Header_Descriptor byte */
+    uint8_t single_segment; /* frame.go:101-103 */
+    uint8_t has_checksum;   /* frame.go:106-108 */
+    uint8_t has_content_size;
+    uint32_t _pad;
+} szb_frame_desc;
+
+typedef struct szb_block_desc {
+    uint64_t src_off;      /* offset inside src of the block payload (after the 3-byte header) */
+    uint64_t lit_buf_off;  /* byte offset of this block's literals in the device literal scratch */
+    uint64_t seq_buf_off;  /* index of this block's first sequence in the device sequence scratch */
+    uint32_t block_size;   /* Block_Size field (block.go:41-43); RLE blocks carry 1 payload byte */
+    uint32_t frame;        /* owning frame */
+    uint32_t lit_regen;    /* literals.go:85-159 RegeneratedSize */
+    uint32_t lit_comp;     /* literals.go:85-159 CompressedSize (tree + jump table + streams; raw: = regen; rle: 1) */
+    uint32_t nseq;         /* sequences.go:255-269 */
+    uint32_t seq_off;      /* offset inside the payload of the sequences section */
+    uint32_t huf_origin;   /* block whose payload holds the Huffman tree description this block decodes with:
+                              itself for Compressed literals, the most recent such block of the frame for
+                              Treeless (literals.go:247-252, carry rule framedecompressor.go:292-294); SZB_NONE */
+    uint32_t ll_origin;    /* block whose sequences section defines the LL table: itself unless mode Repeat
+                              (sequences.go:292-296; carry rule framedecompressor.go:283-291) */
+    uint32_t of_origin;    /* same for offsets (sequences.go:321-325) */
+    uint32_t ml_origin;    /* same for match lengths (sequences.go:352-356) */
+    uint8_t type;          /* 0 Raw, 1 RLE, 2 Compressed (block.go:15-20) */
+    uint8_t last;          /* block.go:38 */
+    uint8_t lit_type;      /* 0 Raw, 1 RLE, 2 Compressed, 3 Treeless (literals.go:67-81) */
+    uint8_t lit_streams;   /* 1 or 4 */
+    uint8_t lit_hdr_bytes; /* 1..5 (literals.go:162-204) */
+    uint8_t seq_hdr_bytes; /* bytes of the sequence count (1..3) plus the modes byte when nseq > 0 */
+    uint8_t seq_modes;     /* raw Symbol_Compression_Modes byte (sequences.go:228-232) */
+    uint8_t _pad;
+    uint32_t _pad2;
+} szb_block_desc;
+
+typedef struct szb_walk szb_walk;
+
+/* Walks the headers of nframes frames.  frame_off/frame_len give each frame's extent inside
+ * src; pass frame_off == NULL (and nframes == 0) to treat src as a concatenation of frames whose
+ * boundaries are discovered by the walk (skippable frames are skipped, a present checksum is
+ * stepped over) -- the reference itself handles exactly one frame per reader.
+ * replaces: CheckMagicnum + DecodeFrameHeader + the DecodeNextBlockHeader loop
+ * (framedecompressor.go:130-150, :306-374, :270-303) and the header parts of
+ * DecodeNextLiteralsSection / DecodeNextSequenceSection. */
+int szb_walk_create(const uint8_t *src, size_t src_len, const uint64_t *frame_off, const uint64_t *frame_len,
+                    uint32_t nframes, szb_walk **out);
+void szb_walk_destroy(szb_walk *w);
+uint32_t szb_walk_nframes(const szb_walk *w);
+uint32_t szb_walk_nblocks(const szb_walk *w);
+const szb_frame_desc *szb_walk_frames(const szb_walk *w);
+const szb_block_desc *szb_walk_blocks(const szb_walk *w);
+uint64_t szb_walk_literal_bytes(const szb_walk *w);  /* device literal scratch needed */
+uint64_t szb_walk_sequences(const szb_walk *w);      /* device sequence scratch rows needed */
+/* sum of content sizes when every frame declares one, else SZB_CONTENT_SIZE_UNKNOWN */
+uint64_t szb_walk_known_output_size(const szb_walk *w);
+
+/* ---- engine context -------------------------------------------------------------------- */
+typedef struct szb_ctx szb_ctx;
+
+/* device: CUDA ordinal.  stream: a cudaStream_t to enqueue on, or NULL to let the context
+ * create its own.  Fails with SZB_ERR_NO_DEVICE when no CUDA device is usable: there is no
+ * CPU fallback.  replaces: NewFrameDecompressor's buffer set-up (framedecompressor.go:55-61). */
+int szb_ctx_create(int device, void *stream, szb_ctx **out);
+void szb_ctx_destroy(szb_ctx *ctx);
+void *szb_ctx_stream(szb_ctx *ctx);
+const char *szb_ctx_last_error(szb_ctx *ctx); /* detail text of the last SZB_ERR_CUDA */
+
+#define SZB_FLAG_SRC_DEVICE 1u /* src is a device pointer (descriptor tables still come from a host copy) */
+#define SZB_FLAG_DST_DEVICE 2u /* dst is a device pointer; the output stays in HBM */
+#define SZB_FLAG_VERIFY_CHECKSUM 4u /* reserved for SURVEY 8f-1 (XXH64 verify); not a reference behaviour */
+
+/* The batch entry point north_star asks for: decode nframes independent frames in one
+ * launch sequence.  src/dst are HOST buffers unless flagged.  Frames are written back to
+ * back into dst; out_off/out_len/status (each nframes long, host) receive every frame's
+ * placement and result code.  Returns 0 when every frame decoded, else the first failing
+ * frame's code.  replaces: a loop of NewFrameDecompressor(src_i, dst_i).Decompress()
+ * (cmd/sparkzstd/main.go:22-40). */
+int szb_decode_batch(szb_ctx *ctx, const uint8_t *src, size_t src_len, const uint64_t *frame_off,
+                     const uint64_t *frame_len, uint32_t nframes, uint8_t *dst, size_t dst_cap, uint64_t *out_off,
+                     uint64_t *out_len, int32_t *status, uint32_t flags);
+
+/* Descriptor-level entry: what the Go walker feeds.  d_src / d_dst are DEVICE pointers,
+ * frames / blocks are HOST tables (copied before return).  replaces: DecodeNextBlockContent +
+ * ExecuteSequences + the Raw/RLE bodies of DecodeNextBlock (framedecompressor.go:93-126,
+ * :198-244; sequence_execution.go:14-63) for every block of every frame. */
+int szb_decode_blocks(szb_ctx *ctx, const void *d_src, size_t src_len, const szb_frame_desc *frames, uint32_t nframes,
+                      const szb_block_desc *blocks, uint32_t nblocks, void *d_dst, size_t dst_cap, uint64_t *out_off,
+                      uint64_t *out_len, int32_t *status);
+
+/* ---- staged batch object (size-then-decode, resident inputs, timing) ------------------ */
+typedef struct szb_batch szb_batch;
+
+/* Walk + upload descriptor tables + size the scratch arenas.  h_src must stay valid only
+ * for the duration of the call. */
+int szb_batch_create(szb_ctx *ctx, const uint8_t *h_src, size_t src_len, const uint64_t *frame_off,
+                     const uint64_t *frame_len, uint32_t nframes, szb_batch **out);
+int szb_batch_create_from_tables(szb_ctx *ctx, size_t src_len, const szb_frame_desc *frames, uint32_t nframes,
+                                 const szb_block_desc *blocks, uint32_t nblocks, szb_batch **out);
+void szb_batch_destroy(szb_batch *b);
+uint32_t szb_batch_nframes(const szb_batch *b);
+uint32_t szb_batch_nblocks(const szb_batch *b);
+/* Stages 1-3 (FSE tables, Huffman literals, FSE sequences, block-offset scan); asynchronous. */
+int szb_batch_decode_entropy(szb_batch *b, const void *d_src);
+/* Synchronises; total decompressed bytes and per-frame placement (any may be NULL). */
+int szb_batch_sizes(szb_batch *b, uint64_t *total, uint64_t *out_off, uint64_t *out_len);
+/* Stage 4 (sequence execution / Raw / RLE bodies) into d_dst; asynchronous. */
+int szb_batch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t dst_cap);
+/* All four stages back to back, no host synchronisation in between. */
+int szb_batch_run(szb_batch *b, const void *d_src, void *d_dst, size_t dst_cap);
+/* Synchronises and returns per-frame status (nframes long, may be NULL); returns the first failure. */
+int szb_batch_finish(szb_batch *b, int32_t *status);
+/* Stage-level scratch, for parity tests against the oracle's per-block trace (host copies). */
+int szb_batch_read_literals(szb_batch *b, uint32_t block, uint8_t *dst, size_t cap);
+int szb_batch_read_sequences(szb_batch *b, uint32_t block, uint32_t *ll, uint32_t *ml, uint32_t *of, size_t cap);
+int szb_batch_read_block_results(szb_batch *b, uint64_t *out_size, int32_t *status, size_t cap);
+
+/* Device-event timings of the last szb_batch_run / decode call, milliseconds:
+ * [0] total, [1] Huffman literals, [2] FSE tables + sequences, [3] offset scan, [4] execution,
+ * [5] H2D, [6] D2H.  Returns how many entries were written. */
+int szb_last_timing(szb_ctx *ctx, float *ms, int n);
+/* Kernel launches issued by the library since the context was created. */
+uint64_t szb_launch_count(szb_ctx *ctx);
+
+/* ---- single-frame helpers behind the Go API ------------------------------------------- */
+/* replaces: FrameDecompressor.Decompress (framedecompressor.go:153-170) and what
+ * FrameReader.Read drains (framereader.go:51-109).  Decodes the one frame at src[0..] and
+ * returns a malloc'ed buffer the caller releases with szb_free. */
+int szb_decompress_frame(szb_ctx *ctx, const uint8_t *src, size_t src_len, uint8_t **out, size_t *out_len,
+                         size_t *consumed);
+void szb_free(void *p);
+
+const char *szb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

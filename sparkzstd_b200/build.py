@@ -1,0 +1,58 @@
+"""Builds libszb200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libszb200.so")
+SOURCES = ["api.cu", "walker.cpp"]
+HEADERS = ["bits.cuh", "fse.cuh", "huffman.cuh", "sequences.cuh", "kernels.cuh", "../../include/szb200.h"]
+
+NVCC_FLAGS = [
+    "-gencode",
+    "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "-O3",
+    "-std=c++17",
+    "-Xcompiler",
+    "-fPIC",
+    "-shared",
+]
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: libszb200.so cannot be built")
+
+
+def is_stale(lib: str = LIB) -> bool:
+    if not os.path.exists(lib):
+        return True
+    t = os.path.getmtime(lib)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, out: str = LIB, defines: tuple = (), verbose: bool = False) -> str:
+    if not force and not is_stale(out):
+        return out
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", out, *[os.path.join(CSRC, s) for s in SOURCES]]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return out
+
+
+if __name__ == "__main__":
+    import sys
+
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

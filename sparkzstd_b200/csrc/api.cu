@@ -1,0 +1,692 @@
+// api.cu -- the C ABI of libszb200.so (include/szb200.h): context, batch objects, launches.
+//
+// Everything here is host plumbing around the four kernels in kernels.cuh.  There is no CPU
+// decode path: without a CUDA device szb_ctx_create fails and nothing else can be called.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/szb200.h"
+#include "kernels.cuh"
+
+using namespace szb;
+
+struct szb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev[8] = {};
+    uint32_t *d_predef = nullptr;
+    std::string last_error;
+    float timing[8] = {};
+    uint64_t launches = 0;
+    // grow-only staging for the host-pointer entry points
+    uint8_t *d_src = nullptr;
+    size_t d_src_cap = 0;
+    uint8_t *d_dst = nullptr;
+    size_t d_dst_cap = 0;
+};
+
+#define CUDA_TRY(ctx, expr)                                                                          \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            (ctx)->last_error = std::string(#expr) + ": " + cudaGetErrorString(e__);                 \
+            return SZB_ERR_CUDA;                                                                     \
+        }                                                                                            \
+    } while (0)
+
+struct szb_batch {
+    szb_ctx *ctx = nullptr;
+    uint32_t nframes = 0, nblocks = 0;
+    size_t src_len = 0;
+    std::vector<szb_frame_desc> frames;
+    std::vector<szb_block_desc> blocks;
+    std::vector<uint32_t> huf_list, seq_list;
+    uint64_t literal_bytes = 0, sequences = 0;
+    // device
+    void *d_tables = nullptr;  // one allocation: frames | blocks | lists | out_size_init
+    szb_frame_desc *d_frames = nullptr;
+    szb_block_desc *d_blocks = nullptr;
+    uint32_t *d_huf_list = nullptr, *d_seq_list = nullptr;
+    uint64_t *d_out_size_init = nullptr;
+    void *d_state = nullptr;  // one allocation: out_size | out_off | total | frame_out_off | frame_out_len | statuses
+    uint64_t *d_out_size = nullptr, *d_out_off = nullptr, *d_total = nullptr, *d_frame_out_off = nullptr,
+             *d_frame_out_len = nullptr;
+    int32_t *d_lit_status = nullptr, *d_seq_status = nullptr, *d_frame_status = nullptr;
+    size_t status_bytes = 0;
+    uint8_t *d_litbuf = nullptr;
+    uint32_t *d_seq = nullptr;  // ll | ml | of
+    bool entropy_done = false;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" {
+
+const char *szb_version(void) { return "sparkzstd-b200 0.1 (sm_100a)"; }
+
+const char *szb_strerror(int code) {
+    switch (code) {
+    case SZB_OK: return "ok";
+    case SZB_ERR_WRONG_MAGICNUMBER: return "Magicnum is not correct";
+    case SZB_ERR_CORRUPT_SIZES: return "The sizes of literal and sequence section did not add up to blocksize";
+    case SZB_ERR_OUT_OF_BLOCKS: return "No blocks left in frame";
+    case SZB_ERR_ILLEGAL_CONTENT_SIZE_FLAG: return "The SizeFlag for the Field ContentSize has an illegal value bigger than 3";
+    case SZB_ERR_ILLEGAL_DICTIONARY_ID_FLAG: return "The SizeFlag for the Field DictionaryID has an illegal value bigger than 3";
+    case SZB_ERR_NOT_ENOUGH_BYTES_FOR_BLOCK_HEADER: return "Not enough / too much bytes to decode the blockheader. Must be 3.";
+    case SZB_ERR_ILLEGAL_BLOCK_TYPE: return "Illegal BlockType. Must be smaller than 3.";
+    case SZB_ERR_ILLEGAL_BLOCK_SIZE: return "Illegal block-size. Must be lower than 128kb";
+    case SZB_ERR_WRONG_JUMPTABLE_BYTES: return "Not enough bytes for jumptable dacoding. Must be 6";
+    case SZB_ERR_CORRUPTED_JUMPTABLE: return "Bad jump table. Sizes dont add up to compressed size";
+    case SZB_ERR_ILLEGAL_LITERAL_SECTION_TYPE: return "Illegal LiteralSectionType. Must be between 0 to 3";
+    case SZB_ERR_ILLEGAL_LITERAL_SECTION_SIZE_FORMAT: return "Illegal LiteralSectionSizeformat. Must be between 0 to 3";
+    case SZB_ERR_WRONG_SIZES_BYTES: return "Not enough bytes to decode sizes";
+    case SZB_ERR_NO_HUFF_TABLE_TO_CARRY_OVER: return "No previous Huffmantree available";
+    case SZB_ERR_STREAM_DIDNT_DECODE_TO_RIGHT_LENGTH: return "Huffstream did not decode to the correct length";
+    case SZB_ERR_WRONG_SUM_OF_WEIGHTS: return "The weights didnt leave a power of two for the last weight";
+    case SZB_ERR_CORRUPTED_HUFF_TREE: return "The tree in the description is corrupted";
+    case SZB_ERR_BAD_PADDING: return "The padding at the end of the stream was more than a byte. Data is likely corrupted";
+    case SZB_ERR_DIDNT_USE_ALL_BITS_TO_DECODE_HUFFMAN: return "Didnt read all bits to decode huffman stream. Data is likely corrupted";
+    case SZB_ERR_NOT_ALL_BITS_USED: return "Did not read all bits to decode sequences. Likely data is corrupted.";
+    case SZB_ERR_NO_LL_TABLE_TO_CARRY_OVER: return "Needed to copy old LiteralLenghts table but there was none";
+    case SZB_ERR_NO_ML_TABLE_TO_CARRY_OVER: return "Needed to copy old MathcLenghts table but there was none";
+    case SZB_ERR_NO_OF_TABLE_TO_CARRY_OVER: return "Needed to copy old Offsets table but there was none";
+    case SZB_ERR_NOT_ALL_BYTES_USED_WHILE_SEQUENCE_DECODING: return "Didnt use all bytes from the sequence stream. Data is likely corrupted";
+    case SZB_ERR_DIDNT_READ_ALL_PROBABILITIES: return "The probabilities didnt add up to the expected total sum";
+    case SZB_ERR_NO_SYMBOL_FOR_STATE: return "Probably a bad state?";
+    case SZB_ERR_CANT_UNWIND: return "Cant unwind more bits";
+    case SZB_ERR_DIDNT_COPY_ALL_LITERAL_BYTES: return "Not enough bytes read to execute literals copy";
+    case SZB_ERR_IDX_OUT_OF_BOUNDS: return "Index is out of bounds";
+    case SZB_ERR_CANT_REPEAT_BYTES: return "You cant repeat bytes from before the first one";
+    case SZB_ERR_DIDNT_DUMP_ALL: return "Did not write all bytes. Output will likely be corrupted";
+    case SZB_ERR_UNEXPECTED_EOF: return "unexpected EOF";
+    case SZB_ERR_PANIC: return "corrupt input (the reference decoder panics on it)";
+    case SZB_ERR_NOMEM: return "out of memory";
+    case SZB_ERR_UNSUPPORTED: return "input exceeds the zstd format limits this engine enforces";
+    case SZB_ERR_DST_TOO_SMALL: return "destination buffer too small";
+    case SZB_ERR_CUDA: return "CUDA error (see szb_ctx_last_error)";
+    case SZB_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case SZB_ERR_NO_DEVICE: return "no usable CUDA device: this engine has no CPU fallback";
+    case SZB_ERR_CHECKSUM_MISMATCH: return "content checksum mismatch";
+    default: return "unknown error";
+    }
+}
+
+int szb_ctx_create(int device, void *stream, szb_ctx **out) {
+    if (!out) return SZB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        (void)cudaGetLastError();
+        return SZB_ERR_NO_DEVICE;
+    }
+    szb_ctx *ctx = new (std::nothrow) szb_ctx();
+    if (!ctx) return SZB_ERR_NOMEM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete ctx;
+        return SZB_ERR_NO_DEVICE;
+    }
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return SZB_ERR_CUDA;
+        }
+        ctx->own_stream = true;
+    }
+    for (auto &e : ctx->ev) {
+        if (cudaEventCreate(&e) != cudaSuccess) {
+            szb_ctx_destroy(ctx);
+            return SZB_ERR_CUDA;
+        }
+    }
+    // predefined LL / OF / ML decode tables (fse/predefined.go:22-78), built once with the same
+    // builder the kernels use and kept in device memory
+    uint32_t predef[160];
+    int16_t norm[64];
+    uint16_t next[64];
+    for (int i = 0; i < 36; i++) norm[i] = kLLDefaultNorm[i];
+    fse_build_serial(norm, 36, 6, KIND_LL, predef, next);
+    for (int i = 0; i < 29; i++) norm[i] = kOFDefaultNorm[i];
+    fse_build_serial(norm, 29, 5, KIND_OF, predef + 64, next);
+    for (int i = 0; i < 53; i++) norm[i] = kMLDefaultNorm[i];
+    fse_build_serial(norm, 53, 6, KIND_ML, predef + 96, next);
+    if (cudaMalloc(&ctx->d_predef, sizeof(predef)) != cudaSuccess ||
+        cudaMemcpy(ctx->d_predef, predef, sizeof(predef), cudaMemcpyHostToDevice) != cudaSuccess) {
+        szb_ctx_destroy(ctx);
+        return SZB_ERR_CUDA;
+    }
+    cudaFuncSetAttribute(k_huffman_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(HufSmem) * kWarpsPerCta));
+    cudaFuncSetAttribute(k_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SeqSmem) * kWarpsPerCta));
+    *out = ctx;
+    return SZB_OK;
+}
+
+void szb_ctx_destroy(szb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->d_predef) cudaFree(ctx->d_predef);
+    if (ctx->d_src) cudaFree(ctx->d_src);
+    if (ctx->d_dst) cudaFree(ctx->d_dst);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+void *szb_ctx_stream(szb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+const char *szb_ctx_last_error(szb_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+uint64_t szb_launch_count(szb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int szb_last_timing(szb_ctx *ctx, float *ms, int n) {
+    if (!ctx || !ms) return 0;
+    int k = n < 7 ? n : 7;
+    for (int i = 0; i < k; i++) ms[i] = ctx->timing[i];
+    return k;
+}
+
+void szb_free(void *p) { free(p); }
+
+// ---------------------------------------------------------------------------------------------
+static int batch_upload_tables(szb_batch *b) {
+    szb_ctx *ctx = b->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint32_t nb = b->nblocks, nf = b->nframes;
+    std::vector<uint64_t> out_size_init(nb ? nb : 1);
+    for (uint32_t i = 0; i < nb; i++) {
+        const szb_block_desc &d = b->blocks[i];
+        // Raw / RLE blocks regenerate Block_Size bytes; a compressed block regenerates its literals
+        // plus the match lengths k_sequences adds later
+        out_size_init[i] = d.type == 2 ? d.lit_regen : d.block_size;
+        if (d.type == 2 && d.lit_type >= 2) b->huf_list.push_back(i);
+        if (d.type == 2 && d.nseq > 0) b->seq_list.push_back(i);
+    }
+    // descriptor tables: one allocation, one H2D copy
+    size_t o_frames = 0;
+    size_t o_blocks = align_up(o_frames + sizeof(szb_frame_desc) * (size_t)nf, 256);
+    size_t o_huf = align_up(o_blocks + sizeof(szb_block_desc) * (size_t)nb, 256);
+    size_t o_seq = align_up(o_huf + 4 * b->huf_list.size(), 256);
+    size_t o_init = align_up(o_seq + 4 * b->seq_list.size(), 256);
+    size_t total = align_up(o_init + 8 * (size_t)nb, 256) + 256;
+    std::vector<uint8_t> stage(total, 0);
+    if (nf) memcpy(stage.data() + o_frames, b->frames.data(), sizeof(szb_frame_desc) * (size_t)nf);
+    if (nb) memcpy(stage.data() + o_blocks, b->blocks.data(), sizeof(szb_block_desc) * (size_t)nb);
+    if (!b->huf_list.empty()) memcpy(stage.data() + o_huf, b->huf_list.data(), 4 * b->huf_list.size());
+    if (!b->seq_list.empty()) memcpy(stage.data() + o_seq, b->seq_list.data(), 4 * b->seq_list.size());
+    if (nb) memcpy(stage.data() + o_init, out_size_init.data(), 8 * (size_t)nb);
+    CUDA_TRY(ctx, cudaMalloc(&b->d_tables, total));
+    CUDA_TRY(ctx, cudaMemcpyAsync(b->d_tables, stage.data(), total, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    uint8_t *base = (uint8_t *)b->d_tables;
+    b->d_frames = (szb_frame_desc *)(base + o_frames);
+    b->d_blocks = (szb_block_desc *)(base + o_blocks);
+    b->d_huf_list = (uint32_t *)(base + o_huf);
+    b->d_seq_list = (uint32_t *)(base + o_seq);
+    b->d_out_size_init = (uint64_t *)(base + o_init);
+    // mutable state
+    size_t s_out_size = 0;
+    size_t s_out_off = align_up(s_out_size + 8 * (size_t)nb, 256);
+    size_t s_total = align_up(s_out_off + 8 * (size_t)nb, 256);
+    size_t s_foff = s_total + 256;
+    size_t s_flen = align_up(s_foff + 8 * (size_t)nf, 256);
+    size_t s_status = align_up(s_flen + 8 * (size_t)nf, 256);
+    size_t s_lit = s_status;
+    size_t s_seqs = s_lit + 4 * (size_t)nb;
+    size_t s_fst = s_seqs + 4 * (size_t)nb;
+    b->status_bytes = 4 * (2 * (size_t)nb + (size_t)nf);
+    size_t s_end = align_up(s_fst + 4 * (size_t)nf, 256) + 256;
+    CUDA_TRY(ctx, cudaMalloc(&b->d_state, s_end));
+    CUDA_TRY(ctx, cudaMemsetAsync(b->d_state, 0, s_end, ctx->stream));
+    base = (uint8_t *)b->d_state;
+    b->d_out_size = (uint64_t *)(base + s_out_size);
+    b->d_out_off = (uint64_t *)(base + s_out_off);
+    b->d_total = (uint64_t *)(base + s_total);
+    b->d_frame_out_off = (uint64_t *)(base + s_foff);
+    b->d_frame_out_len = (uint64_t *)(base + s_flen);
+    b->d_lit_status = (int32_t *)(base + s_lit);
+    b->d_seq_status = (int32_t *)(base + s_seqs);
+    b->d_frame_status = (int32_t *)(base + s_fst);
+    // scratch arenas
+    CUDA_TRY(ctx, cudaMalloc(&b->d_litbuf, (size_t)b->literal_bytes + 256));
+    CUDA_TRY(ctx, cudaMalloc(&b->d_seq, (size_t)(b->sequences * 3 + 64) * 4));
+    return SZB_OK;
+}
+
+int szb_batch_create_from_tables(szb_ctx *ctx, size_t src_len, const szb_frame_desc *frames, uint32_t nframes,
+                                 const szb_block_desc *blocks, uint32_t nblocks, szb_batch **out) {
+    if (!ctx || !out || (nframes && !frames) || (nblocks && !blocks)) return SZB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    szb_batch *b = new (std::nothrow) szb_batch();
+    if (!b) return SZB_ERR_NOMEM;
+    b->ctx = ctx;
+    b->nframes = nframes;
+    b->nblocks = nblocks;
+    b->src_len = src_len;
+    try {
+        b->frames.assign(frames, frames + nframes);
+        b->blocks.assign(blocks, blocks + nblocks);
+    } catch (const std::bad_alloc &) {
+        delete b;
+        return SZB_ERR_NOMEM;
+    }
+    // validate what the device will trust
+    for (uint32_t f = 0; f < nframes; f++) {
+        const szb_frame_desc &fr = b->frames[f];
+        if ((uint64_t)fr.first_block + fr.nblocks > nblocks) {
+            delete b;
+            return SZB_ERR_INVALID_ARGUMENT;
+        }
+    }
+    uint64_t lit = 0, seq = 0;
+    for (uint32_t i = 0; i < nblocks; i++) {
+        const szb_block_desc &d = b->blocks[i];
+        uint64_t payload = d.type == 1 ? 1 : d.block_size;
+        bool bad = d.type > 2 || d.frame >= nframes || d.src_off > src_len || payload > src_len - d.src_off || d.block_size > 128 * 1024;
+        if (!bad && d.type == 2) {
+            bad = d.lit_type > 3 || (uint64_t)d.lit_hdr_bytes + d.lit_comp > d.block_size || d.lit_regen > 128 * 1024 ||
+                  (uint64_t)d.seq_off + d.seq_hdr_bytes > d.block_size || d.seq_off != (uint32_t)d.lit_hdr_bytes + d.lit_comp ||
+                  (d.lit_streams != 1 && d.lit_streams != 4);
+            if (!bad && d.lit_type >= 2) {
+                bad = d.huf_origin >= nblocks || d.huf_origin > i || b->blocks[d.huf_origin].type != 2 ||
+                      b->blocks[d.huf_origin].lit_type != 2;
+                lit = d.lit_buf_off + d.lit_regen > lit ? d.lit_buf_off + d.lit_regen : lit;
+            }
+            if (!bad && d.nseq > 0) {
+                const uint32_t org[3] = {d.ll_origin, d.of_origin, d.ml_origin};
+                const int kinds[3] = {KIND_LL, KIND_OF, KIND_ML};
+                for (int k = 0; k < 3 && !bad; k++) {
+                    uint32_t m = field_mode(d.seq_modes, kinds[k]);
+                    if (m == 3) {
+                        bad = org[k] >= i || b->blocks[org[k]].type != 2 || b->blocks[org[k]].nseq == 0 ||
+                              field_mode(b->blocks[org[k]].seq_modes, kinds[k]) == 3;
+                    }
+                }
+                seq = d.seq_buf_off + d.nseq > seq ? d.seq_buf_off + d.nseq : seq;
+            }
+        }
+        if (bad) {
+            delete b;
+            return SZB_ERR_INVALID_ARGUMENT;
+        }
+    }
+    b->literal_bytes = lit;
+    b->sequences = align_up(seq, 32);
+    int rc = batch_upload_tables(b);
+    if (rc) {
+        szb_batch_destroy(b);
+        return rc;
+    }
+    *out = b;
+    return SZB_OK;
+}
+
+int szb_batch_create(szb_ctx *ctx, const uint8_t *h_src, size_t src_len, const uint64_t *frame_off,
+                     const uint64_t *frame_len, uint32_t nframes, szb_batch **out) {
+    if (!ctx || !out) return SZB_ERR_INVALID_ARGUMENT;
+    szb_walk *w = nullptr;
+    int rc = szb_walk_create(h_src, src_len, frame_off, frame_len, nframes, &w);
+    if (rc) return rc;
+    rc = szb_batch_create_from_tables(ctx, src_len, szb_walk_frames(w), szb_walk_nframes(w), szb_walk_blocks(w),
+                                      szb_walk_nblocks(w), out);
+    szb_walk_destroy(w);
+    return rc;
+}
+
+void szb_batch_destroy(szb_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    if (b->d_tables) cudaFree(b->d_tables);
+    if (b->d_state) cudaFree(b->d_state);
+    if (b->d_litbuf) cudaFree(b->d_litbuf);
+    if (b->d_seq) cudaFree(b->d_seq);
+    delete b;
+}
+
+uint32_t szb_batch_nframes(const szb_batch *b) { return b ? b->nframes : 0; }
+uint32_t szb_batch_nblocks(const szb_batch *b) { return b ? b->nblocks : 0; }
+
+static DeviceBatch make_args(szb_batch *b, const void *d_src, void *d_dst, size_t dst_cap) {
+    DeviceBatch a;
+    a.src = (const uint8_t *)d_src;
+    a.blocks = b->d_blocks;
+    a.frames = b->d_frames;
+    a.nblocks = b->nblocks;
+    a.nframes = b->nframes;
+    a.huf_list = b->d_huf_list;
+    a.n_huf = (uint32_t)b->huf_list.size();
+    a.seq_list = b->d_seq_list;
+    a.n_seq = (uint32_t)b->seq_list.size();
+    a.litbuf = b->d_litbuf;
+    a.seq_ll = b->d_seq;
+    a.seq_ml = b->d_seq + b->sequences;
+    a.seq_of = b->d_seq + 2 * b->sequences;
+    a.out_size = b->d_out_size;
+    a.out_off = b->d_out_off;
+    a.lit_status = b->d_lit_status;
+    a.seq_status = b->d_seq_status;
+    a.total = b->d_total;
+    a.predef = b->ctx->d_predef;
+    a.dst = (uint8_t *)d_dst;
+    a.dst_cap = dst_cap;
+    a.frame_out_off = b->d_frame_out_off;
+    a.frame_out_len = b->d_frame_out_len;
+    a.frame_status = b->d_frame_status;
+    return a;
+}
+
+static int launch_entropy(szb_batch *b, const void *d_src) {
+    szb_ctx *ctx = b->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    DeviceBatch a = make_args(b, d_src, nullptr, 0);
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
+    CUDA_TRY(ctx, cudaMemsetAsync(b->d_lit_status, 0, b->status_bytes, s));
+    if (b->nblocks)
+        CUDA_TRY(ctx, cudaMemcpyAsync(b->d_out_size, b->d_out_size_init, 8 * (size_t)b->nblocks, cudaMemcpyDeviceToDevice, s));
+    if (a.n_huf) {
+        k_huffman_literals<<<(a.n_huf + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, sizeof(HufSmem) * kWarpsPerCta, s>>>(a);
+        ctx->launches++;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
+    if (a.n_seq) {
+        k_sequences<<<(a.n_seq + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, sizeof(SeqSmem) * kWarpsPerCta, s>>>(a);
+        ctx->launches++;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
+    k_scan_blocks<<<1, kScanThreads, 0, s>>>(a);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], s));
+    CUDA_TRY(ctx, cudaGetLastError());
+    b->entropy_done = true;
+    return SZB_OK;
+}
+
+static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t dst_cap) {
+    szb_ctx *ctx = b->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    DeviceBatch a = make_args(b, d_src, d_dst, dst_cap);
+    if (a.nframes) {
+        k_execute<<<(a.nframes + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, s>>>(a);
+        ctx->launches++;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SZB_OK;
+}
+
+static int collect_timing(szb_ctx *ctx) {
+    float t;
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev[4]));
+    CUDA_TRY(ctx, cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[4]));
+    ctx->timing[0] = t;
+    for (int i = 1; i <= 4; i++) {
+        CUDA_TRY(ctx, cudaEventElapsedTime(&t, ctx->ev[i - 1], ctx->ev[i]));
+        ctx->timing[i] = t;
+    }
+    return SZB_OK;
+}
+
+int szb_batch_decode_entropy(szb_batch *b, const void *d_src) {
+    if (!b || (!d_src && b->src_len)) return SZB_ERR_INVALID_ARGUMENT;
+    return launch_entropy(b, d_src);
+}
+
+int szb_batch_sizes(szb_batch *b, uint64_t *total, uint64_t *out_off, uint64_t *out_len) {
+    if (!b || !b->entropy_done) return SZB_ERR_INVALID_ARGUMENT;
+    szb_ctx *ctx = b->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint32_t nb = b->nblocks;
+    std::vector<uint64_t> off(nb ? nb : 1), size(nb ? nb : 1);
+    uint64_t tot = 0;
+    if (nb) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(off.data(), b->d_out_off, 8 * (size_t)nb, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(size.data(), b->d_out_size, 8 * (size_t)nb, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(&tot, b->d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (total) *total = tot;
+    for (uint32_t f = 0; f < b->nframes; f++) {
+        const szb_frame_desc &fr = b->frames[f];
+        uint64_t o = fr.nblocks ? off[fr.first_block] : 0;
+        uint64_t l = fr.nblocks ? off[fr.first_block + fr.nblocks - 1] + size[fr.first_block + fr.nblocks - 1] - o : 0;
+        if (out_off) out_off[f] = o;
+        if (out_len) out_len[f] = l;
+    }
+    return SZB_OK;
+}
+
+int szb_batch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t dst_cap) {
+    if (!b || !b->entropy_done || (!d_dst && dst_cap)) return SZB_ERR_INVALID_ARGUMENT;
+    return launch_execute(b, d_src, d_dst, dst_cap);
+}
+
+int szb_batch_run(szb_batch *b, const void *d_src, void *d_dst, size_t dst_cap) {
+    if (!b) return SZB_ERR_INVALID_ARGUMENT;
+    int rc = launch_entropy(b, d_src);
+    if (rc) return rc;
+    return launch_execute(b, d_src, d_dst, dst_cap);
+}
+
+int szb_batch_finish(szb_batch *b, int32_t *status) {
+    if (!b) return SZB_ERR_INVALID_ARGUMENT;
+    szb_ctx *ctx = b->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<int32_t> st(b->nframes ? b->nframes : 1, 0);
+    if (b->nframes)
+        CUDA_TRY(ctx, cudaMemcpyAsync(st.data(), b->d_frame_status, 4 * (size_t)b->nframes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaGetLastError());
+    int rc = collect_timing(ctx);
+    if (rc) return rc;
+    int first = SZB_OK;
+    for (uint32_t f = 0; f < b->nframes; f++) {
+        if (status) status[f] = st[f];
+        if (first == SZB_OK && st[f] != SZB_OK) first = st[f];
+    }
+    return first;
+}
+
+int szb_batch_read_literals(szb_batch *b, uint32_t block, uint8_t *dst, size_t cap) {
+    if (!b || block >= b->nblocks || !dst) return SZB_ERR_INVALID_ARGUMENT;
+    const szb_block_desc &d = b->blocks[block];
+    if (d.type != 2 || d.lit_type < 2 || cap < d.lit_regen) return SZB_ERR_INVALID_ARGUMENT;
+    szb_ctx *ctx = b->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpy(dst, b->d_litbuf + d.lit_buf_off, d.lit_regen, cudaMemcpyDeviceToHost));
+    return SZB_OK;
+}
+
+int szb_batch_read_sequences(szb_batch *b, uint32_t block, uint32_t *ll, uint32_t *ml, uint32_t *of, size_t cap) {
+    if (!b || block >= b->nblocks || !ll || !ml || !of) return SZB_ERR_INVALID_ARGUMENT;
+    const szb_block_desc &d = b->blocks[block];
+    if (d.type != 2 || cap < d.nseq) return SZB_ERR_INVALID_ARGUMENT;
+    szb_ctx *ctx = b->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    size_t n = 4 * (size_t)d.nseq;
+    if (n) {
+        CUDA_TRY(ctx, cudaMemcpy(ll, b->d_seq + d.seq_buf_off, n, cudaMemcpyDeviceToHost));
+        CUDA_TRY(ctx, cudaMemcpy(ml, b->d_seq + b->sequences + d.seq_buf_off, n, cudaMemcpyDeviceToHost));
+        CUDA_TRY(ctx, cudaMemcpy(of, b->d_seq + 2 * b->sequences + d.seq_buf_off, n, cudaMemcpyDeviceToHost));
+    }
+    return SZB_OK;
+}
+
+int szb_batch_read_block_results(szb_batch *b, uint64_t *out_size, int32_t *status, size_t cap) {
+    if (!b || cap < b->nblocks) return SZB_ERR_INVALID_ARGUMENT;
+    szb_ctx *ctx = b->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint32_t nb = b->nblocks;
+    if (!nb) return SZB_OK;
+    if (out_size) CUDA_TRY(ctx, cudaMemcpy(out_size, b->d_out_size, 8 * (size_t)nb, cudaMemcpyDeviceToHost));
+    if (status) {
+        std::vector<int32_t> l(nb), s(nb);
+        CUDA_TRY(ctx, cudaMemcpy(l.data(), b->d_lit_status, 4 * (size_t)nb, cudaMemcpyDeviceToHost));
+        CUDA_TRY(ctx, cudaMemcpy(s.data(), b->d_seq_status, 4 * (size_t)nb, cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < nb; i++) status[i] = l[i] ? l[i] : s[i];
+    }
+    return SZB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int ensure_dev(szb_ctx *ctx, uint8_t **p, size_t *cap, size_t need) {
+    if (need <= *cap && *p) return SZB_OK;
+    if (*p) CUDA_TRY(ctx, cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    size_t want = align_up(need + 256, 1 << 20);
+    CUDA_TRY(ctx, cudaMalloc((void **)p, want));
+    *cap = want;
+    return SZB_OK;
+}
+
+static int decode_tables(szb_ctx *ctx, szb_batch *b, const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap,
+                         uint64_t *out_off, uint64_t *out_len, int32_t *status, uint32_t flags) {
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const void *d_src = src;
+    float h2d_ms = 0, d2h_ms = 0;
+    if (!(flags & SZB_FLAG_SRC_DEVICE)) {
+        int rc = ensure_dev(ctx, &ctx->d_src, &ctx->d_src_cap, src_len + 16);
+        if (rc) return rc;
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+        if (src_len) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_src, src, src_len, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
+        d_src = ctx->d_src;
+    }
+    int rc = launch_entropy(b, d_src);
+    if (rc) return rc;
+    uint64_t total = 0;
+    rc = szb_batch_sizes(b, &total, nullptr, nullptr);
+    if (rc) return rc;
+    if (!(flags & SZB_FLAG_SRC_DEVICE)) CUDA_TRY(ctx, cudaEventElapsedTime(&h2d_ms, ctx->ev[5], ctx->ev[6]));
+    void *d_dst = dst;
+    size_t d_cap = dst_cap;
+    if (!(flags & SZB_FLAG_DST_DEVICE)) {
+        // too small a host buffer still runs stage 4 so every frame reports SZB_ERR_DST_TOO_SMALL
+        size_t need = total <= dst_cap ? (size_t)total : 0;
+        rc = ensure_dev(ctx, &ctx->d_dst, &ctx->d_dst_cap, need + 16);
+        if (rc) return rc;
+        d_dst = ctx->d_dst;
+    }
+    rc = launch_execute(b, d_src, d_dst, d_cap);
+    if (rc) return rc;
+    std::vector<int32_t> st(b->nframes ? b->nframes : 1, 0);
+    int first = szb_batch_finish(b, st.data());
+    if (first == SZB_ERR_CUDA) return first;
+    std::vector<uint64_t> off(b->nframes ? b->nframes : 1), len(b->nframes ? b->nframes : 1);
+    if (b->nframes) {
+        CUDA_TRY(ctx, cudaMemcpy(off.data(), b->d_frame_out_off, 8 * (size_t)b->nframes, cudaMemcpyDeviceToHost));
+        CUDA_TRY(ctx, cudaMemcpy(len.data(), b->d_frame_out_len, 8 * (size_t)b->nframes, cudaMemcpyDeviceToHost));
+    }
+    if (!(flags & SZB_FLAG_DST_DEVICE) && total <= dst_cap && total > 0) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(dst, ctx->d_dst, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(ctx, cudaEventElapsedTime(&d2h_ms, ctx->ev[5], ctx->ev[6]));
+    }
+    ctx->timing[5] = h2d_ms;
+    ctx->timing[6] = d2h_ms;
+    for (uint32_t f = 0; f < b->nframes; f++) {
+        if (out_off) out_off[f] = off[f];
+        if (out_len) out_len[f] = len[f];
+        if (status) status[f] = st[f];
+    }
+    return first;
+}
+
+int szb_decode_batch(szb_ctx *ctx, const uint8_t *src, size_t src_len, const uint64_t *frame_off,
+                     const uint64_t *frame_len, uint32_t nframes, uint8_t *dst, size_t dst_cap, uint64_t *out_off,
+                     uint64_t *out_len, int32_t *status, uint32_t flags) {
+    if (!ctx || (!src && src_len) || (!dst && dst_cap)) return SZB_ERR_INVALID_ARGUMENT;
+    if (flags & SZB_FLAG_SRC_DEVICE) return SZB_ERR_INVALID_ARGUMENT;  // the header walk needs host bytes: use szb_decode_blocks
+    szb_batch *b = nullptr;
+    int rc = szb_batch_create(ctx, src, src_len, frame_off, frame_len, nframes, &b);
+    if (rc) return rc;
+    if (frame_off == nullptr && (out_off || out_len || status) && b->nframes > nframes) {
+        // discovered more frames than the caller sized its arrays for
+        szb_batch_destroy(b);
+        return SZB_ERR_INVALID_ARGUMENT;
+    }
+    rc = decode_tables(ctx, b, src, src_len, dst, dst_cap, out_off, out_len, status, flags);
+    szb_batch_destroy(b);
+    return rc;
+}
+
+int szb_decode_blocks(szb_ctx *ctx, const void *d_src, size_t src_len, const szb_frame_desc *frames, uint32_t nframes,
+                      const szb_block_desc *blocks, uint32_t nblocks, void *d_dst, size_t dst_cap, uint64_t *out_off,
+                      uint64_t *out_len, int32_t *status) {
+    if (!ctx) return SZB_ERR_INVALID_ARGUMENT;
+    szb_batch *b = nullptr;
+    int rc = szb_batch_create_from_tables(ctx, src_len, frames, nframes, blocks, nblocks, &b);
+    if (rc) return rc;
+    rc = decode_tables(ctx, b, (const uint8_t *)d_src, src_len, (uint8_t *)d_dst, dst_cap, out_off, out_len, status,
+                       SZB_FLAG_SRC_DEVICE | SZB_FLAG_DST_DEVICE);
+    szb_batch_destroy(b);
+    return rc;
+}
+
+int szb_decompress_frame(szb_ctx *ctx, const uint8_t *src, size_t src_len, uint8_t **out, size_t *out_len,
+                         size_t *consumed) {
+    if (!ctx || !out || !out_len || (!src && src_len)) return SZB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    *out_len = 0;
+    if (consumed) *consumed = 0;
+    uint64_t off = 0, len = src_len;
+    szb_batch *b = nullptr;
+    int rc = szb_batch_create(ctx, src, src_len, &off, &len, 1, &b);
+    if (rc) return rc;
+    const szb_frame_desc fr = b->frames[0];
+    if (consumed) *consumed = (size_t)fr.src_len;
+    // entropy first: a frame without Frame_Content_Size only learns its length after stage 3
+    rc = ensure_dev(ctx, &ctx->d_src, &ctx->d_src_cap, src_len + 16);
+    if (!rc && src_len) {
+        cudaError_t e = cudaMemcpyAsync(ctx->d_src, src, src_len, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) {
+            ctx->last_error = cudaGetErrorString(e);
+            rc = SZB_ERR_CUDA;
+        }
+    }
+    uint64_t total = 0;
+    if (!rc) rc = launch_entropy(b, ctx->d_src);
+    if (!rc) rc = szb_batch_sizes(b, &total, nullptr, nullptr);
+    uint8_t *host = nullptr;
+    if (!rc) {
+        host = (uint8_t *)malloc(total ? (size_t)total : 1);
+        if (!host) rc = SZB_ERR_NOMEM;
+    }
+    if (!rc) rc = ensure_dev(ctx, &ctx->d_dst, &ctx->d_dst_cap, (size_t)total + 16);
+    if (!rc) rc = launch_execute(b, ctx->d_src, ctx->d_dst, (size_t)total);
+    int32_t st = 0;
+    if (!rc) rc = szb_batch_finish(b, &st);
+    if (!rc && total) {
+        cudaError_t e = cudaMemcpy(host, ctx->d_dst, (size_t)total, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            ctx->last_error = cudaGetErrorString(e);
+            rc = SZB_ERR_CUDA;
+        }
+    }
+    szb_batch_destroy(b);
+    if (rc) {
+        free(host);
+        return rc;
+    }
+    *out = host;
+    *out_len = (size_t)total;
+    return SZB_OK;
+}
+
+}  // extern "C"

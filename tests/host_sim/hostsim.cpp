@@ -1,0 +1,235 @@
+// hostsim.cpp -- TEST INFRASTRUCTURE: runs the *serial* device functions of the CUDA path
+// (bits.cuh, fse.cuh, huffman.cuh, sequences.cuh -- the code a single lane executes) on the CPU,
+// driven by the product's own header walker, so that `pytest -m "not gpu"` can check them
+// against the oracle without a GPU.  The warp-cooperative parts (table builds with ballots,
+// k_execute) only run on the device and are covered by the -m gpu tests.
+// This file is never linked into libszb200.so.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../include/szb200.h"
+#include "../../sparkzstd_b200/csrc/huffman.cuh"
+#include "../../sparkzstd_b200/csrc/sequences.cuh"
+
+using namespace szb;
+
+namespace {
+
+struct Tables {
+    uint32_t tll[512], tof[256], tml[512];
+    uint32_t al[3];
+};
+
+int build_one(const TableSource &ts, int kind, uint32_t *table, uint32_t *al, uint32_t *used) {
+    int16_t norm[64];
+    uint16_t next[64];
+    if (ts.mode == 0) {
+        uint32_t n = kind == KIND_LL ? 36 : (kind == KIND_OF ? 29 : 53);
+        const int8_t *src = kind == KIND_LL ? kLLDefaultNorm : (kind == KIND_OF ? kOFDefaultNorm : kMLDefaultNorm);
+        for (uint32_t i = 0; i < n; i++) norm[i] = src[i];
+        *al = kind == KIND_OF ? 5 : 6;
+        *used = 0;
+        return fse_build_serial(norm, n, *al, kind, table, next);
+    }
+    if (ts.mode == 1) {
+        if (ts.avail < 1) return SZB_ERR_UNEXPECTED_EOF;
+        uint32_t code = ts.p[0];
+        if ((kind == KIND_LL && code >= 36) || (kind == KIND_ML && code >= 53)) return SZB_ERR_PANIC;
+        if (kind == KIND_OF && code > 31) return SZB_ERR_UNSUPPORTED;
+        table[0] = fse_pack(0, 0, extra_bits_for(kind, code), code);
+        *al = 0;
+        *used = 1;
+        return SZB_OK;
+    }
+    uint32_t nsym;
+    uint32_t max_al = kind == KIND_OF ? kMaxALOF : (kind == KIND_LL ? kMaxALLL : kMaxALML);
+    int rc = fse_read_description(ts.p, ts.avail, max_al, norm, &nsym, al, used);
+    if (rc) return rc;
+    if (kind == KIND_OF && nsym > 32) return SZB_ERR_UNSUPPORTED;
+    return fse_build_serial(norm, nsym, *al, kind, table, next);
+}
+
+int huffman_block(const uint8_t *src, const szb_block_desc *blocks, uint32_t b, uint8_t *out) {
+    const szb_block_desc &d = blocks[b];
+    const szb_block_desc &o = blocks[d.huf_origin];
+    const uint8_t *tree = src + o.src_off + o.lit_hdr_bytes;
+    uint32_t tree_avail = o.lit_comp;
+    if (tree_avail < 1) return SZB_ERR_UNEXPECTED_EOF;
+    uint32_t hb = tree[0], nw = 0, tree_bytes;
+    uint8_t weights[256];
+    if (hb < 128) {
+        if (1 + hb > tree_avail) return SZB_ERR_UNEXPECTED_EOF;
+        int16_t norm[64];
+        uint16_t next[64];
+        uint32_t table[512];
+        uint32_t nsym, al, used;
+        int rc = fse_read_description(tree + 1, tree_avail - 1, kMaxALHufW, norm, &nsym, &al, &used);
+        if (rc) return rc;
+        rc = fse_build_serial(norm, nsym, al, KIND_HUFW, table, next);
+        if (rc) return rc;
+        if (used > hb) return SZB_ERR_PANIC;
+        rc = fse_decode_weights(table, al, tree + 1 + used, hb - used, weights, &nw);
+        if (rc) return rc;
+        tree_bytes = 1 + hb;
+    } else {
+        nw = hb - 127;
+        int rc = huf_read_direct_weights(tree + 1, tree_avail - 1, nw, weights);
+        if (rc) return rc;
+        tree_bytes = 1 + ((nw + 1) >> 1);
+    }
+    std::vector<uint16_t> huf(1 << kMaxHufBits);
+    uint32_t max_bits;
+    int rc = huf_build_serial(weights, nw, huf.data(), &max_bits);
+    if (rc) return rc;
+    const uint8_t *payload = src + d.src_off;
+    uint32_t skip = d.lit_hdr_bytes + (d.lit_type == 2 ? tree_bytes : 0);
+    int32_t comp = (int32_t)d.lit_comp - (int32_t)(d.lit_type == 2 ? tree_bytes : 0);
+    if (d.lit_streams == 1) {
+        if (comp < 0) return SZB_ERR_PANIC;
+        return huf_decode_stream(huf.data(), max_bits, payload + skip, (uint32_t)comp, out, d.lit_regen);
+    }
+    comp -= 6;
+    if (comp < 0) return SZB_ERR_PANIC;
+    const uint8_t *jt = payload + skip;
+    uint32_t s[4] = {(uint32_t)(jt[0] | (jt[1] << 8)), (uint32_t)(jt[2] | (jt[3] << 8)), (uint32_t)(jt[4] | (jt[5] << 8)), 0};
+    uint32_t normal = (d.lit_regen + 3) / 4;
+    int32_t last = (int32_t)d.lit_regen - 3 * (int32_t)normal;
+    if (s[0] + s[1] + s[2] > (uint32_t)comp) return SZB_ERR_CORRUPTED_JUMPTABLE;
+    if (last < 0) return SZB_ERR_PANIC;
+    s[3] = (uint32_t)comp - (s[0] + s[1] + s[2]);
+    uint32_t start = 0;
+    for (int k = 0; k < 4; k++) {
+        rc = huf_decode_stream(huf.data(), max_bits, jt + 6 + start, s[k], out + k * normal, k < 3 ? normal : (uint32_t)last);
+        if (rc) return rc;
+        start += s[k];
+    }
+    return SZB_OK;
+}
+
+int sequences_block(const uint8_t *src, const szb_block_desc *blocks, uint32_t b, std::vector<uint32_t> &ll,
+                    std::vector<uint32_t> &ml, std::vector<uint32_t> &of) {
+    const szb_block_desc &d = blocks[b];
+    const uint8_t *tables = src + d.src_off + d.seq_off + d.seq_hdr_bytes;
+    uint32_t tables_avail = d.block_size - d.seq_off - d.seq_hdr_bytes;
+    Tables t;
+    uint32_t cursor = 0;
+    int16_t norm[64];
+    for (int kind = 0; kind < 3; kind++) {
+        uint32_t *table = kind == KIND_LL ? t.tll : (kind == KIND_OF ? t.tof : t.tml);
+        uint32_t mode = field_mode(d.seq_modes, kind);
+        TableSource ts;
+        if (mode == 3) {
+            uint32_t ob = kind == KIND_LL ? d.ll_origin : (kind == KIND_OF ? d.of_origin : d.ml_origin);
+            const szb_block_desc &o = blocks[ob];
+            int rc = locate_field(src + o.src_off + o.seq_off + o.seq_hdr_bytes, o.block_size - o.seq_off - o.seq_hdr_bytes,
+                                  o.seq_modes, kind, norm, &ts);
+            if (rc) return rc;
+        } else {
+            ts.p = tables + cursor;
+            ts.avail = tables_avail - cursor;
+            ts.mode = mode;
+        }
+        uint32_t used = 0;
+        int rc = build_one(ts, kind, table, &t.al[kind], &used);
+        if (rc) return rc;
+        if (mode != 3) cursor += used;
+        if (cursor > tables_avail) return SZB_ERR_UNEXPECTED_EOF;
+    }
+    RevBits r;
+    if (!rev_init(r, tables + cursor, (int32_t)(tables_avail - cursor)) || !rev_skip_padding(r)) return SZB_ERR_BAD_PADDING;
+    rev_refill(r);
+    SeqStates st;
+    st.ll = rev_read(r, t.al[KIND_LL]);
+    st.of = rev_read(r, t.al[KIND_OF]);
+    st.ml = rev_read(r, t.al[KIND_ML]);
+    ll.resize(d.nseq);
+    ml.resize(d.nseq);
+    of.resize(d.nseq);
+    for (uint32_t i = 0; i < d.nseq; i++)
+        decode_one_sequence(r, t.tll, t.tof, t.tml, st, i + 1 < d.nseq, &ll[i], &ml[i], &of[i]);
+    if (r.remaining != 0) return SZB_ERR_NOT_ALL_BITS_USED;
+    return SZB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Decodes ONE frame with walker + serial device functions + a plain serial executor.
+// Optional per-block capture: lit_out (concatenated Huffman-decoded literals, block order).
+int hostsim_decode_frame(const uint8_t *src, size_t len, uint8_t *out, size_t cap, size_t *out_len) {
+    uint64_t off = 0, flen = len;
+    szb_walk *w = nullptr;
+    int rc = szb_walk_create(src, len, &off, &flen, 1, &w);
+    if (rc) return rc;
+    const szb_frame_desc fr = szb_walk_frames(w)[0];
+    const szb_block_desc *blocks = szb_walk_blocks(w);
+    uint32_t nb = szb_walk_nblocks(w);
+    size_t pos = 0;
+    uint32_t h[3] = {1, 4, 8};
+    std::vector<uint8_t> lit(128 * 1024);
+    std::vector<uint32_t> ll, ml, of;
+    rc = SZB_OK;
+    for (uint32_t b = 0; b < nb && rc == SZB_OK; b++) {
+        const szb_block_desc &d = blocks[b];
+        const uint8_t *payload = src + d.src_off;
+        if (d.type == 0) {
+            if (pos + d.block_size > cap) { rc = SZB_ERR_DST_TOO_SMALL; break; }
+            memcpy(out + pos, payload, d.block_size);
+            pos += d.block_size;
+            continue;
+        }
+        if (d.type == 1) {
+            if (pos + d.block_size > cap) { rc = SZB_ERR_DST_TOO_SMALL; break; }
+            memset(out + pos, payload[0], d.block_size);
+            pos += d.block_size;
+            continue;
+        }
+        const uint8_t *lp = nullptr;
+        if (d.lit_type >= 2) {
+            rc = huffman_block(src, blocks, b, lit.data());
+            if (rc) break;
+            lp = lit.data();
+        } else if (d.lit_type == 0) {
+            lp = payload + d.lit_hdr_bytes;
+        }
+        uint8_t rle = d.lit_type == 1 ? payload[d.lit_hdr_bytes] : 0;
+        ll.clear(); ml.clear(); of.clear();
+        if (d.nseq) {
+            rc = sequences_block(src, blocks, b, ll, ml, of);
+            if (rc) break;
+        }
+        uint32_t lit_pos = 0;
+        for (uint32_t i = 0; i < d.nseq && rc == SZB_OK; i++) {
+            if (lit_pos + ll[i] > d.lit_regen) { rc = SZB_ERR_DIDNT_COPY_ALL_LITERAL_BYTES; break; }
+            if (pos + ll[i] + ml[i] > cap) { rc = SZB_ERR_DST_TOO_SMALL; break; }
+            if (d.lit_type == 1) memset(out + pos, rle, ll[i]); else memcpy(out + pos, lp + lit_pos, ll[i]);
+            pos += ll[i];
+            lit_pos += ll[i];
+            uint32_t o;
+            uint32_t v = of[i];
+            if (v > 3) { o = v - 3; h[2] = h[1]; h[1] = h[0]; h[0] = o; }
+            else {
+                uint32_t idx = v - 1 + (ll[i] == 0 ? 1 : 0);
+                if (idx == 0) o = h[0];
+                else if (idx == 1) { o = h[1]; h[1] = h[0]; h[0] = o; }
+                else { o = idx == 2 ? h[2] : h[0] - 1; h[2] = h[1]; h[1] = h[0]; h[0] = o; }
+            }
+            if (o == 0 || o > pos) { rc = SZB_ERR_CANT_REPEAT_BYTES; break; }
+            for (uint32_t k = 0; k < ml[i]; k++) out[pos + k] = out[pos - o + k];
+            pos += ml[i];
+        }
+        if (rc) break;
+        uint32_t rest = d.lit_regen - lit_pos;
+        if (pos + rest > cap) { rc = SZB_ERR_DST_TOO_SMALL; break; }
+        if (d.lit_type == 1) memset(out + pos, rle, rest); else memcpy(out + pos, lp + lit_pos, rest);
+        pos += rest;
+    }
+    if (rc == SZB_OK) rc = fr.status;
+    szb_walk_destroy(w);
+    *out_len = pos;
+    return rc;
+}
+
+}  // extern "C"

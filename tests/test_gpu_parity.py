@@ -1,0 +1,259 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every check goes through the C ABI
+(libszb200.so) and compares with the ORACLE on the same inputs, or with the golden corpus."""
+import hashlib
+import io
+
+import numpy as np
+import pytest
+
+from oracle import pyszo
+from tools import corpus as cg
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from sparkzstd_b200.decompression import Context
+
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _batch_arrays(frames):
+    src = np.frombuffer(b"".join(frames) + b"\0" * 16, dtype=np.uint8)
+    lens = np.array([len(f) for f in frames], dtype=np.uint64)
+    offs = (np.cumsum(lens) - lens).astype(np.uint64)
+    return src, offs, lens
+
+
+# ---- config 1: the reference's golden corpus ------------------------------------------------------
+def test_decodecorpus_batch_byte_exact(ctx, corpus):
+    """All 100 decodecorpus frames in ONE batch launch, byte-exact vs the originals' sha256."""
+    frames = [d for _, d, _, _ in corpus]
+    outs = ctx.decode_batch(frames)
+    bad = [n for (n, _, size, sha), o in zip(corpus, outs) if len(o) != size or hashlib.sha256(o).hexdigest() != sha]
+    assert not bad, bad
+
+
+def test_decodecorpus_frame_reader_api(ctx, corpus):
+    """NewFrameReader(r) / Reset(r) / Read, as cmd/sparkzstd/main.go:59-68,126 uses it."""
+    from sparkzstd_b200.decompression import NewFrameReader
+
+    comp = NewFrameReader(None, ctx)
+    for name, data, size, sha in corpus[::7]:
+        comp.Reset(io.BytesIO(data))
+        h = hashlib.sha256()
+        total = 0
+        while True:
+            chunk = comp.Read(4096)
+            if not chunk:
+                break
+            h.update(chunk)
+            total += len(chunk)
+        assert total == size and h.hexdigest() == sha, name
+
+
+def test_decodecorpus_frame_decompressor_api(ctx, corpus):
+    """NewFrameDecompressor(src, dst).Decompress(), as cmd/sparkzstd/main.go:22-40 uses it."""
+    from sparkzstd_b200.decompression import NewFrameDecompressor
+
+    for name, data, size, sha in corpus[3::9]:
+        target = io.BytesIO()
+        fd = NewFrameDecompressor(io.BytesIO(data), target, ctx)
+        fd.Decompress()
+        out = target.getvalue()
+        assert len(out) == size and hashlib.sha256(out).hexdigest() == sha, name
+        assert fd.BlockCounter == len(pyszo.decode_frame(data, want_trace=True)[1].blocks)
+
+
+def test_stage_level_parity_with_oracle_trace(ctx, corpus):
+    """Literal buffers (stage 2), sequence triples (stage 3) and per-block regenerated sizes of every
+    compressed block of the corpus equal the oracle's per-block trace."""
+    from sparkzstd_b200.decompression import Batch
+
+    frames = [d for _, d, _, _ in corpus]
+    src, offs, lens = _batch_arrays(frames)
+    b = Batch(ctx, src, offs, lens)
+    try:
+        d_src = b.upload(src)
+        b.decode_entropy(d_src)
+        total, foff, flen = b.sizes()
+        sizes, status = b.read_block_results()
+        assert not status.any()
+        assert total == sum(s for _, _, s, _ in corpus)
+        bi = 0
+        checked_lit = checked_seq = 0
+        for fi, (name, data, size, _) in enumerate(corpus):
+            _, tr = pyszo.decode_frame(data, want_trace=True)
+            assert int(flen[fi]) == size, name
+            for blk in tr.blocks:
+                assert int(sizes[bi]) == blk.out_len, (name, bi)
+                if blk.type == 2 and fi % 3 == 0:
+                    if blk.lit_type >= 2:
+                        assert b.read_literals(bi, blk.lit_regen) == blk.literals, (name, bi)
+                        checked_lit += 1
+                    if blk.nseq:
+                        ll, ml, of = b.read_sequences(bi, blk.nseq)
+                        want = np.array(blk.sequences, dtype=np.int64)
+                        assert (ll == want[:, 0]).all() and (ml == want[:, 1]).all() and (of == want[:, 2]).all(), (name, bi)
+                        checked_seq += 1
+                bi += 1
+        assert bi == b.nblocks and checked_lit > 100 and checked_seq > 100
+    finally:
+        b.close()
+
+
+# ---- synthetic corpora of the BASELINE.json shapes, small enough for the oracle ----------------------
+def _check_corpus_vs_oracle(ctx, c):
+    frames = [c.frame(i) for i in range(c.nframes)]
+    outs = ctx.decode_batch(frames)
+    for i, (f, o) in enumerate(zip(frames, outs)):
+        want = pyszo.decode_frame(f)
+        assert o == want, (c.name, i, len(o), len(want))
+        if int(c.raw_hash[i]):
+            assert cg.hash_bytes(np.frombuffer(o, dtype=np.uint8)) == int(c.raw_hash[i])
+
+
+def test_config2_text_frames_small(ctx):
+    _check_corpus_vs_oracle(ctx, cg.config2_text_frames(96))
+
+
+def test_config2_with_checksums(ctx):
+    _check_corpus_vs_oracle(ctx, cg.config2_text_frames(8, checksum=1))
+
+
+def test_config4_literal_heavy_small(ctx):
+    _check_corpus_vs_oracle(ctx, cg.config4_literal_heavy(4, 1 << 20))
+
+
+def test_config3_single_frame_small(ctx):
+    """One streamed multi-block frame: no content size, Treeless literals, cross-block matches."""
+    c = cg.config3_single_frame(12 << 20, window_log=20)
+    _check_corpus_vs_oracle(ctx, c)
+
+
+def test_config5_mixed_small(ctx):
+    c = cg.config5_mixed(24 << 20)
+    _check_corpus_vs_oracle(ctx, c)
+
+
+def test_ragged_frame_sizes(ctx):
+    sizes = [0, 1, 2, 3, 7, 63, 64, 65, 255, 256, 1000, 4095, 4096, 4097, 65535, 65537, 131071, 131072, 131073, 300001]
+    kinds = [cg.KIND_TEXT] * len(sizes)
+    c = cg.generate("ragged", np.array(kinds, np.int32), 77 + np.arange(len(sizes), dtype=np.uint64), np.array(sizes, np.uint64))
+    _check_corpus_vs_oracle(ctx, c)
+    c = cg.generate("ragged_const", np.full(len(sizes), cg.KIND_CONSTANT, np.int32), 99 + np.arange(len(sizes), dtype=np.uint64),
+                    np.array(sizes, np.uint64))
+    _check_corpus_vs_oracle(ctx, c)
+
+
+# ---- size-independent properties at a larger size -----------------------------------------------------
+def test_config2_medium_hash_of_hashes(ctx):
+    """4096 frames (256 MiB): per-frame hash of the GPU output equals the generator's hash of the original."""
+    c = cg.config2_text_frames(4096)
+    dst = np.empty(c.decompressed_bytes + 64, dtype=np.uint8)
+    out_off, out_len, status = ctx.decode_batch_into(c.src, c.frame_off, c.frame_len, dst)
+    assert not status.any()
+    assert (out_len == c.raw_size).all()
+    got = cg.hash_frames(dst, out_off, out_len)
+    assert (got == c.raw_hash).all()
+    # idempotence: decoding the same batch again gives the same bytes
+    dst2 = np.empty_like(dst)
+    ctx.decode_batch_into(c.src, c.frame_off, c.frame_len, dst2)
+    assert (cg.hash_frames(dst2, out_off, out_len) == c.raw_hash).all()
+
+
+# ---- edge cases and error behaviour --------------------------------------------------------------------
+def test_empty_batch_and_empty_frames(ctx, corpus):
+    assert ctx.decode_batch([]) == []
+    empties = [d for _, d, s, _ in corpus if s == 0]
+    assert len(empties) == 3
+    assert ctx.decode_batch(empties) == [b"", b"", b""]
+
+
+def test_wrong_magic_and_truncation(ctx, corpus):
+    from sparkzstd_b200 import decompression as D
+
+    with pytest.raises(D.ErrWrongMagicnumber):
+        D.NewFrameReader(io.BytesIO(b"\x28\xb5\x2f\xfe" + b"\0" * 16), ctx)
+    name, data, size, _ = corpus[0]
+    src, offs, lens = _batch_arrays([data[: len(data) // 2], data, b"\x00\x01\x02\x03\x04"])
+    dst = np.empty(size * 2 + 64, dtype=np.uint8)
+    out_off, out_len, status = ctx.decode_batch_into(src, offs, lens, dst)
+    assert status[0] == -32 and status[1] == 0 and status[2] == -1
+    assert int(out_len[1]) == size and int(out_len[0]) == 0
+    o = int(out_off[1])
+    assert hashlib.sha256(dst[o : o + size].tobytes()).hexdigest() == corpus[0][3]
+
+
+def test_destination_too_small(ctx, corpus):
+    name, data, size, _ = corpus[0]
+    src, offs, lens = _batch_arrays([data])
+    dst = np.empty(size - 1, dtype=np.uint8)
+    _, out_len, status = ctx.decode_batch_into(src, offs, lens, dst)
+    assert status[0] == -64 and int(out_len[0]) == 0
+
+
+def test_corrupted_payloads_never_crash_and_agree_when_valid(ctx, corpus):
+    """Bit flips in the payload: the engine must return (never hang or fault); whenever the oracle
+    still decodes the frame, the GPU output must be identical."""
+    rng = np.random.default_rng(5)
+    frames = []
+    for name, data, size, _ in corpus[:60:2]:
+        if len(data) < 40:
+            continue
+        buf = bytearray(data)
+        for _ in range(3):
+            p = int(rng.integers(12, len(buf) - 4))
+            buf[p] ^= 1 << int(rng.integers(0, 8))
+        frames.append(bytes(buf))
+    src, offs, lens = _batch_arrays(frames)
+    dst = np.empty(64 << 20, dtype=np.uint8)
+    out_off, out_len, status = ctx.decode_batch_into(src, offs, lens, dst)
+    agree = 0
+    for i, f in enumerate(frames):
+        try:
+            want = pyszo.decode_frame(f)
+        except pyszo.OracleError:
+            continue
+        if status[i] == 0:
+            o, l = int(out_off[i]), int(out_len[i])
+            assert dst[o : o + l].tobytes() == want, i
+            agree += 1
+    assert agree >= 0
+
+
+def test_descriptor_level_entry(ctx, corpus):
+    """szb_decode_blocks: host-built descriptor tables + device pointers (what the Go walker feeds)."""
+    import ctypes as C
+
+    import torch
+
+    from sparkzstd_b200.decompression import Walk
+
+    frames = [d for _, d, _, _ in corpus[:20]]
+    src, offs, lens = _batch_arrays(frames)
+    total = sum(s for _, _, s, _ in corpus[:20])
+    with Walk(src, offs, lens) as w:
+        d_src = torch.from_numpy(src.copy()).cuda()
+        d_dst = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
+        n = w.nframes
+        out_off = np.zeros(n, np.uint64)
+        out_len = np.zeros(n, np.uint64)
+        status = np.zeros(n, np.int32)
+        rc = ctx._L.szb_decode_blocks(ctx._h, C.c_void_p(d_src.data_ptr()), src.nbytes, w.frames_ptr(), n, w.blocks_ptr(), w.nblocks,
+                                      C.c_void_p(d_dst.data_ptr()), total + 64, out_off.ctypes.data, out_len.ctypes.data,
+                                      status.ctypes.data)
+        assert rc == 0 and not status.any()
+        host = d_dst.cpu().numpy()
+        for i, (name, _, size, sha) in enumerate(corpus[:20]):
+            o = int(out_off[i])
+            assert int(out_len[i]) == size and hashlib.sha256(host[o : o + size].tobytes()).hexdigest() == sha, name
+
+
+def test_kernels_were_launched(ctx):
+    assert ctx.launch_count() > 0
+    t = ctx.last_timing()
+    assert t["total"] > 0

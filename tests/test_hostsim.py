@@ -1,0 +1,58 @@
+"""The serial device functions of the CUDA path (bits.cuh, fse.cuh, huffman.cuh, sequences.cuh: the code
+one lane runs) compiled for the host and driven by the product's header walker, checked against the
+golden corpus and the oracle.  tests/host_sim/hostsim.cpp is test infrastructure only."""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyszo
+from tools import corpus as cg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIM = os.path.join(ROOT, "tests", "host_sim")
+
+
+@pytest.fixture(scope="module")
+def sim():
+    lib = os.path.join(SIM, "libhostsim.so")
+    srcs = [os.path.join(SIM, "hostsim.cpp"), os.path.join(ROOT, "sparkzstd_b200", "csrc", "walker.cpp")]
+    deps = srcs + [os.path.join(ROOT, "sparkzstd_b200", "csrc", f) for f in ("bits.cuh", "fse.cuh", "huffman.cuh", "sequences.cuh")]
+    if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", lib, *srcs], check=True)
+    L = C.CDLL(lib)
+    L.hostsim_decode_frame.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    return L
+
+
+def _decode(L, data: bytes, cap: int):
+    out = np.empty(cap + 16, dtype=np.uint8)
+    n = C.c_size_t()
+    rc = L.hostsim_decode_frame(data, len(data), out.ctypes.data, cap + 16, C.byref(n))
+    return rc, out[: n.value].tobytes()
+
+
+def test_serial_device_code_decodes_the_golden_corpus(sim, corpus):
+    for name, data, size, sha in corpus:
+        rc, out = _decode(sim, data, size)
+        assert rc == 0 and len(out) == size and hashlib.sha256(out).hexdigest() == sha, name
+
+
+def test_serial_device_code_matches_oracle_on_synthetic_shapes(sim):
+    for c in (cg.config2_text_frames(6), cg.config4_literal_heavy(1, 1 << 19), cg.config3_single_frame(3 << 20, 20), cg.config5_mixed(4 << 20, with_golden=False)):
+        for i in range(min(c.nframes, 12)):
+            f = c.frame(i)
+            want = pyszo.decode_frame(f)
+            rc, out = _decode(sim, f, len(want))
+            assert rc == 0 and out == want, (c.name, i)
+
+
+def test_serial_device_code_error_paths(sim, corpus):
+    name, data, size, _ = corpus[0]
+    rc, _ = _decode(sim, data[: len(data) // 3], size)
+    assert rc == -32
+    rc, _ = _decode(sim, b"\0\0\0\0" + data[4:], size)
+    assert rc == -1
