@@ -302,9 +302,9 @@ static void *gen_worker(void *arg) {
         uint32_t i = __atomic_fetch_add(j->next, 1, __ATOMIC_RELAXED);
         if (i >= j->n || *j->failed) break;
         size_t n = (size_t)j->size[i];
-        if (n > raw_cap) { free(raw); raw = malloc(n ? n : 1); raw_cap = n; }
+        if (n > raw_cap || !raw) { free(raw); raw = malloc(n ? n : 1); raw_cap = n; }
         size_t bound = Z.compressBound(n);
-        if (bound > comp_cap) { free(comp); comp = malloc(bound); comp_cap = bound; }
+        if (bound > comp_cap || !comp) { free(comp); comp = malloc(bound ? bound : 64); comp_cap = bound; }
         if (!raw || !comp) { *j->failed = 1; break; }
         cg_fill(j->kind[i], j->seed[i], raw, n, 0);
         size_t r = Z.compress2(c, comp, comp_cap, raw, n);
