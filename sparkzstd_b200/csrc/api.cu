@@ -4,6 +4,7 @@
 // decode path: without a CUDA device szb_ctx_create fails and nothing else can be called.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -20,7 +21,7 @@ struct szb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[10] = {};
     uint32_t *d_predef = nullptr;
     std::string last_error;
     float timing[8] = {};
@@ -62,6 +63,8 @@ struct szb_batch {
     size_t status_bytes = 0;
     uint8_t *d_litbuf = nullptr;
     uint32_t *d_seq = nullptr;  // ll | ml | of
+    uint32_t *d_seq_tabs = nullptr;  // FSE decode-table arena, kTabSlotWords per block with sequences
+    SeqInfo *d_seq_info = nullptr;
     bool entropy_done = false;
 };
 
@@ -165,7 +168,8 @@ int szb_ctx_create(int device, void *stream, szb_ctx **out) {
         return SZB_ERR_CUDA;
     }
     cudaFuncSetAttribute(k_huffman_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(HufSmem) * kWarpsPerCta));
-    cudaFuncSetAttribute(k_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SeqSmem) * kWarpsPerCta));
+    cudaFuncSetAttribute(k_build_seq_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SeqSmem) * kWarpsPerCta));
+    cudaFuncSetAttribute(k_decode_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSeqLanes * kTabSlotWords * 4));
     *out = ctx;
     return SZB_OK;
 }
@@ -189,7 +193,7 @@ uint64_t szb_launch_count(szb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int szb_last_timing(szb_ctx *ctx, float *ms, int n) {
     if (!ctx || !ms) return 0;
-    int k = n < 7 ? n : 7;
+    int k = n < 8 ? n : 8;
     for (int i = 0; i < k; i++) ms[i] = ctx->timing[i];
     return k;
 }
@@ -210,6 +214,10 @@ static int batch_upload_tables(szb_batch *b) {
         if (d.type == 2 && d.lit_type >= 2) b->huf_list.push_back(i);
         if (d.type == 2 && d.nseq > 0) b->seq_list.push_back(i);
     }
+    // k_decode_sequences runs kSeqLanes blocks per warp in lock step: neighbours should have similar
+    // sequence counts, and the longest blocks should start first
+    std::stable_sort(b->seq_list.begin(), b->seq_list.end(),
+                     [&](uint32_t x, uint32_t y) { return b->blocks[x].nseq > b->blocks[y].nseq; });
     // descriptor tables: one allocation, one H2D copy
     size_t o_frames = 0;
     size_t o_blocks = align_up(o_frames + sizeof(szb_frame_desc) * (size_t)nf, 256);
@@ -258,6 +266,8 @@ static int batch_upload_tables(szb_batch *b) {
     // scratch arenas
     CUDA_TRY(ctx, cudaMalloc(&b->d_litbuf, (size_t)b->literal_bytes + 256));
     CUDA_TRY(ctx, cudaMalloc(&b->d_seq, (size_t)(b->sequences * 3 + 64) * 4));
+    CUDA_TRY(ctx, cudaMalloc(&b->d_seq_tabs, (b->seq_list.size() + 1) * (size_t)kTabSlotWords * 4));
+    CUDA_TRY(ctx, cudaMalloc(&b->d_seq_info, (b->seq_list.size() + 1) * sizeof(SeqInfo)));
     return SZB_OK;
 }
 
@@ -349,6 +359,8 @@ void szb_batch_destroy(szb_batch *b) {
     if (b->d_state) cudaFree(b->d_state);
     if (b->d_litbuf) cudaFree(b->d_litbuf);
     if (b->d_seq) cudaFree(b->d_seq);
+    if (b->d_seq_tabs) cudaFree(b->d_seq_tabs);
+    if (b->d_seq_info) cudaFree(b->d_seq_info);
     delete b;
 }
 
@@ -370,6 +382,8 @@ static DeviceBatch make_args(szb_batch *b, const void *d_src, void *d_dst, size_
     a.seq_ll = b->d_seq;
     a.seq_ml = b->d_seq + b->sequences;
     a.seq_of = b->d_seq + 2 * b->sequences;
+    a.seq_tabs = b->d_seq_tabs;
+    a.seq_info = b->d_seq_info;
     a.out_size = b->d_out_size;
     a.out_off = b->d_out_off;
     a.lit_status = b->d_lit_status;
@@ -399,7 +413,12 @@ static int launch_entropy(szb_batch *b, const void *d_src) {
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
     if (a.n_seq) {
-        k_sequences<<<(a.n_seq + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, sizeof(SeqSmem) * kWarpsPerCta, s>>>(a);
+        k_build_seq_tables<<<(a.n_seq + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, sizeof(SeqSmem) * kWarpsPerCta, s>>>(a);
+        ctx->launches++;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[7], s));
+    if (a.n_seq) {
+        k_decode_sequences<<<(a.n_seq + kSeqLanes - 1) / kSeqLanes, 32, kSeqLanes * kTabSlotWords * 4, s>>>(a);
         ctx->launches++;
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
@@ -434,6 +453,8 @@ static int collect_timing(szb_ctx *ctx) {
         CUDA_TRY(ctx, cudaEventElapsedTime(&t, ctx->ev[i - 1], ctx->ev[i]));
         ctx->timing[i] = t;
     }
+    CUDA_TRY(ctx, cudaEventElapsedTime(&t, ctx->ev[1], ctx->ev[7]));
+    ctx->timing[7] = t;  // table construction share of [2]
     return SZB_OK;
 }
 
@@ -561,9 +582,9 @@ static int decode_tables(szb_ctx *ctx, szb_batch *b, const uint8_t *src, size_t 
     if (!(flags & SZB_FLAG_SRC_DEVICE)) {
         int rc = ensure_dev(ctx, &ctx->d_src, &ctx->d_src_cap, src_len + 16);
         if (rc) return rc;
-        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[8], ctx->stream));
         if (src_len) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_src, src, src_len, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[9], ctx->stream));
         d_src = ctx->d_src;
     }
     int rc = launch_entropy(b, d_src);
@@ -571,7 +592,7 @@ static int decode_tables(szb_ctx *ctx, szb_batch *b, const uint8_t *src, size_t 
     uint64_t total = 0;
     rc = szb_batch_sizes(b, &total, nullptr, nullptr);
     if (rc) return rc;
-    if (!(flags & SZB_FLAG_SRC_DEVICE)) CUDA_TRY(ctx, cudaEventElapsedTime(&h2d_ms, ctx->ev[5], ctx->ev[6]));
+    if (!(flags & SZB_FLAG_SRC_DEVICE)) CUDA_TRY(ctx, cudaEventElapsedTime(&h2d_ms, ctx->ev[8], ctx->ev[9]));
     void *d_dst = dst;
     size_t d_cap = dst_cap;
     if (!(flags & SZB_FLAG_DST_DEVICE)) {
@@ -592,11 +613,11 @@ static int decode_tables(szb_ctx *ctx, szb_batch *b, const uint8_t *src, size_t 
         CUDA_TRY(ctx, cudaMemcpy(len.data(), b->d_frame_out_len, 8 * (size_t)b->nframes, cudaMemcpyDeviceToHost));
     }
     if (!(flags & SZB_FLAG_DST_DEVICE) && total <= dst_cap && total > 0) {
-        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[8], ctx->stream));
         CUDA_TRY(ctx, cudaMemcpyAsync(dst, ctx->d_dst, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[9], ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        CUDA_TRY(ctx, cudaEventElapsedTime(&d2h_ms, ctx->ev[5], ctx->ev[6]));
+        CUDA_TRY(ctx, cudaEventElapsedTime(&d2h_ms, ctx->ev[8], ctx->ev[9]));
     }
     ctx->timing[5] = h2d_ms;
     ctx->timing[6] = d2h_ms;

@@ -3,9 +3,12 @@
 //   k_huffman_literals  stage 1+2: Huffman tree description (direct / FSE-compressed weights),
 //                       decode table in shared memory, 1- or 4-stream literal decode
 //                       (structure/huffman.go, structure/literals.go:209-373)
-//   k_sequences         stage 1+3: LL/OF/ML table selection + construction in shared memory,
-//                       three interleaved FSE states over the backward bitstream
-//                       (fse/fse.go, fse/predefined.go, structure/sequences.go)
+//   k_build_seq_tables  stage 1: LL/OF/ML table selection + construction in shared memory, one
+//                       warp per block, published to a table arena in HBM
+//                       (fse/fse.go, fse/predefined.go, structure/sequences.go:275-369)
+//   k_decode_sequences  stage 3: three interleaved FSE states over the backward bitstream, one
+//                       LANE per block, tables resident in shared memory
+//                       (structure/sequences.go:64-206)
 //   k_scan_blocks       device-wide exclusive prefix sum of per-block regenerated sizes
 //                       (the reference gets positions for free from its ring buffer,
 //                       decompression/ringbuffer.go:102-178)
@@ -31,6 +34,14 @@ constexpr uint32_t kFull = 0xFFFFFFFFu;
 #define SZB_SERIAL_TABLES 0
 #endif
 
+constexpr int kSeqLanes = 21;             // blocks per warp in k_decode_sequences: 21 x 5 KB tables, 2 warps per SM
+constexpr uint32_t kTabSlotWords = 1280;  // LL 512 | ML 512 | OF 256
+
+struct SeqInfo {
+    uint8_t al_ll, al_of, al_ml, pad;
+    uint32_t stream_off;  // offset of the backward bitstream after the sequences-section header
+};
+
 struct DeviceBatch {
     const uint8_t *src;
     const szb_block_desc *blocks;
@@ -42,6 +53,8 @@ struct DeviceBatch {
     uint32_t n_seq;
     uint8_t *litbuf;
     uint32_t *seq_ll, *seq_ml, *seq_of;
+    uint32_t *seq_tabs;     // per seq_list entry: LL(512) | ML(512) | OF(256) decode-table cells
+    SeqInfo *seq_info;      // per seq_list entry
     uint64_t *out_size;     // per block regenerated size (host-initialised for Raw/RLE/zero-sequence blocks)
     uint64_t *out_off;      // per block exclusive prefix
     int32_t *lit_status;    // per block
@@ -291,19 +304,21 @@ __global__ void __launch_bounds__(kCtaThreads) k_huffman_literals(DeviceBatch a)
     if (lane == 0) a.lit_status[b] = rc;
 }
 
-// shared memory per warp, k_sequences
+// shared memory per warp, k_build_seq_tables
 struct SeqSmem {
     uint32_t tll[1 << kMaxALLL];
     uint32_t tml[1 << kMaxALML];
     uint32_t tof[1 << kMaxALOF];
-    uint32_t buf[3][32];
     uint8_t symk[1 << kMaxALLL];
     int16_t norm[kMaxFseSymbols];
     uint16_t next[kMaxFseSymbols];
 };
 
-// One warp per compressed block that has sequences.
-__global__ void __launch_bounds__(kCtaThreads) k_sequences(DeviceBatch a) {
+// Stage 1 for the sequences section: one warp per compressed block that has sequences builds
+// the block's LL / OF / ML decode tables in shared memory (DecodeTables, sequences.go:275-369)
+// and publishes them to the table arena in HBM (slot = position in seq_list), together with
+// the accuracy logs and the offset of the backward bitstream.
+__global__ void __launch_bounds__(kCtaThreads) k_build_seq_tables(DeviceBatch a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t w = blockIdx.x * kWarpsPerCta + warp_in_cta;
@@ -314,17 +329,16 @@ __global__ void __launch_bounds__(kCtaThreads) k_sequences(DeviceBatch a) {
     const uint8_t *tables = a.src + d.src_off + d.seq_off + d.seq_hdr_bytes;
     const uint32_t tables_avail = d.block_size - d.seq_off - d.seq_hdr_bytes;
 
-    // --- DecodeTables: LL, OF, ML in that order (sequences.go:275-369) ---
     uint32_t cursor = 0;
     uint32_t al[3] = {0, 0, 0};
     int rc = SZB_OK;
 #pragma unroll
     for (int i = 0; i < 3 && rc == SZB_OK; i++) {
-        const int kind = i;  // KIND_LL, KIND_OF, KIND_ML
+        const int kind = i;  // KIND_LL, KIND_OF, KIND_ML: the order of the table bytes
         uint32_t *table = kind == KIND_LL ? sm.tll : (kind == KIND_OF ? sm.tof : sm.tml);
         const uint32_t mode = field_mode(d.seq_modes, kind);
         TableSource ts;
-        if (mode == 3) {  // Repeat: rebuild from the origin block's bytes (host chased the chain)
+        if (mode == 3) {  // Repeat: rebuild from the origin block's bytes (the host chased the chain)
             const uint32_t ob = kind == KIND_LL ? d.ll_origin : (kind == KIND_OF ? d.of_origin : d.ml_origin);
             const szb_block_desc o = a.blocks[ob];
             int lrc = SZB_OK;
@@ -350,66 +364,154 @@ __global__ void __launch_bounds__(kCtaThreads) k_sequences(DeviceBatch a) {
         if (lane == 0) a.seq_status[b] = rc;
         return;
     }
-
-    // --- DecodeSequences (sequences.go:126-206) ---
-    const uint8_t *stream = tables + cursor;
-    const uint32_t stream_len = tables_avail - cursor;
-    RevBits r;
-    SeqStates st{0, 0, 0};
+    uint32_t *slot = a.seq_tabs + (size_t)w * kTabSlotWords;
+    for (uint32_t i = lane; i < (1u << al[KIND_LL]); i += 32) slot[i] = sm.tll[i];
+    for (uint32_t i = lane; i < (1u << al[KIND_ML]); i += 32) slot[512 + i] = sm.tml[i];
+    for (uint32_t i = lane; i < (1u << al[KIND_OF]); i += 32) slot[1024 + i] = sm.tof[i];
     if (lane == 0) {
-        if (!rev_init(r, stream, (int32_t)stream_len) || !rev_skip_padding(r)) {
-            rc = SZB_ERR_BAD_PADDING;  // sequences.go:141-143
-        } else {
-            rev_refill(r);
-            st.ll = rev_read(r, al[KIND_LL]);  // InitState order LL, OF, ML (sequences.go:145-159)
-            st.of = rev_read(r, al[KIND_OF]);
-            st.ml = rev_read(r, al[KIND_ML]);
-        }
-    }
-    rc = __shfl_sync(kFull, rc, 0);
-    if (rc != SZB_OK) {
-        if (lane == 0) a.seq_status[b] = rc;
-        return;
-    }
-    const uint32_t nseq = d.nseq;
-    uint32_t *gll = a.seq_ll + d.seq_buf_off, *gml = a.seq_ml + d.seq_buf_off, *gof = a.seq_of + d.seq_buf_off;
-    uint64_t ml_sum = 0;
-    for (uint32_t base = 0; base < nseq; base += 32) {
-        const uint32_t cnt = nseq - base < 32 ? nseq - base : 32;
-        // pull the part of the backward bitstream the next rounds will consume towards L1
-        {
-            const uint32_t nxt = __shfl_sync(kFull, r.next, 0);
-            const int64_t at = (int64_t)nxt - 128 * (int64_t)(lane + 1);
-            if (lane < 4 && at >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(stream + at));
-        }
-        if (lane == 0) {
-            for (uint32_t i = 0; i < cnt; i++) {
-                uint32_t ll, ml, of;
-                decode_one_sequence(r, sm.tll, sm.tof, sm.tml, st, base + i + 1 < nseq, &ll, &ml, &of);
-                sm.buf[0][i] = ll;
-                sm.buf[1][i] = ml;
-                sm.buf[2][i] = of;
-            }
-        }
-        __syncwarp();
-        if (lane < cnt) {
-            gll[base + lane] = sm.buf[0][lane];
-            const uint32_t ml = sm.buf[1][lane];
-            gml[base + lane] = ml;
-            gof[base + lane] = sm.buf[2][lane];
-            ml_sum += ml;
-        }
-        __syncwarp();
-    }
-    for (int dlt = 16; dlt > 0; dlt >>= 1) ml_sum += __shfl_xor_sync(kFull, ml_sum, dlt);
-    if (lane == 0) {
-        // the stream must be consumed exactly (sequences.go:197-204)
-        if (r.remaining != 0) rc = SZB_ERR_NOT_ALL_BITS_USED;
-        a.seq_status[b] = rc;
-        a.out_size[b] = (uint64_t)d.lit_regen + ml_sum;
+        SeqInfo info;
+        info.al_ll = (uint8_t)al[KIND_LL];
+        info.al_of = (uint8_t)al[KIND_OF];
+        info.al_ml = (uint8_t)al[KIND_ML];
+        info.pad = 0;
+        info.stream_off = cursor;
+        a.seq_info[w] = info;
     }
 }
 
+// n (<= 32) bits ending at bit position pos of a backward stream, i.e. bits [pos-n, pos) of the
+// little-endian integer; zero below bit 0 (reversebitstream.go:23-27,67-75).  Byte loads: used at
+// stream start / end and on the rare wide sequence.
+__device__ __forceinline__ uint32_t slow_read_bits(const uint8_t *sp, int64_t pos, uint32_t n) {
+    if (n == 0 || pos <= 0) return 0;
+    const int64_t lo = pos - (int64_t)n;
+    const int64_t l = lo < 0 ? 0 : lo;
+    const int64_t first = l >> 3, last = (pos - 1) >> 3;
+    uint64_t acc = 0;
+    for (int64_t bb = first; bb <= last; bb++) acc |= (uint64_t)sp[bb] << (8 * (bb - first));
+    acc >>= (l & 7);
+    acc &= (1ull << (uint32_t)(pos - l)) - 1;
+    if (lo < 0) acc <<= (uint32_t)(-lo);
+    return (uint32_t)acc;
+}
+
+// Stage 3: DecodeSequences (sequences.go:126-206).  One LANE per block: a warp decodes
+// kSeqLanes blocks in lock step, each lane walking its own backward bitstream with its own three
+// FSE states, the tables of all its blocks resident in shared memory.  A warp instruction thus
+// advances kSeqLanes independent state chains instead of one.
+//
+// Per sequence a lane fetches one 64-bit window ending at its bit position (three aligned 32-bit
+// loads + funnel shifts; the reference does a div/mod Read() per field) and peels the six fields
+// off its top in the reference's order: OF extra, ML extra, LL extra, LL state, ML state, OF state.
+__global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t *tabs = reinterpret_cast<uint32_t *>(smem_raw);
+    const uint32_t lane = threadIdx.x;
+    const uint32_t first = blockIdx.x * kSeqLanes;
+    const uint32_t n_here = a.n_seq - first < (uint32_t)kSeqLanes ? a.n_seq - first : (uint32_t)kSeqLanes;
+
+    // tables: HBM arena -> shared memory, coalesced
+    for (uint32_t j = 0; j < n_here; j++) {
+        const SeqInfo info = a.seq_info[first + j];
+        const uint32_t *slot = a.seq_tabs + (size_t)(first + j) * kTabSlotWords;
+        uint32_t *t = tabs + j * kTabSlotWords;
+        for (uint32_t i = lane; i < (1u << info.al_ll); i += 32) t[i] = slot[i];
+        for (uint32_t i = lane; i < (1u << info.al_ml); i += 32) t[512 + i] = slot[512 + i];
+        for (uint32_t i = lane; i < (1u << info.al_of); i += 32) t[1024 + i] = slot[1024 + i];
+    }
+    __syncwarp();
+    if (lane >= n_here) return;
+
+    const uint32_t w = first + lane;
+    const uint32_t b = a.seq_list[w];
+    if (a.seq_status[b] != SZB_OK) return;  // its tables failed to build
+    const szb_block_desc d = a.blocks[b];
+    const SeqInfo info = a.seq_info[w];
+    const uint32_t *tll = tabs + lane * kTabSlotWords, *tml = tll + 512, *tof = tll + 1024;
+    const uint32_t hdr = d.seq_off + d.seq_hdr_bytes + info.stream_off;
+    const uint8_t *sp = a.src + d.src_off + hdr;
+    const uint32_t len = d.block_size - hdr;
+
+    // padding: zero bits then the first 1 bit, at most 8 (sequences.go:131-143)
+    if (len == 0 || sp[len - 1] == 0) {
+        a.seq_status[b] = SZB_ERR_BAD_PADDING;
+        return;
+    }
+    int64_t pos = (int64_t)len * 8 - (__clz((uint32_t)sp[len - 1]) - 24 + 1);
+    // InitState in the order LL, OF, ML (sequences.go:145-159)
+    uint32_t s_ll = slow_read_bits(sp, pos, info.al_ll);
+    pos -= info.al_ll;
+    uint32_t s_of = slow_read_bits(sp, pos, info.al_of);
+    pos -= info.al_of;
+    uint32_t s_ml = slow_read_bits(sp, pos, info.al_ml);
+    pos -= info.al_ml;
+
+    const uint32_t nseq = d.nseq;
+    uint32_t *gll = a.seq_ll + d.seq_buf_off, *gml = a.seq_ml + d.seq_buf_off, *gof = a.seq_of + d.seq_buf_off;
+    uint64_t ml_sum = 0;
+    for (uint32_t i = 0; i < nseq; i++) {
+        const uint32_t e_of = tof[s_of], e_ll = tll[s_ll], e_ml = tml[s_ml];  // peek OF, LL, ML (sequences.go:67-78)
+        const uint32_t ofc = fse_code(e_of), mlx = fse_extra(e_ml), llx = fse_extra(e_ll);
+        const bool upd = i + 1 < nseq;  // no state update after the last sequence (sequences.go:178)
+        const uint32_t nbl = upd ? fse_nb(e_ll) : 0, nbm = upd ? fse_nb(e_ml) : 0, nbo = upd ? fse_nb(e_of) : 0;
+        const uint32_t total = ofc + mlx + llx + nbl + nbm + nbo;
+        uint32_t x_of, x_ml, x_ll, b_ll, b_ml, b_of;
+        if (pos >= 96 && total <= 57) {
+            // window: the 8 bytes ending at the byte that holds bit pos-1, shifted so that bit sits at bit 63
+            const uint32_t e = (uint32_t)((pos - 1) >> 3);
+            const uint8_t *ap = sp + e - 7;
+            const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(ap) & 3);
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(ap - mis);
+            const uint32_t w0 = wp[0], w1 = wp[1], w2 = mis ? wp[2] : 0u;  // never touch a word that holds no stream byte
+            // the stream is walked backwards ~3 bytes per sequence: pull the sectors ~20 sequences ahead into L1
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(ap - 64));
+            uint32_t lo = __funnelshift_r(w0, w1, mis * 8), hi = __funnelshift_r(w1, w2, mis * 8);
+            const uint32_t k = 7 - ((uint32_t)(pos - 1) & 7);
+            hi = __funnelshift_l(lo, hi, k);
+            lo <<= k;
+#define SZB_TAKE(dst, n)                     \
+    dst = __funnelshift_l(hi, 0u, (n));      \
+    hi = __funnelshift_l(lo, hi, (n));       \
+    lo <<= (n);
+            SZB_TAKE(x_of, ofc)
+            SZB_TAKE(x_ml, mlx)
+            SZB_TAKE(x_ll, llx)
+            SZB_TAKE(b_ll, nbl)
+            SZB_TAKE(b_ml, nbm)
+            SZB_TAKE(b_of, nbo)
+#undef SZB_TAKE
+            pos -= total;
+        } else {  // near the stream start, or a sequence wider than one window
+            x_of = slow_read_bits(sp, pos, ofc);
+            pos -= ofc;
+            x_ml = slow_read_bits(sp, pos, mlx);
+            pos -= mlx;
+            x_ll = slow_read_bits(sp, pos, llx);
+            pos -= llx;
+            b_ll = slow_read_bits(sp, pos, nbl);
+            pos -= nbl;
+            b_ml = slow_read_bits(sp, pos, nbm);
+            pos -= nbm;
+            b_of = slow_read_bits(sp, pos, nbo);
+            pos -= nbo;
+        }
+        const uint32_t ml = ml_base(fse_code(e_ml)) + x_ml;  // sequences.go:106-112
+        gof[i] = (1u << ofc) + x_of;                         // sequences.go:99-104
+        gml[i] = ml;
+        gll[i] = ll_base(fse_code(e_ll)) + x_ll;             // sequences.go:114-120
+        ml_sum += ml;
+        if (upd) {  // update LL, ML, OF (sequences.go:178-194)
+            s_ll = fse_baseline(e_ll) + b_ll;
+            s_ml = fse_baseline(e_ml) + b_ml;
+            s_of = fse_baseline(e_of) + b_of;
+        }
+    }
+    // the stream must be consumed exactly (sequences.go:197-204)
+    a.seq_status[b] = pos == 0 ? SZB_OK : SZB_ERR_NOT_ALL_BITS_USED;
+    a.out_size[b] = (uint64_t)d.lit_regen + ml_sum;
+}
+
+// ---------------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------------
 // Exclusive prefix sum of out_size over all blocks, one CTA.
 constexpr int kScanThreads = 1024;
@@ -485,14 +587,85 @@ __device__ __forceinline__ void warp_fill(uint8_t *dst, uint8_t v, uint64_t n, u
     for (uint64_t i = lane; i < n; i += 32) dst[i] = v;
 }
 
-constexpr uint32_t kLongLit = 32;
-constexpr uint32_t kLongMatch = 64;
+// ---------------------------------------------------------------------------------------------
+// Stage 4.  The reference pushes every literal run and every match through a window ring
+// buffer (ringbuffer.go:102-277).  Here the whole output lives in HBM and the "window" is just
+// earlier output; each warp keeps only the bytes it is currently producing in a shared-memory
+// staging window so that
+//   * literal bytes and match bytes of a round of 32 sequences are assembled at shared-memory
+//     speed, including matches whose source lies inside the same round (dependency rounds),
+//   * match sources that are already in HBM are gathered with 16-byte loads, one gather per round,
+//   * the finished bytes leave as coalesced 16-byte stores.
+constexpr uint32_t kStageBytes = 1024;  // staging window per warp
+constexpr uint32_t kGathStride = 52;    // 3 x 16 B gathered per lane, padded to an odd word count
+constexpr uint32_t kCoopLit = 32;       // literal runs this long are copied by the whole warp
+constexpr uint32_t kCoopMatch = 34;     // matches this long are copied by the whole warp
+
+struct ExecSmem {
+    __align__(16) uint8_t stage[kStageBytes + 16];
+    __align__(16) uint8_t gath[32 * kGathStride];
+};
+
+// stage[i] mirrors dst[base + i] for i < fill; (dst + base) is 16-byte aligned; everything below
+// base is final in HBM.  head_skip > 0: the first head_skip bytes of chunk 0 belong to the
+// previous frame (another warp) and must not be stored.
+struct Stager {
+    uint8_t *stage;
+    uint8_t *dst;
+    uint64_t base;
+    uint32_t fill;
+    uint32_t head_skip;
+};
+
+__device__ __forceinline__ void stager_reset(Stager &s, uint64_t pos, uint64_t frame_base, uint32_t lane) {
+    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(s.dst) + pos) & 15);
+    s.base = pos - mis;
+    s.fill = mis;
+    s.head_skip = s.base < frame_base ? (uint32_t)(frame_base - s.base) : 0;
+    if (lane < mis && lane >= s.head_skip) s.stage[lane] = s.dst[s.base + lane];  // bytes this warp wrote earlier
+    __syncwarp();
+}
+
+// store the full 16-byte chunks, keep the partial tail at the front of the window
+__device__ __forceinline__ void stager_flush_chunks(Stager &s, uint32_t lane) {
+    const uint32_t n = s.fill >> 4;
+    if (n == 0) return;
+    for (uint32_t i = lane; i < n; i += 32) {
+        if (i == 0 && s.head_skip) {
+            for (uint32_t k = s.head_skip; k < 16; k++) s.dst[s.base + k] = s.stage[k];
+        } else {
+            *reinterpret_cast<uint4 *>(s.dst + s.base + 16 * (uint64_t)i) = *reinterpret_cast<const uint4 *>(s.stage + 16 * i);
+        }
+    }
+    const uint32_t tail = s.fill & 15;
+    const uint8_t t = lane < tail ? s.stage[16 * n + lane] : 0;
+    __syncwarp();
+    if (lane < tail) s.stage[lane] = t;
+    s.base += 16 * (uint64_t)n;
+    s.fill = tail;
+    s.head_skip = 0;
+    __syncwarp();
+}
+
+// everything out, including the partial tail (byte stores); the window stays consistent
+__device__ __forceinline__ void stager_flush_all(Stager &s, uint32_t lane) {
+    stager_flush_chunks(s, lane);
+    if (lane < s.fill && lane >= s.head_skip) s.dst[s.base + lane] = s.stage[lane];
+    __syncwarp();
+}
+
+// byte at absolute output position p: from the staging window when it is there, else from HBM
+__device__ __forceinline__ uint8_t stager_byte(const Stager &s, uint64_t p) {
+    return p >= s.base ? s.stage[(uint32_t)(p - s.base)] : s.dst[p];
+}
 
 // One warp per frame; blocks in order; 32 sequences per round.
 __global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
+    __shared__ ExecSmem smem[kWarpsPerCta];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t f = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     if (f >= a.nframes) return;
+    ExecSmem &sm = smem[threadIdx.x >> 5];
     const szb_frame_desc fr = a.frames[f];
     const uint32_t b0 = fr.first_block, nb = fr.nblocks;
     uint8_t *const dst = a.dst;
@@ -528,25 +701,31 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
         return;
     }
 
+    Stager st;
+    st.stage = sm.stage;
+    st.dst = dst;
+    stager_reset(st, frame_base, frame_base, lane);
+    uint8_t *const my_gath = sm.gath + lane * kGathStride;
+
     History hist{1, 4, 8};  // framedecompressor.go:48,59
     for (uint32_t bi = 0; bi < nb && err == SZB_OK; bi++) {
         const uint32_t b = b0 + bi;
         const szb_block_desc d = a.blocks[b];
         const uint8_t *payload = a.src + d.src_off;
         uint64_t out_pos = a.out_off[b];
-        if (d.type == 0) {  // Raw (framedecompressor.go:211-215)
-            warp_copy(dst + out_pos, payload, d.block_size, lane);
+        if (d.type != 2) {  // Raw (framedecompressor.go:211-215) / RLE (framedecompressor.go:229-241) bodies
+            stager_flush_all(st, lane);
+            if (d.type == 0)
+                warp_copy(dst + out_pos, payload, d.block_size, lane);
+            else
+                warp_fill(dst + out_pos, payload[0], d.block_size, lane);
             __syncwarp();
-            continue;
-        }
-        if (d.type == 1) {  // RLE (framedecompressor.go:229-241)
-            warp_fill(dst + out_pos, payload[0], d.block_size, lane);
-            __syncwarp();
+            stager_reset(st, out_pos + d.block_size, frame_base, lane);
             continue;
         }
         // Compressed: ExecuteSequences (sequence_execution.go:14-63)
         const bool lit_rle = d.lit_type == 1;
-        const uint8_t *lit = d.lit_type == 0 ? payload + d.lit_hdr_bytes : a.litbuf + d.lit_buf_off;
+        const uint8_t *__restrict__ lit = d.lit_type == 0 ? payload + d.lit_hdr_bytes : a.litbuf + d.lit_buf_off;
         const uint8_t rle_byte = lit_rle ? payload[d.lit_hdr_bytes] : 0;
         const uint32_t nseq = d.nseq;
         const uint32_t *gll = a.seq_ll + d.seq_buf_off, *gml = a.seq_ml + d.seq_buf_off, *gof = a.seq_of + d.seq_buf_off;
@@ -601,81 +780,165 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
                 err = lit_rle ? SZB_ERR_PANIC : SZB_ERR_DIDNT_COPY_ALL_LITERAL_BYTES;
                 break;
             }
-            const uint64_t my_dst = out_pos + (incl_tot - tot);
+            const uint64_t my_dst = out_pos + (incl_tot - tot);  // absolute position of my literal run
             const uint32_t my_lit = lit_pos + (incl_ll - ll);
-
-            // --- literal runs (sequence_execution.go:19-34) ---
-            if (act && ll > 0 && ll < kLongLit) {
-                if (lit_rle) {
-                    for (uint32_t k = 0; k < ll; k++) dst[my_dst + k] = rle_byte;
-                } else {
-                    for (uint32_t k = 0; k < ll; k++) dst[my_dst + k] = lit[my_lit + k];
-                }
-            }
-            uint32_t long_lit = __ballot_sync(kFull, act && ll >= kLongLit);
-            while (long_lit) {
-                const int j = __ffs(long_lit) - 1;
-                long_lit &= long_lit - 1;
-                const uint32_t L = __shfl_sync(kFull, ll, j);
-                const uint64_t D = __shfl_sync(kFull, my_dst, j);
-                const uint32_t S = __shfl_sync(kFull, my_lit, j);
-                if (lit_rle)
-                    warp_fill(dst + D, rle_byte, L, lane);
-                else
-                    warp_copy(dst + D, lit + S, L, lane);
-            }
-
-            // --- matches (RepeatBeforeIndex, ringbuffer.go:242-277) in dependency rounds ---
-            const uint64_t mdst = my_dst + ll;
+            const uint64_t mdst = my_dst + ll;                   // absolute position of my match
             const bool has_match = act && ml > 0;
             if (__any_sync(kFull, has_match && (off == 0 || (uint64_t)off > mdst - frame_base))) {
                 err = SZB_ERR_CANT_REPEAT_BYTES;  // ringbuffer.go:203-214
                 break;
             }
             const uint64_t msrc = mdst - off;
-            const uint64_t need_end = (msrc + ml < mdst) ? msrc + ml : mdst;  // bytes other lanes may still owe us
-            __syncwarp();
-            uint32_t pending = __ballot_sync(kFull, has_match);
-            while (pending) {
-                const int first = __ffs(pending) - 1;
-                const uint64_t frontier = __shfl_sync(kFull, mdst, first);  // everything below is final
-                const uint32_t first_ml = __shfl_sync(kFull, ml, first);
-                if (first_ml >= kLongMatch) {  // warp-wide copy of one long match
-                    const uint32_t OFF = __shfl_sync(kFull, off, first);
-                    const uint8_t *S = dst + frontier - OFF;
-                    uint8_t *D = dst + frontier;
+            const uint64_t need_end = (msrc + ml < mdst) ? msrc + ml : mdst;  // bytes other lanes of the round may owe me
+
+            // --- the round is executed in segments that fit the staging window (normally one) ---
+            uint32_t start = 0;
+            while (start < cnt) {
+                const uint64_t rel_end64 = my_dst + tot - st.base;
+                const bool fits = lane >= start && lane < cnt && rel_end64 <= kStageBytes;
+                const uint32_t nfit = __popc(__ballot_sync(kFull, fits));  // fitting lanes are a prefix of [start, cnt)
+                if (nfit == 0) {
+                    if (st.fill >= 16) {
+                        stager_flush_chunks(st, lane);
+                        continue;
+                    }
+                    // one sequence larger than the window: straight to HBM, whole warp on it
+                    stager_flush_all(st, lane);
+                    const uint32_t L = __shfl_sync(kFull, ll, start), ML = __shfl_sync(kFull, ml, start);
+                    const uint32_t OFF = __shfl_sync(kFull, off, start), SL = __shfl_sync(kFull, my_lit, start);
+                    const uint64_t D = __shfl_sync(kFull, my_dst, start);
+                    if (lit_rle)
+                        warp_fill(dst + D, rle_byte, L, lane);
+                    else
+                        warp_copy(dst + D, lit + SL, L, lane);
+                    __syncwarp();
+                    uint8_t *MD = dst + D + L;
+                    const uint8_t *MS = MD - OFF;
                     if (OFF >= 32) {
-                        for (uint32_t k0 = 0; k0 < first_ml; k0 += 32) {
+                        for (uint32_t k0 = 0; k0 < ML; k0 += 32) {
                             const uint32_t k = k0 + lane;
-                            if (k < first_ml) D[k] = S[k];
+                            if (k < ML) MD[k] = MS[k];
                             __syncwarp();
                         }
-                    } else {  // overlapping: periodic extension of the OFF bytes before the match
-                        for (uint32_t k = lane; k < first_ml; k += 32) D[k] = S[k % OFF];
+                    } else if (ML) {  // overlapping: periodic extension of the OFF bytes before the match
+                        for (uint32_t k = lane; k < ML; k += 32) MD[k] = MS[k % OFF];
                     }
-                    pending &= ~(1u << first);
                     __syncwarp();
+                    stager_reset(st, D + L + ML, frame_base, lane);
+                    start++;
                     continue;
                 }
-                const bool ready = ((pending >> lane) & 1) && ml < kLongMatch && ((int)lane == first || need_end <= frontier);
-                if (ready) {
-                    for (uint32_t k = 0; k < ml; k++) dst[mdst + k] = dst[msrc + k];  // byte-serial: handles self overlap
+                const uint32_t end = start + nfit;
+                const bool in = lane >= start && lane < end;
+                const uint32_t sd = (uint32_t)(my_dst - st.base);  // my literal run inside the window
+                const uint32_t md = sd + ll;                        // my match inside the window
+
+                // literal runs (sequence_execution.go:19-34)
+                if (in && ll > 0 && ll < kCoopLit) {
+                    if (lit_rle) {
+                        for (uint32_t k = 0; k < ll; k++) st.stage[sd + k] = rle_byte;
+                    } else {
+                        for (uint32_t k = 0; k < ll; k++) st.stage[sd + k] = lit[my_lit + k];
+                    }
                 }
-                pending &= ~__ballot_sync(kFull, ready);
+                uint32_t long_lit = __ballot_sync(kFull, in && ll >= kCoopLit);
+                while (long_lit) {
+                    const int j = __ffs(long_lit) - 1;
+                    long_lit &= long_lit - 1;
+                    const uint32_t L = __shfl_sync(kFull, ll, j), SD = __shfl_sync(kFull, sd, j), SL = __shfl_sync(kFull, my_lit, j);
+                    if (lit_rle)
+                        warp_fill(st.stage + SD, rle_byte, L, lane);
+                    else
+                        warp_copy(st.stage + SD, lit + SL, L, lane);
+                }
+
+                // matches (RepeatBeforeIndex, ringbuffer.go:242-277).  Part of a source that is already in
+                // HBM (below the window) is final: gather it now, 16 bytes at a time, for every short match.
+                const bool has = in && ml > 0;
+                const bool shortm = has && ml < kCoopMatch;
+                uint32_t n_g = 0;
+                if (shortm && msrc < st.base) {
+                    const uint64_t gap = st.base - msrc;
+                    n_g = gap < ml ? (uint32_t)gap : ml;
+                }
+                const uint8_t *gp = dst + msrc;
+                const uint32_t gmis = (uint32_t)(reinterpret_cast<uintptr_t>(gp) & 15);
+                if (n_g) {
+                    const uint4 *ga = reinterpret_cast<const uint4 *>(gp - gmis);
+                    uint32_t *gw = reinterpret_cast<uint32_t *>(my_gath);  // row start is 4-byte aligned only: store words
+                    const uint4 c0 = ga[0];
+                    gw[0] = c0.x; gw[1] = c0.y; gw[2] = c0.z; gw[3] = c0.w;
+                    if (gmis + n_g > 16) {
+                        const uint4 c1 = ga[1];
+                        gw[4] = c1.x; gw[5] = c1.y; gw[6] = c1.z; gw[7] = c1.w;
+                    }
+                    if (gmis + n_g > 32) {
+                        const uint4 c2 = ga[2];
+                        gw[8] = c2.x; gw[9] = c2.y; gw[10] = c2.z; gw[11] = c2.w;
+                    }
+                }
                 __syncwarp();
+                uint32_t pending = __ballot_sync(kFull, has);
+                while (pending) {
+                    const int first = __ffs(pending) - 1;
+                    const uint64_t frontier = __shfl_sync(kFull, mdst, first);  // everything below is final
+                    const uint32_t first_ml = __shfl_sync(kFull, ml, first);
+                    if (first_ml >= kCoopMatch) {  // warp-wide copy of one long match into the window
+                        const uint32_t OFF = __shfl_sync(kFull, off, first);
+                        const uint32_t MD = __shfl_sync(kFull, md, first);
+                        const uint64_t S = frontier - OFF;
+                        if (OFF >= 32) {
+                            for (uint32_t k0 = 0; k0 < first_ml; k0 += 32) {
+                                const uint32_t k = k0 + lane;
+                                if (k < first_ml) st.stage[MD + k] = stager_byte(st, S + k);
+                                __syncwarp();
+                            }
+                        } else {  // overlapping: periodic extension of the OFF bytes before the match
+                            for (uint32_t k = lane; k < first_ml; k += 32) st.stage[MD + k] = stager_byte(st, S + k % OFF);
+                        }
+                        pending &= ~(1u << first);
+                        __syncwarp();
+                        continue;
+                    }
+                    const bool ready = ((pending >> lane) & 1) && shortm && ((int)lane == first || need_end <= frontier);
+                    if (ready) {
+                        uint32_t k = 0;
+                        for (; k < n_g; k++) st.stage[md + k] = my_gath[gmis + k];
+                        const uint32_t so = (uint32_t)(msrc + n_g - st.base) - n_g;  // window offset of source byte 0 (valid for k >= n_g)
+                        for (; k < ml; k++) st.stage[md + k] = st.stage[so + k];       // byte-serial: handles self overlap
+                    }
+                    pending &= ~__ballot_sync(kFull, ready);
+                    __syncwarp();
+                }
+                st.fill = __shfl_sync(kFull, (uint32_t)rel_end64, end - 1);
+                stager_flush_chunks(st, lane);
+                start = end;
             }
             out_pos += round_tot;
             lit_pos += round_ll;
         }
         if (err != SZB_OK) break;
         // trailing literals (sequence_execution.go:55-60, literals.go:411-420)
-        const uint32_t rest = d.lit_regen - lit_pos;
-        if (lit_rle)
-            warp_fill(dst + out_pos, rle_byte, rest, lane);
-        else
-            warp_copy(dst + out_pos, lit + lit_pos, rest, lane);
-        __syncwarp();
+        uint32_t rest = d.lit_regen - lit_pos;
+        while (rest) {
+            uint32_t room = kStageBytes - st.fill;
+            if (room == 0) {
+                stager_flush_chunks(st, lane);
+                continue;
+            }
+            const uint32_t n = rest < room ? rest : room;
+            if (lit_rle)
+                warp_fill(st.stage + st.fill, rle_byte, n, lane);
+            else
+                warp_copy(st.stage + st.fill, lit + lit_pos, n, lane);
+            __syncwarp();
+            st.fill += n;
+            lit_pos += n;
+            rest -= n;
+            stager_flush_chunks(st, lane);
+        }
     }
+    stager_flush_all(st, lane);
     if (lane == 0) {
         a.frame_status[f] = err;
         a.frame_out_off[f] = frame_base;
