@@ -169,7 +169,7 @@ int szb_ctx_create(int device, void *stream, szb_ctx **out) {
     }
     cudaFuncSetAttribute(k_huffman_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(HufSmem) * kWarpsPerCta));
     cudaFuncSetAttribute(k_build_seq_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SeqSmem) * kWarpsPerCta));
-    cudaFuncSetAttribute(k_decode_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSeqLanes * kTabSlotWords * 4));
+    cudaFuncSetAttribute(k_decode_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeqDecodeSmemBytes);
     *out = ctx;
     return SZB_OK;
 }
@@ -418,7 +418,7 @@ static int launch_entropy(szb_batch *b, const void *d_src) {
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[7], s));
     if (a.n_seq) {
-        k_decode_sequences<<<(a.n_seq + kSeqLanes - 1) / kSeqLanes, 32, kSeqLanes * kTabSlotWords * 4, s>>>(a);
+        k_decode_sequences<<<(a.n_seq + kSeqLanes - 1) / kSeqLanes, 32, kSeqDecodeSmemBytes, s>>>(a);
         ctx->launches++;
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));

@@ -34,7 +34,7 @@ constexpr uint32_t kFull = 0xFFFFFFFFu;
 #define SZB_SERIAL_TABLES 0
 #endif
 
-constexpr int kSeqLanes = 21;             // blocks per warp in k_decode_sequences: 21 x 5 KB tables, 2 warps per SM
+constexpr int kSeqLanes = 20;             // blocks per warp in k_decode_sequences: 20 x 2.5 KB tables, 4 warps per SM
 constexpr uint32_t kTabSlotWords = 1280;  // LL 512 | ML 512 | OF 256
 
 struct SeqInfo {
@@ -400,24 +400,132 @@ __device__ __forceinline__ uint32_t slow_read_bits(const uint8_t *sp, int64_t po
 // FSE states, the tables of all its blocks resident in shared memory.  A warp instruction thus
 // advances kSeqLanes independent state chains instead of one.
 //
-// Per sequence a lane fetches one 64-bit window ending at its bit position (three aligned 32-bit
-// loads + funnel shifts; the reference does a div/mod Read() per field) and peels the six fields
-// off its top in the reference's order: OF extra, ML extra, LL extra, LL state, ML state, OF state.
+// Shared-memory budget decides how many chains an SM can run, so the resident cells are 16 bits:
+// symbol (6 bits) and the cell's "next state" counter (10 bits, fse.go:195-196), from which
+// NumberOfBits = AL - highbit(next) and Baseline = (next << NumberOfBits) - 2^AL (fse.go:212-213)
+// are recomputed with two ALU ops each; extra-bit counts and base values (predefined.go:5-20,36-50)
+// come from a 64-entry table shared by the warp.
+//
+// Bit reads (replacing Reversebitstream.Read, reversebitstream.go:17-88): every lane keeps the
+// 64 stream bytes around its read position in a 4 x 16-byte shared-memory ring that is topped up
+// with one 16-byte global load per chunk, issued two chunks ahead of use.  Per sequence a lane
+// builds one 64-bit window ending at its bit position from three ring words and peels the six
+// fields off its top in the reference's order: OF extra, ML extra, LL extra, then (except after
+// the last sequence) LL state, ML state, OF state.  Decoded triples are buffered four deep in
+// registers and leave as 16-byte stores.
+constexpr uint32_t kSeqTabBytes = kSeqLanes * kTabSlotWords * 2;  // u16 cells
+constexpr uint32_t kSeqRingWord = kSeqTabBytes / 4;               // ring[16][32] words
+constexpr uint32_t kSeqLutWord = kSeqRingWord + 16 * 32;          // ll[64] | ml[64]: base | extra << 24
+constexpr uint32_t kSeqDecodeSmemBytes = (kSeqLutWord + 128) * 4;
+
+__device__ __forceinline__ uint32_t cell16(uint32_t packed, uint32_t al) {
+    return ((fse_baseline(packed) + (1u << al)) >> fse_nb(packed)) | (fse_code(packed) << 10);
+}
+
+struct SeqLane {
+    uint32_t s_ll, s_of, s_ml;  // FSE states
+    int32_t pos;                // stream bits not consumed yet
+    int32_t cur;                // ring: chunk (16 B, counted from the chunk holding sp[0]) of the byte with bit pos-1
+    uint4 pending;              // chunk cur-3, in flight
+};
+
+template <bool kUpdate>
+__device__ __forceinline__ void decode_step(const uint32_t *sw, const uint16_t *tll, const uint16_t *tml, const uint16_t *tof,
+                                            uint32_t *ring, const uint8_t *sp, const uint4 *chunk0, uint32_t sp_mis,
+                                            uint32_t al_ll, uint32_t al_ml, uint32_t al_of, SeqLane &L, uint32_t &v_ll,
+                                            uint32_t &v_ml, uint32_t &v_of) {
+    const uint32_t c_of = tof[L.s_of], c_ll = tll[L.s_ll], c_ml = tml[L.s_ml];  // peek OF, LL, ML (sequences.go:67-78)
+    const uint32_t ofc = c_of >> 10;
+    const uint32_t u_ll = sw[kSeqLutWord + (c_ll >> 10)], u_ml = sw[kSeqLutWord + 64 + (c_ml >> 10)];
+    const uint32_t llx = u_ll >> 24, mlx = u_ml >> 24;
+    uint32_t nbl = 0, nbm = 0, nbo = 0;
+    if (kUpdate) {
+        nbl = al_ll - 31 + __clz(c_ll & 1023);
+        nbm = al_ml - 31 + __clz(c_ml & 1023);
+        nbo = al_of - 31 + __clz(c_of & 1023);
+    }
+    const uint32_t total = ofc + mlx + llx + nbl + nbm + nbo;
+    uint32_t x_of, x_ml, x_ll, b_ll = 0, b_ml = 0, b_of = 0;
+    if (L.pos >= 96 && total <= 57) {
+        // window: the 8 bytes ending at the byte that holds bit pos-1, bit pos-1 moved to bit 63
+        const uint32_t ap = sp_mis + ((uint32_t)(L.pos - 1) >> 3) - 7;  // byte address relative to chunk 0
+        const uint32_t mis = ap & 3;
+        const uint32_t o = ap >> 2;
+        const uint32_t w0 = ring[(o & 15) * 32], w1 = ring[((o + 1) & 15) * 32], w2 = ring[((o + 2) & 15) * 32];
+        uint32_t lo = __funnelshift_r(w0, w1, mis * 8), hi = __funnelshift_r(w1, w2, mis * 8);
+        const uint32_t k = 7 - ((uint32_t)(L.pos - 1) & 7);
+        hi = __funnelshift_l(lo, hi, k);
+        lo <<= k;
+#define SZB_TAKE(dst, n)                \
+    dst = __funnelshift_l(hi, 0u, (n)); \
+    hi = __funnelshift_l(lo, hi, (n));  \
+    lo <<= (n);
+        SZB_TAKE(x_of, ofc)
+        SZB_TAKE(x_ml, mlx)
+        SZB_TAKE(x_ll, llx)
+        if (kUpdate) {
+            SZB_TAKE(b_ll, nbl)
+            SZB_TAKE(b_ml, nbm)
+            SZB_TAKE(b_of, nbo)
+        }
+#undef SZB_TAKE
+        L.pos -= (int32_t)total;
+    } else {  // near the stream start, or a sequence wider than one window
+        x_of = slow_read_bits(sp, L.pos, ofc);
+        L.pos -= (int32_t)ofc;
+        x_ml = slow_read_bits(sp, L.pos, mlx);
+        L.pos -= (int32_t)mlx;
+        x_ll = slow_read_bits(sp, L.pos, llx);
+        L.pos -= (int32_t)llx;
+        if (kUpdate) {
+            b_ll = slow_read_bits(sp, L.pos, nbl);
+            L.pos -= (int32_t)nbl;
+            b_ml = slow_read_bits(sp, L.pos, nbm);
+            L.pos -= (int32_t)nbm;
+            b_of = slow_read_bits(sp, L.pos, nbo);
+            L.pos -= (int32_t)nbo;
+        }
+    }
+    // keep the ring two chunks ahead of the read position (a sequence moves it by less than 16 bytes)
+    const int32_t now = (int32_t)((sp_mis + ((uint32_t)(L.pos > 0 ? L.pos - 1 : 0) >> 3)) >> 4);
+    if (now < L.cur) {
+        L.cur = now;
+        uint32_t *r = ring + (((uint32_t)(now - 2) & 3) << 2) * 32;
+        r[0] = L.pending.x;
+        r[32] = L.pending.y;
+        r[64] = L.pending.z;
+        r[96] = L.pending.w;
+        L.pending = now >= 3 ? chunk0[now - 3] : make_uint4(0, 0, 0, 0);
+    }
+    v_of = (1u << ofc) + x_of;              // sequences.go:99-104
+    v_ml = (u_ml & 0xFFFFFF) + x_ml;        // sequences.go:106-112
+    v_ll = (u_ll & 0xFFFFFF) + x_ll;        // sequences.go:114-120
+    if (kUpdate) {  // update LL, ML, OF (sequences.go:178-194); Baseline = (next << nb) - 2^AL
+        L.s_ll = ((c_ll & 1023) << nbl) - (1u << al_ll) + b_ll;
+        L.s_ml = ((c_ml & 1023) << nbm) - (1u << al_ml) + b_ml;
+        L.s_of = ((c_of & 1023) << nbo) - (1u << al_of) + b_of;
+    }
+}
+
 __global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint32_t *tabs = reinterpret_cast<uint32_t *>(smem_raw);
+    extern __shared__ __align__(16) uint32_t sw[];
     const uint32_t lane = threadIdx.x;
     const uint32_t first = blockIdx.x * kSeqLanes;
     const uint32_t n_here = a.n_seq - first < (uint32_t)kSeqLanes ? a.n_seq - first : (uint32_t)kSeqLanes;
+    uint16_t *tabs = reinterpret_cast<uint16_t *>(sw);
 
-    // tables: HBM arena -> shared memory, coalesced
+    // tables: HBM arena (32-bit cells) -> shared memory (16-bit cells), coalesced
     for (uint32_t j = 0; j < n_here; j++) {
         const SeqInfo info = a.seq_info[first + j];
         const uint32_t *slot = a.seq_tabs + (size_t)(first + j) * kTabSlotWords;
-        uint32_t *t = tabs + j * kTabSlotWords;
-        for (uint32_t i = lane; i < (1u << info.al_ll); i += 32) t[i] = slot[i];
-        for (uint32_t i = lane; i < (1u << info.al_ml); i += 32) t[512 + i] = slot[512 + i];
-        for (uint32_t i = lane; i < (1u << info.al_of); i += 32) t[1024 + i] = slot[1024 + i];
+        uint16_t *t = tabs + j * kTabSlotWords;
+        for (uint32_t i = lane; i < (1u << info.al_ll); i += 32) t[i] = (uint16_t)cell16(slot[i], info.al_ll);
+        for (uint32_t i = lane; i < (1u << info.al_ml); i += 32) t[512 + i] = (uint16_t)cell16(slot[512 + i], info.al_ml);
+        for (uint32_t i = lane; i < (1u << info.al_of); i += 32) t[1024 + i] = (uint16_t)cell16(slot[1024 + i], info.al_of);
+    }
+    for (uint32_t i = lane; i < 64; i += 32) {
+        sw[kSeqLutWord + i] = kLLBaseDev[i] | ((uint32_t)kLLExtraDev[i] << 24);
+        sw[kSeqLutWord + 64 + i] = kMLBaseDev[i] | ((uint32_t)kMLExtraDev[i] << 24);
     }
     __syncwarp();
     if (lane >= n_here) return;
@@ -427,7 +535,8 @@ __global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
     if (a.seq_status[b] != SZB_OK) return;  // its tables failed to build
     const szb_block_desc d = a.blocks[b];
     const SeqInfo info = a.seq_info[w];
-    const uint32_t *tll = tabs + lane * kTabSlotWords, *tml = tll + 512, *tof = tll + 1024;
+    const uint16_t *tll = tabs + lane * kTabSlotWords, *tml = tll + 512, *tof = tll + 1024;
+    const uint32_t al_ll = info.al_ll, al_ml = info.al_ml, al_of = info.al_of;
     const uint32_t hdr = d.seq_off + d.seq_hdr_bytes + info.stream_off;
     const uint8_t *sp = a.src + d.src_off + hdr;
     const uint32_t len = d.block_size - hdr;
@@ -437,77 +546,62 @@ __global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
         a.seq_status[b] = SZB_ERR_BAD_PADDING;
         return;
     }
-    int64_t pos = (int64_t)len * 8 - (__clz((uint32_t)sp[len - 1]) - 24 + 1);
+    SeqLane L;
+    L.pos = (int32_t)(len * 8) - (__clz((uint32_t)sp[len - 1]) - 24 + 1);
     // InitState in the order LL, OF, ML (sequences.go:145-159)
-    uint32_t s_ll = slow_read_bits(sp, pos, info.al_ll);
-    pos -= info.al_ll;
-    uint32_t s_of = slow_read_bits(sp, pos, info.al_of);
-    pos -= info.al_of;
-    uint32_t s_ml = slow_read_bits(sp, pos, info.al_ml);
-    pos -= info.al_ml;
+    L.s_ll = slow_read_bits(sp, L.pos, al_ll);
+    L.pos -= (int32_t)al_ll;
+    L.s_of = slow_read_bits(sp, L.pos, al_of);
+    L.pos -= (int32_t)al_of;
+    L.s_ml = slow_read_bits(sp, L.pos, al_ml);
+    L.pos -= (int32_t)al_ml;
+
+    // ring of 16-byte chunks; chunk c covers bytes [16c, 16c+16) counted from the aligned address at or below sp
+    uint32_t *ring = sw + kSeqRingWord + lane;  // ring word k of this lane: ring[k * 32] (own bank)
+    const uint32_t sp_mis = (uint32_t)(reinterpret_cast<uintptr_t>(sp) & 15);
+    const uint4 *chunk0 = reinterpret_cast<const uint4 *>(sp - sp_mis);
+    L.cur = (int32_t)((sp_mis + ((uint32_t)(L.pos > 0 ? L.pos - 1 : 0) >> 3)) >> 4);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int32_t c = L.cur - k;
+        const uint4 v = c >= 0 ? chunk0[c] : make_uint4(0, 0, 0, 0);
+        uint32_t *r = ring + (((uint32_t)c & 3) << 2) * 32;
+        r[0] = v.x;
+        r[32] = v.y;
+        r[64] = v.z;
+        r[96] = v.w;
+    }
+    L.pending = L.cur >= 3 ? chunk0[L.cur - 3] : make_uint4(0, 0, 0, 0);
 
     const uint32_t nseq = d.nseq;
     uint32_t *gll = a.seq_ll + d.seq_buf_off, *gml = a.seq_ml + d.seq_buf_off, *gof = a.seq_of + d.seq_buf_off;
     uint64_t ml_sum = 0;
-    for (uint32_t i = 0; i < nseq; i++) {
-        const uint32_t e_of = tof[s_of], e_ll = tll[s_ll], e_ml = tml[s_ml];  // peek OF, LL, ML (sequences.go:67-78)
-        const uint32_t ofc = fse_code(e_of), mlx = fse_extra(e_ml), llx = fse_extra(e_ll);
-        const bool upd = i + 1 < nseq;  // no state update after the last sequence (sequences.go:178)
-        const uint32_t nbl = upd ? fse_nb(e_ll) : 0, nbm = upd ? fse_nb(e_ml) : 0, nbo = upd ? fse_nb(e_of) : 0;
-        const uint32_t total = ofc + mlx + llx + nbl + nbm + nbo;
-        uint32_t x_of, x_ml, x_ll, b_ll, b_ml, b_of;
-        if (pos >= 96 && total <= 57) {
-            // window: the 8 bytes ending at the byte that holds bit pos-1, shifted so that bit sits at bit 63
-            const uint32_t e = (uint32_t)((pos - 1) >> 3);
-            const uint8_t *ap = sp + e - 7;
-            const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(ap) & 3);
-            const uint32_t *wp = reinterpret_cast<const uint32_t *>(ap - mis);
-            const uint32_t w0 = wp[0], w1 = wp[1], w2 = mis ? wp[2] : 0u;  // never touch a word that holds no stream byte
-            // the stream is walked backwards ~3 bytes per sequence: pull the sectors ~20 sequences ahead into L1
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(ap - 64));
-            uint32_t lo = __funnelshift_r(w0, w1, mis * 8), hi = __funnelshift_r(w1, w2, mis * 8);
-            const uint32_t k = 7 - ((uint32_t)(pos - 1) & 7);
-            hi = __funnelshift_l(lo, hi, k);
-            lo <<= k;
-#define SZB_TAKE(dst, n)                     \
-    dst = __funnelshift_l(hi, 0u, (n));      \
-    hi = __funnelshift_l(lo, hi, (n));       \
-    lo <<= (n);
-            SZB_TAKE(x_of, ofc)
-            SZB_TAKE(x_ml, mlx)
-            SZB_TAKE(x_ll, llx)
-            SZB_TAKE(b_ll, nbl)
-            SZB_TAKE(b_ml, nbm)
-            SZB_TAKE(b_of, nbo)
-#undef SZB_TAKE
-            pos -= total;
-        } else {  // near the stream start, or a sequence wider than one window
-            x_of = slow_read_bits(sp, pos, ofc);
-            pos -= ofc;
-            x_ml = slow_read_bits(sp, pos, mlx);
-            pos -= mlx;
-            x_ll = slow_read_bits(sp, pos, llx);
-            pos -= llx;
-            b_ll = slow_read_bits(sp, pos, nbl);
-            pos -= nbl;
-            b_ml = slow_read_bits(sp, pos, nbm);
-            pos -= nbm;
-            b_of = slow_read_bits(sp, pos, nbo);
-            pos -= nbo;
-        }
-        const uint32_t ml = ml_base(fse_code(e_ml)) + x_ml;  // sequences.go:106-112
-        gof[i] = (1u << ofc) + x_of;                         // sequences.go:99-104
-        gml[i] = ml;
-        gll[i] = ll_base(fse_code(e_ll)) + x_ll;             // sequences.go:114-120
-        ml_sum += ml;
-        if (upd) {  // update LL, ML, OF (sequences.go:178-194)
-            s_ll = fse_baseline(e_ll) + b_ll;
-            s_ml = fse_baseline(e_ml) + b_ml;
-            s_of = fse_baseline(e_of) + b_of;
-        }
+    const uint32_t n_upd = nseq - 1;  // every sequence but the last updates the states (sequences.go:178)
+    uint32_t i = 0;
+    for (; i + 4 <= n_upd; i += 4) {
+        uint32_t v_ll[4], v_ml[4], v_of[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            decode_step<true>(sw, tll, tml, tof, ring, sp, chunk0, sp_mis, al_ll, al_ml, al_of, L, v_ll[j], v_ml[j], v_of[j]);
+        // seq_buf_off is a multiple of 32 entries: 16-byte aligned stores
+        *reinterpret_cast<uint4 *>(gll + i) = make_uint4(v_ll[0], v_ll[1], v_ll[2], v_ll[3]);
+        *reinterpret_cast<uint4 *>(gml + i) = make_uint4(v_ml[0], v_ml[1], v_ml[2], v_ml[3]);
+        *reinterpret_cast<uint4 *>(gof + i) = make_uint4(v_of[0], v_of[1], v_of[2], v_of[3]);
+        ml_sum += (uint64_t)v_ml[0] + v_ml[1] + v_ml[2] + v_ml[3];
+    }
+    for (; i < nseq; i++) {
+        uint32_t v_ll, v_ml, v_of;
+        if (i < n_upd)
+            decode_step<true>(sw, tll, tml, tof, ring, sp, chunk0, sp_mis, al_ll, al_ml, al_of, L, v_ll, v_ml, v_of);
+        else
+            decode_step<false>(sw, tll, tml, tof, ring, sp, chunk0, sp_mis, al_ll, al_ml, al_of, L, v_ll, v_ml, v_of);
+        gll[i] = v_ll;
+        gml[i] = v_ml;
+        gof[i] = v_of;
+        ml_sum += v_ml;
     }
     // the stream must be consumed exactly (sequences.go:197-204)
-    a.seq_status[b] = pos == 0 ? SZB_OK : SZB_ERR_NOT_ALL_BITS_USED;
+    a.seq_status[b] = L.pos == 0 ? SZB_OK : SZB_ERR_NOT_ALL_BITS_USED;
     a.out_size[b] = (uint64_t)d.lit_regen + ml_sum;
 }
 
