@@ -414,44 +414,72 @@ __device__ __forceinline__ uint32_t slow_read_bits(const uint8_t *sp, int64_t po
 // the last sequence) LL state, ML state, OF state.  Decoded triples are buffered four deep in
 // registers and leave as 16-byte stores.
 constexpr uint32_t kSeqTabBytes = kSeqLanes * kTabSlotWords * 2;  // u16 cells
-constexpr uint32_t kSeqRingWord = kSeqTabBytes / 4;               // ring[16][32] words
-constexpr uint32_t kSeqLutWord = kSeqRingWord + 16 * 32;          // ll[64] | ml[64]: base | extra << 24
+constexpr uint32_t kSeqRingStride = 144;                          // per lane: 64 B ring + 64 B mirror + 16 B pad
+constexpr uint32_t kSeqRingOff = kSeqTabBytes;                    // byte offset of the rings
+constexpr uint32_t kSeqLutWord = (kSeqRingOff + kSeqLanes * kSeqRingStride) / 4;  // ll[64] | ml[64]: base | extra << 24
 constexpr uint32_t kSeqDecodeSmemBytes = (kSeqLutWord + 128) * 4;
 
+// resident cell: symbol in bits 0-5, next-state counter in bits 6-15
 __device__ __forceinline__ uint32_t cell16(uint32_t packed, uint32_t al) {
-    return ((fse_baseline(packed) + (1u << al)) >> fse_nb(packed)) | (fse_code(packed) << 10);
+    return fse_code(packed) | (((fse_baseline(packed) + (1u << al)) >> fse_nb(packed)) << 6);
+}
+__device__ __forceinline__ uint32_t bfind(uint32_t x) {  // index of the highest set bit (x != 0)
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+}
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g));
 }
 
 struct SeqLane {
     uint32_t s_ll, s_of, s_ml;  // FSE states
     int32_t pos;                // stream bits not consumed yet
     int32_t cur;                // ring: chunk (16 B, counted from the chunk holding sp[0]) of the byte with bit pos-1
-    uint4 pending;              // chunk cur-3, in flight
 };
+
+// Chunk c of the stream goes to ring slot c & 3 and to its mirror 64 bytes above, so a 12-byte window
+// read never wraps.  Asynchronous (cp.async): no register, no scoreboard slot is held while it flies.
+__device__ __forceinline__ void ring_fetch(uint32_t ring_saddr, const uint4 *chunk0, int32_t c) {
+    if (c >= 0) {
+        const uint32_t s = ring_saddr + (((uint32_t)c & 3) << 4);
+        cp_async16(s, chunk0 + c);
+        cp_async16(s + 64, chunk0 + c);
+    }
+    asm volatile("cp.async.commit_group;");
+}
 
 template <bool kUpdate>
 __device__ __forceinline__ void decode_step(const uint32_t *sw, const uint16_t *tll, const uint16_t *tml, const uint16_t *tof,
-                                            uint32_t *ring, const uint8_t *sp, const uint4 *chunk0, uint32_t sp_mis,
-                                            uint32_t al_ll, uint32_t al_ml, uint32_t al_of, SeqLane &L, uint32_t &v_ll,
-                                            uint32_t &v_ml, uint32_t &v_of) {
+                                            const uint8_t *ring, uint32_t ring_saddr, const uint8_t *sp, const uint4 *chunk0,
+                                            uint32_t sp_mis, uint32_t al_ll, uint32_t al_ml, uint32_t al_of, SeqLane &L,
+                                            uint32_t &v_ll, uint32_t &v_ml, uint32_t &v_of) {
     const uint32_t c_of = tof[L.s_of], c_ll = tll[L.s_ll], c_ml = tml[L.s_ml];  // peek OF, LL, ML (sequences.go:67-78)
-    const uint32_t ofc = c_of >> 10;
-    const uint32_t u_ll = sw[kSeqLutWord + (c_ll >> 10)], u_ml = sw[kSeqLutWord + 64 + (c_ml >> 10)];
+    const uint32_t ofc = c_of & 63;
+    const uint32_t u_ll = sw[kSeqLutWord + (c_ll & 63)], u_ml = sw[kSeqLutWord + 64 + (c_ml & 63)];
     const uint32_t llx = u_ll >> 24, mlx = u_ml >> 24;
     uint32_t nbl = 0, nbm = 0, nbo = 0;
-    if (kUpdate) {
-        nbl = al_ll - 31 + __clz(c_ll & 1023);
-        nbm = al_ml - 31 + __clz(c_ml & 1023);
-        nbo = al_of - 31 + __clz(c_of & 1023);
+    if (kUpdate) {  // NumberOfBits = AL - highbit(next) (fse.go:212)
+        nbl = al_ll - bfind(c_ll >> 6);
+        nbm = al_ml - bfind(c_ml >> 6);
+        nbo = al_of - bfind(c_of >> 6);
     }
     const uint32_t total = ofc + mlx + llx + nbl + nbm + nbo;
+    // position of the byte that holds bit pos-1, relative to chunk 0
+    const uint32_t top = sp_mis + ((uint32_t)(L.pos - 1) >> 3);
+    // keep the ring ahead of the read position: chunks cur and cur-1 are resident, cur-2 is landing
+    if ((int32_t)(top >> 4) < L.cur && L.pos > 0) {
+        L.cur = (int32_t)(top >> 4);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");  // chunk cur-1 was requested one crossing ago
+        ring_fetch(ring_saddr, chunk0, L.cur - 2);
+    }
     uint32_t x_of, x_ml, x_ll, b_ll = 0, b_ml = 0, b_of = 0;
     if (L.pos >= 96 && total <= 57) {
-        // window: the 8 bytes ending at the byte that holds bit pos-1, bit pos-1 moved to bit 63
-        const uint32_t ap = sp_mis + ((uint32_t)(L.pos - 1) >> 3) - 7;  // byte address relative to chunk 0
+        // window: the 8 bytes ending at byte `top`, bit pos-1 moved to bit 63
+        const uint32_t ap = top - 7;
         const uint32_t mis = ap & 3;
-        const uint32_t o = ap >> 2;
-        const uint32_t w0 = ring[(o & 15) * 32], w1 = ring[((o + 1) & 15) * 32], w2 = ring[((o + 2) & 15) * 32];
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(ring + ((ap - mis) & 63));
+        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
         uint32_t lo = __funnelshift_r(w0, w1, mis * 8), hi = __funnelshift_r(w1, w2, mis * 8);
         const uint32_t k = 7 - ((uint32_t)(L.pos - 1) & 7);
         hi = __funnelshift_l(lo, hi, k);
@@ -486,24 +514,13 @@ __device__ __forceinline__ void decode_step(const uint32_t *sw, const uint16_t *
             L.pos -= (int32_t)nbo;
         }
     }
-    // keep the ring two chunks ahead of the read position (a sequence moves it by less than 16 bytes)
-    const int32_t now = (int32_t)((sp_mis + ((uint32_t)(L.pos > 0 ? L.pos - 1 : 0) >> 3)) >> 4);
-    if (now < L.cur) {
-        L.cur = now;
-        uint32_t *r = ring + (((uint32_t)(now - 2) & 3) << 2) * 32;
-        r[0] = L.pending.x;
-        r[32] = L.pending.y;
-        r[64] = L.pending.z;
-        r[96] = L.pending.w;
-        L.pending = now >= 3 ? chunk0[now - 3] : make_uint4(0, 0, 0, 0);
-    }
     v_of = (1u << ofc) + x_of;              // sequences.go:99-104
     v_ml = (u_ml & 0xFFFFFF) + x_ml;        // sequences.go:106-112
     v_ll = (u_ll & 0xFFFFFF) + x_ll;        // sequences.go:114-120
-    if (kUpdate) {  // update LL, ML, OF (sequences.go:178-194); Baseline = (next << nb) - 2^AL
-        L.s_ll = ((c_ll & 1023) << nbl) - (1u << al_ll) + b_ll;
-        L.s_ml = ((c_ml & 1023) << nbm) - (1u << al_ml) + b_ml;
-        L.s_of = ((c_of & 1023) << nbo) - (1u << al_of) + b_of;
+    if (kUpdate) {  // update LL, ML, OF (sequences.go:178-194); Baseline = (next << nb) - 2^AL (fse.go:213)
+        L.s_ll = ((c_ll >> 6) << nbl) - (1u << al_ll) + b_ll;
+        L.s_ml = ((c_ml >> 6) << nbm) - (1u << al_ml) + b_ml;
+        L.s_of = ((c_of >> 6) << nbo) - (1u << al_of) + b_of;
     }
 }
 
@@ -557,21 +574,15 @@ __global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
     L.pos -= (int32_t)al_ml;
 
     // ring of 16-byte chunks; chunk c covers bytes [16c, 16c+16) counted from the aligned address at or below sp
-    uint32_t *ring = sw + kSeqRingWord + lane;  // ring word k of this lane: ring[k * 32] (own bank)
+    const uint8_t *ring = reinterpret_cast<const uint8_t *>(sw) + kSeqRingOff + lane * kSeqRingStride;
+    const uint32_t ring_saddr = (uint32_t)__cvta_generic_to_shared(ring);
     const uint32_t sp_mis = (uint32_t)(reinterpret_cast<uintptr_t>(sp) & 15);
     const uint4 *chunk0 = reinterpret_cast<const uint4 *>(sp - sp_mis);
     L.cur = (int32_t)((sp_mis + ((uint32_t)(L.pos > 0 ? L.pos - 1 : 0) >> 3)) >> 4);
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const int32_t c = L.cur - k;
-        const uint4 v = c >= 0 ? chunk0[c] : make_uint4(0, 0, 0, 0);
-        uint32_t *r = ring + (((uint32_t)c & 3) << 2) * 32;
-        r[0] = v.x;
-        r[32] = v.y;
-        r[64] = v.z;
-        r[96] = v.w;
-    }
-    L.pending = L.cur >= 3 ? chunk0[L.cur - 3] : make_uint4(0, 0, 0, 0);
+    ring_fetch(ring_saddr, chunk0, L.cur);
+    ring_fetch(ring_saddr, chunk0, L.cur - 1);
+    ring_fetch(ring_saddr, chunk0, L.cur - 2);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // cur and cur-1 have landed; cur-2 may still fly
 
     const uint32_t nseq = d.nseq;
     uint32_t *gll = a.seq_ll + d.seq_buf_off, *gml = a.seq_ml + d.seq_buf_off, *gof = a.seq_of + d.seq_buf_off;
@@ -582,7 +593,7 @@ __global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
         uint32_t v_ll[4], v_ml[4], v_of[4];
 #pragma unroll
         for (int j = 0; j < 4; j++)
-            decode_step<true>(sw, tll, tml, tof, ring, sp, chunk0, sp_mis, al_ll, al_ml, al_of, L, v_ll[j], v_ml[j], v_of[j]);
+            decode_step<true>(sw, tll, tml, tof, ring, ring_saddr, sp, chunk0, sp_mis, al_ll, al_ml, al_of, L, v_ll[j], v_ml[j], v_of[j]);
         // seq_buf_off is a multiple of 32 entries: 16-byte aligned stores
         *reinterpret_cast<uint4 *>(gll + i) = make_uint4(v_ll[0], v_ll[1], v_ll[2], v_ll[3]);
         *reinterpret_cast<uint4 *>(gml + i) = make_uint4(v_ml[0], v_ml[1], v_ml[2], v_ml[3]);
@@ -592,14 +603,15 @@ __global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
     for (; i < nseq; i++) {
         uint32_t v_ll, v_ml, v_of;
         if (i < n_upd)
-            decode_step<true>(sw, tll, tml, tof, ring, sp, chunk0, sp_mis, al_ll, al_ml, al_of, L, v_ll, v_ml, v_of);
+            decode_step<true>(sw, tll, tml, tof, ring, ring_saddr, sp, chunk0, sp_mis, al_ll, al_ml, al_of, L, v_ll, v_ml, v_of);
         else
-            decode_step<false>(sw, tll, tml, tof, ring, sp, chunk0, sp_mis, al_ll, al_ml, al_of, L, v_ll, v_ml, v_of);
+            decode_step<false>(sw, tll, tml, tof, ring, ring_saddr, sp, chunk0, sp_mis, al_ll, al_ml, al_of, L, v_ll, v_ml, v_of);
         gll[i] = v_ll;
         gml[i] = v_ml;
         gof[i] = v_of;
         ml_sum += v_ml;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     // the stream must be consumed exactly (sequences.go:197-204)
     a.seq_status[b] = L.pos == 0 ? SZB_OK : SZB_ERR_NOT_ALL_BITS_USED;
     a.out_size[b] = (uint64_t)d.lit_regen + ml_sum;
