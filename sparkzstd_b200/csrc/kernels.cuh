@@ -440,13 +440,13 @@ struct SeqLane {
 
 // Chunk c of the stream goes to ring slot c & 3 and to its mirror 64 bytes above, so a 12-byte window
 // read never wraps.  Asynchronous (cp.async): no register, no scoreboard slot is held while it flies.
+// Completion is tracked per warp in commit groups; decode_step commits one group per sequence.
 __device__ __forceinline__ void ring_fetch(uint32_t ring_saddr, const uint4 *chunk0, int32_t c) {
     if (c >= 0) {
         const uint32_t s = ring_saddr + (((uint32_t)c & 3) << 4);
         cp_async16(s, chunk0 + c);
         cp_async16(s + 64, chunk0 + c);
     }
-    asm volatile("cp.async.commit_group;");
 }
 
 template <bool kUpdate>
@@ -467,12 +467,16 @@ __device__ __forceinline__ void decode_step(const uint32_t *sw, const uint16_t *
     const uint32_t total = ofc + mlx + llx + nbl + nbm + nbo;
     // position of the byte that holds bit pos-1, relative to chunk 0
     const uint32_t top = sp_mis + ((uint32_t)(L.pos - 1) >> 3);
-    // keep the ring ahead of the read position: chunks cur and cur-1 are resident, cur-2 is landing
+    // Keep the ring ahead of the read position.  On entering chunk cur the window needs cur and cur-1;
+    // cur-1 was requested two crossings ago (as "cur-3" of that moment).  A lane crosses at most every other sequence and every
+    // sequence commits one group, so that request is at least 4 groups old: wait_group 3 covers it
+    // while the younger requests (cur-2, and cur-3 issued now into the slot cur+1 vacated) keep flying.
     if ((int32_t)(top >> 4) < L.cur && L.pos > 0) {
         L.cur = (int32_t)(top >> 4);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");  // chunk cur-1 was requested one crossing ago
-        ring_fetch(ring_saddr, chunk0, L.cur - 2);
+        asm volatile("cp.async.wait_group 3;" ::: "memory");
+        ring_fetch(ring_saddr, chunk0, L.cur - 3);
     }
+    asm volatile("cp.async.commit_group;");
     uint32_t x_of, x_ml, x_ll, b_ll = 0, b_ml = 0, b_of = 0;
     if (L.pos >= 96 && total <= 57) {
         // window: the 8 bytes ending at byte `top`, bit pos-1 moved to bit 63
@@ -582,7 +586,9 @@ __global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
     ring_fetch(ring_saddr, chunk0, L.cur);
     ring_fetch(ring_saddr, chunk0, L.cur - 1);
     ring_fetch(ring_saddr, chunk0, L.cur - 2);
-    asm volatile("cp.async.wait_group 1;" ::: "memory");  // cur and cur-1 have landed; cur-2 may still fly
+    ring_fetch(ring_saddr, chunk0, L.cur - 3);  // steady state: cur .. cur-2 resident or landing, cur-3 requested on entry
+    asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 
     const uint32_t nseq = d.nseq;
     uint32_t *gll = a.seq_ll + d.seq_buf_off, *gml = a.seq_ml + d.seq_buf_off, *gof = a.seq_of + d.seq_buf_off;
