@@ -48,13 +48,15 @@ struct szb_batch {
     size_t src_len = 0;
     std::vector<szb_frame_desc> frames;
     std::vector<szb_block_desc> blocks;
-    std::vector<uint32_t> huf_list, seq_list;
+    std::vector<uint32_t> huf_list, seq_list, hufo_list, huf_slot;
     uint64_t literal_bytes = 0, sequences = 0;
     // device
     void *d_tables = nullptr;  // one allocation: frames | blocks | lists | out_size_init
     szb_frame_desc *d_frames = nullptr;
     szb_block_desc *d_blocks = nullptr;
-    uint32_t *d_huf_list = nullptr, *d_seq_list = nullptr;
+    uint32_t *d_huf_list = nullptr, *d_seq_list = nullptr, *d_hufo_list = nullptr, *d_huf_slot = nullptr;
+    uint16_t *d_huf_tabs = nullptr;
+    HufInfo *d_huf_info = nullptr;
     uint64_t *d_out_size_init = nullptr;
     void *d_state = nullptr;  // one allocation: out_size | out_off | total | frame_out_off | frame_out_len | statuses
     uint64_t *d_out_size = nullptr, *d_out_off = nullptr, *d_total = nullptr, *d_frame_out_off = nullptr,
@@ -167,7 +169,7 @@ int szb_ctx_create(int device, void *stream, szb_ctx **out) {
         szb_ctx_destroy(ctx);
         return SZB_ERR_CUDA;
     }
-    cudaFuncSetAttribute(k_huffman_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(HufSmem) * kWarpsPerCta));
+    cudaFuncSetAttribute(k_build_huf_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(HufSmem) * kWarpsPerCta));
     cudaFuncSetAttribute(k_build_seq_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SeqSmem) * kWarpsPerCta));
     cudaFuncSetAttribute(k_decode_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeqDecodeSmemBytes);
     *out = ctx;
@@ -214,6 +216,17 @@ static int batch_upload_tables(szb_batch *b) {
         if (d.type == 2 && d.lit_type >= 2) b->huf_list.push_back(i);
         if (d.type == 2 && d.nseq > 0) b->seq_list.push_back(i);
     }
+    {   // blocks that carry a tree description get a table slot; every Huffman block points at its origin's slot
+        std::vector<uint32_t> slot_of_block(nb ? nb : 1, SZB_NONE);
+        for (uint32_t i = 0; i < nb; i++) {
+            const szb_block_desc &d = b->blocks[i];
+            if (d.type == 2 && d.lit_type == 2) {
+                slot_of_block[i] = (uint32_t)b->hufo_list.size();
+                b->hufo_list.push_back(i);
+            }
+        }
+        for (uint32_t i : b->huf_list) b->huf_slot.push_back(slot_of_block[b->blocks[i].huf_origin]);
+    }
     // k_decode_sequences runs kSeqLanes blocks per warp in lock step: neighbours should have similar
     // sequence counts, and the longest blocks should start first
     std::stable_sort(b->seq_list.begin(), b->seq_list.end(),
@@ -223,13 +236,17 @@ static int batch_upload_tables(szb_batch *b) {
     size_t o_blocks = align_up(o_frames + sizeof(szb_frame_desc) * (size_t)nf, 256);
     size_t o_huf = align_up(o_blocks + sizeof(szb_block_desc) * (size_t)nb, 256);
     size_t o_seq = align_up(o_huf + 4 * b->huf_list.size(), 256);
-    size_t o_init = align_up(o_seq + 4 * b->seq_list.size(), 256);
+    size_t o_hufo = align_up(o_seq + 4 * b->seq_list.size(), 256);
+    size_t o_slot = align_up(o_hufo + 4 * b->hufo_list.size(), 256);
+    size_t o_init = align_up(o_slot + 4 * b->huf_slot.size(), 256);
     size_t total = align_up(o_init + 8 * (size_t)nb, 256) + 256;
     std::vector<uint8_t> stage(total, 0);
     if (nf) memcpy(stage.data() + o_frames, b->frames.data(), sizeof(szb_frame_desc) * (size_t)nf);
     if (nb) memcpy(stage.data() + o_blocks, b->blocks.data(), sizeof(szb_block_desc) * (size_t)nb);
     if (!b->huf_list.empty()) memcpy(stage.data() + o_huf, b->huf_list.data(), 4 * b->huf_list.size());
     if (!b->seq_list.empty()) memcpy(stage.data() + o_seq, b->seq_list.data(), 4 * b->seq_list.size());
+    if (!b->hufo_list.empty()) memcpy(stage.data() + o_hufo, b->hufo_list.data(), 4 * b->hufo_list.size());
+    if (!b->huf_slot.empty()) memcpy(stage.data() + o_slot, b->huf_slot.data(), 4 * b->huf_slot.size());
     if (nb) memcpy(stage.data() + o_init, out_size_init.data(), 8 * (size_t)nb);
     CUDA_TRY(ctx, cudaMalloc(&b->d_tables, total));
     CUDA_TRY(ctx, cudaMemcpyAsync(b->d_tables, stage.data(), total, cudaMemcpyHostToDevice, ctx->stream));
@@ -239,6 +256,8 @@ static int batch_upload_tables(szb_batch *b) {
     b->d_blocks = (szb_block_desc *)(base + o_blocks);
     b->d_huf_list = (uint32_t *)(base + o_huf);
     b->d_seq_list = (uint32_t *)(base + o_seq);
+    b->d_hufo_list = (uint32_t *)(base + o_hufo);
+    b->d_huf_slot = (uint32_t *)(base + o_slot);
     b->d_out_size_init = (uint64_t *)(base + o_init);
     // mutable state
     size_t s_out_size = 0;
@@ -268,6 +287,8 @@ static int batch_upload_tables(szb_batch *b) {
     CUDA_TRY(ctx, cudaMalloc(&b->d_seq, (size_t)(b->sequences * 3 + 64) * 4));
     CUDA_TRY(ctx, cudaMalloc(&b->d_seq_tabs, (b->seq_list.size() + 1) * (size_t)kTabSlotWords * 4));
     CUDA_TRY(ctx, cudaMalloc(&b->d_seq_info, (b->seq_list.size() + 1) * sizeof(SeqInfo)));
+    CUDA_TRY(ctx, cudaMalloc(&b->d_huf_tabs, (b->hufo_list.size() + 1) * (size_t)(2u << kMaxHufBits)));
+    CUDA_TRY(ctx, cudaMalloc(&b->d_huf_info, (b->hufo_list.size() + 1) * sizeof(HufInfo)));
     return SZB_OK;
 }
 
@@ -361,6 +382,8 @@ void szb_batch_destroy(szb_batch *b) {
     if (b->d_seq) cudaFree(b->d_seq);
     if (b->d_seq_tabs) cudaFree(b->d_seq_tabs);
     if (b->d_seq_info) cudaFree(b->d_seq_info);
+    if (b->d_huf_tabs) cudaFree(b->d_huf_tabs);
+    if (b->d_huf_info) cudaFree(b->d_huf_info);
     delete b;
 }
 
@@ -376,6 +399,11 @@ static DeviceBatch make_args(szb_batch *b, const void *d_src, void *d_dst, size_
     a.nframes = b->nframes;
     a.huf_list = b->d_huf_list;
     a.n_huf = (uint32_t)b->huf_list.size();
+    a.hufo_list = b->d_hufo_list;
+    a.n_hufo = (uint32_t)b->hufo_list.size();
+    a.huf_slot = b->d_huf_slot;
+    a.huf_tabs = b->d_huf_tabs;
+    a.huf_info = b->d_huf_info;
     a.seq_list = b->d_seq_list;
     a.n_seq = (uint32_t)b->seq_list.size();
     a.litbuf = b->d_litbuf;
@@ -407,8 +435,13 @@ static int launch_entropy(szb_batch *b, const void *d_src) {
     CUDA_TRY(ctx, cudaMemsetAsync(b->d_lit_status, 0, b->status_bytes, s));
     if (b->nblocks)
         CUDA_TRY(ctx, cudaMemcpyAsync(b->d_out_size, b->d_out_size_init, 8 * (size_t)b->nblocks, cudaMemcpyDeviceToDevice, s));
+    if (a.n_hufo) {
+        k_build_huf_tables<<<(a.n_hufo + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, sizeof(HufSmem) * kWarpsPerCta, s>>>(a);
+        ctx->launches++;
+    }
     if (a.n_huf) {
-        k_huffman_literals<<<(a.n_huf + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, sizeof(HufSmem) * kWarpsPerCta, s>>>(a);
+        const uint32_t groups = (a.n_huf + kHufGroup - 1) / kHufGroup;
+        k_decode_literals<<<(groups + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, s>>>(a);
         ctx->launches++;
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));

@@ -1,8 +1,10 @@
 // kernels.cuh -- the four GPU stages of the decode path (sm_100a).
 //
-//   k_huffman_literals  stage 1+2: Huffman tree description (direct / FSE-compressed weights),
-//                       decode table in shared memory, 1- or 4-stream literal decode
-//                       (structure/huffman.go, structure/literals.go:209-373)
+//   k_build_huf_tables  stage 1: Huffman tree description (direct / FSE-compressed weights) and
+//                       decode table in shared memory, one warp per tree, published to HBM
+//                       (structure/huffman.go:40-190)
+//   k_decode_literals   stage 2: 1- or 4-stream literal decode, one LANE per stream, 8 blocks per warp
+//                       (structure/huffman.go:192-264, structure/literals.go:209-373)
 //   k_build_seq_tables  stage 1: LL/OF/ML table selection + construction in shared memory, one
 //                       warp per block, published to a table arena in HBM
 //                       (fse/fse.go, fse/predefined.go, structure/sequences.go:275-369)
@@ -42,6 +44,12 @@ struct SeqInfo {
     uint32_t stream_off;  // offset of the backward bitstream after the sequences-section header
 };
 
+struct HufInfo {
+    uint8_t max_bits, pad;
+    uint16_t tree_bytes;  // size of the tree description inside the origin block's literals section
+    int32_t status;
+};
+
 struct DeviceBatch {
     const uint8_t *src;
     const szb_block_desc *blocks;
@@ -49,6 +57,11 @@ struct DeviceBatch {
     uint32_t nblocks, nframes;
     const uint32_t *huf_list;  // blocks with Huffman-coded literals
     uint32_t n_huf;
+    const uint32_t *hufo_list; // blocks that carry a Huffman tree description (literals type Compressed)
+    uint32_t n_hufo;
+    const uint32_t *huf_slot;  // per huf_list entry: position of its origin block in hufo_list
+    uint16_t *huf_tabs;        // per hufo_list entry: 2^kMaxHufBits decode-table cells
+    HufInfo *huf_info;         // per hufo_list entry
     const uint32_t *seq_list;  // blocks with nseq > 0
     uint32_t n_seq;
     uint8_t *litbuf;
@@ -191,7 +204,7 @@ __device__ __forceinline__ int huf_build_warp(const uint8_t *weights, uint32_t n
     return SZB_OK;
 }
 
-// shared memory per warp, k_huffman_literals
+// shared memory per warp, k_build_huf_tables
 struct HufSmem {
     union {
         uint16_t huf[1 << kMaxHufBits];  // 4 KB
@@ -204,18 +217,20 @@ struct HufSmem {
     uint16_t next[kMaxFseSymbols];
 };
 
-// One warp per block with Huffman-coded (Compressed or Treeless) literals.
-__global__ void __launch_bounds__(kCtaThreads) k_huffman_literals(DeviceBatch a) {
+// Stage 1 for literals: one warp per block that CARRIES a Huffman tree description (literals type
+// Compressed) decodes the weights (direct or FSE-compressed, huffman.go:40-107), builds the decode
+// table in shared memory (huffman.go:112-190) and publishes it to the table arena in HBM.  Treeless
+// blocks (literals.go:247-252) later read the table of their origin block: it is built once, not
+// once per user.
+__global__ void __launch_bounds__(kCtaThreads) k_build_huf_tables(DeviceBatch a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t w = blockIdx.x * kWarpsPerCta + warp_in_cta;
-    if (w >= a.n_huf) return;
+    if (w >= a.n_hufo) return;
     HufSmem &sm = reinterpret_cast<HufSmem *>(smem_raw)[warp_in_cta];
-    const uint32_t b = a.huf_list[w];
-    const szb_block_desc d = a.blocks[b];
-    const szb_block_desc o = a.blocks[d.huf_origin];
+    const szb_block_desc o = a.blocks[a.hufo_list[w]];
 
-    // --- tree description of the origin block (huffman.go:40-107) ---
+    // --- tree description (huffman.go:40-107) ---
     const uint8_t *tree = a.src + o.src_off + o.lit_hdr_bytes;
     const uint32_t tree_avail = o.lit_comp;
     int rc = SZB_OK;
@@ -227,7 +242,7 @@ __global__ void __launch_bounds__(kCtaThreads) k_huffman_literals(DeviceBatch a)
         hb = tree[0];
     if (rc == SZB_OK) {
         if (hb < 128) {  // FSE-compressed weights
-            TableSource ts{tree + 1, tree_avail - 1 < hb ? tree_avail - 1 : hb, 2};
+            TableSource ts{tree + 1, tree_avail - 1, 2};
             uint32_t al = 0, used = 0;
             if (1 + hb > tree_avail) rc = SZB_ERR_UNEXPECTED_EOF;
             if (rc == SZB_OK) rc = build_fse_table(ts, KIND_HUFW, a.predef, sm.t.fse, sm.norm, sm.next, sm.symk, &al, &used);
@@ -261,47 +276,176 @@ __global__ void __launch_bounds__(kCtaThreads) k_huffman_literals(DeviceBatch a)
 #endif
     }
     __syncwarp();
-    if (rc != SZB_OK) {
-        if (lane == 0) a.lit_status[b] = rc;
-        return;
+    if (rc == SZB_OK) {
+        uint16_t *slot = a.huf_tabs + (size_t)w * (1u << kMaxHufBits);
+        for (uint32_t i = lane; i < (1u << max_bits); i += 32) slot[i] = sm.t.huf[i];
     }
+    if (lane == 0) {
+        HufInfo info;
+        info.max_bits = (uint8_t)max_bits;
+        info.pad = 0;
+        info.tree_bytes = (uint16_t)tree_bytes;
+        info.status = rc;
+        a.huf_info[w] = info;
+    }
+}
 
-    // --- this block's streams (literals.go:270-371) ---
-    const uint8_t *payload = a.src + d.src_off;
-    uint32_t skip = d.lit_hdr_bytes + (d.lit_type == 2 ? tree_bytes : 0);
-    int32_t comp = (int32_t)d.lit_comp - (int32_t)(d.lit_type == 2 ? tree_bytes : 0);
-    uint8_t *out = a.litbuf + d.lit_buf_off;
-    const uint32_t regen = d.lit_regen;
+// HuffmanDecodingTable.DecodeStream (huffman.go:221-264) for one stream, one lane; same recurrence as
+// huf_decode_stream (huffman.cuh) with the symbols buffered 16 deep in registers so they leave as
+// aligned 16-byte stores, and one refill check per two symbols (2 x 11 bits <= the 32 guaranteed).
+__device__ __forceinline__ int huf_decode_stream_vec(const uint16_t *table, uint32_t max_bits, const uint8_t *p, uint32_t len,
+                                                     uint8_t *out, uint32_t expected) {
+    RevBits r;
+    if (!rev_init(r, p, (int32_t)len) || !rev_skip_padding(r)) return SZB_ERR_BAD_PADDING;
+    uint32_t n = 0;
+    uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15)) & 15;
+    if (head > expected) head = expected;
+    for (; n < head; n++) {
+        rev_refill(r);
+        const uint32_t e = table[rev_peek(r, max_bits)];
+        out[n] = (uint8_t)e;
+        rev_skip(r, e >> 8);
+    }
+    while (n + 16 <= expected) {
+        uint32_t wv[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                if ((t & 1) == 0) rev_refill(r);
+                const uint32_t e = table[rev_peek(r, max_bits)];
+                acc |= (e & 0xFF) << (8 * t);
+                rev_skip(r, e >> 8);
+            }
+            wv[q] = acc;
+        }
+        *reinterpret_cast<uint4 *>(out + n) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        n += 16;
+    }
+    for (; n < expected; n++) {
+        rev_refill(r);
+        const uint32_t e = table[rev_peek(r, max_bits)];
+        out[n] = (uint8_t)e;
+        rev_skip(r, e >> 8);
+    }
+    if (r.remaining > 0) return SZB_ERR_STREAM_DIDNT_DECODE_TO_RIGHT_LENGTH;  // more symbols than its slot holds
+    if (r.remaining < 0) return SZB_ERR_DIDNT_USE_ALL_BITS_TO_DECODE_HUFFMAN;
+    return SZB_OK;
+}
+
+constexpr uint32_t kHufGroup = 8;         // blocks per warp in k_decode_literals (4 lanes each)
+constexpr uint32_t kHufCellsPerWarp = 4096;  // 8 KB of decode tables resident per warp
+
+// Stage 2: one LANE per Huffman stream (literals.go:295-371): a warp decodes the streams of up to 8
+// blocks at once.  The blocks' decode tables are copied from the arena into the warp's 8 KB of shared
+// memory; neighbouring blocks that share a table (a Compressed block followed by its Treeless users)
+// share one copy.  When 8 tables do not fit (maxBits 11 = 4 KB each) the group is done in passes.
+__global__ void __launch_bounds__(kCtaThreads) k_decode_literals(DeviceBatch a) {
+    __shared__ __align__(16) uint16_t tabs_all[kWarpsPerCta][kHufCellsPerWarp];
+    const uint32_t warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t g = blockIdx.x * kWarpsPerCta + warp_in_cta;
+    const uint32_t first = g * kHufGroup;
+    if (first >= a.n_huf) return;
+    uint16_t *tabs = tabs_all[warp_in_cta];
+    const uint32_t n_entries = a.n_huf - first < kHufGroup ? a.n_huf - first : kHufGroup;
+
+    // lanes 0..7 fetch the per-entry facts; everyone reads them through shuffles
+    uint32_t e_slot = 0, e_bits = 0, e_tree = 0;
+    int e_rc = SZB_OK;
+    if (lane < n_entries) {
+        e_slot = a.huf_slot[first + lane];
+        const HufInfo info = a.huf_info[e_slot];
+        e_bits = info.max_bits;
+        e_tree = info.tree_bytes;
+        e_rc = info.status;
+    }
+    const uint32_t my_e = lane >> 2, my_k = lane & 3;
     int my_rc = SZB_OK;
-    if (d.lit_streams == 1) {
-        if (comp < 0)
-            rc = SZB_ERR_PANIC;
-        else if (lane == 0)
-            my_rc = huf_decode_stream(sm.t.huf, max_bits, payload + skip, (uint32_t)comp, out, regen);
-    } else {
-        comp -= 6;
-        if (comp < 0) {
-            rc = SZB_ERR_PANIC;  // literals.go:283 negative slice bound
-        } else {
-            const uint8_t *jt = payload + skip;  // literals.go:46-58 jump table, 3 x u16 LE
-            const uint32_t s1 = jt[0] | (jt[1] << 8), s2 = jt[2] | (jt[3] << 8), s3 = jt[4] | (jt[5] << 8);
-            const uint32_t normal = (regen + 3) / 4;  // literals.go:306-311
-            const int32_t last = (int32_t)regen - 3 * (int32_t)normal;
-            if (s1 + s2 + s3 > (uint32_t)comp)
-                rc = SZB_ERR_CORRUPTED_JUMPTABLE;  // literals.go:54-56 (the reference drops this error and re-slices)
-            else if (last < 0)
-                rc = SZB_ERR_PANIC;  // literals.go:311 inverted slice
-            else if (lane < 4) {
-                const uint32_t s4 = (uint32_t)comp - (s1 + s2 + s3);
-                const uint32_t start = lane == 0 ? 0 : (lane == 1 ? s1 : (lane == 2 ? s1 + s2 : s1 + s2 + s3));
-                const uint32_t len = lane == 0 ? s1 : (lane == 1 ? s2 : (lane == 2 ? s3 : s4));
-                const uint32_t expected = lane < 3 ? normal : (uint32_t)last;
-                my_rc = huf_decode_stream(sm.t.huf, max_bits, jt + 6 + start, len, out + lane * normal, expected);
+    const int rc0 = __shfl_sync(kFull, e_rc, my_e);
+    const uint32_t bits = __shfl_sync(kFull, e_bits, my_e);
+    const uint32_t tree_b = __shfl_sync(kFull, e_tree, my_e);
+
+    uint32_t next_e = 0;
+    while (next_e < n_entries) {
+        // take entries while their tables fit; consecutive entries with the same table share it
+        uint32_t used = 0, count = 0, my_off = 0;
+        uint32_t prev_slot = 0xFFFFFFFFu, prev_off = 0;
+        for (uint32_t e = next_e; e < n_entries; e++) {
+            const uint32_t slot = __shfl_sync(kFull, e_slot, e);
+            const uint32_t ebits = __shfl_sync(kFull, e_bits, e);
+            const int rc = __shfl_sync(kFull, e_rc, e);
+            uint32_t off;
+            if (rc != SZB_OK) {
+                off = 0;  // nothing to load: the block inherits the failure
+            } else if (slot == prev_slot) {
+                off = prev_off;
+            } else {
+                const uint32_t size = 1u << ebits;
+                if (used + size > kHufCellsPerWarp) break;
+                off = used;
+                const uint16_t *src_tab = a.huf_tabs + (size_t)slot * (1u << kMaxHufBits);
+                for (uint32_t i = lane; i < size; i += 32) tabs[off + i] = src_tab[i];
+                used += size;
+                prev_slot = slot;
+                prev_off = off;
+            }
+            if (e == my_e) my_off = off;
+            count++;
+        }
+        __syncwarp();
+        if (my_e >= next_e && my_e < next_e + count) {
+            const uint32_t b = a.huf_list[first + my_e];
+            const szb_block_desc d = a.blocks[b];
+            if (rc0 != SZB_OK) {
+                my_rc = rc0;
+            } else {
+                // --- this block's streams (literals.go:270-371) ---
+                const uint8_t *payload = a.src + d.src_off;
+                const uint32_t own_tree = d.lit_type == 2 ? tree_b : 0;
+                const uint32_t skip = d.lit_hdr_bytes + own_tree;
+                int32_t comp = (int32_t)d.lit_comp - (int32_t)own_tree;
+                uint8_t *out = a.litbuf + d.lit_buf_off;
+                const uint32_t regen = d.lit_regen;
+                if (d.lit_streams == 1) {
+                    if (comp < 0)
+                        my_rc = SZB_ERR_PANIC;
+                    else if (my_k == 0)
+                        my_rc = huf_decode_stream_vec(tabs + my_off, bits, payload + skip, (uint32_t)comp, out, regen);
+                } else {
+                    comp -= 6;
+                    if (comp < 0) {
+                        my_rc = SZB_ERR_PANIC;  // literals.go:283 negative slice bound
+                    } else {
+                        const uint8_t *jt = payload + skip;  // literals.go:46-58 jump table, 3 x u16 LE
+                        const uint32_t s1 = jt[0] | (jt[1] << 8), s2 = jt[2] | (jt[3] << 8), s3 = jt[4] | (jt[5] << 8);
+                        const uint32_t normal = (regen + 3) / 4;  // literals.go:306-311
+                        const int32_t last = (int32_t)regen - 3 * (int32_t)normal;
+                        if (s1 + s2 + s3 > (uint32_t)comp) {
+                            my_rc = SZB_ERR_CORRUPTED_JUMPTABLE;  // literals.go:54-56 (the reference drops this error and re-slices)
+                        } else if (last < 0) {
+                            my_rc = SZB_ERR_PANIC;  // literals.go:311 inverted slice
+                        } else {
+                            const uint32_t s4 = (uint32_t)comp - (s1 + s2 + s3);
+                            const uint32_t start = my_k == 0 ? 0 : (my_k == 1 ? s1 : (my_k == 2 ? s1 + s2 : s1 + s2 + s3));
+                            const uint32_t len = my_k == 0 ? s1 : (my_k == 1 ? s2 : (my_k == 2 ? s3 : s4));
+                            const uint32_t expected = my_k < 3 ? normal : (uint32_t)last;
+                            my_rc = huf_decode_stream_vec(tabs + my_off, bits, jt + 6 + start, len, out + my_k * normal, expected);
+                        }
+                    }
+                }
             }
         }
+        __syncwarp();
+        next_e += count;
     }
-    if (rc == SZB_OK) rc = warp_first_error(my_rc);  // streams are checked in order 1..4 by the reference
-    if (lane == 0) a.lit_status[b] = rc;
+    // per block: the first failing stream in the order 1..4 decides (the reference decodes them in order)
+    int rc = my_rc;
+    for (int k = 1; k < 4; k++) {
+        const int other = __shfl_sync(kFull, my_rc, (lane & ~3u) + k);
+        if (rc == SZB_OK) rc = other;
+    }
+    if (my_k == 0 && my_e < n_entries) a.lit_status[a.huf_list[first + my_e]] = rc;
 }
 
 // shared memory per warp, k_build_seq_tables
