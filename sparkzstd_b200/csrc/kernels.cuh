@@ -1044,8 +1044,6 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
                 err = SZB_ERR_CANT_REPEAT_BYTES;  // ringbuffer.go:203-214
                 break;
             }
-            const uint64_t msrc = mdst - off;
-            const uint64_t need_end = (msrc + ml < mdst) ? msrc + ml : mdst;  // bytes other lanes of the round may owe me
 
             // --- the round is executed in segments that fit the staging window (normally one) ---
             uint32_t start = 0;
@@ -1108,18 +1106,18 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
                         warp_copy(st.stage + SD, lit + SL, L, lane);
                 }
 
-                // matches (RepeatBeforeIndex, ringbuffer.go:242-277).  Part of a source that is already in
-                // HBM (below the window) is final: gather it now, 16 bytes at a time, for every short match.
+                // matches (RepeatBeforeIndex, ringbuffer.go:242-277).  Positions below are relative to the
+                // window base; a negative source position lies in HBM, below the window, and is final.
                 const bool has = in && ml > 0;
                 const bool shortm = has && ml < kCoopMatch;
-                uint32_t n_g = 0;
-                if (shortm && msrc < st.base) {
-                    const uint64_t gap = st.base - msrc;
-                    n_g = gap < ml ? (uint32_t)gap : ml;
-                }
-                const uint8_t *gp = dst + msrc;
-                const uint32_t gmis = (uint32_t)(reinterpret_cast<uintptr_t>(gp) & 15);
+                const int32_t s_rel = (int32_t)md - (int32_t)off;  // source of my match
+                const int32_t e_rel = (s_rel + (int32_t)ml < (int32_t)md) ? s_rel + (int32_t)ml : (int32_t)md;
+                uint32_t n_g = 0;  // leading bytes of the source that come from HBM
+                if (shortm && s_rel < 0) n_g = (uint32_t)(-s_rel) < ml ? (uint32_t)(-s_rel) : ml;
+                // phase G: gather the HBM part with 16-byte loads and drop it at its destination right away
                 if (n_g) {
+                    const uint8_t *gp = dst + st.base + (int64_t)s_rel;
+                    const uint32_t gmis = (uint32_t)(reinterpret_cast<uintptr_t>(gp) & 15);
                     const uint4 *ga = reinterpret_cast<const uint4 *>(gp - gmis);
                     uint32_t *gw = reinterpret_cast<uint32_t *>(my_gath);  // row start is 4-byte aligned only: store words
                     const uint4 c0 = ga[0];
@@ -1132,39 +1130,52 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
                         const uint4 c2 = ga[2];
                         gw[8] = c2.x; gw[9] = c2.y; gw[10] = c2.z; gw[11] = c2.w;
                     }
+                    const uint8_t *gs = my_gath + gmis;
+                    uint8_t *gd = st.stage + md;
+                    for (uint32_t k = 0; k < n_g; k++) gd[k] = gs[k];
                 }
+                // what is left depends on bytes produced inside the window: dependency rounds
+                const bool pend_lane = has && (!shortm || n_g < ml);
                 __syncwarp();
-                uint32_t pending = __ballot_sync(kFull, has);
-                while (pending) {
-                    const int first = __ffs(pending) - 1;
-                    const uint64_t frontier = __shfl_sync(kFull, mdst, first);  // everything below is final
-                    const uint32_t first_ml = __shfl_sync(kFull, ml, first);
-                    if (first_ml >= kCoopMatch) {  // warp-wide copy of one long match into the window
-                        const uint32_t OFF = __shfl_sync(kFull, off, first);
-                        const uint32_t MD = __shfl_sync(kFull, md, first);
-                        const uint64_t S = frontier - OFF;
-                        if (OFF >= 32) {
-                            for (uint32_t k0 = 0; k0 < first_ml; k0 += 32) {
-                                const uint32_t k = k0 + lane;
-                                if (k < first_ml) st.stage[MD + k] = stager_byte(st, S + k);
-                                __syncwarp();
+                uint32_t pending = __ballot_sync(kFull, pend_lane);
+                if (pending) {
+                    // dep: the pending lanes before me whose match output overlaps the window part of my source
+                    uint32_t dep = 0;
+                    for (uint32_t pm = pending; pm; pm &= pm - 1) {
+                        const int j = __ffs(pm) - 1;
+                        const int32_t dj = (int32_t)__shfl_sync(kFull, md, j);
+                        const int32_t ej = dj + (int32_t)__shfl_sync(kFull, ml, j);
+                        if (j < (int)lane && ej > s_rel && dj < e_rel) dep |= 1u << j;
+                    }
+                    while (pending) {
+                        const int first = __ffs(pending) - 1;  // the first pending lane never waits for anyone
+                        const uint32_t first_ml = __shfl_sync(kFull, ml, first);
+                        if (first_ml >= kCoopMatch) {  // warp-wide copy of one long match into the window
+                            const uint32_t OFF = __shfl_sync(kFull, off, first);
+                            const uint32_t MD = __shfl_sync(kFull, md, first);
+                            const uint64_t S = st.base + MD - OFF;
+                            if (OFF >= 32) {
+                                for (uint32_t k0 = 0; k0 < first_ml; k0 += 32) {
+                                    const uint32_t k = k0 + lane;
+                                    if (k < first_ml) st.stage[MD + k] = stager_byte(st, S + k);
+                                    __syncwarp();
+                                }
+                            } else {  // overlapping: periodic extension of the OFF bytes before the match
+                                for (uint32_t k = lane; k < first_ml; k += 32) st.stage[MD + k] = stager_byte(st, S + k % OFF);
                             }
-                        } else {  // overlapping: periodic extension of the OFF bytes before the match
-                            for (uint32_t k = lane; k < first_ml; k += 32) st.stage[MD + k] = stager_byte(st, S + k % OFF);
+                            pending &= ~(1u << first);
+                            __syncwarp();
+                            continue;
                         }
-                        pending &= ~(1u << first);
+                        const bool ready = ((pending >> lane) & 1) && shortm && (dep & pending) == 0;
+                        if (ready) {
+                            const uint8_t *ss = st.stage + s_rel;  // valid from byte n_g on
+                            uint8_t *sdst = st.stage + md;
+                            for (uint32_t k = n_g; k < ml; k++) sdst[k] = ss[k];  // byte-serial: handles self overlap
+                        }
+                        pending &= ~__ballot_sync(kFull, ready);
                         __syncwarp();
-                        continue;
                     }
-                    const bool ready = ((pending >> lane) & 1) && shortm && ((int)lane == first || need_end <= frontier);
-                    if (ready) {
-                        uint32_t k = 0;
-                        for (; k < n_g; k++) st.stage[md + k] = my_gath[gmis + k];
-                        const uint32_t so = (uint32_t)(msrc + n_g - st.base) - n_g;  // window offset of source byte 0 (valid for k >= n_g)
-                        for (; k < ml; k++) st.stage[md + k] = st.stage[so + k];       // byte-serial: handles self overlap
-                    }
-                    pending &= ~__ballot_sync(kFull, ready);
-                    __syncwarp();
                 }
                 st.fill = __shfl_sync(kFull, (uint32_t)rel_end64, end - 1);
                 stager_flush_chunks(st, lane);
