@@ -33,6 +33,9 @@ struct szb_ctx {
     size_t d_dst_cap = 0;
 };
 
+static cudaError_t pool_alloc(szb_ctx *ctx, void **p, size_t bytes);
+static void pool_free(szb_ctx *ctx, void *p);
+
 #define CUDA_TRY(ctx, expr)                                                                          \
     do {                                                                                             \
         cudaError_t e__ = (expr);                                                                    \
@@ -71,6 +74,13 @@ struct szb_batch {
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Scratch arenas come from the device's stream-ordered memory pool with an unlimited release
+// threshold: after the first batch of a given shape, creating a batch costs no cudaMalloc.
+static cudaError_t pool_alloc(szb_ctx *ctx, void **p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 256, ctx->stream); }
+static void pool_free(szb_ctx *ctx, void *p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
 
 extern "C" {
 
@@ -147,6 +157,13 @@ int szb_ctx_create(int device, void *stream, szb_ctx **out) {
         }
         ctx->own_stream = true;
     }
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     for (auto &e : ctx->ev) {
         if (cudaEventCreate(&e) != cudaSuccess) {
             szb_ctx_destroy(ctx);
@@ -172,6 +189,7 @@ int szb_ctx_create(int device, void *stream, szb_ctx **out) {
     cudaFuncSetAttribute(k_build_huf_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(HufSmem) * kWarpsPerCta));
     cudaFuncSetAttribute(k_build_seq_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SeqSmem) * kWarpsPerCta));
     cudaFuncSetAttribute(k_decode_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeqDecodeSmemBytes);
+    cudaFuncSetAttribute(k_decode_literals, cudaFuncAttributePreferredSharedMemoryCarveout, 50);  // leave L1 for the streams
     *out = ctx;
     return SZB_OK;
 }
@@ -248,7 +266,7 @@ static int batch_upload_tables(szb_batch *b) {
     if (!b->hufo_list.empty()) memcpy(stage.data() + o_hufo, b->hufo_list.data(), 4 * b->hufo_list.size());
     if (!b->huf_slot.empty()) memcpy(stage.data() + o_slot, b->huf_slot.data(), 4 * b->huf_slot.size());
     if (nb) memcpy(stage.data() + o_init, out_size_init.data(), 8 * (size_t)nb);
-    CUDA_TRY(ctx, cudaMalloc(&b->d_tables, total));
+    CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_tables, total));
     CUDA_TRY(ctx, cudaMemcpyAsync(b->d_tables, stage.data(), total, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     uint8_t *base = (uint8_t *)b->d_tables;
@@ -271,7 +289,7 @@ static int batch_upload_tables(szb_batch *b) {
     size_t s_fst = s_seqs + 4 * (size_t)nb;
     b->status_bytes = 4 * (2 * (size_t)nb + (size_t)nf);
     size_t s_end = align_up(s_fst + 4 * (size_t)nf, 256) + 256;
-    CUDA_TRY(ctx, cudaMalloc(&b->d_state, s_end));
+    CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_state, s_end));
     CUDA_TRY(ctx, cudaMemsetAsync(b->d_state, 0, s_end, ctx->stream));
     base = (uint8_t *)b->d_state;
     b->d_out_size = (uint64_t *)(base + s_out_size);
@@ -283,12 +301,12 @@ static int batch_upload_tables(szb_batch *b) {
     b->d_seq_status = (int32_t *)(base + s_seqs);
     b->d_frame_status = (int32_t *)(base + s_fst);
     // scratch arenas
-    CUDA_TRY(ctx, cudaMalloc(&b->d_litbuf, (size_t)b->literal_bytes + 256));
-    CUDA_TRY(ctx, cudaMalloc(&b->d_seq, (size_t)(b->sequences * 3 + 64) * 4));
-    CUDA_TRY(ctx, cudaMalloc(&b->d_seq_tabs, (b->seq_list.size() + 1) * (size_t)kTabSlotWords * 4));
-    CUDA_TRY(ctx, cudaMalloc(&b->d_seq_info, (b->seq_list.size() + 1) * sizeof(SeqInfo)));
-    CUDA_TRY(ctx, cudaMalloc(&b->d_huf_tabs, (b->hufo_list.size() + 1) * (size_t)(2u << kMaxHufBits)));
-    CUDA_TRY(ctx, cudaMalloc(&b->d_huf_info, (b->hufo_list.size() + 1) * sizeof(HufInfo)));
+    CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_litbuf, (size_t)b->literal_bytes + 256));
+    CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_seq, (size_t)(b->sequences * 3 + 64) * 4));
+    CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_seq_tabs, (b->seq_list.size() + 1) * (size_t)kTabSlotWords * 4));
+    CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_seq_info, (b->seq_list.size() + 1) * sizeof(SeqInfo)));
+    CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_huf_tabs, (b->hufo_list.size() + 1) * (size_t)(2u << kMaxHufBits)));
+    CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_huf_info, (b->hufo_list.size() + 1) * sizeof(HufInfo)));
     return SZB_OK;
 }
 
@@ -376,14 +394,14 @@ void szb_batch_destroy(szb_batch *b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
-    if (b->d_tables) cudaFree(b->d_tables);
-    if (b->d_state) cudaFree(b->d_state);
-    if (b->d_litbuf) cudaFree(b->d_litbuf);
-    if (b->d_seq) cudaFree(b->d_seq);
-    if (b->d_seq_tabs) cudaFree(b->d_seq_tabs);
-    if (b->d_seq_info) cudaFree(b->d_seq_info);
-    if (b->d_huf_tabs) cudaFree(b->d_huf_tabs);
-    if (b->d_huf_info) cudaFree(b->d_huf_info);
+    pool_free(b->ctx, b->d_tables);
+    pool_free(b->ctx, b->d_state);
+    pool_free(b->ctx, b->d_litbuf);
+    pool_free(b->ctx, b->d_seq);
+    pool_free(b->ctx, b->d_seq_tabs);
+    pool_free(b->ctx, b->d_seq_info);
+    pool_free(b->ctx, b->d_huf_tabs);
+    pool_free(b->ctx, b->d_huf_info);
     delete b;
 }
 

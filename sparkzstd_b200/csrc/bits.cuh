@@ -36,6 +36,11 @@ SZB_HD void rev_refill(RevBits &r) {
     if (r.avail <= 32) {
         if (r.next >= 4) {
             uint32_t w = load_u32_aligned(r.base + r.next - 4);
+#if defined(__CUDA_ARCH__)
+            // lanes of a warp walk unrelated streams in lock step: one lane's miss stalls all 32, so
+            // every lane pulls the sectors it will need two refills-of-a-sector ahead into L1
+            if (r.next >= 100) asm volatile("prefetch.global.L1 [%0];" ::"l"(r.base + r.next - 100));
+#endif
             r.next -= 4;
             r.win |= (uint64_t)w << (32 - r.avail);
             r.avail += 32;

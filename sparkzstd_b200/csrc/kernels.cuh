@@ -335,12 +335,13 @@ __device__ __forceinline__ int huf_decode_stream_vec(const uint16_t *table, uint
 }
 
 constexpr uint32_t kHufGroup = 8;         // blocks per warp in k_decode_literals (4 lanes each)
-constexpr uint32_t kHufCellsPerWarp = 4096;  // 8 KB of decode tables resident per warp
+constexpr uint32_t kHufCellsPerWarp = 2048;  // 4 KB of decode tables resident per warp (one maxBits-11 table)
 
 // Stage 2: one LANE per Huffman stream (literals.go:295-371): a warp decodes the streams of up to 8
 // blocks at once.  The blocks' decode tables are copied from the arena into the warp's 8 KB of shared
 // memory; neighbouring blocks that share a table (a Compressed block followed by its Treeless users)
-// share one copy.  When 8 tables do not fit (maxBits 11 = 4 KB each) the group is done in passes.
+// share one copy.  When the tables do not fit (maxBits 11 = 4 KB each) the group is done in passes.
+// Shared memory is kept small on purpose: the streams are read through L1, which needs the room.
 __global__ void __launch_bounds__(kCtaThreads) k_decode_literals(DeviceBatch a) {
     __shared__ __align__(16) uint16_t tabs_all[kWarpsPerCta][kHufCellsPerWarp];
     const uint32_t warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -843,6 +844,49 @@ __device__ __forceinline__ void warp_fill(uint8_t *dst, uint8_t v, uint64_t n, u
     for (uint64_t i = lane; i < n; i += 32) dst[i] = v;
 }
 
+// Bulk copy by one warp for large bodies (Raw blocks, long literal tails): destination words are
+// written whole (4-byte aligned), each assembled from the two aligned source words that cover it.
+// src and dst must not overlap.  Reads only aligned words that contain at least one source byte.
+__device__ __forceinline__ void warp_memcpy(uint8_t *dst, const uint8_t *src, uint64_t n, uint32_t lane) {
+    if (n < 64) {
+        warp_copy(dst, src, n, lane);
+        return;
+    }
+    const uint32_t head = (4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3)) & 3;
+    if (lane < head) dst[lane] = src[lane];
+    dst += head;
+    src += head;
+    n -= head;
+    const uint64_t words = n >> 2;
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3);
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(src - mis);
+    uint32_t *dw = reinterpret_cast<uint32_t *>(dst);
+    if (mis == 0) {
+        for (uint64_t i = lane; i < words; i += 32) dw[i] = sw[i];
+    } else {
+        for (uint64_t i = lane; i < words; i += 32) dw[i] = __funnelshift_r(sw[i], sw[i + 1], mis * 8);
+    }
+    const uint32_t tail = (uint32_t)(n & 3);
+    if (lane < tail) dst[(words << 2) + lane] = src[(words << 2) + lane];
+}
+__device__ __forceinline__ void warp_memset(uint8_t *dst, uint8_t v, uint64_t n, uint32_t lane) {
+    if (n < 64) {
+        warp_fill(dst, v, n, lane);
+        return;
+    }
+    const uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+    if (lane < head) dst[lane] = v;
+    dst += head;
+    n -= head;
+    const uint32_t w = v * 0x01010101u;
+    const uint4 q = make_uint4(w, w, w, w);
+    uint4 *dq = reinterpret_cast<uint4 *>(dst);
+    const uint64_t quads = n >> 4;
+    for (uint64_t i = lane; i < quads; i += 32) dq[i] = q;
+    const uint32_t tail = (uint32_t)(n & 15);
+    if (lane < tail) dst[(quads << 4) + lane] = v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Stage 4.  The reference pushes every literal run and every match through a window ring
 // buffer (ringbuffer.go:102-277).  Here the whole output lives in HBM and the "window" is just
@@ -972,9 +1016,9 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
         if (d.type != 2) {  // Raw (framedecompressor.go:211-215) / RLE (framedecompressor.go:229-241) bodies
             stager_flush_all(st, lane);
             if (d.type == 0)
-                warp_copy(dst + out_pos, payload, d.block_size, lane);
+                warp_memcpy(dst + out_pos, payload, d.block_size, lane);
             else
-                warp_fill(dst + out_pos, payload[0], d.block_size, lane);
+                warp_memset(dst + out_pos, payload[0], d.block_size, lane);
             __syncwarp();
             stager_reset(st, out_pos + d.block_size, frame_base, lane);
             continue;
@@ -1187,6 +1231,16 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
         if (err != SZB_OK) break;
         // trailing literals (sequence_execution.go:55-60, literals.go:411-420)
         uint32_t rest = d.lit_regen - lit_pos;
+        if (rest >= 512) {  // a long tail (e.g. a block without sequences) goes straight to HBM
+            stager_flush_all(st, lane);
+            if (lit_rle)
+                warp_memset(dst + out_pos, rle_byte, rest, lane);
+            else
+                warp_memcpy(dst + out_pos, lit + lit_pos, rest, lane);
+            __syncwarp();
+            stager_reset(st, out_pos + rest, frame_base, lane);
+            rest = 0;
+        }
         while (rest) {
             uint32_t room = kStageBytes - st.fill;
             if (room == 0) {
