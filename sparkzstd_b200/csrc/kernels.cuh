@@ -290,21 +290,118 @@ __global__ void __launch_bounds__(kCtaThreads) k_build_huf_tables(DeviceBatch a)
     }
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g));
+}
+
+// Reverse bit reader for one lane of k_decode_literals: the 64-bit window of bits.cuh, refilled with
+// 32-bit words from a per-lane shared-memory ring of eight 16-byte chunks of the stream.  The ring is
+// topped up with cp.async four chunks ahead of the read position, so no lane ever waits for HBM while
+// its 31 neighbours (which walk unrelated streams in lock step) are ready.  Completion is tracked in
+// commit groups: hring_refill commits one group per call, a chunk holds >= 11 symbols (128 bits /
+// maxBits 11) and refill is called at least once per two symbols, so the chunk being entered was
+// requested >= 20 groups ago and wait_group 16 covers it.
+constexpr uint32_t kHufRingStride = 144;  // 128 B ring + pad (keeps 16-byte alignment, spreads banks)
+struct HufBits {
+    uint64_t win;
+    int32_t avail;
+    int32_t next;        // stream bytes [0, next) not yet moved into the window
+    int32_t remaining;   // real bits not consumed yet
+    int32_t cur;         // chunk (16 B units from the aligned address at or below the stream) being read
+    uint32_t mis;        // stream address & 15
+    uint32_t ring_saddr; // shared-space address of this lane's ring
+    const uint8_t *ring;
+    const uint8_t *base;
+    const uint4 *chunk0;
+};
+
+__device__ __forceinline__ void hring_fetch(const HufBits &r, int32_t c) {
+    if (c >= 0) cp_async16(r.ring_saddr + (((uint32_t)c & 7) << 4), r.chunk0 + c);
+}
+
+__device__ __forceinline__ void hring_refill(HufBits &r) {
+    if (r.avail <= 32) {
+        if (r.next >= 4) {
+            const uint32_t wa = r.mis + (uint32_t)r.next - 4;  // word position relative to chunk 0
+            const int32_t c = (int32_t)(wa >> 4);
+            if (c < r.cur) {
+                r.cur = c;
+                asm volatile("cp.async.wait_group 16;" ::: "memory");
+                hring_fetch(r, c - 4);
+            }
+            const uint32_t w = *reinterpret_cast<const uint32_t *>(r.ring + (wa & 127));
+            r.next -= 4;
+            r.win |= (uint64_t)w << (32 - r.avail);
+            r.avail += 32;
+        } else {
+            while (r.next > 0) {
+                const uint32_t b = r.base[--r.next];
+                r.win |= (uint64_t)b << (56 - r.avail);
+                r.avail += 8;
+            }
+            r.avail = 64;  // zero fill below the stream start (reversebitstream.go:23-27,67-75)
+        }
+    }
+    asm volatile("cp.async.commit_group;");
+}
+
+__device__ __forceinline__ bool hring_init(HufBits &r, const uint8_t *data, int32_t len, uint8_t *ring) {
+    r.base = data;
+    r.next = len;
+    r.avail = 0;
+    r.win = 0;
+    r.remaining = len * 8;
+    r.ring = ring;
+    r.ring_saddr = (uint32_t)__cvta_generic_to_shared(ring);
+    r.mis = (uint32_t)(reinterpret_cast<uintptr_t>(data) & 15);
+    r.chunk0 = reinterpret_cast<const uint4 *>(data - r.mis);
+    if (len <= 0) {
+        r.avail = 64;
+        r.cur = 0;
+        return false;
+    }
+    r.cur = (int32_t)((r.mis + (uint32_t)len - 1) >> 4);
+    for (int k = 0; k < 5; k++) hring_fetch(r, r.cur - k);
+    asm volatile("cp.async.commit_group;");
+    // byte loads until the unread length is a multiple of 4 from an aligned address
+    while (r.next > 0 && ((r.mis + (uint32_t)r.next) & 3) != 0) {
+        const uint32_t b = r.base[--r.next];
+        r.win |= (uint64_t)b << (56 - r.avail);
+        r.avail += 8;
+    }
+    if (r.next == 0) r.avail = 64;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    hring_refill(r);
+    return true;
+}
+
+__device__ __forceinline__ uint32_t hring_peek(const HufBits &r, uint32_t n) { return (uint32_t)((r.win >> 1) >> (63 - n)); }
+__device__ __forceinline__ void hring_skip(HufBits &r, uint32_t n) {
+    r.win <<= n;
+    r.avail -= (int32_t)n;
+    r.remaining -= (int32_t)n;
+}
+
 // HuffmanDecodingTable.DecodeStream (huffman.go:221-264) for one stream, one lane; same recurrence as
 // huf_decode_stream (huffman.cuh) with the symbols buffered 16 deep in registers so they leave as
 // aligned 16-byte stores, and one refill check per two symbols (2 x 11 bits <= the 32 guaranteed).
 __device__ __forceinline__ int huf_decode_stream_vec(const uint16_t *table, uint32_t max_bits, const uint8_t *p, uint32_t len,
-                                                     uint8_t *out, uint32_t expected) {
-    RevBits r;
-    if (!rev_init(r, p, (int32_t)len) || !rev_skip_padding(r)) return SZB_ERR_BAD_PADDING;
+                                                     uint8_t *out, uint32_t expected, uint8_t *ring) {
+    HufBits r;
+    if (!hring_init(r, p, (int32_t)len, ring)) return SZB_ERR_BAD_PADDING;
+    {   // skip padding: zero bits then the first 1 bit, at most 8 (huffman.go:227-238)
+        uint32_t top = (uint32_t)(r.win >> 56);
+        if (top == 0) return SZB_ERR_BAD_PADDING;
+        hring_skip(r, (uint32_t)__clz(top) - 24 + 1);
+    }
     uint32_t n = 0;
     uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15)) & 15;
     if (head > expected) head = expected;
     for (; n < head; n++) {
-        rev_refill(r);
-        const uint32_t e = table[rev_peek(r, max_bits)];
+        hring_refill(r);
+        const uint32_t e = table[hring_peek(r, max_bits)];
         out[n] = (uint8_t)e;
-        rev_skip(r, e >> 8);
+        hring_skip(r, e >> 8);
     }
     while (n + 16 <= expected) {
         uint32_t wv[4];
@@ -313,10 +410,10 @@ __device__ __forceinline__ int huf_decode_stream_vec(const uint16_t *table, uint
             uint32_t acc = 0;
 #pragma unroll
             for (int t = 0; t < 4; t++) {
-                if ((t & 1) == 0) rev_refill(r);
-                const uint32_t e = table[rev_peek(r, max_bits)];
+                if ((t & 1) == 0) hring_refill(r);
+                const uint32_t e = table[hring_peek(r, max_bits)];
                 acc |= (e & 0xFF) << (8 * t);
-                rev_skip(r, e >> 8);
+                hring_skip(r, e >> 8);
             }
             wv[q] = acc;
         }
@@ -324,11 +421,12 @@ __device__ __forceinline__ int huf_decode_stream_vec(const uint16_t *table, uint
         n += 16;
     }
     for (; n < expected; n++) {
-        rev_refill(r);
-        const uint32_t e = table[rev_peek(r, max_bits)];
+        hring_refill(r);
+        const uint32_t e = table[hring_peek(r, max_bits)];
         out[n] = (uint8_t)e;
-        rev_skip(r, e >> 8);
+        hring_skip(r, e >> 8);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (r.remaining > 0) return SZB_ERR_STREAM_DIDNT_DECODE_TO_RIGHT_LENGTH;  // more symbols than its slot holds
     if (r.remaining < 0) return SZB_ERR_DIDNT_USE_ALL_BITS_TO_DECODE_HUFFMAN;
     return SZB_OK;
@@ -344,11 +442,13 @@ constexpr uint32_t kHufCellsPerWarp = 2048;  // 4 KB of decode tables resident p
 // Shared memory is kept small on purpose: the streams are read through L1, which needs the room.
 __global__ void __launch_bounds__(kCtaThreads) k_decode_literals(DeviceBatch a) {
     __shared__ __align__(16) uint16_t tabs_all[kWarpsPerCta][kHufCellsPerWarp];
+    __shared__ __align__(16) uint8_t rings_all[kWarpsPerCta][32 * kHufRingStride];
     const uint32_t warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t g = blockIdx.x * kWarpsPerCta + warp_in_cta;
     const uint32_t first = g * kHufGroup;
     if (first >= a.n_huf) return;
     uint16_t *tabs = tabs_all[warp_in_cta];
+    uint8_t *my_ring = rings_all[warp_in_cta] + lane * kHufRingStride;
     const uint32_t n_entries = a.n_huf - first < kHufGroup ? a.n_huf - first : kHufGroup;
 
     // lanes 0..7 fetch the per-entry facts; everyone reads them through shuffles
@@ -412,7 +512,7 @@ __global__ void __launch_bounds__(kCtaThreads) k_decode_literals(DeviceBatch a) 
                     if (comp < 0)
                         my_rc = SZB_ERR_PANIC;
                     else if (my_k == 0)
-                        my_rc = huf_decode_stream_vec(tabs + my_off, bits, payload + skip, (uint32_t)comp, out, regen);
+                        my_rc = huf_decode_stream_vec(tabs + my_off, bits, payload + skip, (uint32_t)comp, out, regen, my_ring);
                 } else {
                     comp -= 6;
                     if (comp < 0) {
@@ -431,7 +531,7 @@ __global__ void __launch_bounds__(kCtaThreads) k_decode_literals(DeviceBatch a) 
                             const uint32_t start = my_k == 0 ? 0 : (my_k == 1 ? s1 : (my_k == 2 ? s1 + s2 : s1 + s2 + s3));
                             const uint32_t len = my_k == 0 ? s1 : (my_k == 1 ? s2 : (my_k == 2 ? s3 : s4));
                             const uint32_t expected = my_k < 3 ? normal : (uint32_t)last;
-                            my_rc = huf_decode_stream_vec(tabs + my_off, bits, jt + 6 + start, len, out + my_k * normal, expected);
+                            my_rc = huf_decode_stream_vec(tabs + my_off, bits, jt + 6 + start, len, out + my_k * normal, expected, my_ring);
                         }
                     }
                 }
@@ -572,9 +672,6 @@ __device__ __forceinline__ uint32_t bfind(uint32_t x) {  // index of the highest
     uint32_t r;
     asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
     return r;
-}
-__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *g) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g));
 }
 
 struct SeqLane {
