@@ -51,7 +51,7 @@ struct szb_batch {
     size_t src_len = 0;
     std::vector<szb_frame_desc> frames;
     std::vector<szb_block_desc> blocks;
-    std::vector<uint32_t> huf_list, seq_list, hufo_list, huf_slot;
+    std::vector<uint32_t> huf_list, seq_list, hufo_list, huf_slot, body_list;
     uint64_t literal_bytes = 0, sequences = 0;
     // device
     void *d_tables = nullptr;  // one allocation: frames | blocks | lists | out_size_init
@@ -60,6 +60,7 @@ struct szb_batch {
     uint32_t *d_huf_list = nullptr, *d_seq_list = nullptr, *d_hufo_list = nullptr, *d_huf_slot = nullptr;
     uint16_t *d_huf_tabs = nullptr;
     HufInfo *d_huf_info = nullptr;
+    uint32_t *d_body_list = nullptr;
     uint64_t *d_out_size_init = nullptr;
     void *d_state = nullptr;  // one allocation: out_size | out_off | total | frame_out_off | frame_out_len | statuses
     uint64_t *d_out_size = nullptr, *d_out_off = nullptr, *d_total = nullptr, *d_frame_out_off = nullptr,
@@ -233,6 +234,7 @@ static int batch_upload_tables(szb_batch *b) {
         out_size_init[i] = d.type == 2 ? d.lit_regen : d.block_size;
         if (d.type == 2 && d.lit_type >= 2) b->huf_list.push_back(i);
         if (d.type == 2 && d.nseq > 0) b->seq_list.push_back(i);
+        if ((d.type != 2 && d.block_size > 0) || (d.type == 2 && d.nseq == 0 && d.lit_regen > 0)) b->body_list.push_back(i);
     }
     {   // blocks that carry a tree description get a table slot; every Huffman block points at its origin's slot
         std::vector<uint32_t> slot_of_block(nb ? nb : 1, SZB_NONE);
@@ -256,7 +258,8 @@ static int batch_upload_tables(szb_batch *b) {
     size_t o_seq = align_up(o_huf + 4 * b->huf_list.size(), 256);
     size_t o_hufo = align_up(o_seq + 4 * b->seq_list.size(), 256);
     size_t o_slot = align_up(o_hufo + 4 * b->hufo_list.size(), 256);
-    size_t o_init = align_up(o_slot + 4 * b->huf_slot.size(), 256);
+    size_t o_body = align_up(o_slot + 4 * b->huf_slot.size(), 256);
+    size_t o_init = align_up(o_body + 4 * b->body_list.size(), 256);
     size_t total = align_up(o_init + 8 * (size_t)nb, 256) + 256;
     std::vector<uint8_t> stage(total, 0);
     if (nf) memcpy(stage.data() + o_frames, b->frames.data(), sizeof(szb_frame_desc) * (size_t)nf);
@@ -265,6 +268,7 @@ static int batch_upload_tables(szb_batch *b) {
     if (!b->seq_list.empty()) memcpy(stage.data() + o_seq, b->seq_list.data(), 4 * b->seq_list.size());
     if (!b->hufo_list.empty()) memcpy(stage.data() + o_hufo, b->hufo_list.data(), 4 * b->hufo_list.size());
     if (!b->huf_slot.empty()) memcpy(stage.data() + o_slot, b->huf_slot.data(), 4 * b->huf_slot.size());
+    if (!b->body_list.empty()) memcpy(stage.data() + o_body, b->body_list.data(), 4 * b->body_list.size());
     if (nb) memcpy(stage.data() + o_init, out_size_init.data(), 8 * (size_t)nb);
     CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_tables, total));
     CUDA_TRY(ctx, cudaMemcpyAsync(b->d_tables, stage.data(), total, cudaMemcpyHostToDevice, ctx->stream));
@@ -276,6 +280,7 @@ static int batch_upload_tables(szb_batch *b) {
     b->d_seq_list = (uint32_t *)(base + o_seq);
     b->d_hufo_list = (uint32_t *)(base + o_hufo);
     b->d_huf_slot = (uint32_t *)(base + o_slot);
+    b->d_body_list = (uint32_t *)(base + o_body);
     b->d_out_size_init = (uint64_t *)(base + o_init);
     // mutable state
     size_t s_out_size = 0;
@@ -441,6 +446,8 @@ static DeviceBatch make_args(szb_batch *b, const void *d_src, void *d_dst, size_
     a.frame_out_off = b->d_frame_out_off;
     a.frame_out_len = b->d_frame_out_len;
     a.frame_status = b->d_frame_status;
+    a.body_list = b->d_body_list;
+    a.n_body = (uint32_t)b->body_list.size();
     return a;
 }
 
@@ -487,6 +494,14 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
     cudaStream_t s = ctx->stream;
     DeviceBatch a = make_args(b, d_src, d_dst, dst_cap);
     if (a.nframes) {
+        k_frame_verdict<<<(a.nframes + 127) / 128, 128, 0, s>>>(a);
+        ctx->launches++;
+    }
+    if (a.n_body) {
+        k_execute_bodies<<<(a.n_body + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, s>>>(a);
+        ctx->launches++;
+    }
+    if (a.nframes && a.n_seq) {
         k_execute<<<(a.nframes + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, s>>>(a);
         ctx->launches++;
     }

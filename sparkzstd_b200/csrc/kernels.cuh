@@ -78,6 +78,8 @@ struct DeviceBatch {
     uint64_t dst_cap;
     uint64_t *frame_out_off, *frame_out_len;
     int32_t *frame_status;
+    const uint32_t *body_list;  // Raw / RLE / zero-sequence blocks: output independent of earlier output
+    uint32_t n_body;
 };
 
 __device__ __forceinline__ int warp_first_error(int rc) {
@@ -958,10 +960,26 @@ __device__ __forceinline__ void warp_memcpy(uint8_t *dst, const uint8_t *src, ui
     const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3);
     const uint32_t *sw = reinterpret_cast<const uint32_t *>(src - mis);
     uint32_t *dw = reinterpret_cast<uint32_t *>(dst);
+    uint64_t i = lane;
     if (mis == 0) {
-        for (uint64_t i = lane; i < words; i += 32) dw[i] = sw[i];
+        for (; i + 96 < words; i += 128) {  // four independent loads in flight per lane
+            const uint32_t v0 = sw[i], v1 = sw[i + 32], v2 = sw[i + 64], v3 = sw[i + 96];
+            dw[i] = v0;
+            dw[i + 32] = v1;
+            dw[i + 64] = v2;
+            dw[i + 96] = v3;
+        }
+        for (; i < words; i += 32) dw[i] = sw[i];
     } else {
-        for (uint64_t i = lane; i < words; i += 32) dw[i] = __funnelshift_r(sw[i], sw[i + 1], mis * 8);
+        for (; i + 96 < words; i += 128) {
+            const uint32_t a0 = sw[i], a1 = sw[i + 1], b0 = sw[i + 32], b1 = sw[i + 33];
+            const uint32_t c0 = sw[i + 64], c1 = sw[i + 65], d0 = sw[i + 96], d1 = sw[i + 97];
+            dw[i] = __funnelshift_r(a0, a1, mis * 8);
+            dw[i + 32] = __funnelshift_r(b0, b1, mis * 8);
+            dw[i + 64] = __funnelshift_r(c0, c1, mis * 8);
+            dw[i + 96] = __funnelshift_r(d0, d1, mis * 8);
+        }
+        for (; i < words; i += 32) dw[i] = __funnelshift_r(sw[i], sw[i + 1], mis * 8);
     }
     const uint32_t tail = (uint32_t)(n & 3);
     if (lane < tail) dst[(words << 2) + lane] = src[(words << 2) + lane];
@@ -1056,6 +1074,51 @@ __device__ __forceinline__ uint8_t stager_byte(const Stager &s, uint64_t p) {
     return p >= s.base ? s.stage[(uint32_t)(p - s.base)] : s.dst[p];
 }
 
+// One thread per frame, before any output is written: the frame's verdict (the first failing
+// block decides, as in the sequential reference; then the header walk's verdict; then capacity)
+// and its placement in dst.
+__global__ void k_frame_verdict(DeviceBatch a) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.nframes) return;
+    const szb_frame_desc fr = a.frames[f];
+    const uint32_t b0 = fr.first_block, nb = fr.nblocks;
+    int err = SZB_OK;
+    for (uint32_t i = 0; i < nb && err == SZB_OK; i++) {
+        const int ls = a.lit_status[b0 + i], ss = a.seq_status[b0 + i];
+        if ((ls | ss) != 0) err = ls ? ls : ss;
+    }
+    if (err == SZB_OK) err = fr.status;  // blocks after a failing header are absent from the table
+    if (err == SZB_OK && a.total[0] > a.dst_cap) err = SZB_ERR_DST_TOO_SMALL;
+    const uint64_t frame_base = nb ? a.out_off[b0] : 0;
+    a.frame_status[f] = err;
+    a.frame_out_off[f] = frame_base;
+    a.frame_out_len[f] = (nb && err == SZB_OK) ? a.out_off[b0 + nb - 1] + a.out_size[b0 + nb - 1] - frame_base : 0;
+}
+
+// Blocks whose output does not depend on earlier output -- Raw bodies (framedecompressor.go:211-215),
+// RLE bodies (:229-241) and compressed blocks without sequences, whose output is their literals
+// (sequences.go:395-400, sequence_execution.go:55-60) -- are written by one warp each, all in
+// parallel, before the per-frame sequence execution starts.
+__global__ void __launch_bounds__(kCtaThreads) k_execute_bodies(DeviceBatch a) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    if (w >= a.n_body) return;
+    const uint32_t b = a.body_list[w];
+    const szb_block_desc d = a.blocks[b];
+    if (a.frame_status[d.frame] != SZB_OK) return;
+    uint8_t *out = a.dst + a.out_off[b];
+    const uint8_t *payload = a.src + d.src_off;
+    if (d.type == 0) {
+        warp_memcpy(out, payload, d.block_size, lane);
+    } else if (d.type == 1) {
+        warp_memset(out, payload[0], d.block_size, lane);
+    } else if (d.lit_type == 1) {
+        warp_memset(out, payload[d.lit_hdr_bytes], d.lit_regen, lane);
+    } else {
+        warp_memcpy(out, d.lit_type == 0 ? payload + d.lit_hdr_bytes : a.litbuf + d.lit_buf_off, d.lit_regen, lane);
+    }
+}
+
 // One warp per frame; blocks in order; 32 sequences per round.
 __global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
     __shared__ ExecSmem smem[kWarpsPerCta];
@@ -1067,36 +1130,9 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
     const uint32_t b0 = fr.first_block, nb = fr.nblocks;
     uint8_t *const dst = a.dst;
 
-    // the first failing block decides the frame's status, as in the sequential reference
-    int err = SZB_OK;
-    {
-        uint32_t first_bad = 0xFFFFFFFFu;
-        for (uint32_t i = lane; i < nb; i += 32) {
-            if ((a.lit_status[b0 + i] | a.seq_status[b0 + i]) != 0 && i < first_bad) first_bad = i;
-        }
-        for (int dlt = 16; dlt > 0; dlt >>= 1) {
-            uint32_t t = __shfl_xor_sync(kFull, first_bad, dlt);
-            first_bad = t < first_bad ? t : first_bad;
-        }
-        if (first_bad != 0xFFFFFFFFu) {
-            const int ls = a.lit_status[b0 + first_bad];
-            err = ls ? ls : a.seq_status[b0 + first_bad];
-        } else {
-            err = fr.status;  // the header walk's verdict (blocks after the failing header are absent)
-        }
-    }
+    int err = a.frame_status[f];  // k_frame_verdict
+    if (err != SZB_OK) return;
     const uint64_t frame_base = nb ? a.out_off[b0] : 0;
-    uint64_t frame_len = 0;
-    if (nb) frame_len = a.out_off[b0 + nb - 1] + a.out_size[b0 + nb - 1] - frame_base;
-    if (err == SZB_OK && a.total[0] > a.dst_cap) err = SZB_ERR_DST_TOO_SMALL;
-    if (err != SZB_OK) {
-        if (lane == 0) {
-            a.frame_status[f] = err;
-            a.frame_out_off[f] = frame_base;
-            a.frame_out_len[f] = 0;
-        }
-        return;
-    }
 
     Stager st;
     st.stage = sm.stage;
@@ -1110,14 +1146,9 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
         const szb_block_desc d = a.blocks[b];
         const uint8_t *payload = a.src + d.src_off;
         uint64_t out_pos = a.out_off[b];
-        if (d.type != 2) {  // Raw (framedecompressor.go:211-215) / RLE (framedecompressor.go:229-241) bodies
+        if (d.type != 2 || d.nseq == 0) {  // written by k_execute_bodies already: step over it
             stager_flush_all(st, lane);
-            if (d.type == 0)
-                warp_memcpy(dst + out_pos, payload, d.block_size, lane);
-            else
-                warp_memset(dst + out_pos, payload[0], d.block_size, lane);
-            __syncwarp();
-            stager_reset(st, out_pos + d.block_size, frame_base, lane);
+            stager_reset(st, out_pos + a.out_size[b], frame_base, lane);
             continue;
         }
         // Compressed: ExecuteSequences (sequence_execution.go:14-63)
@@ -1357,10 +1388,9 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
         }
     }
     stager_flush_all(st, lane);
-    if (lane == 0) {
+    if (lane == 0 && err != SZB_OK) {  // failed while executing (bad offset, literals ran dry)
         a.frame_status[f] = err;
-        a.frame_out_off[f] = frame_base;
-        a.frame_out_len[f] = err == SZB_OK ? frame_len : 0;
+        a.frame_out_len[f] = 0;
     }
 }
 
