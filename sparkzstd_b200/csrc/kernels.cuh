@@ -1158,12 +1158,20 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
         const uint32_t nseq = d.nseq;
         const uint32_t *gll = a.seq_ll + d.seq_buf_off, *gml = a.seq_ml + d.seq_buf_off, *gof = a.seq_of + d.seq_buf_off;
         uint32_t lit_pos = 0;
+        // the sequence triples of the next round are loaded while the current one executes
+        uint32_t n_ll = lane < nseq ? gll[lane] : 0, n_ml = lane < nseq ? gml[lane] : 0, n_of = lane < nseq ? gof[lane] : 4;
         for (uint32_t base = 0; base < nseq; base += 32) {
             const uint32_t cnt = nseq - base < 32 ? nseq - base : 32;
             const bool act = lane < cnt;
-            const uint32_t ll = act ? gll[base + lane] : 0;
-            const uint32_t ml = act ? gml[base + lane] : 0;
-            const uint32_t ofv = act ? gof[base + lane] : 4;
+            const uint32_t ll = n_ll, ml = n_ml, ofv = n_of;
+            {
+                const uint32_t nx = base + 32 + lane;
+                const bool more = nx < nseq;
+                n_ll = more ? gll[nx] : 0;
+                n_ml = more ? gml[nx] : 0;
+                n_of = more ? gof[nx] : 4;
+                if (!lit_rle && lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(lit + lit_pos + 128));
+            }
 
             // --- offsets through the 3-entry history (nextOffset) ---
             uint32_t off;
