@@ -1019,6 +1019,7 @@ constexpr uint32_t kCoopMatch = 34;     // matches this long are copied by the w
 struct ExecSmem {
     __align__(16) uint8_t stage[kStageBytes + 16];
     __align__(16) uint8_t gath[32 * kGathStride];
+    __align__(16) uint8_t lits[kStageBytes + 16];  // the literal bytes of the segment in flight, fetched coalesced
 };
 
 // stage[i] mirrors dst[base + i] for i < fill; (dst + base) is 16-byte aligned; everything below
@@ -1267,23 +1268,39 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
                 const uint32_t sd = (uint32_t)(my_dst - st.base);  // my literal run inside the window
                 const uint32_t md = sd + ll;                        // my match inside the window
 
-                // literal runs (sequence_execution.go:19-34)
-                if (in && ll > 0 && ll < kCoopLit) {
-                    if (lit_rle) {
+                // literal runs (sequence_execution.go:19-34).  The segment's literals are contiguous in the
+                // literal buffer: fetch them once, coalesced, then every lane places its own run.
+                if (lit_rle) {
+                    if (in && ll > 0 && ll < kCoopLit)
                         for (uint32_t k = 0; k < ll; k++) st.stage[sd + k] = rle_byte;
-                    } else {
-                        for (uint32_t k = 0; k < ll; k++) st.stage[sd + k] = lit[my_lit + k];
+                    uint32_t long_lit = __ballot_sync(kFull, in && ll >= kCoopLit);
+                    while (long_lit) {
+                        const int j = __ffs(long_lit) - 1;
+                        long_lit &= long_lit - 1;
+                        warp_fill(st.stage + __shfl_sync(kFull, sd, j), rle_byte, __shfl_sync(kFull, ll, j), lane);
                     }
-                }
-                uint32_t long_lit = __ballot_sync(kFull, in && ll >= kCoopLit);
-                while (long_lit) {
-                    const int j = __ffs(long_lit) - 1;
-                    long_lit &= long_lit - 1;
-                    const uint32_t L = __shfl_sync(kFull, ll, j), SD = __shfl_sync(kFull, sd, j), SL = __shfl_sync(kFull, my_lit, j);
-                    if (lit_rle)
-                        warp_fill(st.stage + SD, rle_byte, L, lane);
-                    else
-                        warp_copy(st.stage + SD, lit + SL, L, lane);
+                } else {
+                    const uint32_t l0 = __shfl_sync(kFull, my_lit, start);
+                    const uint32_t l1 = __shfl_sync(kFull, my_lit + ll, end - 1);
+                    const uint8_t *lsrc = lit + l0;
+                    const uint32_t lmis = (uint32_t)(reinterpret_cast<uintptr_t>(lsrc) & 3);
+                    const uint32_t nwords = (lmis + (l1 - l0) + 3) >> 2;
+                    const uint32_t *lw = reinterpret_cast<const uint32_t *>(lsrc - lmis);
+                    uint32_t *ls = reinterpret_cast<uint32_t *>(sm.lits);
+                    for (uint32_t wd = lane; wd < nwords; wd += 32) ls[wd] = lw[wd];
+                    __syncwarp();
+                    if (in && ll > 0 && ll < kCoopLit) {
+                        const uint8_t *from = sm.lits + lmis + (my_lit - l0);
+                        uint8_t *to = st.stage + sd;
+                        for (uint32_t k = 0; k < ll; k++) to[k] = from[k];
+                    }
+                    uint32_t long_lit = __ballot_sync(kFull, in && ll >= kCoopLit);
+                    while (long_lit) {
+                        const int j = __ffs(long_lit) - 1;
+                        long_lit &= long_lit - 1;
+                        const uint32_t L = __shfl_sync(kFull, ll, j), SD = __shfl_sync(kFull, sd, j), SL = __shfl_sync(kFull, my_lit, j);
+                        warp_copy(st.stage + SD, sm.lits + lmis + (SL - l0), L, lane);
+                    }
                 }
 
                 // matches (RepeatBeforeIndex, ringbuffer.go:242-277).  Positions below are relative to the
@@ -1319,14 +1336,21 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
                 __syncwarp();
                 uint32_t pending = __ballot_sync(kFull, pend_lane);
                 if (pending) {
-                    // dep: the pending lanes before me whose match output overlaps the window part of my source
-                    uint32_t dep = 0;
-                    for (uint32_t pm = pending; pm; pm &= pm - 1) {
-                        const int j = __ffs(pm) - 1;
-                        const int32_t dj = (int32_t)__shfl_sync(kFull, md, j);
-                        const int32_t ej = dj + (int32_t)__shfl_sync(kFull, ml, j);
-                        if (j < (int)lane && ej > s_rel && dj < e_rel) dep |= 1u << j;
+                    // dep: the pending lanes before me whose output overlaps the window part of my source.
+                    // The end positions of the sequences of a segment grow with the lane number, so both
+                    // ends of that lane range come out of a 5-step binary search over shuffles.
+                    const uint32_t seq_end = lane < start ? 0u : (lane < end ? md + ml : 0x7FFFFFFFu);
+                    const uint32_t seq_md = lane < start ? 0u : (lane < end ? md : 0x7FFFFFFFu);
+                    uint32_t lo = 0, hi = 0;  // lo: lanes whose output ends at or before my source; hi: lanes whose match starts before my source ends
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const int32_t v1 = (int32_t)__shfl_sync(kFull, seq_end, lo + step - 1);
+                        const int32_t v2 = (int32_t)__shfl_sync(kFull, seq_md, hi + step - 1);
+                        if (v1 <= s_rel) lo += step;
+                        if (v2 < e_rel) hi += step;
                     }
+                    if (hi > lane) hi = lane;
+                    const uint32_t dep = hi > lo ? (((1u << hi) - 1) & ~((1u << lo) - 1)) : 0u;
                     while (pending) {
                         const int first = __ffs(pending) - 1;  // the first pending lane never waits for anyone
                         const uint32_t first_ml = __shfl_sync(kFull, ml, first);
