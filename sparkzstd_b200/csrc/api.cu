@@ -69,7 +69,7 @@ struct szb_batch {
     size_t status_bytes = 0;
     uint8_t *d_litbuf = nullptr;
     uint32_t *d_seq = nullptr;  // ll | ml | of
-    uint32_t *d_seq_tabs = nullptr;  // FSE decode-table arena, kTabSlotWords per block with sequences
+    uint16_t *d_seq_tabs = nullptr;  // FSE decode-table arena, kTabSlotWords 16-bit cells per block with sequences
     SeqInfo *d_seq_info = nullptr;
     bool entropy_done = false;
 };
@@ -308,7 +308,7 @@ static int batch_upload_tables(szb_batch *b) {
     // scratch arenas
     CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_litbuf, (size_t)b->literal_bytes + 256));
     CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_seq, (size_t)(b->sequences * 3 + 64) * 4));
-    CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_seq_tabs, (b->seq_list.size() + 1) * (size_t)kTabSlotWords * 4));
+    CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_seq_tabs, (b->seq_list.size() + 1) * (size_t)kTabSlotWords * 2 + 256));
     CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_seq_info, (b->seq_list.size() + 1) * sizeof(SeqInfo)));
     CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_huf_tabs, (b->hufo_list.size() + 1) * (size_t)(2u << kMaxHufBits)));
     CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_huf_info, (b->hufo_list.size() + 1) * sizeof(HufInfo)));

@@ -66,7 +66,7 @@ struct DeviceBatch {
     uint32_t n_seq;
     uint8_t *litbuf;
     uint32_t *seq_ll, *seq_ml, *seq_of;
-    uint32_t *seq_tabs;     // per seq_list entry: LL(512) | ML(512) | OF(256) decode-table cells
+    uint16_t *seq_tabs;     // per seq_list entry: LL(512) | ML(512) | OF(256) 16-bit decode-table cells
     SeqInfo *seq_info;      // per seq_list entry
     uint64_t *out_size;     // per block regenerated size (host-initialised for Raw/RLE/zero-sequence blocks)
     uint64_t *out_off;      // per block exclusive prefix
@@ -551,6 +551,11 @@ __global__ void __launch_bounds__(kCtaThreads) k_decode_literals(DeviceBatch a) 
     if (my_k == 0 && my_e < n_entries) a.lit_status[a.huf_list[first + my_e]] = rc;
 }
 
+// resident cell: symbol in bits 0-5, next-state counter in bits 6-15
+__device__ __forceinline__ uint32_t cell16(uint32_t packed, uint32_t al) {
+    return fse_code(packed) | (((fse_baseline(packed) + (1u << al)) >> fse_nb(packed)) << 6);
+}
+
 // shared memory per warp, k_build_seq_tables
 struct SeqSmem {
     uint32_t tll[1 << kMaxALLL];
@@ -611,10 +616,11 @@ __global__ void __launch_bounds__(kCtaThreads) k_build_seq_tables(DeviceBatch a)
         if (lane == 0) a.seq_status[b] = rc;
         return;
     }
-    uint32_t *slot = a.seq_tabs + (size_t)w * kTabSlotWords;
-    for (uint32_t i = lane; i < (1u << al[KIND_LL]); i += 32) slot[i] = sm.tll[i];
-    for (uint32_t i = lane; i < (1u << al[KIND_ML]); i += 32) slot[512 + i] = sm.tml[i];
-    for (uint32_t i = lane; i < (1u << al[KIND_OF]); i += 32) slot[1024 + i] = sm.tof[i];
+    // published as the 16-bit resident cells k_decode_sequences works on (symbol | next << 6)
+    uint16_t *slot = a.seq_tabs + (size_t)w * kTabSlotWords;
+    for (uint32_t i = lane; i < (1u << al[KIND_LL]); i += 32) slot[i] = (uint16_t)cell16(sm.tll[i], al[KIND_LL]);
+    for (uint32_t i = lane; i < (1u << al[KIND_ML]); i += 32) slot[512 + i] = (uint16_t)cell16(sm.tml[i], al[KIND_ML]);
+    for (uint32_t i = lane; i < (1u << al[KIND_OF]); i += 32) slot[1024 + i] = (uint16_t)cell16(sm.tof[i], al[KIND_OF]);
     if (lane == 0) {
         SeqInfo info;
         info.al_ll = (uint8_t)al[KIND_LL];
@@ -666,10 +672,6 @@ constexpr uint32_t kSeqRingOff = kSeqTabBytes;                    // byte offset
 constexpr uint32_t kSeqLutWord = (kSeqRingOff + kSeqLanes * kSeqRingStride) / 4;  // ll[64] | ml[64]: base | extra << 24
 constexpr uint32_t kSeqDecodeSmemBytes = (kSeqLutWord + 128) * 4;
 
-// resident cell: symbol in bits 0-5, next-state counter in bits 6-15
-__device__ __forceinline__ uint32_t cell16(uint32_t packed, uint32_t al) {
-    return fse_code(packed) | (((fse_baseline(packed) + (1u << al)) >> fse_nb(packed)) << 6);
-}
 __device__ __forceinline__ uint32_t bfind(uint32_t x) {  // index of the highest set bit (x != 0)
     uint32_t r;
     asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
@@ -779,19 +781,19 @@ __global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
     const uint32_t n_here = a.n_seq - first < (uint32_t)kSeqLanes ? a.n_seq - first : (uint32_t)kSeqLanes;
     uint16_t *tabs = reinterpret_cast<uint16_t *>(sw);
 
-    // tables: HBM arena (32-bit cells) -> shared memory (16-bit cells), coalesced
-    for (uint32_t j = 0; j < n_here; j++) {
-        const SeqInfo info = a.seq_info[first + j];
-        const uint32_t *slot = a.seq_tabs + (size_t)(first + j) * kTabSlotWords;
-        uint16_t *t = tabs + j * kTabSlotWords;
-        for (uint32_t i = lane; i < (1u << info.al_ll); i += 32) t[i] = (uint16_t)cell16(slot[i], info.al_ll);
-        for (uint32_t i = lane; i < (1u << info.al_ml); i += 32) t[512 + i] = (uint16_t)cell16(slot[512 + i], info.al_ml);
-        for (uint32_t i = lane; i < (1u << info.al_of); i += 32) t[1024 + i] = (uint16_t)cell16(slot[1024 + i], info.al_of);
+    // tables: HBM arena -> shared memory, 2560 contiguous bytes per block, all copies in flight at once
+    {
+        const uint32_t tabs_saddr = (uint32_t)__cvta_generic_to_shared(tabs);
+        const uint8_t *arena = reinterpret_cast<const uint8_t *>(a.seq_tabs + (size_t)first * kTabSlotWords);
+        const uint32_t chunks = n_here * (kTabSlotWords * 2 / 16);
+        for (uint32_t c = lane; c < chunks; c += 32) cp_async16(tabs_saddr + c * 16, arena + (size_t)c * 16);
+        asm volatile("cp.async.commit_group;");
     }
     for (uint32_t i = lane; i < 64; i += 32) {
         sw[kSeqLutWord + i] = kLLBaseDev[i] | ((uint32_t)kLLExtraDev[i] << 24);
         sw[kSeqLutWord + 64 + i] = kMLBaseDev[i] | ((uint32_t)kMLExtraDev[i] << 24);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     if (lane >= n_here) return;
 
