@@ -36,7 +36,7 @@ constexpr uint32_t kFull = 0xFFFFFFFFu;
 #define SZB_SERIAL_TABLES 0
 #endif
 
-constexpr int kSeqLanes = 20;             // blocks per warp in k_decode_sequences: 20 x 2.5 KB tables, 4 warps per SM
+constexpr int kSeqLanes = 21;             // blocks per warp in k_decode_sequences: 21 x 2.6 KB (tables + bit ring), 4 warps per SM
 constexpr uint32_t kTabSlotWords = 1280;  // LL 512 | ML 512 | OF 256
 
 struct SeqInfo {
@@ -667,7 +667,7 @@ __device__ __forceinline__ uint32_t slow_read_bits(const uint8_t *sp, int64_t po
 // the last sequence) LL state, ML state, OF state.  Decoded triples are buffered four deep in
 // registers and leave as 16-byte stores.
 constexpr uint32_t kSeqTabBytes = kSeqLanes * kTabSlotWords * 2;  // u16 cells
-constexpr uint32_t kSeqRingStride = 144;                          // per lane: 64 B ring + 64 B mirror + 16 B pad
+constexpr uint32_t kSeqRingStride = 80;                           // per lane: 64 B ring + a mirror of its first 16 B
 constexpr uint32_t kSeqRingOff = kSeqTabBytes;                    // byte offset of the rings
 constexpr uint32_t kSeqLutWord = (kSeqRingOff + kSeqLanes * kSeqRingStride) / 4;  // ll[64] | ml[64]: base | extra << 24
 constexpr uint32_t kSeqDecodeSmemBytes = (kSeqLutWord + 128) * 4;
@@ -684,14 +684,15 @@ struct SeqLane {
     int32_t cur;                // ring: chunk (16 B, counted from the chunk holding sp[0]) of the byte with bit pos-1
 };
 
-// Chunk c of the stream goes to ring slot c & 3 and to its mirror 64 bytes above, so a 12-byte window
-// read never wraps.  Asynchronous (cp.async): no register, no scoreboard slot is held while it flies.
+// Chunk c of the stream goes to ring slot c & 3 (slot 0 also to a mirror above slot 3), so a 12-byte
+// window read never wraps.  Asynchronous (cp.async): no register, no scoreboard slot is held while it flies.
 // Completion is tracked per warp in commit groups; decode_step commits one group per sequence.
 __device__ __forceinline__ void ring_fetch(uint32_t ring_saddr, const uint4 *chunk0, int32_t c) {
     if (c >= 0) {
-        const uint32_t s = ring_saddr + (((uint32_t)c & 3) << 4);
+        const uint32_t slot = (uint32_t)c & 3;
+        const uint32_t s = ring_saddr + (slot << 4);
         cp_async16(s, chunk0 + c);
-        cp_async16(s + 64, chunk0 + c);
+        if (slot == 0) cp_async16(s + 64, chunk0 + c);  // a window read starts below byte 64 and is 12 bytes long: only slot 0 is mirrored
     }
 }
 
