@@ -31,6 +31,8 @@ struct szb_ctx {
     size_t d_src_cap = 0;
     uint8_t *d_dst = nullptr;
     size_t d_dst_cap = 0;
+    // copy streams for the pipelined host-buffer path
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
 };
 
 static cudaError_t pool_alloc(szb_ctx *ctx, void **p, size_t bytes);
@@ -53,6 +55,7 @@ struct szb_batch {
     std::vector<szb_block_desc> blocks;
     std::vector<uint32_t> huf_list, seq_list, hufo_list, huf_slot, body_list;
     uint64_t literal_bytes = 0, sequences = 0;
+    std::vector<uint8_t> stage;  // host image of the descriptor tables (kept until the upload has certainly happened)
     // device
     void *d_tables = nullptr;  // one allocation: frames | blocks | lists | out_size_init
     szb_frame_desc *d_frames = nullptr;
@@ -204,6 +207,8 @@ void szb_ctx_destroy(szb_ctx *ctx) {
     if (ctx->d_predef) cudaFree(ctx->d_predef);
     if (ctx->d_src) cudaFree(ctx->d_src);
     if (ctx->d_dst) cudaFree(ctx->d_dst);
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -261,7 +266,8 @@ static int batch_upload_tables(szb_batch *b) {
     size_t o_body = align_up(o_slot + 4 * b->huf_slot.size(), 256);
     size_t o_init = align_up(o_body + 4 * b->body_list.size(), 256);
     size_t total = align_up(o_init + 8 * (size_t)nb, 256) + 256;
-    std::vector<uint8_t> stage(total, 0);
+    std::vector<uint8_t> &stage = b->stage;
+    stage.assign(total, 0);
     if (nf) memcpy(stage.data() + o_frames, b->frames.data(), sizeof(szb_frame_desc) * (size_t)nf);
     if (nb) memcpy(stage.data() + o_blocks, b->blocks.data(), sizeof(szb_block_desc) * (size_t)nb);
     if (!b->huf_list.empty()) memcpy(stage.data() + o_huf, b->huf_list.data(), 4 * b->huf_list.size());
@@ -272,7 +278,6 @@ static int batch_upload_tables(szb_batch *b) {
     if (nb) memcpy(stage.data() + o_init, out_size_init.data(), 8 * (size_t)nb);
     CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_tables, total));
     CUDA_TRY(ctx, cudaMemcpyAsync(b->d_tables, stage.data(), total, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     uint8_t *base = (uint8_t *)b->d_tables;
     b->d_frames = (szb_frame_desc *)(base + o_frames);
     b->d_blocks = (szb_block_desc *)(base + o_blocks);
@@ -695,11 +700,153 @@ static int decode_tables(szb_ctx *ctx, szb_batch *b, const uint8_t *src, size_t 
     return first;
 }
 
+// Host-buffer batch decode with the copies overlapped with the kernels: the frames are
+// cut into chunks of consecutive frames; chunk i+1's compressed bytes travel H2D and chunk i-1's
+// output travels D2H while chunk i's kernels run.  Needs every frame's content size (so that each
+// chunk's place in dst is known without a device round trip); otherwise the caller falls back to the
+// size-then-decode path.  Returns 1 when it did not apply.
+static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_len, const uint64_t *frame_off,
+                                  const uint64_t *frame_len, uint32_t nframes, uint8_t *dst, size_t dst_cap,
+                                  uint64_t *out_off, uint64_t *out_len, int32_t *status, int *first_rc) {
+    constexpr size_t kChunkBytes = 96u << 20;  // compressed bytes per chunk
+    if (!frame_off || !frame_len || nframes < 64 || src_len < 2 * kChunkBytes) return 1;
+    // sizes from the frame headers only (frame.go:49-61); any frame without one -> not applicable
+    std::vector<uint64_t> fcs(nframes);
+    uint64_t total = 0;
+    for (uint32_t f = 0; f < nframes; f++) {
+        const uint64_t off = frame_off[f], len = frame_len[f];
+        if (off > src_len || len > src_len - off || len < 6) return 1;
+        const uint8_t *p = src + off;
+        if (!(p[0] == 0x28 && p[1] == 0xB5 && p[2] == 0x2F && p[3] == 0xFD)) return 1;
+        const uint8_t fhd = p[4];
+        const bool single = (fhd >> 5) & 1;
+        const uint32_t flag = fhd >> 6;
+        const uint32_t fcs_bytes = flag == 0 ? (single ? 1 : 0) : (flag == 1 ? 2 : (flag == 2 ? 4 : 8));
+        const uint32_t dict_bytes = (fhd & 3) == 3 ? 4 : (fhd & 3);
+        const uint32_t at = 5 + (single ? 0 : 1) + dict_bytes;
+        if (fcs_bytes == 0 || at + fcs_bytes > len) return 1;
+        uint64_t v = 0;
+        for (uint32_t i = 0; i < fcs_bytes; i++) v |= (uint64_t)p[at + i] << (8 * i);
+        if (fcs_bytes == 2) v += 256;
+        fcs[f] = v;
+        total += v;
+    }
+    if (total > dst_cap) return 1;  // let the plain path report SZB_ERR_DST_TOO_SMALL per frame
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->s_h2d) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+    if (!ctx->s_d2h) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    int rc = ensure_dev(ctx, &ctx->d_src, &ctx->d_src_cap, src_len + 16);
+    if (rc) return rc;
+    rc = ensure_dev(ctx, &ctx->d_dst, &ctx->d_dst_cap, (size_t)total + 16);
+    if (rc) return rc;
+
+    struct Chunk {
+        uint32_t f0, f1;
+        uint64_t src_lo, src_hi, dst_lo, dst_len;
+        szb_batch *batch;
+        cudaEvent_t up, done;
+    };
+    std::vector<Chunk> chunks;
+    uint64_t covered = 0;
+    for (uint32_t f = 0; f < nframes;) {
+        Chunk c{};
+        c.f0 = f;
+        c.src_lo = ~0ull;
+        uint64_t bytes = 0, dpos = 0;
+        for (uint32_t g = 0; g < f; g++) (void)g;
+        while (f < nframes && (bytes < kChunkBytes || f == c.f0)) {
+            c.src_lo = frame_off[f] < c.src_lo ? frame_off[f] : c.src_lo;
+            c.src_hi = frame_off[f] + frame_len[f] > c.src_hi ? frame_off[f] + frame_len[f] : c.src_hi;
+            bytes += frame_len[f];
+            dpos += fcs[f];
+            f++;
+        }
+        c.f1 = f;
+        c.dst_len = dpos;
+        covered += c.src_hi - c.src_lo;
+        chunks.push_back(c);
+    }
+    if (covered > src_len + src_len / 2) return 1;  // frames are scattered through src: chunk copies would overlap too much
+    {
+        uint64_t pos = 0;
+        for (auto &c : chunks) {
+            c.dst_lo = pos;
+            pos += c.dst_len;
+        }
+    }
+    cudaEvent_t ev_begin;
+    CUDA_TRY(ctx, cudaEventCreate(&ev_begin));
+    CUDA_TRY(ctx, cudaEventRecord(ev_begin, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_h2d, ev_begin, 0));
+    int fail = SZB_OK;
+    for (auto &c : chunks) {
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&c.up, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+        // compressed bytes of this chunk: H2D on the copy stream
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_src + c.src_lo, src + c.src_lo, (size_t)(c.src_hi - c.src_lo), cudaMemcpyHostToDevice, ctx->s_h2d));
+        CUDA_TRY(ctx, cudaEventRecord(c.up, ctx->s_h2d));
+        // header walk on the host (overlaps the GPU work of the previous chunks), tables upload, kernels
+        rc = szb_batch_create(ctx, src, src_len, frame_off + c.f0, frame_len + c.f0, c.f1 - c.f0, &c.batch);
+        if (rc) {
+            fail = rc;
+            break;
+        }
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, c.up, 0));
+        rc = launch_entropy(c.batch, ctx->d_src);
+        if (!rc) rc = launch_execute(c.batch, ctx->d_src, ctx->d_dst + c.dst_lo, (size_t)(total - c.dst_lo));
+        if (rc) {
+            fail = rc;
+            break;
+        }
+        CUDA_TRY(ctx, cudaEventRecord(c.done, ctx->stream));
+        // output of this chunk: D2H on the other copy stream
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_d2h, c.done, 0));
+        if (c.dst_len) CUDA_TRY(ctx, cudaMemcpyAsync(dst + c.dst_lo, ctx->d_dst + c.dst_lo, (size_t)c.dst_len, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    }
+    cudaStreamSynchronize(ctx->s_h2d);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->s_d2h);
+    *first_rc = SZB_OK;
+    for (auto &c : chunks) {
+        if (c.batch && fail == SZB_OK) {
+            const uint32_t n = c.f1 - c.f0;
+            std::vector<int32_t> st(n);
+            std::vector<uint64_t> off(n), len(n);
+            cudaMemcpy(st.data(), c.batch->d_frame_status, 4 * (size_t)n, cudaMemcpyDeviceToHost);
+            cudaMemcpy(off.data(), c.batch->d_frame_out_off, 8 * (size_t)n, cudaMemcpyDeviceToHost);
+            cudaMemcpy(len.data(), c.batch->d_frame_out_len, 8 * (size_t)n, cudaMemcpyDeviceToHost);
+            for (uint32_t i = 0; i < n; i++) {
+                if (status) status[c.f0 + i] = st[i];
+                if (out_off) out_off[c.f0 + i] = c.dst_lo + off[i];
+                if (out_len) out_len[c.f0 + i] = st[i] == SZB_OK ? len[i] : 0;
+                if (*first_rc == SZB_OK && st[i] != SZB_OK) *first_rc = st[i];
+                // a frame whose header lied about its size would have shifted its neighbours
+                if (st[i] == SZB_OK && len[i] != fcs[c.f0 + i]) fail = SZB_ERR_CORRUPT_SIZES;
+            }
+        }
+        if (c.batch) szb_batch_destroy(c.batch);
+        if (c.up) cudaEventDestroy(c.up);
+        if (c.done) cudaEventDestroy(c.done);
+    }
+    cudaEventDestroy(ev_begin);
+    if (fail == SZB_ERR_CORRUPT_SIZES) return 1;  // redo on the plain path, which places frames by their decoded sizes
+    if (fail != SZB_OK) return fail;
+    (void)collect_timing(ctx);
+    ctx->timing[5] = ctx->timing[6] = 0;
+    return SZB_OK;
+}
+
 int szb_decode_batch(szb_ctx *ctx, const uint8_t *src, size_t src_len, const uint64_t *frame_off,
                      const uint64_t *frame_len, uint32_t nframes, uint8_t *dst, size_t dst_cap, uint64_t *out_off,
                      uint64_t *out_len, int32_t *status, uint32_t flags) {
     if (!ctx || (!src && src_len) || (!dst && dst_cap)) return SZB_ERR_INVALID_ARGUMENT;
     if (flags & SZB_FLAG_SRC_DEVICE) return SZB_ERR_INVALID_ARGUMENT;  // the header walk needs host bytes: use szb_decode_blocks
+    if (!(flags & SZB_FLAG_DST_DEVICE)) {
+        int first = SZB_OK;
+        int prc = decode_batch_pipelined(ctx, src, src_len, frame_off, frame_len, nframes, dst, dst_cap, out_off, out_len, status, &first);
+        if (prc == SZB_OK) return first;
+        if (prc != 1) return prc;
+    }
     szb_batch *b = nullptr;
     int rc = szb_batch_create(ctx, src, src_len, frame_off, frame_len, nframes, &b);
     if (rc) return rc;

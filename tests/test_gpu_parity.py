@@ -165,6 +165,18 @@ def test_config2_medium_hash_of_hashes(ctx):
     assert (cg.hash_frames(dst2, out_off, out_len) == c.raw_hash).all()
 
 
+def test_large_host_batch_takes_the_pipelined_path(ctx):
+    """> 192 MB of compressed frames with content sizes: szb_decode_batch overlaps H2D / kernels / D2H in
+    chunks of consecutive frames; the result must be indistinguishable from the plain path."""
+    c = cg.config2_text_frames(10000)
+    assert c.compressed_bytes > (192 << 20)
+    dst = np.empty(c.decompressed_bytes + 64, dtype=np.uint8)
+    out_off, out_len, status = ctx.decode_batch_into(c.src, c.frame_off, c.frame_len, dst)
+    assert not status.any() and (out_len == c.raw_size).all()
+    assert (out_off == np.cumsum(c.raw_size) - c.raw_size).all()  # frames back to back, in frame order
+    assert (cg.hash_frames(dst, out_off, out_len) == c.raw_hash).all()
+
+
 # ---- edge cases and error behaviour --------------------------------------------------------------------
 def test_empty_batch_and_empty_frames(ctx, corpus):
     assert ctx.decode_batch([]) == []
