@@ -162,12 +162,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # exactly ONE JSON line may reach stdout: libraries (NCCL prints its version on stdout) get stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         if rank != 0:
             return 0
         c = build_corpus(args, 0)
-        print(json.dumps(cpu_reference_arm(args, c, rank, world)), flush=True)
+        print(json.dumps(cpu_reference_arm(args, c, rank, world)), file=json_out, flush=True)
         return 0
 
     import torch
@@ -308,7 +312,7 @@ def main():
     }
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # rank 0 at N=1 only
         r = cpu_reference_arm(argparse.Namespace(**{**vars(args), "steps": 2, "warmup": 1}), c, 0, 1)
         cpu = r["cpu_baseline"]
 
@@ -324,7 +328,7 @@ def main():
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "verified": verified,
     }
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
