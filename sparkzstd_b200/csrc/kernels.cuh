@@ -730,7 +730,9 @@ __device__ __forceinline__ void decode_step(const uint32_t *sw, const uint16_t *
         const uint32_t ap = top - 7;
         const uint32_t mis = ap & 3;
         const uint32_t *wp = reinterpret_cast<const uint32_t *>(ring + ((ap - mis) & 63));
-        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+        // the third word only matters when the window start is not word aligned; when it is, that word may lie in
+        // the ring slot that is being refilled asynchronously, so it is not touched at all
+        const uint32_t w0 = wp[0], w1 = wp[1], w2 = mis ? wp[2] : 0u;
         uint32_t lo = __funnelshift_r(w0, w1, mis * 8), hi = __funnelshift_r(w1, w2, mis * 8);
         const uint32_t k = 7 - ((uint32_t)(L.pos - 1) & 7);
         hi = __funnelshift_l(lo, hi, k);
