@@ -71,7 +71,10 @@ func (c *Ctx) DecompressFrame(src []byte) ([]byte, int, error) {
 // DecodeBatch decodes independent frames in one launch sequence.  frames[i] = src[off[i]:off[i]+len[i]].
 // dst receives the frames back to back; the returned slices say where.  The library copies what it
 // needs before returning: no Go pointer is retained (cgo rule).
-func (c *Ctx) DecodeBatch(src []byte, off, length []uint64, dst []byte) (outOff, outLen []uint64, status []int32, err error) {
+// FlagVerifyChecksum asks the GPU to verify each frame's content checksum (the reference never does).
+const FlagVerifyChecksum = uint32(C.SZB_FLAG_VERIFY_CHECKSUM)
+
+func (c *Ctx) DecodeBatch(src []byte, off, length []uint64, dst []byte, flags uint32) (outOff, outLen []uint64, status []int32, err error) {
 	n := len(off)
 	if n == 0 {
 		return nil, nil, nil, nil
@@ -90,7 +93,7 @@ func (c *Ctx) DecodeBatch(src []byte, off, length []uint64, dst []byte) (outOff,
 		(*C.uint64_t)(unsafe.Pointer(&off[0])), (*C.uint64_t)(unsafe.Pointer(&length[0])), C.uint32_t(n),
 		dp, C.size_t(len(dst)),
 		(*C.uint64_t)(unsafe.Pointer(&outOff[0])), (*C.uint64_t)(unsafe.Pointer(&outLen[0])),
-		(*C.int32_t)(unsafe.Pointer(&status[0])), 0)
+		(*C.int32_t)(unsafe.Pointer(&status[0])), C.uint32_t(flags))
 	if rc == C.SZB_ERR_CUDA || rc == C.SZB_ERR_INVALID_ARGUMENT || rc == C.SZB_ERR_NOMEM {
 		return nil, nil, nil, Error(rc)
 	}

@@ -97,7 +97,7 @@ typedef struct szb_frame_desc {
     uint8_t single_segment; /* frame.go:101-103 */
     uint8_t has_checksum;   /* frame.go:106-108 */
     uint8_t has_content_size;
-    uint32_t _pad;
+    uint32_t checksum_valid; /* 1 when has_checksum and the 4 checksum bytes lay inside the frame's extent */
 } szb_frame_desc;
 
 typedef struct szb_block_desc {
@@ -162,7 +162,8 @@ const char *szb_ctx_last_error(szb_ctx *ctx); /* detail text of the last SZB_ERR
 
 #define SZB_FLAG_SRC_DEVICE 1u /* src is a device pointer (descriptor tables still come from a host copy) */
 #define SZB_FLAG_DST_DEVICE 2u /* dst is a device pointer; the output stays in HBM */
-#define SZB_FLAG_VERIFY_CHECKSUM 4u /* reserved for SURVEY 8f-1 (XXH64 verify); not a reference behaviour */
+#define SZB_FLAG_VERIFY_CHECKSUM 4u /* verify the content checksum (XXH64 low 32 bits) on the GPU; SURVEY 8f-1.
+                                       NOT a reference behaviour: the reference leaves those 4 bytes unread */
 
 /* The batch entry point north_star asks for: decode nframes independent frames in one
  * launch sequence.  src/dst are HOST buffers unless flagged.  Frames are written back to
@@ -202,6 +203,9 @@ int szb_batch_sizes(szb_batch *b, uint64_t *total, uint64_t *out_off, uint64_t *
 int szb_batch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t dst_cap);
 /* All four stages back to back, no host synchronisation in between. */
 int szb_batch_run(szb_batch *b, const void *d_src, void *d_dst, size_t dst_cap);
+/* After szb_batch_execute / szb_batch_run: recompute XXH64 of every frame that carries a content checksum and
+ * mark mismatches SZB_ERR_CHECKSUM_MISMATCH; asynchronous. */
+int szb_batch_verify_checksums(szb_batch *b, void *d_dst);
 /* Synchronises and returns per-frame status (nframes long, may be NULL); returns the first failure. */
 int szb_batch_finish(szb_batch *b, int32_t *status);
 /* Stage-level scratch, for parity tests against the oracle's per-block trace (host copies). */

@@ -26,7 +26,7 @@ class FrameDesc(C.Structure):
         ("single_segment", C.c_uint8),
         ("has_checksum", C.c_uint8),
         ("has_content_size", C.c_uint8),
-        ("_pad", C.c_uint32),
+        ("checksum_valid", C.c_uint32),
     ]
 
 
@@ -85,6 +85,7 @@ SYMBOLS = [
     ("szb_batch_sizes", C.c_int, [_P, C.POINTER(C.c_uint64), _P, _P]),
     ("szb_batch_execute", C.c_int, [_P, _P, _P, C.c_size_t]),
     ("szb_batch_run", C.c_int, [_P, _P, _P, C.c_size_t]),
+    ("szb_batch_verify_checksums", C.c_int, [_P, _P]),
     ("szb_batch_finish", C.c_int, [_P, _P]),
     ("szb_batch_read_literals", C.c_int, [_P, C.c_uint32, _P, C.c_size_t]),
     ("szb_batch_read_sequences", C.c_int, [_P, C.c_uint32, _P, _P, _P, C.c_size_t]),

@@ -570,6 +570,18 @@ int szb_batch_run(szb_batch *b, const void *d_src, void *d_dst, size_t dst_cap) 
     return launch_execute(b, d_src, d_dst, dst_cap);
 }
 
+int szb_batch_verify_checksums(szb_batch *b, void *d_dst) {
+    if (!b || !d_dst) return SZB_ERR_INVALID_ARGUMENT;
+    szb_ctx *ctx = b->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!b->nframes) return SZB_OK;
+    DeviceBatch a = make_args(b, nullptr, d_dst, 0);
+    k_verify_checksums<<<(a.nframes + 63) / 64, 64, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SZB_OK;
+}
+
 int szb_batch_finish(szb_batch *b, int32_t *status) {
     if (!b) return SZB_ERR_INVALID_ARGUMENT;
     szb_ctx *ctx = b->ctx;
@@ -675,6 +687,10 @@ static int decode_tables(szb_ctx *ctx, szb_batch *b, const uint8_t *src, size_t 
     }
     rc = launch_execute(b, d_src, d_dst, d_cap);
     if (rc) return rc;
+    if ((flags & SZB_FLAG_VERIFY_CHECKSUM) && total <= d_cap) {
+        rc = szb_batch_verify_checksums(b, d_dst);
+        if (rc) return rc;
+    }
     std::vector<int32_t> st(b->nframes ? b->nframes : 1, 0);
     int first = szb_batch_finish(b, st.data());
     if (first == SZB_ERR_CUDA) return first;
@@ -707,7 +723,7 @@ static int decode_tables(szb_ctx *ctx, szb_batch *b, const uint8_t *src, size_t 
 // size-then-decode path.  Returns 1 when it did not apply.
 static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_len, const uint64_t *frame_off,
                                   const uint64_t *frame_len, uint32_t nframes, uint8_t *dst, size_t dst_cap,
-                                  uint64_t *out_off, uint64_t *out_len, int32_t *status, int *first_rc) {
+                                  uint64_t *out_off, uint64_t *out_len, int32_t *status, int *first_rc, bool verify) {
     constexpr size_t kChunkBytes = 96u << 20;  // compressed bytes per chunk
     if (!frame_off || !frame_len || nframes < 64 || src_len < 2 * kChunkBytes) return 1;
     // sizes from the frame headers only (frame.go:49-61); any frame without one -> not applicable
@@ -794,6 +810,7 @@ static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_l
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, c.up, 0));
         rc = launch_entropy(c.batch, ctx->d_src);
         if (!rc) rc = launch_execute(c.batch, ctx->d_src, ctx->d_dst + c.dst_lo, (size_t)(total - c.dst_lo));
+        if (!rc && verify) rc = szb_batch_verify_checksums(c.batch, ctx->d_dst + c.dst_lo);
         if (rc) {
             fail = rc;
             break;
@@ -843,7 +860,8 @@ int szb_decode_batch(szb_ctx *ctx, const uint8_t *src, size_t src_len, const uin
     if (flags & SZB_FLAG_SRC_DEVICE) return SZB_ERR_INVALID_ARGUMENT;  // the header walk needs host bytes: use szb_decode_blocks
     if (!(flags & SZB_FLAG_DST_DEVICE)) {
         int first = SZB_OK;
-        int prc = decode_batch_pipelined(ctx, src, src_len, frame_off, frame_len, nframes, dst, dst_cap, out_off, out_len, status, &first);
+        int prc = decode_batch_pipelined(ctx, src, src_len, frame_off, frame_len, nframes, dst, dst_cap, out_off, out_len, status, &first,
+                                         (flags & SZB_FLAG_VERIFY_CHECKSUM) != 0);
         if (prc == SZB_OK) return first;
         if (prc != 1) return prc;
     }

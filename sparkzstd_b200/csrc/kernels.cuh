@@ -1431,4 +1431,89 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Content checksum (NOT a reference behaviour: the reference leaves the 4 bytes
+// unread, frame.go:105-108).  zstd stores the low 32 bits of XXH64(content, seed 0) after the last
+// block.  XXH64 is a chain of four independent accumulator lanes over 32-byte stripes, so a frame
+// offers no more than that; the batch offers one thread per frame.
+__device__ __forceinline__ uint64_t xxh_rotl(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ uint64_t xxh_round(uint64_t acc, uint64_t in) {
+    return xxh_rotl(acc + in * 0xC2B2AE3D27D4EB4FULL, 31) * 0x9E3779B185EBCA87ULL;
+}
+__device__ __forceinline__ uint64_t xxh_merge(uint64_t h, uint64_t v) {
+    return (h ^ xxh_round(0, v)) * 0x9E3779B185EBCA87ULL + 0x85EBCA77C2B2AE63ULL;
+}
+// unaligned little-endian reads assembled from aligned words (only words holding a content byte are touched
+// when n is what the caller needs)
+__device__ __forceinline__ uint64_t xxh_read64(const uint8_t *p) {
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(p - mis);
+    const uint32_t w0 = w[0], w1 = w[1], w2 = mis ? w[2] : 0u;
+    return (uint64_t)__funnelshift_r(w0, w1, mis * 8) | ((uint64_t)__funnelshift_r(w1, w2, mis * 8) << 32);
+}
+__device__ __forceinline__ uint32_t xxh_read32(const uint8_t *p) {
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(p - mis);
+    const uint32_t w0 = w[0], w1 = mis ? w[1] : 0u;
+    return __funnelshift_r(w0, w1, mis * 8);
+}
+__device__ uint64_t xxh64(const uint8_t *p, uint64_t len) {
+    const uint64_t P1 = 0x9E3779B185EBCA87ULL, P2 = 0xC2B2AE3D27D4EB4FULL, P3 = 0x165667B19E3779F9ULL,
+                   P4 = 0x85EBCA77C2B2AE63ULL, P5 = 0x27D4EB2F165667C5ULL;
+    const uint8_t *end = p + len;
+    uint64_t h;
+    if (len >= 32) {
+        uint64_t v1 = P1 + P2, v2 = P2, v3 = 0, v4 = 0 - P1;
+        const uint8_t *limit = end - 32;
+        do {
+            v1 = xxh_round(v1, xxh_read64(p));
+            v2 = xxh_round(v2, xxh_read64(p + 8));
+            v3 = xxh_round(v3, xxh_read64(p + 16));
+            v4 = xxh_round(v4, xxh_read64(p + 24));
+            p += 32;
+        } while (p <= limit);
+        h = xxh_rotl(v1, 1) + xxh_rotl(v2, 7) + xxh_rotl(v3, 12) + xxh_rotl(v4, 18);
+        h = xxh_merge(h, v1);
+        h = xxh_merge(h, v2);
+        h = xxh_merge(h, v3);
+        h = xxh_merge(h, v4);
+    } else {
+        h = P5;
+    }
+    h += len;
+    while (p + 8 <= end) {
+        h ^= xxh_round(0, xxh_read64(p));
+        h = xxh_rotl(h, 27) * P1 + P4;
+        p += 8;
+    }
+    if (p + 4 <= end) {
+        h ^= (uint64_t)xxh_read32(p) * P1;
+        h = xxh_rotl(h, 23) * P2 + P3;
+        p += 4;
+    }
+    while (p < end) {
+        h ^= (uint64_t)(*p) * P5;
+        h = xxh_rotl(h, 11) * P1;
+        p++;
+    }
+    h ^= h >> 33;
+    h *= P2;
+    h ^= h >> 29;
+    h *= P3;
+    h ^= h >> 32;
+    return h;
+}
+
+__global__ void k_verify_checksums(DeviceBatch a) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.nframes) return;
+    const szb_frame_desc *fr = a.frames + f;
+    if (!fr->checksum_valid || a.frame_status[f] != SZB_OK) return;  // no checksum, or its 4 bytes lay outside the caller's extent
+    const uint64_t h = xxh64(a.dst + a.frame_out_off[f], a.frame_out_len[f]);
+    if ((uint32_t)h != fr->checksum) {
+        a.frame_status[f] = SZB_ERR_CHECKSUM_MISMATCH;
+        a.frame_out_len[f] = 0;
+    }
+}
+
 }  // namespace szb

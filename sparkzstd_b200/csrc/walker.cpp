@@ -212,6 +212,7 @@ void walk_frame(szb_walk &w, const uint8_t *src, uint64_t off, uint64_t len, uin
         if (f.has_checksum && c.need(4)) {
             f.checksum = (uint32_t)c.p[c.pos] | ((uint32_t)c.p[c.pos + 1] << 8) | ((uint32_t)c.p[c.pos + 2] << 16) |
                          ((uint32_t)c.p[c.pos + 3] << 24);
+            f.checksum_valid = 1;
         }
     } while (false);
 

@@ -108,8 +108,11 @@ class Context:
         raise error_for(rc, self.last_error() if rc == -65 else "")
 
     # -- the batch entry point (szb_decode_batch) --
-    def decode_batch_into(self, src: np.ndarray, frame_off: np.ndarray, frame_len: np.ndarray, dst: np.ndarray):
-        """src/dst: uint8 numpy arrays (host; pinned is better).  Returns (out_off, out_len, status)."""
+    def decode_batch_into(self, src: np.ndarray, frame_off: np.ndarray, frame_len: np.ndarray, dst: np.ndarray,
+                          verify_checksum: bool = False):
+        """src/dst: uint8 numpy arrays (host; pinned is better).  Returns (out_off, out_len, status).
+        verify_checksum: also check each frame's content checksum on the GPU (status -68 on mismatch);
+        the reference never does (it leaves the 4 bytes unread)."""
         n = len(frame_off)
         fo = np.ascontiguousarray(frame_off, dtype=np.uint64)
         fl = np.ascontiguousarray(frame_len, dtype=np.uint64)
@@ -118,7 +121,7 @@ class Context:
         status = np.zeros(n, dtype=np.int32)
         rc = self._L.szb_decode_batch(
             self._h, src.ctypes.data, src.nbytes, fo.ctypes.data, fl.ctypes.data, n, dst.ctypes.data, dst.nbytes,
-            out_off.ctypes.data, out_len.ctypes.data, status.ctypes.data, 0,
+            out_off.ctypes.data, out_len.ctypes.data, status.ctypes.data, 4 if verify_checksum else 0,
         )
         if rc in (-65, -66, -34):
             self._raise(rc)
@@ -272,7 +275,10 @@ class Batch:
         """Copies src to a torch CUDA tensor (device memory plumbing) and returns its device pointer."""
         import torch
 
-        t = torch.from_numpy(np.ascontiguousarray(src)).to(f"cuda:{self.ctx.device}")
+        host = np.ascontiguousarray(src)
+        if not host.flags.writeable:
+            host = host.copy()
+        t = torch.from_numpy(host).to(f"cuda:{self.ctx.device}")
         pad = torch.zeros(16, dtype=torch.uint8, device=t.device)
         t = torch.cat([t, pad])
         torch.cuda.synchronize(t.device)
@@ -300,6 +306,11 @@ class Batch:
 
     def run(self, d_src: int, d_dst: int, cap: int):
         rc = self._L.szb_batch_run(self._h, C.c_void_p(d_src), C.c_void_p(d_dst), cap)
+        if rc != 0:
+            self.ctx._raise(rc)
+
+    def verify_checksums(self, d_dst: int):
+        rc = self._L.szb_batch_verify_checksums(self._h, C.c_void_p(d_dst))
         if rc != 0:
             self.ctx._raise(rc)
 

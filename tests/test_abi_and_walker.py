@@ -150,3 +150,53 @@ def test_synthetic_corpora_have_the_expected_shapes():
     _, tr = pyszo.decode_frame(c3.frame(0), want_trace=True)
     assert not tr.has_fcs and not tr.single_segment and tr.window_size == 1 << 20
     assert sum(1 for b in tr.blocks if b.type == 2 and b.lit_type == 3) >= len(tr.blocks) // 2
+
+
+def _xxh64(data: bytes) -> int:
+    M = (1 << 64) - 1
+    P1, P2, P3, P4, P5 = 0x9E3779B185EBCA87, 0xC2B2AE3D27D4EB4F, 0x165667B19E3779F9, 0x85EBCA77C2B2AE63, 0x27D4EB2F165667C5
+    rotl = lambda x, r: ((x << r) | (x >> (64 - r))) & M
+    rnd = lambda acc, v: (rotl((acc + v * P2) & M, 31) * P1) & M
+    n, p = len(data), 0
+    if n >= 32:
+        v = [(P1 + P2) & M, P2, 0, (-P1) & M]
+        while p + 32 <= n:
+            for i in range(4):
+                v[i] = rnd(v[i], int.from_bytes(data[p + 8 * i : p + 8 * i + 8], "little"))
+            p += 32
+        h = (rotl(v[0], 1) + rotl(v[1], 7) + rotl(v[2], 12) + rotl(v[3], 18)) & M
+        for x in v:
+            h = ((h ^ rnd(0, x)) * P1 + P4) & M
+    else:
+        h = P5
+    h = (h + n) & M
+    while p + 8 <= n:
+        h = (rotl(h ^ rnd(0, int.from_bytes(data[p : p + 8], "little")), 27) * P1 + P4) & M
+        p += 8
+    if p + 4 <= n:
+        h = (rotl(h ^ (int.from_bytes(data[p : p + 4], "little") * P1 & M), 23) * P2 + P3) & M
+        p += 4
+    while p < n:
+        h = (rotl(h ^ (data[p] * P5 & M), 11) * P1) & M
+        p += 1
+    h ^= h >> 33
+    h = (h * P2) & M
+    h ^= h >> 29
+    h = (h * P3) & M
+    h ^= h >> 32
+    return h
+
+
+def test_walker_reports_the_content_checksum(corpus):
+    """The 4 bytes after the last block are XXH64(content) & 0xFFFFFFFF (zstd format); the walker hands
+    them to the optional GPU verification (the reference never reads them)."""
+    assert _xxh64(b"") == 0xEF46DB3751D8E999
+    checked = 0
+    for name, data, size, _ in corpus:
+        if size > 20000:
+            continue
+        fr, _ = _walk(data)
+        assert fr.checksum_valid == 1
+        assert fr.checksum == _xxh64(pyszo.decode_frame(data)) & 0xFFFFFFFF, name
+        checked += 1
+    assert checked > 40

@@ -237,6 +237,44 @@ def test_corrupted_payloads_never_crash_and_agree_when_valid(ctx, corpus):
     assert agree >= 0
 
 
+def test_content_checksums_verify_on_the_gpu(ctx, corpus):
+    """every decodecorpus frame carries a content checksum the reference never reads; the
+    engine can verify it (XXH64 low 32 bits) and must flag a frame whose checksum bytes were tampered with."""
+    frames = [d for _, d, _, _ in corpus]
+    bad_idx = 5
+    tampered = bytearray(frames[bad_idx])
+    tampered[-1] ^= 0x40
+    frames[bad_idx] = bytes(tampered)
+    src, offs, lens = _batch_arrays(frames)
+    dst = np.empty(sum(s for _, _, s, _ in corpus) + 64, dtype=np.uint8)
+    out_off, out_len, status = ctx.decode_batch_into(src, offs, lens, dst, verify_checksum=True)
+    assert status[bad_idx] == -68 and int(out_len[bad_idx]) == 0
+    assert not np.delete(status, bad_idx).any()
+    # without the flag the same tampered frame decodes fine, like in the reference
+    _, _, status2 = ctx.decode_batch_into(src, offs, lens, dst)
+    assert not status2.any()
+    # and the synthetic frames with checksums
+    c = cg.config2_text_frames(8, checksum=1)
+    d2 = np.empty(c.decompressed_bytes + 64, dtype=np.uint8)
+    _, _, st3 = ctx.decode_batch_into(c.src, c.frame_off, c.frame_len, d2, verify_checksum=True)
+    assert not st3.any()
+
+
+def test_cli_compares_with_originals(ctx, corpus, tmp_path):
+    """cmd/sparkzstd equivalent: decode X.zst, compare with X (main.go:46-111)."""
+    from sparkzstd_b200 import cli
+
+    paths = []
+    for name, data, size, _ in corpus[10:14]:
+        p = tmp_path / name
+        p.write_bytes(data)
+        (tmp_path / name[:-4]).write_bytes(pyszo.decode_frame(data))
+        paths.append(str(p))
+    assert cli.main(paths + ["--verify-checksum"]) == 0
+    (tmp_path / corpus[10][0][:-4]).write_bytes(b"not the original")
+    assert cli.main(paths) == 1
+
+
 def test_descriptor_level_entry(ctx, corpus):
     """szb_decode_blocks: host-built descriptor tables + device pointers (what the Go walker feeds)."""
     import ctypes as C
