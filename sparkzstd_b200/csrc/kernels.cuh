@@ -632,22 +632,6 @@ __global__ void __launch_bounds__(kCtaThreads) k_build_seq_tables(DeviceBatch a)
     }
 }
 
-// n (<= 32) bits ending at bit position pos of a backward stream, i.e. bits [pos-n, pos) of the
-// little-endian integer; zero below bit 0 (reversebitstream.go:23-27,67-75).  Byte loads: used at
-// stream start / end and on the rare wide sequence.
-__device__ __forceinline__ uint32_t slow_read_bits(const uint8_t *sp, int64_t pos, uint32_t n) {
-    if (n == 0 || pos <= 0) return 0;
-    const int64_t lo = pos - (int64_t)n;
-    const int64_t l = lo < 0 ? 0 : lo;
-    const int64_t first = l >> 3, last = (pos - 1) >> 3;
-    uint64_t acc = 0;
-    for (int64_t bb = first; bb <= last; bb++) acc |= (uint64_t)sp[bb] << (8 * (bb - first));
-    acc >>= (l & 7);
-    acc &= (1ull << (uint32_t)(pos - l)) - 1;
-    if (lo < 0) acc <<= (uint32_t)(-lo);
-    return (uint32_t)acc;
-}
-
 // Stage 3: DecodeSequences (sequences.go:126-206).  One LANE per block: a warp decodes
 // kSeqLanes blocks in lock step, each lane walking its own backward bitstream with its own three
 // FSE states, the tables of all its blocks resident in shared memory.  A warp instruction thus
@@ -660,17 +644,30 @@ __device__ __forceinline__ uint32_t slow_read_bits(const uint8_t *sp, int64_t po
 // come from a 64-entry table shared by the warp.
 //
 // Bit reads (replacing Reversebitstream.Read, reversebitstream.go:17-88): every lane keeps the
-// 64 stream bytes around its read position in a 4 x 16-byte shared-memory ring that is topped up
-// with one 16-byte global load per chunk, issued two chunks ahead of use.  Per sequence a lane
-// builds one 64-bit window ending at its bit position from three ring words and peels the six
-// fields off its top in the reference's order: OF extra, ML extra, LL extra, then (except after
-// the last sequence) LL state, ML state, OF state.  Decoded triples are buffered four deep in
-// registers and leave as 16-byte stores.
+// 128 stream bytes around its read position in an 8 x 16-byte shared-memory ring, topped up with
+// 16-byte cp.async copies once per group of four sequences, two groups ahead of use.  Per sequence
+// a lane builds one 64-bit window ending at its bit position from three ring words and peels the
+// six fields off its top in the reference's order: OF extra, ML extra, LL extra, then (except after
+// the last sequence) LL state, ML state, OF state.
+//
+// The four sequences of a group are decoded speculatively on that branch-free path; a sequence
+// wider than the window, a read below the start of the stream or a ring that is not far enough ahead
+// only sets a flag, and a flagged group is decoded again from its saved state with byte reads
+// (slow_step).  Decoded triples leave as 16-byte stores, one group at a time.
 constexpr uint32_t kSeqTabBytes = kSeqLanes * kTabSlotWords * 2;  // u16 cells
-constexpr uint32_t kSeqRingStride = 80;                           // per lane: 64 B ring + a mirror of its first 16 B
+constexpr uint32_t kSeqRingBytes = 128;
+constexpr uint32_t kSeqRingStride = kSeqRingBytes + 16;           // per lane: the ring + a mirror of its first 16 B
 constexpr uint32_t kSeqRingOff = kSeqTabBytes;                    // byte offset of the rings
 constexpr uint32_t kSeqLutWord = (kSeqRingOff + kSeqLanes * kSeqRingStride) / 4;  // ll[64] | ml[64]: base | extra << 24
 constexpr uint32_t kSeqDecodeSmemBytes = (kSeqLutWord + 128) * 4;
+// A group of four window reads consumes at most 4 x 57 bits = 28.5 bytes and a window reaches 10
+// bytes below the byte of its top bit: a group touches nothing below (top - kSeqGroupReach).
+// The top-up of group g requests every chunk down to the one holding (top - kSeqRingAhead); what it
+// requests is only waited for at group g+1 (wait_group 1), i.e. it is there for group g+1, whose top
+// is at most 28.5 bytes lower: kSeqRingAhead >= 28.5 + kSeqGroupReach.  The ring then spans at most
+// chunk(top - 72) .. chunk(top + 4), 7 of its 8 slots, so no copy lands in a slot still being read.
+constexpr int32_t kSeqGroupReach = 39;
+constexpr int32_t kSeqRingAhead = 72;
 
 __device__ __forceinline__ uint32_t bfind(uint32_t x) {  // index of the highest set bit (x != 0)
     uint32_t r;
@@ -681,26 +678,31 @@ __device__ __forceinline__ uint32_t bfind(uint32_t x) {  // index of the highest
 struct SeqLane {
     uint32_t s_ll, s_of, s_ml;  // FSE states
     int32_t pos;                // stream bits not consumed yet
-    int32_t cur;                // ring: chunk (16 B, counted from the chunk holding sp[0]) of the byte with bit pos-1
 };
 
-// Chunk c of the stream goes to ring slot c & 3 (slot 0 also to a mirror above slot 3), so a 12-byte
-// window read never wraps.  Asynchronous (cp.async): no register, no scoreboard slot is held while it flies.
-// Completion is tracked per warp in commit groups; decode_step commits one group per sequence.
-__device__ __forceinline__ void ring_fetch(uint32_t ring_saddr, const uint4 *chunk0, int32_t c) {
-    if (c >= 0) {
-        const uint32_t slot = (uint32_t)c & 3;
-        const uint32_t s = ring_saddr + (slot << 4);
-        cp_async16(s, chunk0 + c);
-        if (slot == 0) cp_async16(s + 64, chunk0 + c);  // a window read starts below byte 64 and is 12 bytes long: only slot 0 is mirrored
+// Requests the chunks (16 B, counted from the aligned chunk holding sp[0]) below `lowreq` down to
+// the one holding byte (top - kSeqRingAhead).  Chunk c goes to ring slot c & 7, slot 0 also to the
+// mirror above slot 7 so that a 12-byte window read never wraps.  cp.async: no register and no
+// scoreboard slot is held while the copy flies; the caller commits and waits.
+__device__ __forceinline__ void ring_topup(uint32_t ring_saddr, const uint4 *chunk0, int32_t top, int32_t &lowreq) {
+    int32_t need = (top - kSeqRingAhead) >> 4;
+    need = need < 0 ? 0 : need;
+    while (lowreq > need) {
+        lowreq--;
+        const uint32_t slot = (uint32_t)lowreq & 7;
+        cp_async16(ring_saddr + (slot << 4), chunk0 + lowreq);
+        if (slot == 0) cp_async16(ring_saddr + kSeqRingBytes, chunk0 + lowreq);
     }
 }
 
+// One sequence on the window path.  `bad` goes negative when the result must not be used: more than
+// 57 bits wanted, or more than the stream still holds (the zero fill of reversebitstream.go:67-75
+// is left to slow_step).  Everything it touches stays in bounds whatever the bits are: ring offsets
+// are masked and an n-bit field cannot push a state out of its table.
 template <bool kUpdate>
-__device__ __forceinline__ void decode_step(const uint32_t *sw, const uint16_t *tll, const uint16_t *tml, const uint16_t *tof,
-                                            const uint8_t *ring, uint32_t ring_saddr, const uint8_t *sp, const uint4 *chunk0,
-                                            uint32_t sp_mis, uint32_t al_ll, uint32_t al_ml, uint32_t al_of, SeqLane &L,
-                                            uint32_t &v_ll, uint32_t &v_ml, uint32_t &v_of) {
+__device__ __forceinline__ void fast_step(const uint32_t *sw, const uint16_t *tll, const uint16_t *tml, const uint16_t *tof,
+                                          const uint8_t *ring, int32_t sp_mis, uint32_t al_ll, uint32_t al_ml, uint32_t al_of,
+                                          SeqLane &L, int32_t &bad, uint32_t &v_ll, uint32_t &v_ml, uint32_t &v_of) {
     const uint32_t c_of = tof[L.s_of], c_ll = tll[L.s_ll], c_ml = tml[L.s_ml];  // peek OF, LL, ML (sequences.go:67-78)
     const uint32_t ofc = c_of & 63;
     const uint32_t u_ll = sw[kSeqLutWord + (c_ll & 63)], u_ml = sw[kSeqLutWord + 64 + (c_ml & 63)];
@@ -712,65 +714,84 @@ __device__ __forceinline__ void decode_step(const uint32_t *sw, const uint16_t *
         nbo = al_of - bfind(c_of >> 6);
     }
     const uint32_t total = ofc + mlx + llx + nbl + nbm + nbo;
-    // position of the byte that holds bit pos-1, relative to chunk 0
-    const uint32_t top = sp_mis + ((uint32_t)(L.pos - 1) >> 3);
-    // Keep the ring ahead of the read position.  On entering chunk cur the window needs cur and cur-1;
-    // cur-1 was requested two crossings ago (as "cur-3" of that moment).  A lane crosses at most every other sequence and every
-    // sequence commits one group, so that request is at least 4 groups old: wait_group 3 covers it
-    // while the younger requests (cur-2, and cur-3 issued now into the slot cur+1 vacated) keep flying.
-    if ((int32_t)(top >> 4) < L.cur && L.pos > 0) {
-        L.cur = (int32_t)(top >> 4);
-        asm volatile("cp.async.wait_group 3;" ::: "memory");
-        ring_fetch(ring_saddr, chunk0, L.cur - 3);
-    }
-    asm volatile("cp.async.commit_group;");
+    // window: the 8 bytes ending at the byte that holds bit pos-1 (byte `top`, counted from chunk 0),
+    // that bit moved to bit 63
+    const int32_t top = sp_mis + ((L.pos - 1) >> 3);
+    const uint32_t ap = (uint32_t)(top - 7);
+    const uint32_t mis = ap & 3;
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(ring + ((ap - mis) & (kSeqRingBytes - 1)));
+    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+    uint32_t lo = __funnelshift_r(w0, w1, mis * 8), hi = __funnelshift_r(w1, w2, mis * 8);
+    const uint32_t k = 7 - ((uint32_t)(L.pos - 1) & 7);
+    hi = __funnelshift_l(lo, hi, k);
+    lo <<= k;
     uint32_t x_of, x_ml, x_ll, b_ll = 0, b_ml = 0, b_of = 0;
-    if (L.pos >= 96 && total <= 57) {
-        // window: the 8 bytes ending at byte `top`, bit pos-1 moved to bit 63
-        const uint32_t ap = top - 7;
-        const uint32_t mis = ap & 3;
-        const uint32_t *wp = reinterpret_cast<const uint32_t *>(ring + ((ap - mis) & 63));
-        // the third word only matters when the window start is not word aligned; when it is, that word may lie in
-        // the ring slot that is being refilled asynchronously, so it is not touched at all
-        const uint32_t w0 = wp[0], w1 = wp[1], w2 = mis ? wp[2] : 0u;
-        uint32_t lo = __funnelshift_r(w0, w1, mis * 8), hi = __funnelshift_r(w1, w2, mis * 8);
-        const uint32_t k = 7 - ((uint32_t)(L.pos - 1) & 7);
-        hi = __funnelshift_l(lo, hi, k);
-        lo <<= k;
 #define SZB_TAKE(dst, n)                \
     dst = __funnelshift_l(hi, 0u, (n)); \
     hi = __funnelshift_l(lo, hi, (n));  \
     lo <<= (n);
-        SZB_TAKE(x_of, ofc)
-        SZB_TAKE(x_ml, mlx)
-        SZB_TAKE(x_ll, llx)
-        if (kUpdate) {
-            SZB_TAKE(b_ll, nbl)
-            SZB_TAKE(b_ml, nbm)
-            SZB_TAKE(b_of, nbo)
-        }
-#undef SZB_TAKE
-        L.pos -= (int32_t)total;
-    } else {  // near the stream start, or a sequence wider than one window
-        x_of = slow_read_bits(sp, L.pos, ofc);
-        L.pos -= (int32_t)ofc;
-        x_ml = slow_read_bits(sp, L.pos, mlx);
-        L.pos -= (int32_t)mlx;
-        x_ll = slow_read_bits(sp, L.pos, llx);
-        L.pos -= (int32_t)llx;
-        if (kUpdate) {
-            b_ll = slow_read_bits(sp, L.pos, nbl);
-            L.pos -= (int32_t)nbl;
-            b_ml = slow_read_bits(sp, L.pos, nbm);
-            L.pos -= (int32_t)nbm;
-            b_of = slow_read_bits(sp, L.pos, nbo);
-            L.pos -= (int32_t)nbo;
-        }
+    SZB_TAKE(x_of, ofc)
+    SZB_TAKE(x_ml, mlx)
+    SZB_TAKE(x_ll, llx)
+    if (kUpdate) {
+        SZB_TAKE(b_ll, nbl)
+        SZB_TAKE(b_ml, nbm)
+        SZB_TAKE(b_of, nbo)
     }
+#undef SZB_TAKE
+    L.pos -= (int32_t)total;
+    bad |= (57 - (int32_t)total) | L.pos;
     v_of = (1u << ofc) + x_of;              // sequences.go:99-104
     v_ml = (u_ml & 0xFFFFFF) + x_ml;        // sequences.go:106-112
     v_ll = (u_ll & 0xFFFFFF) + x_ll;        // sequences.go:114-120
     if (kUpdate) {  // update LL, ML, OF (sequences.go:178-194); Baseline = (next << nb) - 2^AL (fse.go:213)
+        L.s_ll = ((c_ll >> 6) << nbl) - (1u << al_ll) + b_ll;
+        L.s_ml = ((c_ml >> 6) << nbm) - (1u << al_ml) + b_ml;
+        L.s_of = ((c_of >> 6) << nbo) - (1u << al_of) + b_of;
+    }
+}
+
+// n (<= 32) bits ending at bit position pos of a backward stream, i.e. bits [pos-n, pos) of the
+// little-endian integer; zero below bit 0 (reversebitstream.go:23-27,67-75).  Byte loads.
+__device__ __noinline__ uint32_t slow_read_bits(const uint8_t *sp, int32_t pos, uint32_t n) {
+    if (n == 0 || pos <= 0) return 0;
+    const int32_t lo = pos - (int32_t)n;
+    const int32_t l = lo < 0 ? 0 : lo;
+    const int32_t first = l >> 3, last = (pos - 1) >> 3;
+    uint64_t acc = 0;
+    for (int32_t bb = first; bb <= last; bb++) acc |= (uint64_t)sp[bb] << (8 * (bb - first));
+    acc >>= (l & 7);
+    acc &= (1ull << (uint32_t)(pos - l)) - 1;
+    if (lo < 0) acc <<= (uint32_t)(-lo);
+    return (uint32_t)acc;
+}
+
+// The same sequence with one byte-wise read per field: any width, any position.  Rare.
+template <bool kUpdate>
+__device__ __noinline__ void slow_step(const uint32_t *sw, const uint16_t *tll, const uint16_t *tml, const uint16_t *tof,
+                                       const uint8_t *sp, uint32_t al_ll, uint32_t al_ml, uint32_t al_of, SeqLane &L,
+                                       uint32_t &v_ll, uint32_t &v_ml, uint32_t &v_of) {
+    const uint32_t c_of = tof[L.s_of], c_ll = tll[L.s_ll], c_ml = tml[L.s_ml];
+    const uint32_t ofc = c_of & 63;
+    const uint32_t u_ll = sw[kSeqLutWord + (c_ll & 63)], u_ml = sw[kSeqLutWord + 64 + (c_ml & 63)];
+    const uint32_t llx = u_ll >> 24, mlx = u_ml >> 24;
+    const uint32_t x_of = slow_read_bits(sp, L.pos, ofc);
+    L.pos -= (int32_t)ofc;
+    const uint32_t x_ml = slow_read_bits(sp, L.pos, mlx);
+    L.pos -= (int32_t)mlx;
+    const uint32_t x_ll = slow_read_bits(sp, L.pos, llx);
+    L.pos -= (int32_t)llx;
+    v_of = (1u << ofc) + x_of;
+    v_ml = (u_ml & 0xFFFFFF) + x_ml;
+    v_ll = (u_ll & 0xFFFFFF) + x_ll;
+    if (kUpdate) {
+        const uint32_t nbl = al_ll - bfind(c_ll >> 6), nbm = al_ml - bfind(c_ml >> 6), nbo = al_of - bfind(c_of >> 6);
+        const uint32_t b_ll = slow_read_bits(sp, L.pos, nbl);
+        L.pos -= (int32_t)nbl;
+        const uint32_t b_ml = slow_read_bits(sp, L.pos, nbm);
+        L.pos -= (int32_t)nbm;
+        const uint32_t b_of = slow_read_bits(sp, L.pos, nbo);
+        L.pos -= (int32_t)nbo;
         L.s_ll = ((c_ll >> 6) << nbl) - (1u << al_ll) + b_ll;
         L.s_ml = ((c_ml >> 6) << nbm) - (1u << al_ml) + b_ml;
         L.s_of = ((c_of >> 6) << nbo) - (1u << al_of) + b_of;
@@ -826,18 +847,14 @@ __global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
     L.s_ml = slow_read_bits(sp, L.pos, al_ml);
     L.pos -= (int32_t)al_ml;
 
-    // ring of 16-byte chunks; chunk c covers bytes [16c, 16c+16) counted from the aligned address at or below sp
     const uint8_t *ring = reinterpret_cast<const uint8_t *>(sw) + kSeqRingOff + lane * kSeqRingStride;
     const uint32_t ring_saddr = (uint32_t)__cvta_generic_to_shared(ring);
-    const uint32_t sp_mis = (uint32_t)(reinterpret_cast<uintptr_t>(sp) & 15);
+    const int32_t sp_mis = (int32_t)(reinterpret_cast<uintptr_t>(sp) & 15);
     const uint4 *chunk0 = reinterpret_cast<const uint4 *>(sp - sp_mis);
-    L.cur = (int32_t)((sp_mis + ((uint32_t)(L.pos > 0 ? L.pos - 1 : 0) >> 3)) >> 4);
-    ring_fetch(ring_saddr, chunk0, L.cur);
-    ring_fetch(ring_saddr, chunk0, L.cur - 1);
-    ring_fetch(ring_saddr, chunk0, L.cur - 2);
-    ring_fetch(ring_saddr, chunk0, L.cur - 3);  // steady state: cur .. cur-2 resident or landing, cur-3 requested on entry
+    // lowest chunk requested so far; everything from the chunk of the last stream byte down is wanted
+    int32_t lowreq = ((sp_mis + (int32_t)len - 1) >> 4) + 1;
+    ring_topup(ring_saddr, chunk0, sp_mis + ((L.pos - 1) >> 3), lowreq);
     asm volatile("cp.async.commit_group;");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
 
     const uint32_t nseq = d.nseq;
     uint32_t *gll = a.seq_ll + d.seq_buf_off, *gml = a.seq_ml + d.seq_buf_off, *gof = a.seq_of + d.seq_buf_off;
@@ -845,28 +862,67 @@ __global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
     const uint32_t n_upd = nseq - 1;  // every sequence but the last updates the states (sequences.go:178)
     uint32_t i = 0;
     for (; i + 4 <= n_upd; i += 4) {
+        // what was requested before this top-up has landed once wait_group 1 returns
+        const int32_t landed = lowreq ? (lowreq << 4) : -64;
+        const int32_t top = sp_mis + ((L.pos - 1) >> 3);
+        ring_topup(ring_saddr, chunk0, top, lowreq);
+        asm volatile("cp.async.commit_group;");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        const SeqLane S = L;
+        int32_t bad = top - kSeqGroupReach - landed;
         uint32_t v_ll[4], v_ml[4], v_of[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-            decode_step<true>(sw, tll, tml, tof, ring, ring_saddr, sp, chunk0, sp_mis, al_ll, al_ml, al_of, L, v_ll[j], v_ml[j], v_of[j]);
+        for (int j = 0; j < 4; j++) fast_step<true>(sw, tll, tml, tof, ring, sp_mis, al_ll, al_ml, al_of, L, bad, v_ll[j], v_ml[j], v_of[j]);
+        if (bad < 0) {  // T and o are what the out-of-line call sees: L and the v arrays stay in registers
+            SeqLane T = S;
+            uint32_t o[12];
+            for (int j = 0; j < 4; j++) slow_step<true>(sw, tll, tml, tof, sp, al_ll, al_ml, al_of, T, o[j], o[4 + j], o[8 + j]);
+            L = T;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                v_ll[j] = o[j];
+                v_ml[j] = o[4 + j];
+                v_of[j] = o[8 + j];
+            }
+        }
         // seq_buf_off is a multiple of 32 entries: 16-byte aligned stores
         *reinterpret_cast<uint4 *>(gll + i) = make_uint4(v_ll[0], v_ll[1], v_ll[2], v_ll[3]);
         *reinterpret_cast<uint4 *>(gml + i) = make_uint4(v_ml[0], v_ml[1], v_ml[2], v_ml[3]);
         *reinterpret_cast<uint4 *>(gof + i) = make_uint4(v_of[0], v_of[1], v_of[2], v_of[3]);
         ml_sum += (uint64_t)v_ml[0] + v_ml[1] + v_ml[2] + v_ml[3];
     }
-    for (; i < nseq; i++) {
-        uint32_t v_ll, v_ml, v_of;
-        if (i < n_upd)
-            decode_step<true>(sw, tll, tml, tof, ring, ring_saddr, sp, chunk0, sp_mis, al_ll, al_ml, al_of, L, v_ll, v_ml, v_of);
-        else
-            decode_step<false>(sw, tll, tml, tof, ring, ring_saddr, sp, chunk0, sp_mis, al_ll, al_ml, al_of, L, v_ll, v_ml, v_of);
-        gll[i] = v_ll;
-        gml[i] = v_ml;
-        gof[i] = v_of;
-        ml_sum += v_ml;
+    {   // the last (at most four) sequences one at a time; the ring is made to cover them all at once
+        const int32_t top = sp_mis + ((L.pos - 1) >> 3);
+        ring_topup(ring_saddr, chunk0, top, lowreq);
+        asm volatile("cp.async.commit_group;");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const int32_t landed = lowreq ? (lowreq << 4) : -64;
+        for (; i < nseq; i++) {
+            uint32_t v_ll, v_ml, v_of;
+            const SeqLane S = L;
+            int32_t bad = sp_mis + ((L.pos - 1) >> 3) - 10 - landed;
+            if (i < n_upd)
+                fast_step<true>(sw, tll, tml, tof, ring, sp_mis, al_ll, al_ml, al_of, L, bad, v_ll, v_ml, v_of);
+            else
+                fast_step<false>(sw, tll, tml, tof, ring, sp_mis, al_ll, al_ml, al_of, L, bad, v_ll, v_ml, v_of);
+            if (bad < 0) {
+                SeqLane T = S;
+                uint32_t o[3];
+                if (i < n_upd)
+                    slow_step<true>(sw, tll, tml, tof, sp, al_ll, al_ml, al_of, T, o[0], o[1], o[2]);
+                else
+                    slow_step<false>(sw, tll, tml, tof, sp, al_ll, al_ml, al_of, T, o[0], o[1], o[2]);
+                L = T;
+                v_ll = o[0];
+                v_ml = o[1];
+                v_of = o[2];
+            }
+            gll[i] = v_ll;
+            gml[i] = v_ml;
+            gof[i] = v_of;
+            ml_sum += v_ml;
+        }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
     // the stream must be consumed exactly (sequences.go:197-204)
     a.seq_status[b] = L.pos == 0 ? SZB_OK : SZB_ERR_NOT_ALL_BITS_USED;
     a.out_size[b] = (uint64_t)d.lit_regen + ml_sum;
