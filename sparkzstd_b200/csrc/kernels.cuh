@@ -662,12 +662,12 @@ constexpr uint32_t kSeqLutWord = (kSeqRingOff + kSeqLanes * kSeqRingStride) / 4;
 constexpr uint32_t kSeqDecodeSmemBytes = (kSeqLutWord + 128) * 4;
 // A group of four window reads consumes at most 4 x 57 bits = 28.5 bytes and a window reaches 10
 // bytes below the byte of its top bit: a group touches nothing below (top - kSeqGroupReach).
-// The top-up of group g requests every chunk down to the one holding (top - kSeqRingAhead); what it
-// requests is only waited for at group g+1 (wait_group 1), i.e. it is there for group g+1, whose top
-// is at most 28.5 bytes lower: kSeqRingAhead >= 28.5 + kSeqGroupReach.  The ring then spans at most
-// chunk(top - 72) .. chunk(top + 4), 7 of its 8 slots, so no copy lands in a slot still being read.
+// The top-up of group g requests chunks down to the one holding (top - kSeqRingAhead); what it
+// requests is only waited for at group g+2 (wait_group 2), whose top is at most 57 bytes lower:
+// kSeqRingAhead >= 57 + kSeqGroupReach.  The ring then spans at most chunk(top - 96) .. chunk(top + 4),
+// and a copy for chunk c lands in the slot of chunk c + 8 >= chunk(top + 32): never one still being read.
 constexpr int32_t kSeqGroupReach = 39;
-constexpr int32_t kSeqRingAhead = 72;
+constexpr int32_t kSeqRingAhead = 96;
 
 __device__ __forceinline__ uint32_t bfind(uint32_t x) {  // index of the highest set bit (x != 0)
     uint32_t r;
@@ -680,19 +680,36 @@ struct SeqLane {
     int32_t pos;                // stream bits not consumed yet
 };
 
-// Requests the chunks (16 B, counted from the aligned chunk holding sp[0]) below `lowreq` down to
-// the one holding byte (top - kSeqRingAhead).  Chunk c goes to ring slot c & 7, slot 0 also to the
-// mirror above slot 7 so that a 12-byte window read never wraps.  cp.async: no register and no
-// scoreboard slot is held while the copy flies; the caller commits and waits.
+// Chunk c (16 B, counted from the aligned chunk holding sp[0]) goes to ring slot c & 7, slot 0 also
+// to the mirror above slot 7 so that a 12-byte window read never wraps.  cp.async: no register and
+// no scoreboard slot is held while the copy flies; the caller commits and waits.
+__device__ __forceinline__ void ring_fetch_if(bool p, uint32_t ring_saddr, const uint4 *chunk0, int32_t c) {
+    const uint32_t slot = (uint32_t)c & 7;
+    const uint32_t dst = ring_saddr + (slot << 4);
+    const uint4 *src = chunk0 + c;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %0, 0;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@p cp.async.cg.shared.global [%2], [%4], 16;\n\t"
+        "@q cp.async.cg.shared.global [%3], [%4], 16;\n\t}"
+        ::"r"((uint32_t)p), "r"((uint32_t)(p && slot == 0)), "r"(dst), "r"(ring_saddr + kSeqRingBytes), "l"(src)
+        : "memory");
+}
+// Stream start: requests every chunk below `lowreq` down to the one holding byte (top - kSeqRingAhead).
+__device__ __forceinline__ void ring_fill(uint32_t ring_saddr, const uint4 *chunk0, int32_t top, int32_t &lowreq) {
+    int32_t need = (top - kSeqRingAhead) >> 4;
+    need = need < 0 ? 0 : need;
+    while (lowreq > need) ring_fetch_if(true, ring_saddr, chunk0, --lowreq);
+}
+// Steady state, no branch: at most two more chunks, which is more than a group of window reads consumes.
 __device__ __forceinline__ void ring_topup(uint32_t ring_saddr, const uint4 *chunk0, int32_t top, int32_t &lowreq) {
     int32_t need = (top - kSeqRingAhead) >> 4;
     need = need < 0 ? 0 : need;
-    while (lowreq > need) {
-        lowreq--;
-        const uint32_t slot = (uint32_t)lowreq & 7;
-        cp_async16(ring_saddr + (slot << 4), chunk0 + lowreq);
-        if (slot == 0) cp_async16(ring_saddr + kSeqRingBytes, chunk0 + lowreq);
-    }
+    const bool p1 = lowreq - 1 >= need, p2 = lowreq - 2 >= need;
+    ring_fetch_if(p1, ring_saddr, chunk0, lowreq - 1);
+    ring_fetch_if(p2, ring_saddr, chunk0, lowreq - 2);
+    lowreq -= (int32_t)p1 + (int32_t)p2;
 }
 
 // One sequence on the window path.  `bad` goes negative when the result must not be used: more than
@@ -853,21 +870,25 @@ __global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
     const uint4 *chunk0 = reinterpret_cast<const uint4 *>(sp - sp_mis);
     // lowest chunk requested so far; everything from the chunk of the last stream byte down is wanted
     int32_t lowreq = ((sp_mis + (int32_t)len - 1) >> 4) + 1;
-    ring_topup(ring_saddr, chunk0, sp_mis + ((L.pos - 1) >> 3), lowreq);
+    ring_fill(ring_saddr, chunk0, sp_mis + ((L.pos - 1) >> 3), lowreq);
     asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 
     const uint32_t nseq = d.nseq;
     uint32_t *gll = a.seq_ll + d.seq_buf_off, *gml = a.seq_ml + d.seq_buf_off, *gof = a.seq_of + d.seq_buf_off;
     uint64_t ml_sum = 0;
     const uint32_t n_upd = nseq - 1;  // every sequence but the last updates the states (sequences.go:178)
     uint32_t i = 0;
+    int32_t low1 = lowreq, low2 = lowreq;  // lowreq one and two top-ups ago
     for (; i + 4 <= n_upd; i += 4) {
-        // what was requested before this top-up has landed once wait_group 1 returns
-        const int32_t landed = lowreq ? (lowreq << 4) : -64;
+        // what was requested two top-ups ago has landed once wait_group 2 returns
+        const int32_t landed = low2 ? (low2 << 4) : -64;
         const int32_t top = sp_mis + ((L.pos - 1) >> 3);
         ring_topup(ring_saddr, chunk0, top, lowreq);
         asm volatile("cp.async.commit_group;");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        low2 = low1;
+        low1 = lowreq;
         const SeqLane S = L;
         int32_t bad = top - kSeqGroupReach - landed;
         uint32_t v_ll[4], v_ml[4], v_of[4];
@@ -892,8 +913,7 @@ __global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
         ml_sum += (uint64_t)v_ml[0] + v_ml[1] + v_ml[2] + v_ml[3];
     }
     {   // the last (at most four) sequences one at a time; the ring is made to cover them all at once
-        const int32_t top = sp_mis + ((L.pos - 1) >> 3);
-        ring_topup(ring_saddr, chunk0, top, lowreq);
+        ring_fill(ring_saddr, chunk0, sp_mis + ((L.pos - 1) >> 3), lowreq);
         asm volatile("cp.async.commit_group;");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         const int32_t landed = lowreq ? (lowreq << 4) : -64;
