@@ -507,7 +507,10 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
         ctx->launches++;
     }
     if (a.nframes && a.n_seq) {
-        k_execute<<<(a.nframes + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, s>>>(a);
+        // experiment knob: dynamic shared memory that is never touched, to cap the CTAs per SM
+        static const int pad = getenv("SZB_EXEC_PAD") ? atoi(getenv("SZB_EXEC_PAD")) : 0;
+        if (pad) cudaFuncSetAttribute(k_execute, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+        k_execute<<<(a.nframes + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, pad, s>>>(a);
         ctx->launches++;
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));

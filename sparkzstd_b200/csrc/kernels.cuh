@@ -1086,74 +1086,145 @@ __device__ __forceinline__ void warp_memset(uint8_t *dst, uint8_t v, uint64_t n,
 // ---------------------------------------------------------------------------------------------
 // Stage 4.  The reference pushes every literal run and every match through a window ring
 // buffer (ringbuffer.go:102-277).  Here the whole output lives in HBM and the "window" is just
-// earlier output; each warp keeps only the bytes it is currently producing in a shared-memory
-// staging window so that
-//   * literal bytes and match bytes of a round of 32 sequences are assembled at shared-memory
-//     speed, including matches whose source lies inside the same round (dependency rounds),
-//   * match sources that are already in HBM are gathered with 16-byte loads, one gather per round,
-//   * the finished bytes leave as coalesced 16-byte stores.
-constexpr uint32_t kStageBytes = 1024;  // staging window per warp
-constexpr uint32_t kGathStride = 52;    // 3 x 16 B gathered per lane, padded to an odd word count
-constexpr uint32_t kCoopLit = 32;       // literal runs this long are copied by the whole warp
-constexpr uint32_t kCoopMatch = 34;     // matches this long are copied by the whole warp
-
+// earlier output.  Execution is split in two halves that meet in shared memory:
+//
+//   * the PRODUCER side takes 32 sequences per round, resolves what is sequential about them with
+//     warp scans (offsets through the repeat history, positions as prefix sums) and appends
+//     their SEGMENTS -- a literal run or a match, each a contiguous piece of output with a
+//     contiguous source -- to a ring: one 64-bit word per segment (source address minus output
+//     position, so source = word + position for every byte of it) plus one bit in a position bitmap;
+//   * the CONSUMER side produces the output in address order, one aligned 128-byte line per step,
+//     lane i making bytes i, 32+i, 64+i, 96+i of the line.  A byte finds its segment with a
+//     popcount over the bitmap, loads its source byte, and the line leaves as one word per lane.
+//     Neighbouring lanes read neighbouring bytes, so a step touches a handful of cache lines.
+//     A source below the line is already in memory (written by an earlier step, block or kernel)
+//     and is read back through L1/L2; a source inside the line (offset < 128) is another byte of
+//     the step: earlier 32-byte chunks are exchanged through shared memory, the own chunk by
+//     pointer jumping over shuffles.
+constexpr uint32_t kRingBits = 4096;              // output positions the bitmap covers
+constexpr uint32_t kSpanBytes = kRingBits - 256;  // a round may reach this far past the line being consumed
+constexpr uint32_t kSegRing = 256;                // >= 2 x 64 segments of two rounds + the segments of a partial line (<= 64) + 1
+constexpr uint64_t kSegLit = 1ull << 63;          // literal segment: never depends on bytes of the step
+constexpr uint64_t kSegConst = 1ull << 62;        // RLE literals: the byte is in the low bits, there is no source
 struct ExecSmem {
-    __align__(16) uint8_t stage[kStageBytes + 16];
-    __align__(16) uint8_t gath[32 * kGathStride];
-    __align__(16) uint8_t lits[kStageBytes + 16];  // the literal bytes of the segment in flight, fetched coalesced
+    unsigned long long seg[kSegRing];
+    __align__(16) uint32_t bits[kRingBits / 32];  // bit p % kRingBits set: a segment starts at output position p
+    __align__(16) uint8_t grp[128];               // the bytes of the step in flight
 };
 
-// stage[i] mirrors dst[base + i] for i < fill; (dst + base) is 16-byte aligned; everything below
-// base is final in HBM.  head_skip > 0: the first head_skip bytes of chunk 0 belong to the
-// previous frame (another warp) and must not be stored.
-struct Stager {
-    uint8_t *stage;
-    uint8_t *dst;
-    uint64_t base;
-    uint32_t fill;
-    uint32_t head_skip;
+struct ExecState {
+    uint64_t line;  // next line to produce (multiple of 128)
+    uint64_t head;  // output below this position is in memory
+    uint64_t prod;  // segments cover the output up to here
+    uint32_t seen;  // segments that start below max(line, head)
+    uint32_t nseg;  // segments appended so far
 };
 
-__device__ __forceinline__ void stager_reset(Stager &s, uint64_t pos, uint64_t frame_base, uint32_t lane) {
-    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(s.dst) + pos) & 15);
-    s.base = pos - mis;
-    s.fill = mis;
-    s.head_skip = s.base < frame_base ? (uint32_t)(frame_base - s.base) : 0;
-    if (lane < mis && lane >= s.head_skip) s.stage[lane] = s.dst[s.base + lane];  // bytes this warp wrote earlier
-    __syncwarp();
-}
-
-// store the full 16-byte chunks, keep the partial tail at the front of the window
-__device__ __forceinline__ void stager_flush_chunks(Stager &s, uint32_t lane) {
-    const uint32_t n = s.fill >> 4;
-    if (n == 0) return;
-    for (uint32_t i = lane; i < n; i += 32) {
-        if (i == 0 && s.head_skip) {
-            for (uint32_t k = s.head_skip; k < 16; k++) s.dst[s.base + k] = s.stage[k];
-        } else {
-            *reinterpret_cast<uint4 *>(s.dst + s.base + 16 * (uint64_t)i) = *reinterpret_cast<const uint4 *>(s.stage + 16 * i);
+// Produces the bytes [lo, hi) of the line at st.line (positions relative to the line; kFull: all 128).
+template <bool kFull>
+__device__ __forceinline__ void place_step(ExecSmem &sm, uint8_t *dst, ExecState &st, uint32_t lo, uint32_t hi, uint32_t lane,
+                                           uint32_t le_mask) {
+    uint32_t *bw = &sm.bits[(uint32_t)(st.line >> 5) & (kRingBits / 32 - 1)];
+    const uint4 m4 = *reinterpret_cast<const uint4 *>(bw);
+    const uint32_t m[4] = {m4.x, m4.y, m4.z, m4.w};
+    const uint64_t my_pos = st.line + lane;  // output position of my byte of chunk 0
+    const uint32_t dst_lo = (uint32_t)reinterpret_cast<uintptr_t>(dst);
+    uint32_t last = st.seen - 1;  // the last segment that starts below the chunk
+    uint32_t v[4], sg[4];
+    bool ing[4];
+    // every byte of the line finds its segment and issues its load
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const uint32_t rel = (c << 5) + lane;
+        const uint32_t ord = last + __popc(m[c] & le_mask);  // the last segment that starts at or before my byte
+        last += __popc(m[c]);
+        const bool live = kFull || (rel >= lo && rel < hi);
+        const unsigned long long sgm = sm.seg[ord & (kSegRing - 1)];
+        const uint32_t hi32 = (uint32_t)(sgm >> 32);
+        const uint32_t offv = dst_lo - (uint32_t)sgm;  // match: its offset
+        // a match byte whose source is at or above `lo` repeats a byte of this step: not in memory yet
+        ing[c] = live && (hi32 >> 30) == 0 && offv <= rel - lo;
+        sg[c] = rel - offv;
+        const uint8_t *src = reinterpret_cast<const uint8_t *>((sgm & ~(kSegLit | kSegConst)) + my_pos) + (c << 5);
+        v[c] = (uint32_t)sgm & 0xFF;
+        if (live && !ing[c] && !(hi32 & (uint32_t)(kSegConst >> 32))) v[c] = *src;
+    }
+    st.seen = last + 1;
+    uint8_t *const my_grp = sm.grp + lane;
+    if (!__any_sync(kFull, ing[0] | ing[1] | ing[2] | ing[3])) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) my_grp[c << 5] = (uint8_t)v[c];
+    } else {
+        // bytes that repeat bytes of this step: earlier chunks through shared memory, the own chunk by
+        // pointer jumping over shuffles (chains of in-chunk sources halve every round)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            bool unres = ing[c];
+            if (c > 0) {
+                __syncwarp();
+                if (unres && (sg[c] >> 5) < (uint32_t)c) {
+                    v[c] = sm.grp[sg[c]];
+                    unres = false;
+                }
+            }
+            uint32_t par = sg[c] & 31;
+            uint32_t open = __ballot_sync(kFull, unres);
+            while (open) {
+                const uint32_t pv = __shfl_sync(kFull, v[c], par);
+                const uint32_t pp = __shfl_sync(kFull, par, par);
+                if (unres) {
+                    if (!((open >> par) & 1)) {
+                        v[c] = pv;
+                        unres = false;
+                    } else {
+                        par = pp;
+                    }
+                }
+                open = __ballot_sync(kFull, unres);
+            }
+            my_grp[c << 5] = (uint8_t)v[c];
         }
     }
-    const uint32_t tail = s.fill & 15;
-    const uint8_t t = lane < tail ? s.stage[16 * n + lane] : 0;
     __syncwarp();
-    if (lane < tail) s.stage[lane] = t;
-    s.base += 16 * (uint64_t)n;
-    s.fill = tail;
-    s.head_skip = 0;
+    // out: one aligned word per lane, a full line per warp; single bytes where the line is partial
+    const uint32_t wrel = lane << 2;
+    const uint32_t word = reinterpret_cast<const uint32_t *>(sm.grp)[lane];
+    uint8_t *out = dst + st.line;
+    if (kFull || (wrel >= lo && wrel + 4 <= hi)) {
+        *reinterpret_cast<uint32_t *>(out + wrel) = word;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (wrel + k >= lo && wrel + k < hi) out[wrel + k] = (uint8_t)(word >> (8 * k));
+    }
+    if (lane < 4) bw[lane] = 0;  // the bitmap is a ring: leave it clean for the next lap
     __syncwarp();
 }
 
-// everything out, including the partial tail (byte stores); the window stays consistent
-__device__ __forceinline__ void stager_flush_all(Stager &s, uint32_t lane) {
-    stager_flush_chunks(s, lane);
-    if (lane < s.fill && lane >= s.head_skip) s.dst[s.base + lane] = s.stage[lane];
-    __syncwarp();
+// produce every complete line below `limit` (<= st.prod)
+__device__ __forceinline__ void exec_drain(ExecSmem &sm, uint8_t *dst, ExecState &st, uint64_t limit, uint32_t lane, uint32_t le_mask) {
+    while (limit >= st.line + 128) {
+        if (st.head > st.line)
+            place_step<false>(sm, dst, st, (uint32_t)(st.head - st.line), 128, lane, le_mask);
+        else
+            place_step<true>(sm, dst, st, 0, 128, lane, le_mask);
+        st.line += 128;
+    }
 }
-
-// byte at absolute output position p: from the staging window when it is there, else from HBM
-__device__ __forceinline__ uint8_t stager_byte(const Stager &s, uint64_t p) {
-    return p >= s.base ? s.stage[(uint32_t)(p - s.base)] : s.dst[p];
+// produce everything the ring holds, the last, partial line included: everything below st.prod is then in memory
+__device__ __forceinline__ void exec_flush(ExecSmem &sm, uint8_t *dst, ExecState &st, uint32_t lane, uint32_t le_mask) {
+    exec_drain(sm, dst, st, st.prod, lane, le_mask);
+    if (st.prod > st.head) {
+        const uint32_t lo = st.head > st.line ? (uint32_t)(st.head - st.line) : 0;
+        place_step<false>(sm, dst, st, lo, (uint32_t)(st.prod - st.line), lane, le_mask);
+        st.head = st.prod;
+    }
+}
+// continue at another output position (everything flushed)
+__device__ __forceinline__ void exec_seek(ExecState &st, uint64_t pos) {
+    st.line = pos & ~(uint64_t)127;
+    st.head = pos;
+    st.prod = pos;
 }
 
 // One thread per frame, before any output is written: the frame's verdict (the first failing
@@ -1201,8 +1272,11 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute_bodies(DeviceBatch a) {
     }
 }
 
-// One warp per frame; blocks in order; 32 sequences per round.
-__global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
+// One warp per frame; blocks in order; 32 sequences per round (sequence_execution.go:14-63).
+#ifndef SZB_EXEC_MIN_CTAS
+#define SZB_EXEC_MIN_CTAS 7
+#endif
+__global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(DeviceBatch a) {
     __shared__ ExecSmem smem[kWarpsPerCta];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t f = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
@@ -1215,23 +1289,26 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
     int err = a.frame_status[f];  // k_frame_verdict
     if (err != SZB_OK) return;
     const uint64_t frame_base = nb ? a.out_off[b0] : 0;
+    const uint32_t le_mask = 0xFFFFFFFFu >> (31 - lane);  // bits 0..lane
+    const uint32_t lt_mask = le_mask >> 1;                // bits 0..lane-1
 
-    Stager st;
-    st.stage = sm.stage;
-    st.dst = dst;
-    stager_reset(st, frame_base, frame_base, lane);
-    uint8_t *const my_gath = sm.gath + lane * kGathStride;
+    for (uint32_t wd = lane; wd < kRingBits / 32; wd += 32) sm.bits[wd] = 0;
+    __syncwarp();
+    ExecState st;
+    exec_seek(st, frame_base);
+    st.seen = 0;
+    st.nseg = 0;
 
     History hist{1, 4, 8};  // framedecompressor.go:48,59
     for (uint32_t bi = 0; bi < nb && err == SZB_OK; bi++) {
         const uint32_t b = b0 + bi;
         const szb_block_desc d = a.blocks[b];
+        if (d.type != 2 || d.nseq == 0) continue;  // written by k_execute_bodies already
         const uint8_t *payload = a.src + d.src_off;
         uint64_t out_pos = a.out_off[b];
-        if (d.type != 2 || d.nseq == 0) {  // written by k_execute_bodies already: step over it
-            stager_flush_all(st, lane);
-            stager_reset(st, out_pos + a.out_size[b], frame_base, lane);
-            continue;
+        if (out_pos != st.prod) {  // blocks in between were written elsewhere
+            exec_flush(sm, dst, st, lane, le_mask);
+            exec_seek(st, out_pos);
         }
         // Compressed: ExecuteSequences (sequence_execution.go:14-63)
         const bool lit_rle = d.lit_type == 1;
@@ -1240,20 +1317,19 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
         const uint32_t nseq = d.nseq;
         const uint32_t *gll = a.seq_ll + d.seq_buf_off, *gml = a.seq_ml + d.seq_buf_off, *gof = a.seq_of + d.seq_buf_off;
         uint32_t lit_pos = 0;
-        // the sequence triples of the next round are loaded while the current one executes
-        uint32_t n_ll = lane < nseq ? gll[lane] : 0, n_ml = lane < nseq ? gml[lane] : 0, n_of = lane < nseq ? gof[lane] : 4;
+        // the triples are prefetched to L1 two rounds ahead (one line per array and round)
+        if (lane < 3) {
+            const uint32_t *g = lane == 0 ? gll : (lane == 1 ? gml : gof);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(g));
+            if (nseq > 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(g + 32));
+        }
         for (uint32_t base = 0; base < nseq; base += 32) {
             const uint32_t cnt = nseq - base < 32 ? nseq - base : 32;
             const bool act = lane < cnt;
-            const uint32_t ll = n_ll, ml = n_ml, ofv = n_of;
-            {
-                const uint32_t nx = base + 32 + lane;
-                const bool more = nx < nseq;
-                n_ll = more ? gll[nx] : 0;
-                n_ml = more ? gml[nx] : 0;
-                n_of = more ? gof[nx] : 4;
-                if (!lit_rle && lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(lit + lit_pos + 128));
-            }
+            const uint32_t ll = act ? gll[base + lane] : 0, ml = act ? gml[base + lane] : 0, ofv = act ? gof[base + lane] : 4;
+            if (!lit_rle && lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(lit + lit_pos + 256));
+            if (lane < 3 && base + 64 < nseq)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"((lane == 0 ? gll : (lane == 1 ? gml : gof)) + base + 64));
 
             // --- offsets through the 3-entry history (nextOffset) ---
             uint32_t off;
@@ -1307,26 +1383,21 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
                 break;
             }
 
-            // --- the round is executed in segments that fit the staging window (normally one) ---
+            // --- the round's segments go to the ring, as many sequences at a time as the bitmap holds (normally all) ---
             uint32_t start = 0;
             while (start < cnt) {
-                const uint64_t rel_end64 = my_dst + tot - st.base;
-                const bool fits = lane >= start && lane < cnt && rel_end64 <= kStageBytes;
+                const bool fits = lane >= start && lane < cnt && my_dst + tot - st.line <= kSpanBytes;
                 const uint32_t nfit = __popc(__ballot_sync(kFull, fits));  // fitting lanes are a prefix of [start, cnt)
                 if (nfit == 0) {
-                    if (st.fill >= 16) {
-                        stager_flush_chunks(st, lane);
-                        continue;
-                    }
-                    // one sequence larger than the window: straight to HBM, whole warp on it
-                    stager_flush_all(st, lane);
+                    // one sequence longer than the ring: the whole warp on its literals, then on its match
+                    exec_flush(sm, dst, st, lane, le_mask);
                     const uint32_t L = __shfl_sync(kFull, ll, start), ML = __shfl_sync(kFull, ml, start);
                     const uint32_t OFF = __shfl_sync(kFull, off, start), SL = __shfl_sync(kFull, my_lit, start);
                     const uint64_t D = __shfl_sync(kFull, my_dst, start);
                     if (lit_rle)
-                        warp_fill(dst + D, rle_byte, L, lane);
+                        warp_memset(dst + D, rle_byte, L, lane);
                     else
-                        warp_copy(dst + D, lit + SL, L, lane);
+                        warp_memcpy(dst + D, lit + SL, L, lane);
                     __syncwarp();
                     uint8_t *MD = dst + D + L;
                     const uint8_t *MS = MD - OFF;
@@ -1340,167 +1411,64 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute(DeviceBatch a) {
                         for (uint32_t k = lane; k < ML; k += 32) MD[k] = MS[k % OFF];
                     }
                     __syncwarp();
-                    stager_reset(st, D + L + ML, frame_base, lane);
+                    exec_seek(st, D + L + ML);
                     start++;
                     continue;
                 }
                 const uint32_t end = start + nfit;
                 const bool in = lane >= start && lane < end;
-                const uint32_t sd = (uint32_t)(my_dst - st.base);  // my literal run inside the window
-                const uint32_t md = sd + ll;                        // my match inside the window
-
-                // literal runs (sequence_execution.go:19-34).  The segment's literals are contiguous in the
-                // literal buffer: fetch them once, coalesced, then every lane places its own run.
-                if (lit_rle) {
-                    if (in && ll > 0 && ll < kCoopLit)
-                        for (uint32_t k = 0; k < ll; k++) st.stage[sd + k] = rle_byte;
-                    uint32_t long_lit = __ballot_sync(kFull, in && ll >= kCoopLit);
-                    while (long_lit) {
-                        const int j = __ffs(long_lit) - 1;
-                        long_lit &= long_lit - 1;
-                        warp_fill(st.stage + __shfl_sync(kFull, sd, j), rle_byte, __shfl_sync(kFull, ll, j), lane);
+                const uint32_t no_lit = __ballot_sync(kFull, in && ll == 0);
+                const uint32_t no_match = __ballot_sync(kFull, in && ml == 0);  // cannot happen: ML codes start at 3 (predefined.go:36-50)
+                if (in) {
+                    uint32_t ord = st.nseg + 2 * (lane - start) - __popc((no_lit | 0) & lt_mask) - __popc(no_match & lt_mask);
+                    if (ll) {
+                        sm.seg[ord & (kSegRing - 1)] =
+                            lit_rle ? (kSegLit | kSegConst | rle_byte) : (kSegLit | (reinterpret_cast<uintptr_t>(lit) + my_lit - my_dst));
+                        atomicOr(&sm.bits[(uint32_t)(my_dst >> 5) & (kRingBits / 32 - 1)], 1u << ((uint32_t)my_dst & 31));
+                        ord++;
                     }
-                } else {
-                    const uint32_t l0 = __shfl_sync(kFull, my_lit, start);
-                    const uint32_t l1 = __shfl_sync(kFull, my_lit + ll, end - 1);
-                    const uint8_t *lsrc = lit + l0;
-                    const uint32_t lmis = (uint32_t)(reinterpret_cast<uintptr_t>(lsrc) & 3);
-                    const uint32_t nwords = (lmis + (l1 - l0) + 3) >> 2;
-                    const uint32_t *lw = reinterpret_cast<const uint32_t *>(lsrc - lmis);
-                    uint32_t *ls = reinterpret_cast<uint32_t *>(sm.lits);
-                    for (uint32_t wd = lane; wd < nwords; wd += 32) ls[wd] = lw[wd];
-                    __syncwarp();
-                    if (in && ll > 0 && ll < kCoopLit) {
-                        const uint8_t *from = sm.lits + lmis + (my_lit - l0);
-                        uint8_t *to = st.stage + sd;
-                        for (uint32_t k = 0; k < ll; k++) to[k] = from[k];
-                    }
-                    uint32_t long_lit = __ballot_sync(kFull, in && ll >= kCoopLit);
-                    while (long_lit) {
-                        const int j = __ffs(long_lit) - 1;
-                        long_lit &= long_lit - 1;
-                        const uint32_t L = __shfl_sync(kFull, ll, j), SD = __shfl_sync(kFull, sd, j), SL = __shfl_sync(kFull, my_lit, j);
-                        warp_copy(st.stage + SD, sm.lits + lmis + (SL - l0), L, lane);
+                    if (ml) {
+                        sm.seg[ord & (kSegRing - 1)] = reinterpret_cast<uintptr_t>(dst) - off;
+                        atomicOr(&sm.bits[(uint32_t)(mdst >> 5) & (kRingBits / 32 - 1)], 1u << ((uint32_t)mdst & 31));
+                        // the consumer gets here about a round later: have the source on its way to L1
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(dst + mdst - off));
                     }
                 }
-
-                // matches (RepeatBeforeIndex, ringbuffer.go:242-277).  Positions below are relative to the
-                // window base; a negative source position lies in HBM, below the window, and is final.
-                const bool has = in && ml > 0;
-                const bool shortm = has && ml < kCoopMatch;
-                const int32_t s_rel = (int32_t)md - (int32_t)off;  // source of my match
-                const int32_t e_rel = (s_rel + (int32_t)ml < (int32_t)md) ? s_rel + (int32_t)ml : (int32_t)md;
-                uint32_t n_g = 0;  // leading bytes of the source that come from HBM
-                if (shortm && s_rel < 0) n_g = (uint32_t)(-s_rel) < ml ? (uint32_t)(-s_rel) : ml;
-                // phase G: gather the HBM part with 16-byte loads and drop it at its destination right away
-                if (n_g) {
-                    const uint8_t *gp = dst + st.base + (int64_t)s_rel;
-                    const uint32_t gmis = (uint32_t)(reinterpret_cast<uintptr_t>(gp) & 15);
-                    const uint4 *ga = reinterpret_cast<const uint4 *>(gp - gmis);
-                    uint32_t *gw = reinterpret_cast<uint32_t *>(my_gath);  // row start is 4-byte aligned only: store words
-                    const uint4 c0 = ga[0];
-                    gw[0] = c0.x; gw[1] = c0.y; gw[2] = c0.z; gw[3] = c0.w;
-                    if (gmis + n_g > 16) {
-                        const uint4 c1 = ga[1];
-                        gw[4] = c1.x; gw[5] = c1.y; gw[6] = c1.z; gw[7] = c1.w;
-                    }
-                    if (gmis + n_g > 32) {
-                        const uint4 c2 = ga[2];
-                        gw[8] = c2.x; gw[9] = c2.y; gw[10] = c2.z; gw[11] = c2.w;
-                    }
-                    const uint8_t *gs = my_gath + gmis;
-                    uint8_t *gd = st.stage + md;
-                    for (uint32_t k = 0; k < n_g; k++) gd[k] = gs[k];
-                }
-                // what is left depends on bytes produced inside the window: dependency rounds
-                const bool pend_lane = has && (!shortm || n_g < ml);
+                st.nseg += 2 * nfit - __popc(no_lit) - __popc(no_match);
+                const uint64_t prev_prod = st.prod;
+                st.prod = __shfl_sync(kFull, my_dst + tot, end - 1);
                 __syncwarp();
-                uint32_t pending = __ballot_sync(kFull, pend_lane);
-                if (pending) {
-                    // dep: the pending lanes before me whose output overlaps the window part of my source.
-                    // The end positions of the sequences of a segment grow with the lane number, so both
-                    // ends of that lane range come out of a 5-step binary search over shuffles.
-                    const uint32_t seq_end = lane < start ? 0u : (lane < end ? md + ml : 0x7FFFFFFFu);
-                    const uint32_t seq_md = lane < start ? 0u : (lane < end ? md : 0x7FFFFFFFu);
-                    uint32_t lo = 0, hi = 0;  // lo: lanes whose output ends at or before my source; hi: lanes whose match starts before my source ends
-#pragma unroll
-                    for (int step = 16; step > 0; step >>= 1) {
-                        const int32_t v1 = (int32_t)__shfl_sync(kFull, seq_end, lo + step - 1);
-                        const int32_t v2 = (int32_t)__shfl_sync(kFull, seq_md, hi + step - 1);
-                        if (v1 <= s_rel) lo += step;
-                        if (v2 < e_rel) hi += step;
-                    }
-                    if (hi > lane) hi = lane;
-                    const uint32_t dep = hi > lo ? (((1u << hi) - 1) & ~((1u << lo) - 1)) : 0u;
-                    while (pending) {
-                        const int first = __ffs(pending) - 1;  // the first pending lane never waits for anyone
-                        const uint32_t first_ml = __shfl_sync(kFull, ml, first);
-                        if (first_ml >= kCoopMatch) {  // warp-wide copy of one long match into the window
-                            const uint32_t OFF = __shfl_sync(kFull, off, first);
-                            const uint32_t MD = __shfl_sync(kFull, md, first);
-                            const uint64_t S = st.base + MD - OFF;
-                            if (OFF >= 32) {
-                                for (uint32_t k0 = 0; k0 < first_ml; k0 += 32) {
-                                    const uint32_t k = k0 + lane;
-                                    if (k < first_ml) st.stage[MD + k] = stager_byte(st, S + k);
-                                    __syncwarp();
-                                }
-                            } else {  // overlapping: periodic extension of the OFF bytes before the match
-                                for (uint32_t k = lane; k < first_ml; k += 32) st.stage[MD + k] = stager_byte(st, S + k % OFF);
-                            }
-                            pending &= ~(1u << first);
-                            __syncwarp();
-                            continue;
-                        }
-                        const bool ready = ((pending >> lane) & 1) && shortm && (dep & pending) == 0;
-                        if (ready) {
-                            const uint8_t *ss = st.stage + s_rel;  // valid from byte n_g on
-                            uint8_t *sdst = st.stage + md;
-                            for (uint32_t k = n_g; k < ml; k++) sdst[k] = ss[k];  // byte-serial: handles self overlap
-                        }
-                        pending &= ~__ballot_sync(kFull, ready);
-                        __syncwarp();
-                    }
-                }
-                st.fill = __shfl_sync(kFull, (uint32_t)rel_end64, end - 1);
-                stager_flush_chunks(st, lane);
+                exec_drain(sm, dst, st, prev_prod, lane, le_mask);  // stays one append behind, so that the prefetches have time to land
                 start = end;
             }
             out_pos += round_tot;
             lit_pos += round_ll;
         }
         if (err != SZB_OK) break;
-        // trailing literals (sequence_execution.go:55-60, literals.go:411-420)
-        uint32_t rest = d.lit_regen - lit_pos;
-        if (rest >= 512) {  // a long tail (e.g. a block without sequences) goes straight to HBM
-            stager_flush_all(st, lane);
+        // trailing literals (sequence_execution.go:55-60, literals.go:411-420): one more segment, or a bulk copy
+        const uint32_t rest = d.lit_regen - lit_pos;
+        if (rest && out_pos + rest - st.line <= kSpanBytes) {
+            if (lane == 0) {
+                sm.seg[st.nseg & (kSegRing - 1)] =
+                    lit_rle ? (kSegLit | kSegConst | rle_byte) : (kSegLit | (reinterpret_cast<uintptr_t>(lit) + lit_pos - out_pos));
+                atomicOr(&sm.bits[(uint32_t)(out_pos >> 5) & (kRingBits / 32 - 1)], 1u << ((uint32_t)out_pos & 31));
+            }
+            st.nseg++;
+            st.prod = out_pos + rest;
+            __syncwarp();
+            exec_drain(sm, dst, st, st.prod, lane, le_mask);
+        } else if (rest) {
+            exec_flush(sm, dst, st, lane, le_mask);
             if (lit_rle)
                 warp_memset(dst + out_pos, rle_byte, rest, lane);
             else
                 warp_memcpy(dst + out_pos, lit + lit_pos, rest, lane);
             __syncwarp();
-            stager_reset(st, out_pos + rest, frame_base, lane);
-            rest = 0;
-        }
-        while (rest) {
-            uint32_t room = kStageBytes - st.fill;
-            if (room == 0) {
-                stager_flush_chunks(st, lane);
-                continue;
-            }
-            const uint32_t n = rest < room ? rest : room;
-            if (lit_rle)
-                warp_fill(st.stage + st.fill, rle_byte, n, lane);
-            else
-                warp_copy(st.stage + st.fill, lit + lit_pos, n, lane);
-            __syncwarp();
-            st.fill += n;
-            lit_pos += n;
-            rest -= n;
-            stager_flush_chunks(st, lane);
+            exec_seek(st, out_pos + rest);
         }
     }
-    stager_flush_all(st, lane);
+    // On an error the frame's output is void; what the ring still holds is written anyway (it is within the frame's range).
+    exec_flush(sm, dst, st, lane, le_mask);
     if (lane == 0 && err != SZB_OK) {  // failed while executing (bad offset, literals ran dry)
         a.frame_status[f] = err;
         a.frame_out_len[f] = 0;
