@@ -23,6 +23,7 @@ struct szb_ctx {
     bool own_stream = false;
     cudaEvent_t ev[10] = {};
     uint32_t *d_predef = nullptr;
+    uint8_t *d_bytefill = nullptr;  // 256 rows of 256 equal bytes: the source of RLE literal runs (kernels.cuh, stage 4)
     std::string last_error;
     float timing[8] = {};
     uint64_t launches = 0;
@@ -190,6 +191,15 @@ int szb_ctx_create(int device, void *stream, szb_ctx **out) {
         szb_ctx_destroy(ctx);
         return SZB_ERR_CUDA;
     }
+    {
+        std::vector<uint8_t> fill(256 * 256);
+        for (int v = 0; v < 256; v++) memset(fill.data() + 256 * v, v, 256);
+        if (cudaMalloc(&ctx->d_bytefill, fill.size()) != cudaSuccess ||
+            cudaMemcpy(ctx->d_bytefill, fill.data(), fill.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+            szb_ctx_destroy(ctx);
+            return SZB_ERR_CUDA;
+        }
+    }
     cudaFuncSetAttribute(k_build_huf_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(HufSmem) * kWarpsPerCta));
     cudaFuncSetAttribute(k_build_seq_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SeqSmem) * kWarpsPerCta));
     cudaFuncSetAttribute(k_decode_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeqDecodeSmemBytes);
@@ -205,6 +215,7 @@ void szb_ctx_destroy(szb_ctx *ctx) {
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->d_predef) cudaFree(ctx->d_predef);
+    if (ctx->d_bytefill) cudaFree(ctx->d_bytefill);
     if (ctx->d_src) cudaFree(ctx->d_src);
     if (ctx->d_dst) cudaFree(ctx->d_dst);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
@@ -446,6 +457,7 @@ static DeviceBatch make_args(szb_batch *b, const void *d_src, void *d_dst, size_
     a.seq_status = b->d_seq_status;
     a.total = b->d_total;
     a.predef = b->ctx->d_predef;
+    a.bytefill = b->ctx->d_bytefill;
     a.dst = (uint8_t *)d_dst;
     a.dst_cap = dst_cap;
     a.frame_out_off = b->d_frame_out_off;

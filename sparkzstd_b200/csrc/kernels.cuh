@@ -74,6 +74,7 @@ struct DeviceBatch {
     int32_t *seq_status;    // per block
     uint64_t *total;        // [0] = total output bytes
     const uint32_t *predef; // predefined LL(64) | OF(32) | ML(64) decode tables
+    const uint8_t *bytefill; // 256 rows of 256 equal bytes (row v holds v)
     uint8_t *dst;
     uint64_t dst_cap;
     uint64_t *frame_out_off, *frame_out_len;
@@ -1104,19 +1105,18 @@ __device__ __forceinline__ void warp_memset(uint8_t *dst, uint8_t v, uint64_t n,
 constexpr uint32_t kRingBits = 4096;              // output positions the bitmap covers
 constexpr uint32_t kSpanBytes = kRingBits - 256;  // a round may reach this far past the line being consumed
 constexpr uint32_t kSegRing = 256;                // >= 2 x 64 segments of two rounds + the segments of a partial line (<= 64) + 1
-constexpr uint64_t kSegLit = 1ull << 63;          // literal segment: never depends on bytes of the step
-constexpr uint64_t kSegConst = 1ull << 62;        // RLE literals: the byte is in the low bits, there is no source
+constexpr uint32_t kConstRun = 256;               // RLE literal runs up to this long are segments (their source is a row of DeviceBatch::bytefill)
 struct ExecSmem {
-    unsigned long long seg[kSegRing];
+    unsigned long long seg[kSegRing];             // per segment: source address minus output position
     __align__(16) uint32_t bits[kRingBits / 32];  // bit p % kRingBits set: a segment starts at output position p
     __align__(16) uint8_t grp[128];               // the bytes of the step in flight
 };
 
 struct ExecState {
     uint64_t line;  // next line to produce (multiple of 128)
-    uint64_t head;  // output below this position is in memory
-    uint64_t prod;  // segments cover the output up to here
-    uint32_t seen;  // segments that start below max(line, head)
+    uint32_t prod;  // segments cover the output up to line + prod
+    uint32_t head;  // output below line + head is in memory already (0 .. 128)
+    uint32_t seen;  // segments that start below line + head
     uint32_t nseg;  // segments appended so far
 };
 
@@ -1128,7 +1128,8 @@ __device__ __forceinline__ void place_step(ExecSmem &sm, uint8_t *dst, ExecState
     const uint4 m4 = *reinterpret_cast<const uint4 *>(bw);
     const uint32_t m[4] = {m4.x, m4.y, m4.z, m4.w};
     const uint64_t my_pos = st.line + lane;  // output position of my byte of chunk 0
-    const uint32_t dst_lo = (uint32_t)reinterpret_cast<uintptr_t>(dst);
+    const uint64_t low_addr = reinterpret_cast<uintptr_t>(dst) + st.line + lo;  // a source at or above this address is a byte of this step
+    const uint32_t low_lo = (uint32_t)low_addr, low_hi = (uint32_t)(low_addr >> 32);
     uint32_t last = st.seen - 1;  // the last segment that starts below the chunk
     uint32_t v[4], sg[4];
     bool ing[4];
@@ -1139,15 +1140,14 @@ __device__ __forceinline__ void place_step(ExecSmem &sm, uint8_t *dst, ExecState
         const uint32_t ord = last + __popc(m[c] & le_mask);  // the last segment that starts at or before my byte
         last += __popc(m[c]);
         const bool live = kFull || (rel >= lo && rel < hi);
-        const unsigned long long sgm = sm.seg[ord & (kSegRing - 1)];
-        const uint32_t hi32 = (uint32_t)(sgm >> 32);
-        const uint32_t offv = dst_lo - (uint32_t)sgm;  // match: its offset
-        // a match byte whose source is at or above `lo` repeats a byte of this step: not in memory yet
-        ing[c] = live && (hi32 >> 30) == 0 && offv <= rel - lo;
-        sg[c] = rel - offv;
-        const uint8_t *src = reinterpret_cast<const uint8_t *>((sgm & ~(kSegLit | kSegConst)) + my_pos) + (c << 5);
-        v[c] = (uint32_t)sgm & 0xFF;
-        if (live && !ing[c] && !(hi32 & (uint32_t)(kSegConst >> 32))) v[c] = *src;
+        const uint64_t src = sm.seg[ord & (kSegRing - 1)] + my_pos + (c << 5);
+        // Sources in [low_addr, my own address) repeat a byte of this step that is not in memory yet.  Only a match can
+        // point there, and a line does not straddle a 4 GiB boundary: compare the low words, then the high ones.
+        sg[c] = (uint32_t)src - low_lo;
+        ing[c] = live && sg[c] < rel - lo && (uint32_t)(src >> 32) == low_hi;
+        sg[c] += lo;  // position in the line
+        v[c] = 0;
+        if (live && !ing[c]) v[c] = *reinterpret_cast<const uint8_t *>(src);
     }
     st.seen = last + 1;
     uint8_t *const my_grp = sm.grp + lane;
@@ -1201,30 +1201,31 @@ __device__ __forceinline__ void place_step(ExecSmem &sm, uint8_t *dst, ExecState
     __syncwarp();
 }
 
-// produce every complete line below `limit` (<= st.prod)
-__device__ __forceinline__ void exec_drain(ExecSmem &sm, uint8_t *dst, ExecState &st, uint64_t limit, uint32_t lane, uint32_t le_mask) {
-    while (limit >= st.line + 128) {
-        if (st.head > st.line)
-            place_step<false>(sm, dst, st, (uint32_t)(st.head - st.line), 128, lane, le_mask);
+// produce every complete line below line + limit (limit <= st.prod)
+__device__ __forceinline__ void exec_drain(ExecSmem &sm, uint8_t *dst, ExecState &st, uint32_t limit, uint32_t lane, uint32_t le_mask) {
+    while (limit >= 128) {
+        if (st.head)
+            place_step<false>(sm, dst, st, st.head, 128, lane, le_mask);
         else
             place_step<true>(sm, dst, st, 0, 128, lane, le_mask);
         st.line += 128;
+        st.prod -= 128;
+        st.head = 0;
+        limit -= 128;
     }
 }
-// produce everything the ring holds, the last, partial line included: everything below st.prod is then in memory
+// produce everything the ring holds, the last, partial line included: everything below line + prod is then in memory
 __device__ __forceinline__ void exec_flush(ExecSmem &sm, uint8_t *dst, ExecState &st, uint32_t lane, uint32_t le_mask) {
     exec_drain(sm, dst, st, st.prod, lane, le_mask);
     if (st.prod > st.head) {
-        const uint32_t lo = st.head > st.line ? (uint32_t)(st.head - st.line) : 0;
-        place_step<false>(sm, dst, st, lo, (uint32_t)(st.prod - st.line), lane, le_mask);
+        place_step<false>(sm, dst, st, st.head, st.prod, lane, le_mask);
         st.head = st.prod;
     }
 }
 // continue at another output position (everything flushed)
 __device__ __forceinline__ void exec_seek(ExecState &st, uint64_t pos) {
     st.line = pos & ~(uint64_t)127;
-    st.head = pos;
-    st.prod = pos;
+    st.head = st.prod = (uint32_t)pos & 127;
 }
 
 // One thread per frame, before any output is written: the frame's verdict (the first failing
@@ -1306,30 +1307,37 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
         if (d.type != 2 || d.nseq == 0) continue;  // written by k_execute_bodies already
         const uint8_t *payload = a.src + d.src_off;
         uint64_t out_pos = a.out_off[b];
-        if (out_pos != st.prod) {  // blocks in between were written elsewhere
+        if (out_pos != st.line + st.prod) {  // blocks in between were written elsewhere
             exec_flush(sm, dst, st, lane, le_mask);
             exec_seek(st, out_pos);
         }
         // Compressed: ExecuteSequences (sequence_execution.go:14-63)
         const bool lit_rle = d.lit_type == 1;
-        const uint8_t *__restrict__ lit = d.lit_type == 0 ? payload + d.lit_hdr_bytes : a.litbuf + d.lit_buf_off;
-        const uint8_t rle_byte = lit_rle ? payload[d.lit_hdr_bytes] : 0;
+        // RLE literals: every literal byte is payload[lit_hdr_bytes]; runs read it from that byte's row of the fill table
+        const uint8_t *__restrict__ lit = lit_rle ? a.bytefill + 256 * (uint32_t)payload[d.lit_hdr_bytes]
+                                                  : (d.lit_type == 0 ? payload + d.lit_hdr_bytes : a.litbuf + d.lit_buf_off);
         const uint32_t nseq = d.nseq;
-        const uint32_t *gll = a.seq_ll + d.seq_buf_off, *gml = a.seq_ml + d.seq_buf_off, *gof = a.seq_of + d.seq_buf_off;
+        const uint64_t sbo = d.seq_buf_off;
         uint32_t lit_pos = 0;
         // the triples are prefetched to L1 two rounds ahead (one line per array and round)
         if (lane < 3) {
-            const uint32_t *g = lane == 0 ? gll : (lane == 1 ? gml : gof);
+            const uint32_t *g = (lane == 0 ? a.seq_ll : (lane == 1 ? a.seq_ml : a.seq_of)) + sbo;
             asm volatile("prefetch.global.L1 [%0];" ::"l"(g));
             if (nseq > 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(g + 32));
         }
         for (uint32_t base = 0; base < nseq; base += 32) {
             const uint32_t cnt = nseq - base < 32 ? nseq - base : 32;
             const bool act = lane < cnt;
-            const uint32_t ll = act ? gll[base + lane] : 0, ml = act ? gml[base + lane] : 0, ofv = act ? gof[base + lane] : 4;
+            const uint64_t si = sbo + base + lane;  // the arrays are padded to whole rounds: no bounds needed
+            uint32_t ll = a.seq_ll[si], ml = a.seq_ml[si], ofv = a.seq_of[si];
+            if (!act) {
+                ll = 0;
+                ml = 0;
+                ofv = 4;
+            }
             if (!lit_rle && lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(lit + lit_pos + 256));
             if (lane < 3 && base + 64 < nseq)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"((lane == 0 ? gll : (lane == 1 ? gml : gof)) + base + 64));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"((lane == 0 ? a.seq_ll : (lane == 1 ? a.seq_ml : a.seq_of)) + sbo + base + 64));
 
             // --- offsets through the 3-entry history (nextOffset) ---
             uint32_t off;
@@ -1374,30 +1382,33 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
                 err = lit_rle ? SZB_ERR_PANIC : SZB_ERR_DIDNT_COPY_ALL_LITERAL_BYTES;
                 break;
             }
-            const uint64_t my_dst = out_pos + (incl_tot - tot);  // absolute position of my literal run
-            const uint32_t my_lit = lit_pos + (incl_ll - ll);
-            const uint64_t mdst = my_dst + ll;                   // absolute position of my match
-            const bool has_match = act && ml > 0;
-            if (__any_sync(kFull, has_match && (off == 0 || (uint64_t)off > mdst - frame_base))) {
-                err = SZB_ERR_CANT_REPEAT_BYTES;  // ringbuffer.go:203-214
-                break;
+            const uint32_t excl_tot = incl_tot - tot;  // my literal run starts at out_pos + excl_tot
+            const uint32_t excl_ll = incl_ll - ll;     // and reads the literals from lit_pos + excl_ll
+            {
+                const uint64_t before = out_pos - frame_base + excl_tot + ll;  // frame bytes in front of my match
+                if (__any_sync(kFull, act && ml > 0 && (off == 0 || off > before))) {
+                    err = SZB_ERR_CANT_REPEAT_BYTES;  // ringbuffer.go:203-214
+                    break;
+                }
             }
 
             // --- the round's segments go to the ring, as many sequences at a time as the bitmap holds (normally all) ---
             uint32_t start = 0;
             while (start < cnt) {
-                const bool fits = lane >= start && lane < cnt && my_dst + tot - st.line <= kSpanBytes;
-                const uint32_t nfit = __popc(__ballot_sync(kFull, fits));  // fitting lanes are a prefix of [start, cnt)
+                const uint32_t my_rel = (uint32_t)(out_pos - st.line) + excl_tot;  // my literal run, relative to the line being consumed
+                const bool fits = my_rel + tot <= kSpanBytes && !(lit_rle && ll > kConstRun);
+                const uint32_t fitmask = __ballot_sync(kFull, fits && lane < cnt) >> start;
+                const uint32_t nfit = fitmask == (0xFFFFFFFFu >> start) ? 32 - start : __ffs(~fitmask) - 1;  // leading fits
                 if (nfit == 0) {
                     // one sequence longer than the ring: the whole warp on its literals, then on its match
                     exec_flush(sm, dst, st, lane, le_mask);
                     const uint32_t L = __shfl_sync(kFull, ll, start), ML = __shfl_sync(kFull, ml, start);
-                    const uint32_t OFF = __shfl_sync(kFull, off, start), SL = __shfl_sync(kFull, my_lit, start);
-                    const uint64_t D = __shfl_sync(kFull, my_dst, start);
+                    const uint32_t OFF = __shfl_sync(kFull, off, start);
+                    const uint64_t D = out_pos + __shfl_sync(kFull, excl_tot, start);
                     if (lit_rle)
-                        warp_memset(dst + D, rle_byte, L, lane);
+                        warp_memset(dst + D, lit[0], L, lane);
                     else
-                        warp_memcpy(dst + D, lit + SL, L, lane);
+                        warp_memcpy(dst + D, lit + lit_pos + __shfl_sync(kFull, excl_ll, start), L, lane);
                     __syncwarp();
                     uint8_t *MD = dst + D + L;
                     const uint8_t *MS = MD - OFF;
@@ -1420,23 +1431,27 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
                 const uint32_t no_lit = __ballot_sync(kFull, in && ll == 0);
                 const uint32_t no_match = __ballot_sync(kFull, in && ml == 0);  // cannot happen: ML codes start at 3 (predefined.go:36-50)
                 if (in) {
-                    uint32_t ord = st.nseg + 2 * (lane - start) - __popc((no_lit | 0) & lt_mask) - __popc(no_match & lt_mask);
+                    uint32_t ord = st.nseg + 2 * (lane - start) - __popc(no_lit & lt_mask) - __popc(no_match & lt_mask);
+                    const uint32_t bit0 = ((uint32_t)st.line & (kRingBits - 1)) + my_rel;  // my literal run in the bitmap
                     if (ll) {
-                        sm.seg[ord & (kSegRing - 1)] =
-                            lit_rle ? (kSegLit | kSegConst | rle_byte) : (kSegLit | (reinterpret_cast<uintptr_t>(lit) + my_lit - my_dst));
-                        atomicOr(&sm.bits[(uint32_t)(my_dst >> 5) & (kRingBits / 32 - 1)], 1u << ((uint32_t)my_dst & 31));
+                        // literal byte at output position p: lit[lit_pos + excl_ll + (p - my start)]; a run of RLE literals reads
+                        // the first bytes of the fill row
+                        const uint64_t my_start = out_pos + excl_tot;
+                        sm.seg[ord & (kSegRing - 1)] = reinterpret_cast<uintptr_t>(lit) + (lit_rle ? 0 : lit_pos + excl_ll) - my_start;
+                        atomicOr(&sm.bits[(bit0 >> 5) & (kRingBits / 32 - 1)], 1u << (bit0 & 31));
                         ord++;
                     }
                     if (ml) {
+                        const uint32_t bit1 = bit0 + ll;
                         sm.seg[ord & (kSegRing - 1)] = reinterpret_cast<uintptr_t>(dst) - off;
-                        atomicOr(&sm.bits[(uint32_t)(mdst >> 5) & (kRingBits / 32 - 1)], 1u << ((uint32_t)mdst & 31));
+                        atomicOr(&sm.bits[(bit1 >> 5) & (kRingBits / 32 - 1)], 1u << (bit1 & 31));
                         // the consumer gets here about a round later: have the source on its way to L1
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(dst + mdst - off));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(dst + (out_pos + excl_tot + ll - off)));
                     }
                 }
                 st.nseg += 2 * nfit - __popc(no_lit) - __popc(no_match);
-                const uint64_t prev_prod = st.prod;
-                st.prod = __shfl_sync(kFull, my_dst + tot, end - 1);
+                const uint32_t prev_prod = st.prod;
+                st.prod = __shfl_sync(kFull, my_rel + tot, end - 1);
                 __syncwarp();
                 exec_drain(sm, dst, st, prev_prod, lane, le_mask);  // stays one append behind, so that the prefetches have time to land
                 start = end;
@@ -1447,20 +1462,20 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
         if (err != SZB_OK) break;
         // trailing literals (sequence_execution.go:55-60, literals.go:411-420): one more segment, or a bulk copy
         const uint32_t rest = d.lit_regen - lit_pos;
-        if (rest && out_pos + rest - st.line <= kSpanBytes) {
+        if (rest && st.prod + rest <= kSpanBytes && !(lit_rle && rest > kConstRun)) {
             if (lane == 0) {
-                sm.seg[st.nseg & (kSegRing - 1)] =
-                    lit_rle ? (kSegLit | kSegConst | rle_byte) : (kSegLit | (reinterpret_cast<uintptr_t>(lit) + lit_pos - out_pos));
-                atomicOr(&sm.bits[(uint32_t)(out_pos >> 5) & (kRingBits / 32 - 1)], 1u << ((uint32_t)out_pos & 31));
+                const uint32_t bit0 = ((uint32_t)st.line & (kRingBits - 1)) + st.prod;
+                sm.seg[st.nseg & (kSegRing - 1)] = reinterpret_cast<uintptr_t>(lit) + (lit_rle ? 0 : lit_pos) - out_pos;
+                atomicOr(&sm.bits[(bit0 >> 5) & (kRingBits / 32 - 1)], 1u << (bit0 & 31));
             }
             st.nseg++;
-            st.prod = out_pos + rest;
+            st.prod += rest;
             __syncwarp();
             exec_drain(sm, dst, st, st.prod, lane, le_mask);
         } else if (rest) {
             exec_flush(sm, dst, st, lane, le_mask);
             if (lit_rle)
-                warp_memset(dst + out_pos, rle_byte, rest, lane);
+                warp_memset(dst + out_pos, lit[0], rest, lane);
             else
                 warp_memcpy(dst + out_pos, lit + lit_pos, rest, lane);
             __syncwarp();
