@@ -18,7 +18,7 @@ NVCC_FLAGS = [
     "-O3",
     "-std=c++17",
     "-Xcompiler",
-    "-fPIC",
+    "-fPIC,-pthread",
     "-shared",
 ]
 

@@ -5,11 +5,13 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/szb200.h"
@@ -519,10 +521,7 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
         ctx->launches++;
     }
     if (a.nframes && a.n_seq) {
-        // experiment knob: dynamic shared memory that is never touched, to cap the CTAs per SM
-        static const int pad = getenv("SZB_EXEC_PAD") ? atoi(getenv("SZB_EXEC_PAD")) : 0;
-        if (pad) cudaFuncSetAttribute(k_execute, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-        k_execute<<<(a.nframes + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, pad, s>>>(a);
+        k_execute<<<(a.nframes + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, s>>>(a);
         ctx->launches++;
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
@@ -776,6 +775,8 @@ static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_l
         uint64_t src_lo, src_hi, dst_lo, dst_len;
         szb_batch *batch;
         cudaEvent_t up, done;
+        szb_walk *walk;
+        int walk_rc;
     };
     std::vector<Chunk> chunks;
     uint64_t covered = 0;
@@ -805,19 +806,59 @@ static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_l
             pos += c.dst_len;
         }
     }
+    // The header walks (host only, frames are independent) run on worker threads, chunk by chunk, ahead of the
+    // submission loop below; otherwise the single submitting thread, not the copy engines, sets the pace.
+    std::vector<std::atomic<int>> walked(chunks.size());
+    for (auto &w : walked) w.store(0, std::memory_order_relaxed);
+    std::atomic<size_t> next_chunk{0};
+    std::atomic<bool> stop{false};
+    auto worker = [&]() {
+        for (;;) {
+            const size_t i = next_chunk.fetch_add(1);
+            if (i >= chunks.size() || stop.load()) return;
+            Chunk &c = chunks[i];
+            c.walk_rc = szb_walk_create(src, src_len, frame_off + c.f0, frame_len + c.f0, c.f1 - c.f0, &c.walk);
+            walked[i].store(1, std::memory_order_release);
+        }
+    };
+    unsigned nthreads = std::thread::hardware_concurrency();
+    nthreads = nthreads < 2 ? 1 : (nthreads > 8 ? 8 : nthreads - 1);
+    if (nthreads > chunks.size()) nthreads = (unsigned)chunks.size();
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nthreads; t++) pool.emplace_back(worker);
+    struct PoolJoin {
+        std::vector<std::thread> &p;
+        std::atomic<bool> &stop;
+        ~PoolJoin() {
+            stop.store(true);
+            for (auto &t : p)
+                if (t.joinable()) t.join();
+        }
+    } pool_join{pool, stop};
+
     cudaEvent_t ev_begin;
     CUDA_TRY(ctx, cudaEventCreate(&ev_begin));
     CUDA_TRY(ctx, cudaEventRecord(ev_begin, ctx->stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_h2d, ev_begin, 0));
     int fail = SZB_OK;
-    for (auto &c : chunks) {
+    for (size_t ci = 0; ci < chunks.size(); ci++) {
+        Chunk &c = chunks[ci];
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&c.up, cudaEventDisableTiming));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
         // compressed bytes of this chunk: H2D on the copy stream
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_src + c.src_lo, src + c.src_lo, (size_t)(c.src_hi - c.src_lo), cudaMemcpyHostToDevice, ctx->s_h2d));
         CUDA_TRY(ctx, cudaEventRecord(c.up, ctx->s_h2d));
-        // header walk on the host (overlaps the GPU work of the previous chunks), tables upload, kernels
-        rc = szb_batch_create(ctx, src, src_len, frame_off + c.f0, frame_len + c.f0, c.f1 - c.f0, &c.batch);
+        // descriptor tables of this chunk (walked by a worker), their upload, the kernels
+        while (!walked[ci].load(std::memory_order_acquire)) std::this_thread::yield();
+        rc = c.walk_rc;
+        if (!rc) {
+            rc = szb_batch_create_from_tables(ctx, src_len, szb_walk_frames(c.walk), szb_walk_nframes(c.walk), szb_walk_blocks(c.walk),
+                                              szb_walk_nblocks(c.walk), &c.batch);
+        }
+        if (c.walk) {
+            szb_walk_destroy(c.walk);
+            c.walk = nullptr;
+        }
         if (rc) {
             fail = rc;
             break;
@@ -835,11 +876,14 @@ static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_l
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_d2h, c.done, 0));
         if (c.dst_len) CUDA_TRY(ctx, cudaMemcpyAsync(dst + c.dst_lo, ctx->d_dst + c.dst_lo, (size_t)c.dst_len, cudaMemcpyDeviceToHost, ctx->s_d2h));
     }
+    stop.store(true);
+    for (auto &t : pool) t.join();
     cudaStreamSynchronize(ctx->s_h2d);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->s_d2h);
     *first_rc = SZB_OK;
     for (auto &c : chunks) {
+        if (c.walk) szb_walk_destroy(c.walk);
         if (c.batch && fail == SZB_OK) {
             const uint32_t n = c.f1 - c.f0;
             std::vector<int32_t> st(n);

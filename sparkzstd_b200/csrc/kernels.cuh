@@ -14,10 +14,14 @@
 //   k_scan_blocks       device-wide exclusive prefix sum of per-block regenerated sizes
 //                       (the reference gets positions for free from its ring buffer,
 //                       decompression/ringbuffer.go:102-178)
-//   k_execute           stage 4: literal copies, repeat-offset history, match copies against
-//                       the output itself, Raw / RLE block bodies
-//                       (decompression/sequence_execution.go:14-114, ringbuffer.go:197-277,
-//                       framedecompressor.go:211-241)
+//   k_frame_verdict     per frame: first failing block, placement in the output
+//   k_execute_bodies    Raw / RLE block bodies and blocks without sequences, one warp each
+//                       (framedecompressor.go:211-241)
+//   k_execute           stage 4, one warp per frame: repeat-offset history and positions by warp scans,
+//                       then the output produced in address order, 128 bytes per step, every lane
+//                       fetching the source byte of its output byte (literal or match)
+//                       (decompression/sequence_execution.go:14-114, ringbuffer.go:197-277)
+//   k_verify_checksums  optional XXH64 content checksum, one thread per frame
 //
 // All arithmetic is integer; there is no tensor-core work on this path.
 #pragma once
@@ -1275,7 +1279,7 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute_bodies(DeviceBatch a) {
 
 // One warp per frame; blocks in order; 32 sequences per round (sequence_execution.go:14-63).
 #ifndef SZB_EXEC_MIN_CTAS
-#define SZB_EXEC_MIN_CTAS 7
+#define SZB_EXEC_MIN_CTAS 8
 #endif
 __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(DeviceBatch a) {
     __shared__ ExecSmem smem[kWarpsPerCta];
