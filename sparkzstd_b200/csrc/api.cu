@@ -56,7 +56,7 @@ struct szb_batch {
     size_t src_len = 0;
     std::vector<szb_frame_desc> frames;
     std::vector<szb_block_desc> blocks;
-    std::vector<uint32_t> huf_list, seq_list, hufo_list, huf_slot, body_list;
+    std::vector<uint32_t> huf_list, seq_list, hufo_list, huf_slot, body_list, exec_list;
     uint64_t literal_bytes = 0, sequences = 0;
     std::vector<uint8_t> stage;  // host image of the descriptor tables (kept until the upload has certainly happened)
     // device
@@ -67,6 +67,7 @@ struct szb_batch {
     uint16_t *d_huf_tabs = nullptr;
     HufInfo *d_huf_info = nullptr;
     uint32_t *d_body_list = nullptr;
+    uint32_t *d_exec_list = nullptr;
     uint64_t *d_out_size_init = nullptr;
     void *d_state = nullptr;  // one allocation: out_size | out_off | total | frame_out_off | frame_out_len | statuses
     uint64_t *d_out_size = nullptr, *d_out_off = nullptr, *d_total = nullptr, *d_frame_out_off = nullptr,
@@ -205,7 +206,7 @@ int szb_ctx_create(int device, void *stream, szb_ctx **out) {
     cudaFuncSetAttribute(k_build_huf_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(HufSmem) * kWarpsPerCta));
     cudaFuncSetAttribute(k_build_seq_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SeqSmem) * kWarpsPerCta));
     cudaFuncSetAttribute(k_decode_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeqDecodeSmemBytes);
-    cudaFuncSetAttribute(k_decode_literals, cudaFuncAttributePreferredSharedMemoryCarveout, 50);  // leave L1 for the streams
+    cudaFuncSetAttribute(k_decode_literals, cudaFuncAttributePreferredSharedMemoryCarveout, 100);  // streams arrive by cp.async: L1 is not needed, resident warps are
     *out = ctx;
     return SZB_OK;
 }
@@ -269,6 +270,15 @@ static int batch_upload_tables(szb_batch *b) {
     // sequence counts, and the longest blocks should start first
     std::stable_sort(b->seq_list.begin(), b->seq_list.end(),
                      [&](uint32_t x, uint32_t y) { return b->blocks[x].nseq > b->blocks[y].nseq; });
+    // k_execute runs one warp per frame and a frame is sequential: the frames with the most sequences start first,
+    // so that the longest one does not begin when the rest of the grid is already draining
+    {
+        std::vector<uint64_t> work(nf ? nf : 1, 0);
+        for (uint32_t i : b->seq_list) work[b->blocks[i].frame] += b->blocks[i].nseq;
+        b->exec_list.resize(nf);
+        for (uint32_t f = 0; f < nf; f++) b->exec_list[f] = f;
+        std::stable_sort(b->exec_list.begin(), b->exec_list.end(), [&](uint32_t x, uint32_t y) { return work[x] > work[y]; });
+    }
     // descriptor tables: one allocation, one H2D copy
     size_t o_frames = 0;
     size_t o_blocks = align_up(o_frames + sizeof(szb_frame_desc) * (size_t)nf, 256);
@@ -277,7 +287,8 @@ static int batch_upload_tables(szb_batch *b) {
     size_t o_hufo = align_up(o_seq + 4 * b->seq_list.size(), 256);
     size_t o_slot = align_up(o_hufo + 4 * b->hufo_list.size(), 256);
     size_t o_body = align_up(o_slot + 4 * b->huf_slot.size(), 256);
-    size_t o_init = align_up(o_body + 4 * b->body_list.size(), 256);
+    size_t o_exec = align_up(o_body + 4 * b->body_list.size(), 256);
+    size_t o_init = align_up(o_exec + 4 * b->exec_list.size(), 256);
     size_t total = align_up(o_init + 8 * (size_t)nb, 256) + 256;
     std::vector<uint8_t> &stage = b->stage;
     stage.assign(total, 0);
@@ -288,6 +299,7 @@ static int batch_upload_tables(szb_batch *b) {
     if (!b->hufo_list.empty()) memcpy(stage.data() + o_hufo, b->hufo_list.data(), 4 * b->hufo_list.size());
     if (!b->huf_slot.empty()) memcpy(stage.data() + o_slot, b->huf_slot.data(), 4 * b->huf_slot.size());
     if (!b->body_list.empty()) memcpy(stage.data() + o_body, b->body_list.data(), 4 * b->body_list.size());
+    if (!b->exec_list.empty()) memcpy(stage.data() + o_exec, b->exec_list.data(), 4 * b->exec_list.size());
     if (nb) memcpy(stage.data() + o_init, out_size_init.data(), 8 * (size_t)nb);
     CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_tables, total));
     CUDA_TRY(ctx, cudaMemcpyAsync(b->d_tables, stage.data(), total, cudaMemcpyHostToDevice, ctx->stream));
@@ -299,6 +311,7 @@ static int batch_upload_tables(szb_batch *b) {
     b->d_hufo_list = (uint32_t *)(base + o_hufo);
     b->d_huf_slot = (uint32_t *)(base + o_slot);
     b->d_body_list = (uint32_t *)(base + o_body);
+    b->d_exec_list = (uint32_t *)(base + o_exec);
     b->d_out_size_init = (uint64_t *)(base + o_init);
     // mutable state
     size_t s_out_size = 0;
@@ -465,6 +478,7 @@ static DeviceBatch make_args(szb_batch *b, const void *d_src, void *d_dst, size_
     a.frame_out_off = b->d_frame_out_off;
     a.frame_out_len = b->d_frame_out_len;
     a.frame_status = b->d_frame_status;
+    a.exec_list = b->d_exec_list;
     a.body_list = b->d_body_list;
     a.n_body = (uint32_t)b->body_list.size();
     return a;

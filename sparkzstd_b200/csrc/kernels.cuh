@@ -83,6 +83,7 @@ struct DeviceBatch {
     uint64_t dst_cap;
     uint64_t *frame_out_off, *frame_out_len;
     int32_t *frame_status;
+    const uint32_t *exec_list;  // frames in the order k_execute starts them (most sequences first)
     const uint32_t *body_list;  // Raw / RLE / zero-sequence blocks: output independent of earlier output
     uint32_t n_body;
 };
@@ -1284,8 +1285,9 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute_bodies(DeviceBatch a) {
 __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(DeviceBatch a) {
     __shared__ ExecSmem smem[kWarpsPerCta];
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t f = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    if (f >= a.nframes) return;
+    const uint32_t slot = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    if (slot >= a.nframes) return;
+    const uint32_t f = a.exec_list[slot];
     ExecSmem &sm = smem[threadIdx.x >> 5];
     const szb_frame_desc fr = a.frames[f];
     const uint32_t b0 = fr.first_block, nb = fr.nblocks;
