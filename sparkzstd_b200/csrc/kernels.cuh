@@ -303,19 +303,25 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *g) {
 }
 
 // Reverse bit reader for one lane of k_decode_literals: the 64-bit window of bits.cuh, refilled with
-// 32-bit words from a per-lane shared-memory ring of eight 16-byte chunks of the stream.  The ring is
-// topped up with cp.async four chunks ahead of the read position, so no lane ever waits for HBM while
-// its 31 neighbours (which walk unrelated streams in lock step) are ready.  Completion is tracked in
-// commit groups: hring_refill commits one group per call, a chunk holds >= 11 symbols (128 bits /
-// maxBits 11) and refill is called at least once per two symbols, so the chunk being entered was
-// requested >= 20 groups ago and wait_group 16 covers it.
-constexpr uint32_t kHufRingStride = 144;  // 128 B ring + pad (keeps 16-byte alignment, spreads banks)
+// 32-bit words from a per-lane shared-memory ring of four 16-byte chunks of the stream.  The ring is
+// topped up with cp.async once per group of eight symbols, by all lanes at the same point of the
+// program (the lanes walk unrelated streams in lock step), one group ahead of use, so that no lane waits
+// for HBM while its neighbours are ready.
+//
+// Eight symbols are at most 88 bits: the refills of one group move at most four words (16 bytes) out of
+// the ring.  The top-up of group g requests every chunk down to the one holding byte (next - kHufRingAhead)
+// and is waited for at group g+1 (wait_group 1), whose reads stay above next_g - 32: kHufRingAhead = 32.
+// The ring then spans chunk(next - 32) .. chunk(next - 1), three of its four slots, so a copy never
+// lands in a slot that is still being read.
+constexpr uint32_t kHufRingBytes = 64;
+constexpr uint32_t kHufRingStride = 80;  // 64 B ring + pad (keeps 16-byte alignment, spreads banks)
+constexpr int32_t kHufRingAhead = 32;
 struct HufBits {
     uint64_t win;
     int32_t avail;
     int32_t next;        // stream bytes [0, next) not yet moved into the window
     int32_t remaining;   // real bits not consumed yet
-    int32_t cur;         // chunk (16 B units from the aligned address at or below the stream) being read
+    int32_t lowreq;      // lowest chunk (16 B units from the aligned address at or below the stream) requested so far
     uint32_t mis;        // stream address & 15
     uint32_t ring_saddr; // shared-space address of this lane's ring
     const uint8_t *ring;
@@ -323,21 +329,40 @@ struct HufBits {
     const uint4 *chunk0;
 };
 
-__device__ __forceinline__ void hring_fetch(const HufBits &r, int32_t c) {
-    if (c >= 0) cp_async16(r.ring_saddr + (((uint32_t)c & 7) << 4), r.chunk0 + c);
+__device__ __forceinline__ void hring_fetch_if(const HufBits &r, bool p, int32_t c) {
+    const uint32_t dst = r.ring_saddr + (((uint32_t)c & (kHufRingBytes / 16 - 1)) << 4);
+    const uint4 *src = r.chunk0 + c;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %0, 0;\n\t"
+        "@p cp.async.cg.shared.global [%1], [%2], 16;\n\t}"
+        ::"r"((uint32_t)p), "r"(dst), "l"(src)
+        : "memory");
+}
+// steady state, no branch: at most two more chunks, which is what a group can consume
+__device__ __forceinline__ void hring_topup(HufBits &r) {
+    int32_t need = ((int32_t)r.mis + r.next - kHufRingAhead) >> 4;
+    need = need < 0 ? 0 : need;
+    const bool p1 = r.lowreq - 1 >= need, p2 = r.lowreq - 2 >= need;
+    hring_fetch_if(r, p1, r.lowreq - 1);
+    hring_fetch_if(r, p2, r.lowreq - 2);
+    r.lowreq -= (int32_t)p1 + (int32_t)p2;
+    asm volatile("cp.async.commit_group;");
+}
+// everything down to (next - kHufRingAhead), and wait for it: stream start, and around the unaligned head and tail
+__device__ __forceinline__ void hring_fill(HufBits &r) {
+    int32_t need = ((int32_t)r.mis + r.next - kHufRingAhead) >> 4;
+    need = need < 0 ? 0 : need;
+    while (r.lowreq > need) hring_fetch_if(r, true, --r.lowreq);
+    asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 __device__ __forceinline__ void hring_refill(HufBits &r) {
     if (r.avail <= 32) {
         if (r.next >= 4) {
             const uint32_t wa = r.mis + (uint32_t)r.next - 4;  // word position relative to chunk 0
-            const int32_t c = (int32_t)(wa >> 4);
-            if (c < r.cur) {
-                r.cur = c;
-                asm volatile("cp.async.wait_group 16;" ::: "memory");
-                hring_fetch(r, c - 4);
-            }
-            const uint32_t w = *reinterpret_cast<const uint32_t *>(r.ring + (wa & 127));
+            const uint32_t w = *reinterpret_cast<const uint32_t *>(r.ring + (wa & (kHufRingBytes - 1)));
             r.next -= 4;
             r.win |= (uint64_t)w << (32 - r.avail);
             r.avail += 32;
@@ -350,7 +375,6 @@ __device__ __forceinline__ void hring_refill(HufBits &r) {
             r.avail = 64;  // zero fill below the stream start (reversebitstream.go:23-27,67-75)
         }
     }
-    asm volatile("cp.async.commit_group;");
 }
 
 __device__ __forceinline__ bool hring_init(HufBits &r, const uint8_t *data, int32_t len, uint8_t *ring) {
@@ -363,14 +387,12 @@ __device__ __forceinline__ bool hring_init(HufBits &r, const uint8_t *data, int3
     r.ring_saddr = (uint32_t)__cvta_generic_to_shared(ring);
     r.mis = (uint32_t)(reinterpret_cast<uintptr_t>(data) & 15);
     r.chunk0 = reinterpret_cast<const uint4 *>(data - r.mis);
+    r.lowreq = 0;
     if (len <= 0) {
         r.avail = 64;
-        r.cur = 0;
         return false;
     }
-    r.cur = (int32_t)((r.mis + (uint32_t)len - 1) >> 4);
-    for (int k = 0; k < 5; k++) hring_fetch(r, r.cur - k);
-    asm volatile("cp.async.commit_group;");
+    r.lowreq = (int32_t)((r.mis + (uint32_t)len - 1) >> 4) + 1;
     // byte loads until the unread length is a multiple of 4 from an aligned address
     while (r.next > 0 && ((r.mis + (uint32_t)r.next) & 3) != 0) {
         const uint32_t b = r.base[--r.next];
@@ -378,7 +400,7 @@ __device__ __forceinline__ bool hring_init(HufBits &r, const uint8_t *data, int3
         r.avail += 8;
     }
     if (r.next == 0) r.avail = 64;
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    hring_fill(r);
     hring_refill(r);
     return true;
 }
@@ -405,16 +427,22 @@ __device__ __forceinline__ int huf_decode_stream_vec(const uint16_t *table, uint
     uint32_t n = 0;
     uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15)) & 15;
     if (head > expected) head = expected;
+    // up to 15 single symbols (165 bits) to reach a 16-byte aligned output address: within what hring_init made resident
     for (; n < head; n++) {
         hring_refill(r);
         const uint32_t e = table[hring_peek(r, max_bits)];
         out[n] = (uint8_t)e;
         hring_skip(r, e >> 8);
     }
+    hring_fill(r);
     while (n + 16 <= expected) {
         uint32_t wv[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
+            if ((q & 1) == 0) {  // a group of eight symbols
+                hring_topup(r);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            }
             uint32_t acc = 0;
 #pragma unroll
             for (int t = 0; t < 4; t++) {
@@ -428,13 +456,13 @@ __device__ __forceinline__ int huf_decode_stream_vec(const uint16_t *table, uint
         *reinterpret_cast<uint4 *>(out + n) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
         n += 16;
     }
+    hring_fill(r);
     for (; n < expected; n++) {
         hring_refill(r);
         const uint32_t e = table[hring_peek(r, max_bits)];
         out[n] = (uint8_t)e;
         hring_skip(r, e >> 8);
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (r.remaining > 0) return SZB_ERR_STREAM_DIDNT_DECODE_TO_RIGHT_LENGTH;  // more symbols than its slot holds
     if (r.remaining < 0) return SZB_ERR_DIDNT_USE_ALL_BITS_TO_DECODE_HUFFMAN;
     return SZB_OK;
@@ -447,7 +475,8 @@ constexpr uint32_t kHufCellsPerWarp = 2048;  // 4 KB of decode tables resident p
 // blocks at once.  The blocks' decode tables are copied from the arena into the warp's 8 KB of shared
 // memory; neighbouring blocks that share a table (a Compressed block followed by its Treeless users)
 // share one copy.  When the tables do not fit (maxBits 11 = 4 KB each) the group is done in passes.
-// Shared memory is kept small on purpose: the streams are read through L1, which needs the room.
+// 6.5 KB of shared memory per warp (tables + bit rings): eight CTAs per SM; a deeper ring (three copy
+// groups in flight) costs two of them and measured slower.
 __global__ void __launch_bounds__(kCtaThreads) k_decode_literals(DeviceBatch a) {
     __shared__ __align__(16) uint16_t tabs_all[kWarpsPerCta][kHufCellsPerWarp];
     __shared__ __align__(16) uint8_t rings_all[kWarpsPerCta][32 * kHufRingStride];
