@@ -23,7 +23,7 @@ struct szb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    cudaEvent_t ev[10] = {};
+    cudaEvent_t ev[11] = {};
     uint32_t *d_predef = nullptr;
     uint8_t *d_bytefill = nullptr;  // 256 rows of 256 equal bytes: the source of RLE literal runs (kernels.cuh, stage 4)
     std::string last_error;
@@ -36,6 +36,8 @@ struct szb_ctx {
     size_t d_dst_cap = 0;
     // copy streams for the pipelined host-buffer path
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t s_lit = nullptr;          // the literal chain runs beside the sequence chain (they meet at stage 4)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 static cudaError_t pool_alloc(szb_ctx *ctx, void **p, size_t bytes);
@@ -223,6 +225,9 @@ void szb_ctx_destroy(szb_ctx *ctx) {
     if (ctx->d_dst) cudaFree(ctx->d_dst);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    if (ctx->s_lit) cudaStreamDestroy(ctx->s_lit);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -489,20 +494,21 @@ static int launch_entropy(szb_batch *b, const void *d_src) {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     DeviceBatch a = make_args(b, d_src, nullptr, 0);
+    if (!ctx->s_lit) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_lit, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
+    cudaStream_t sl = ctx->s_lit;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
     CUDA_TRY(ctx, cudaMemsetAsync(b->d_lit_status, 0, b->status_bytes, s));
     if (b->nblocks)
         CUDA_TRY(ctx, cudaMemcpyAsync(b->d_out_size, b->d_out_size_init, 8 * (size_t)b->nblocks, cudaMemcpyDeviceToDevice, s));
-    if (a.n_hufo) {
-        k_build_huf_tables<<<(a.n_hufo + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, sizeof(HufSmem) * kWarpsPerCta, s>>>(a);
-        ctx->launches++;
-    }
-    if (a.n_huf) {
-        const uint32_t groups = (a.n_huf + kHufGroup - 1) / kHufGroup;
-        k_decode_literals<<<(groups + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, s>>>(a);
-        ctx->launches++;
-    }
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
+    // Stage 2 (literals) and stage 3 (sequences) are independent until stage 4.  The sequence kernel is
+    // launched first and owns the SMs (shared memory); the literal chain, on its own stream, fills the
+    // SMs the last, partial wave of the sequence kernel leaves idle.
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, s));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(sl, ctx->ev_fork, 0));
     if (a.n_seq) {
         k_build_seq_tables<<<(a.n_seq + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, sizeof(SeqSmem) * kWarpsPerCta, s>>>(a);
         ctx->launches++;
@@ -513,6 +519,19 @@ static int launch_entropy(szb_batch *b, const void *d_src) {
         ctx->launches++;
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
+    if (a.n_hufo) {
+        k_build_huf_tables<<<(a.n_hufo + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, sizeof(HufSmem) * kWarpsPerCta, sl>>>(a);
+        ctx->launches++;
+    }
+    if (a.n_huf) {
+        const uint32_t groups = (a.n_huf + kHufGroup - 1) / kHufGroup;
+        k_decode_literals<<<(groups + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, sl>>>(a);
+        ctx->launches++;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], sl));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, sl));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[10], s));
     k_scan_blocks<<<1, kScanThreads, 0, s>>>(a);
     ctx->launches++;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], s));
@@ -544,15 +563,20 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
 }
 
 static int collect_timing(szb_ctx *ctx) {
+    // [1] literals and [2] sequences both start at ev[0] and overlap; [3] scan starts when both are done
     float t;
     CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev[4]));
     CUDA_TRY(ctx, cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[4]));
     ctx->timing[0] = t;
-    for (int i = 1; i <= 4; i++) {
-        CUDA_TRY(ctx, cudaEventElapsedTime(&t, ctx->ev[i - 1], ctx->ev[i]));
-        ctx->timing[i] = t;
-    }
-    CUDA_TRY(ctx, cudaEventElapsedTime(&t, ctx->ev[1], ctx->ev[7]));
+    CUDA_TRY(ctx, cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]));
+    ctx->timing[1] = t;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[2]));
+    ctx->timing[2] = t;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&t, ctx->ev[10], ctx->ev[3]));
+    ctx->timing[3] = t;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[4]));
+    ctx->timing[4] = t;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[7]));
     ctx->timing[7] = t;  // table construction share of [2]
     return SZB_OK;
 }
