@@ -239,6 +239,21 @@ def main():
     lit_huf = int(sum(int(b.lit_regen) for b in blocks if b.type == 2 and b.lit_type >= 2))
     lit_comp = int(sum(int(b.lit_comp) for b in blocks if b.type == 2 and b.lit_type >= 2))
 
+    # which format paths the timed corpus exercises (SURVEY.md section 8d asks for this next to the mixed result)
+    cov = {"block_types": [0, 0, 0], "literal_types": [0, 0, 0, 0], "ll_modes": [0, 0, 0, 0], "of_modes": [0, 0, 0, 0], "ml_modes": [0, 0, 0, 0]}
+    for b in blocks:
+        cov["block_types"][b.type] += 1
+        if b.type == 2:
+            cov["literal_types"][b.lit_type] += 1
+            if b.nseq:
+                cov["ll_modes"][b.seq_modes >> 6] += 1
+                cov["of_modes"][(b.seq_modes >> 4) & 3] += 1
+                cov["ml_modes"][(b.seq_modes >> 2) & 3] += 1
+    cov["legend"] = "block types Raw/RLE/Compressed; literal types Raw/RLE/Compressed/Treeless; modes Predefined/RLE/FSE/Repeat"
+    if args.workload == "mixed":
+        assert all(cov["block_types"]) and all(cov["literal_types"]) and all(cov["ll_modes"]) and all(cov["of_modes"]) and \
+            all(cov["ml_modes"]), f"the mixed corpus misses a format path: {cov}"
+
     verified = None
     if not args.no_verify:
         host = d_dst_t[:D].cpu().numpy()
@@ -331,7 +346,7 @@ def main():
                    "sequences_per_gpu": nseq, "compressed_bytes_per_gpu": C_bytes, "decompressed_bytes_per_gpu": D,
                    "parallelism": f"frame-sharded x{world}, no collective",
                    "l2": "inputs (compressed + scratch + output, > 5 GB) are larger than the 126 MB L2; no flush needed",
-                   "header_walk_s": walk_s},
+                   "header_walk_s": walk_s, "format_coverage_per_gpu": cov},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "verified": verified,
     }
