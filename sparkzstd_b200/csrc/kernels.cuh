@@ -1193,28 +1193,31 @@ __device__ __forceinline__ void place_step(ExecSmem &sm, uint8_t *dst, ExecState
         // pointer jumping over shuffles (chains of in-chunk sources halve every round)
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            bool unres = ing[c];
-            if (c > 0) {
-                __syncwarp();
-                if (unres && (sg[c] >> 5) < (uint32_t)c) {
-                    v[c] = sm.grp[sg[c]];
-                    unres = false;
-                }
-            }
-            uint32_t par = sg[c] & 31;
-            uint32_t open = __ballot_sync(kFull, unres);
-            while (open) {
-                const uint32_t pv = __shfl_sync(kFull, v[c], par);
-                const uint32_t pp = __shfl_sync(kFull, par, par);
-                if (unres) {
-                    if (!((open >> par) & 1)) {
-                        v[c] = pv;
+            uint32_t open = __ballot_sync(kFull, ing[c]);
+            if (open) {
+                bool unres = ing[c];
+                if (c > 0) {
+                    __syncwarp();  // the chunks before this one are in sm.grp
+                    if (unres && (sg[c] >> 5) < (uint32_t)c) {
+                        v[c] = sm.grp[sg[c]];
                         unres = false;
-                    } else {
-                        par = pp;
                     }
+                    open = __ballot_sync(kFull, unres);
                 }
-                open = __ballot_sync(kFull, unres);
+                uint32_t par = sg[c] & 31;
+                while (open) {
+                    const uint32_t pv = __shfl_sync(kFull, v[c], par);
+                    const uint32_t pp = __shfl_sync(kFull, par, par);
+                    if (unres) {
+                        if (!((open >> par) & 1)) {
+                            v[c] = pv;
+                            unres = false;
+                        } else {
+                            par = pp;
+                        }
+                    }
+                    open = __ballot_sync(kFull, unres);
+                }
             }
             my_grp[c << 5] = (uint8_t)v[c];
         }
