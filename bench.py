@@ -134,12 +134,29 @@ def cpu_reference_arm(args, c, rank, world):
     ms = 1e3 * float(np.mean(times))
     value = sample_bytes / (ms * 1e-3) / 1e9
     sample = f"first {nsample} frames of the workload ({sample_bytes / 1e6:.0f} MB decompressed) per step"
+    # two more CPU lines SURVEY.md section 8d asks for, each on a couple of seconds of work: the same port on ONE thread, and
+    # libzstd 1.5.5 (dlopen) on all threads -- an industrial decoder, NOT the reference, for scale only
+    extra = {}
+    n1 = int(max(1, min(nsample, nsample * 2.0 / max(1e-3, ms * 1e-3) / max(1, cores))))
+    t0 = time.perf_counter()
+    _, st1 = pyszo.decode_batch_mt(c.src, c.frame_off[:n1], c.frame_len[:n1], 1)
+    dt = time.perf_counter() - t0
+    if not st1.any():
+        extra["port_1_thread"] = {"value": float(c.raw_size[:n1].sum()) / dt / 1e9, "unit": UNIT, "frames": n1}
+    if cg.zstd_available():
+        cg.zstd_decode_batch_mt(c, min(nsample, 4 * cores), cores)  # warm
+        t0 = time.perf_counter()
+        failed = cg.zstd_decode_batch_mt(c, nsample, cores)
+        dt = time.perf_counter() - t0
+        if failed == 0:
+            extra["libzstd_1_5_5"] = {"value": sample_bytes / dt / 1e9, "unit": UNIT, "cores": cores, "frames": nsample,
+                                      "note": "not the reference: libzstd via dlopen, for scale"}
     return {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": c.meta.get("workload", c.name), "note": "CPU arm: oracle (C restatement of sparkzstd), one decoder per host thread; Go toolchain absent"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, **extra},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
 

@@ -48,6 +48,8 @@ def lib():
         L.cg_compress_stream.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int]
         L.cg_zstd_decompress.restype = C.c_size_t
         L.cg_zstd_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.cg_zstd_decompress_batch_mt.restype = C.c_uint32
+        L.cg_zstd_decompress_batch_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]
         L.cg_generate_frames.restype = C.c_uint64
         L.cg_generate_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -116,6 +118,14 @@ def hash_frames(base: np.ndarray, off: np.ndarray, length: np.ndarray, nthreads:
     out = np.zeros(len(off), dtype=np.uint64)
     lib().cg_hash_frames(base.ctypes.data, off.ctypes.data, length.ctypes.data, len(off), out.ctypes.data, nthreads or host_threads())
     return out
+
+
+def zstd_decode_batch_mt(c: "Corpus", nframes: int, nthreads: int) -> int:
+    """libzstd (dlopen) over the first nframes frames, outputs discarded; returns how many frames failed."""
+    off = np.ascontiguousarray(c.frame_off[:nframes], dtype=np.uint64)
+    ln = np.ascontiguousarray(c.frame_len[:nframes], dtype=np.uint64)
+    raw = np.ascontiguousarray(c.raw_size[:nframes], dtype=np.uint64)
+    return int(lib().cg_zstd_decompress_batch_mt(c.src.ctypes.data, off.ctypes.data, ln.ctypes.data, raw.ctypes.data, nframes, nthreads))
 
 
 def generate(name: str, kinds, seeds, sizes, level: int = 3, checksum: int = 0, nthreads: Optional[int] = None,

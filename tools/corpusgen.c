@@ -276,6 +276,54 @@ size_t cg_zstd_decompress(const uint8_t *src, size_t n, uint8_t *dst, size_t cap
     return Z.isError(r) ? (size_t)-1 : r;
 }
 
+/* libzstd over a batch of independent frames, one frame per task, nthreads workers; each worker decodes into its own
+ * scratch buffer (the output is discarded, as in the reference arm).  Returns the number of frames that failed.
+ * Only used by bench.py for the "industrial CPU" line next to the reference port. */
+typedef struct {
+    const uint8_t *base;
+    const uint64_t *off, *len, *raw;
+    uint32_t n;
+    volatile uint32_t *next;
+    volatile uint32_t *failed;
+} zdec_job;
+static void *zdec_worker(void *arg) {
+    zdec_job *j = (zdec_job *)arg;
+    size_t cap = 1 << 16;
+    uint8_t *buf = (uint8_t *)malloc(cap);
+    for (;;) {
+        uint32_t i = __atomic_fetch_add(j->next, 16, __ATOMIC_RELAXED);
+        if (i >= j->n || !buf) break;
+        uint32_t e = i + 16 < j->n ? i + 16 : j->n;
+        for (; i < e; i++) {
+            size_t need = (size_t)j->raw[i] + 64;
+            if (need > cap) {
+                free(buf);
+                cap = need;
+                buf = (uint8_t *)malloc(cap);
+                if (!buf) break;
+            }
+            size_t r = Z.decompress(buf, cap, j->base + j->off[i], (size_t)j->len[i]);
+            if (Z.isError(r) || r != (size_t)j->raw[i]) __atomic_fetch_add(j->failed, 1, __ATOMIC_RELAXED);
+        }
+    }
+    free(buf);
+    return NULL;
+}
+uint32_t cg_zstd_decompress_batch_mt(const uint8_t *base, const uint64_t *off, const uint64_t *len, const uint64_t *raw, uint32_t n,
+                                     int nthreads) {
+    if (!cg_zstd_available()) return n;
+    volatile uint32_t next = 0, failed = 0;
+    zdec_job job = {base, off, len, raw, n, &next, &failed};
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    pthread_t th[256];
+    int started = 0;
+    for (int t = 0; t < nthreads; t++) if (pthread_create(&th[t], NULL, zdec_worker, &job) == 0) started++; else break;
+    if (!started) zdec_worker(&job);
+    for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+    return failed;
+}
+
 /* ---- batch of independent frames, multi-threaded ---- */
 typedef struct {
     const int32_t *kind;      /* per frame */
