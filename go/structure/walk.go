@@ -199,5 +199,14 @@ func WalkFrame(src []byte) (*Walk, error) {
 	}
 	f.src_len = C_uint64(pos)
 	f.nblocks = C_uint32(len(w.Blocks))
+	// The reference leaves the optional content checksum unread (frame.go:105-108).  It is recorded so that
+	// szb200.FlagVerifyChecksum can have the GPU check it; src_len stays "up to the end of the last block".
+	if (fhd>>2)&1 == 1 {
+		f.has_checksum = 1
+		if w.Err == nil && need(4) {
+			f.checksum = C_uint32(uint32(src[pos]) | uint32(src[pos+1])<<8 | uint32(src[pos+2])<<16 | uint32(src[pos+3])<<24)
+			f.checksum_valid = 1
+		}
+	}
 	return w, nil
 }
