@@ -863,7 +863,12 @@ static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_l
     nthreads = nthreads < 2 ? 1 : (nthreads > 8 ? 8 : nthreads - 1);
     if (nthreads > chunks.size()) nthreads = (unsigned)chunks.size();
     std::vector<std::thread> pool;
-    for (unsigned t = 0; t < nthreads; t++) pool.emplace_back(worker);
+    try {
+        for (unsigned t = 0; t < nthreads; t++) pool.emplace_back(worker);
+    } catch (...) {
+        // no (more) threads to be had: whatever started keeps going, and with none at all the walks happen right here
+    }
+    if (pool.empty()) worker();
     struct PoolJoin {
         std::vector<std::thread> &p;
         std::atomic<bool> &stop;
