@@ -1378,27 +1378,35 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
                 asm volatile("prefetch.global.L1 [%0];" ::"l"((lane == 0 ? a.seq_ll : (lane == 1 ? a.seq_ml : a.seq_of)) + sbo + base + 64));
 
             // --- offsets through the 3-entry history (nextOffset) ---
-            uint32_t off;
-            const uint32_t rep_mask = __ballot_sync(kFull, act && ofv <= 3);
-            if (rep_mask == 0) {
-                off = ofv - 3;
-                const uint32_t o1 = __shfl_sync(kFull, off, cnt - 1);
-                const uint32_t o2 = __shfl_sync(kFull, off, cnt >= 2 ? cnt - 2 : 0);
-                const uint32_t o3 = __shfl_sync(kFull, off, cnt >= 3 ? cnt - 3 : 0);
-                if (cnt >= 3) {
-                    hist = History{o1, o2, o3};
-                } else if (cnt == 2) {
-                    hist = History{o1, o2, hist.h0};
-                } else {
-                    hist = History{o1, hist.h0, hist.h1};
-                }
-            } else {
-                off = 0;
-                for (uint32_t j = 0; j < cnt; j++) {  // serial, every lane tracks the same history
+            // A sequence with a direct offset (offset value > 3) pushes it onto the history whatever the history
+            // holds; only the repeat codes look at it.  So the walk jumps from repeat code to repeat code: the run of
+            // direct sequences in between is folded in at once (its last three offsets are the new history).
+            uint32_t off = ofv - 3;
+            {
+                uint32_t rm = __ballot_sync(kFull, act && ofv <= 3);
+                uint32_t p = 0;  // sequences [0, p) are folded into hist
+                for (;;) {
+                    const uint32_t j = rm ? (uint32_t)__ffs(rm) - 1 : cnt;  // the next repeat code, or the end of the round
+                    const uint32_t n = j - p;
+                    if (n) {
+                        const uint32_t o1 = __shfl_sync(kFull, off, j - 1);
+                        const uint32_t o2 = __shfl_sync(kFull, off, n >= 2 ? j - 2 : 0);
+                        const uint32_t o3 = __shfl_sync(kFull, off, n >= 3 ? j - 3 : 0);
+                        if (n >= 3) {
+                            hist = History{o1, o2, o3};
+                        } else if (n == 2) {
+                            hist = History{o1, o2, hist.h0};
+                        } else {
+                            hist = History{o1, hist.h0, hist.h1};
+                        }
+                    }
+                    if (j >= cnt) break;
                     const uint32_t v = __shfl_sync(kFull, ofv, j);
                     const uint32_t l = __shfl_sync(kFull, ll, j);
-                    const uint32_t o = next_offset(hist, v, l == 0);
+                    const uint32_t o = next_offset(hist, v, l == 0);  // every lane tracks the same history
                     if (lane == j) off = o;
+                    rm &= rm - 1;
+                    p = j + 1;
                 }
             }
 
