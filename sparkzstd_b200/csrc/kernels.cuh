@@ -1412,13 +1412,26 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
 
             // --- positions: prefix sums over the round ---
             const uint32_t tot = ll + ml;
-            uint32_t incl_ll = ll, incl_tot = tot;
-            for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                const uint32_t t1 = __shfl_up_sync(kFull, incl_ll, dlt);
-                const uint32_t t2 = __shfl_up_sync(kFull, incl_tot, dlt);
-                if ((int)lane >= dlt) {
-                    incl_ll += t1;
-                    incl_tot += t2;
+            uint32_t incl_ll, incl_tot;
+            if (__reduce_max_sync(kFull, tot) < 2048) {
+                // both sums stay below 2^16: one scan over (literals | literals + match << 16)
+                uint32_t x = ll | (tot << 16);
+                for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                    const uint32_t t = __shfl_up_sync(kFull, x, dlt);
+                    if ((int)lane >= dlt) x += t;
+                }
+                incl_ll = x & 0xFFFF;
+                incl_tot = x >> 16;
+            } else {
+                incl_ll = ll;
+                incl_tot = tot;
+                for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                    const uint32_t t1 = __shfl_up_sync(kFull, incl_ll, dlt);
+                    const uint32_t t2 = __shfl_up_sync(kFull, incl_tot, dlt);
+                    if ((int)lane >= dlt) {
+                        incl_ll += t1;
+                        incl_tot += t2;
+                    }
                 }
             }
             const uint32_t round_ll = __shfl_sync(kFull, incl_ll, 31);
@@ -1431,9 +1444,17 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
             const uint32_t excl_tot = incl_tot - tot;  // my literal run starts at out_pos + excl_tot
             const uint32_t excl_ll = incl_ll - ll;     // and reads the literals from lit_pos + excl_ll
             {
-                const uint64_t before = out_pos - frame_base + excl_tot + ll;  // frame bytes in front of my match
-                if (__any_sync(kFull, act && ml > 0 && (off == 0 || off > before))) {
-                    err = SZB_ERR_CANT_REPEAT_BYTES;  // ringbuffer.go:203-214
+                // every match must lie inside the frame (ringbuffer.go:203-214); a match length of 0 cannot come out of
+                // stage 3 (ML codes start at 3, predefined.go:36-50) and would break the segment count below
+                const uint64_t fb = out_pos - frame_base;  // frame bytes in front of the round
+                bool bad;
+                if (fb < 0x7F000000u) {
+                    bad = off > (uint32_t)fb + excl_tot + ll;
+                } else {
+                    bad = off > fb + excl_tot + ll;
+                }
+                if (__any_sync(kFull, act && (bad || off == 0 || ml == 0))) {
+                    err = SZB_ERR_CANT_REPEAT_BYTES;
                     break;
                 }
             }
@@ -1441,10 +1462,16 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
             // --- the round's segments go to the ring, as many sequences at a time as the bitmap holds (normally all) ---
             uint32_t start = 0;
             while (start < cnt) {
-                const uint32_t my_rel = (uint32_t)(out_pos - st.line) + excl_tot;  // my literal run, relative to the line being consumed
-                const bool fits = my_rel + tot <= kSpanBytes && !(lit_rle && ll > kConstRun);
-                const uint32_t fitmask = __ballot_sync(kFull, fits && lane < cnt) >> start;
-                const uint32_t nfit = fitmask == (0xFFFFFFFFu >> start) ? 32 - start : __ffs(~fitmask) - 1;  // leading fits
+                const uint32_t out_rel = (uint32_t)(out_pos - st.line);
+                const uint32_t my_rel = out_rel + excl_tot;  // my literal run, relative to the line being consumed
+                uint32_t nfit;
+                if (start == 0 && !lit_rle && out_rel + round_tot <= kSpanBytes) {
+                    nfit = cnt;  // the usual case: the whole round fits the ring
+                } else {
+                    const bool fits = my_rel + tot <= kSpanBytes && !(lit_rle && ll > kConstRun);
+                    const uint32_t fitmask = __ballot_sync(kFull, fits && lane < cnt) >> start;
+                    nfit = fitmask == (0xFFFFFFFFu >> start) ? 32 - start : __ffs(~fitmask) - 1;  // leading fits
+                }
                 if (nfit == 0) {
                     // one sequence longer than the ring: the whole warp on its literals, then on its match
                     exec_flush(sm, dst, st, lane, le_mask);
@@ -1475,9 +1502,8 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
                 const uint32_t end = start + nfit;
                 const bool in = lane >= start && lane < end;
                 const uint32_t no_lit = __ballot_sync(kFull, in && ll == 0);
-                const uint32_t no_match = __ballot_sync(kFull, in && ml == 0);  // cannot happen: ML codes start at 3 (predefined.go:36-50)
                 if (in) {
-                    uint32_t ord = st.nseg + 2 * (lane - start) - __popc(no_lit & lt_mask) - __popc(no_match & lt_mask);
+                    uint32_t ord = st.nseg + 2 * (lane - start) - __popc(no_lit & lt_mask);
                     const uint32_t bit0 = ((uint32_t)st.line & (kRingBits - 1)) + my_rel;  // my literal run in the bitmap
                     if (ll) {
                         // literal byte at output position p: lit[lit_pos + excl_ll + (p - my start)]; a run of RLE literals reads
@@ -1487,7 +1513,7 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
                         atomicOr(&sm.bits[(bit0 >> 5) & (kRingBits / 32 - 1)], 1u << (bit0 & 31));
                         ord++;
                     }
-                    if (ml) {
+                    {
                         const uint32_t bit1 = bit0 + ll;
                         sm.seg[ord & (kSegRing - 1)] = reinterpret_cast<uintptr_t>(dst) - off;
                         atomicOr(&sm.bits[(bit1 >> 5) & (kRingBits / 32 - 1)], 1u << (bit1 & 31));
@@ -1495,7 +1521,7 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(dst + (out_pos + excl_tot + ll - off)));
                     }
                 }
-                st.nseg += 2 * nfit - __popc(no_lit) - __popc(no_match);
+                st.nseg += 2 * nfit - __popc(no_lit);
                 const uint32_t prev_prod = st.prod;
                 st.prod = __shfl_sync(kFull, my_rel + tot, end - 1);
                 __syncwarp();
