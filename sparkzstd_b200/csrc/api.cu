@@ -469,6 +469,7 @@ static DeviceBatch make_args(szb_batch *b, const void *d_src, void *d_dst, size_
     a.seq_ll = b->d_seq;
     a.seq_ml = b->d_seq + b->sequences;
     a.seq_of = b->d_seq + 2 * b->sequences;
+    a.seq_stride = b->sequences;
     a.seq_tabs = b->d_seq_tabs;
     a.seq_info = b->d_seq_info;
     a.out_size = b->d_out_size;

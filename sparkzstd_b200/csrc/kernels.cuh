@@ -69,7 +69,8 @@ struct DeviceBatch {
     const uint32_t *seq_list;  // blocks with nseq > 0
     uint32_t n_seq;
     uint8_t *litbuf;
-    uint32_t *seq_ll, *seq_ml, *seq_of;
+    uint32_t *seq_ll, *seq_ml, *seq_of;  // one allocation: seq_ml = seq_ll + seq_stride, seq_of = seq_ll + 2 * seq_stride
+    uint64_t seq_stride;
     uint16_t *seq_tabs;     // per seq_list entry: LL(512) | ML(512) | OF(256) 16-bit decode-table cells
     SeqInfo *seq_info;      // per seq_list entry
     uint64_t *out_size;     // per block regenerated size (host-initialised for Raw/RLE/zero-sequence blocks)
@@ -1240,15 +1241,18 @@ __device__ __forceinline__ void place_step(ExecSmem &sm, uint8_t *dst, ExecState
 
 // produce every complete line below line + limit (limit <= st.prod)
 __device__ __forceinline__ void exec_drain(ExecSmem &sm, uint8_t *dst, ExecState &st, uint32_t limit, uint32_t lane, uint32_t le_mask) {
-    while (limit >= 128) {
-        if (st.head)
-            place_step<false>(sm, dst, st, st.head, 128, lane, le_mask);
-        else
-            place_step<true>(sm, dst, st, 0, 128, lane, le_mask);
+    uint32_t n = limit >> 7;
+    if (n == 0) return;
+    st.prod -= n << 7;
+    if (st.head) {  // the rest of a line that was flushed in part
+        place_step<false>(sm, dst, st, st.head, 128, lane, le_mask);
         st.line += 128;
-        st.prod -= 128;
         st.head = 0;
-        limit -= 128;
+        n--;
+    }
+    for (; n; n--) {
+        place_step<true>(sm, dst, st, 0, 128, lane, le_mask);
+        st.line += 128;
     }
 }
 // produce everything the ring holds, the last, partial line included: everything below line + prod is then in memory
@@ -1357,25 +1361,24 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
         const uint32_t nseq = d.nseq;
         const uint64_t sbo = d.seq_buf_off;
         uint32_t lit_pos = 0;
-        // the triples are prefetched to L1 two rounds ahead (one line per array and round)
+        // the triples are prefetched to L1 two rounds ahead (one line per array and round): lanes 0..2 take one array each
+        const uint32_t *const my_seq = a.seq_ll + sbo + (lane < 3 ? lane : 0) * a.seq_stride;
         if (lane < 3) {
-            const uint32_t *g = (lane == 0 ? a.seq_ll : (lane == 1 ? a.seq_ml : a.seq_of)) + sbo;
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(g));
-            if (nseq > 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(g + 32));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(my_seq));
+            if (nseq > 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(my_seq + 32));
         }
         for (uint32_t base = 0; base < nseq; base += 32) {
             const uint32_t cnt = nseq - base < 32 ? nseq - base : 32;
             const bool act = lane < cnt;
-            const uint64_t si = sbo + base + lane;  // the arrays are padded to whole rounds: no bounds needed
-            uint32_t ll = a.seq_ll[si], ml = a.seq_ml[si], ofv = a.seq_of[si];
+            const uint32_t *const tr = a.seq_ll + (sbo + base + lane);  // the arrays are padded to whole rounds: no bounds needed
+            uint32_t ll = tr[0], ml = tr[a.seq_stride], ofv = tr[2 * a.seq_stride];
             if (!act) {
                 ll = 0;
                 ml = 0;
                 ofv = 4;
             }
             if (!lit_rle && lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(lit + lit_pos + 256));
-            if (lane < 3 && base + 64 < nseq)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"((lane == 0 ? a.seq_ll : (lane == 1 ? a.seq_ml : a.seq_of)) + sbo + base + 64));
+            if (lane < 3 && base + 64 < nseq) asm volatile("prefetch.global.L1 [%0];" ::"l"(my_seq + base + 64));
 
             // --- offsets through the 3-entry history (nextOffset) ---
             // A sequence with a direct offset (offset value > 3) pushes it onto the history whatever the history
