@@ -357,16 +357,16 @@ def main():
         "k_execute": {"ms": stage["execute"], "bytes": D + M + lit_huf + 12 * nseq},
     }
     # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of one ncu --set full capture of this very
-    # command, profiles/r01b_ncu_full_summary.txt; only the default workload at its default size was captured.
+    # command, profiles/r01c_ncu_full_summary.txt; only the default workload at its default size was captured.
     ncu_traffic = {}
     if args.workload == "text" and c.nframes == 65536:
-        ncu_traffic = {"k_execute": 20.997e9 + 4.316e9, "k_sequences": 1.235e9 + 4.686e9, "k_huffman_literals": 0.813e9 + 0.997e9}
+        ncu_traffic = {"k_execute": 21.316e9 + 4.339e9, "k_sequences": 1.236e9 + 4.687e9, "k_huffman_literals": 0.812e9 + 0.996e9}
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
     dom_ach = kernels[dom]["bytes"] / max(kernels[dom]["ms"], 1e-6) / 1e6
     pipe_ach = (C_bytes + D + M) / (ms_step * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": dom_ach, "peak": peak, "unit": "GB/s", "frac": dom_ach / peak, "traffic": ncu_traffic.get(dom),
-        "traffic_unit": "bytes per launch, ncu dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01b_ncu_full_summary.txt)",
+        "traffic_unit": "bytes per launch, ncu dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01c_ncu_full_summary.txt)",
         "peak_source": peak_src,
         "kernel_bytes": "bytes this kernel must read+write per launch (DESIGN.md section 5)",
         "pipeline": {"algorithmic_bytes": C_bytes + D + M, "C": C_bytes, "D": D, "M": M, "achieved": pipe_ach, "frac": pipe_ach / peak,
