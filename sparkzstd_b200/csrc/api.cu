@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -429,6 +430,19 @@ int szb_batch_create(szb_ctx *ctx, const uint8_t *h_src, size_t src_len, const u
                                       szb_walk_nblocks(w), out);
     szb_walk_destroy(w);
     return rc;
+}
+
+// The stage scratch (literals, sequences, decode tables) is dead once the batch's kernels are in the stream: giving it
+// back with cudaFreeAsync lets the next batch on the same stream reuse the very same memory (stream-ordered pool)
+// instead of asking the driver for more.  The descriptor and status tables stay until szb_batch_destroy.
+static void batch_release_scratch(szb_batch *b) {
+    szb_ctx *ctx = b->ctx;
+    void **p[] = {(void **)&b->d_litbuf, (void **)&b->d_seq, (void **)&b->d_seq_tabs, (void **)&b->d_seq_info, (void **)&b->d_huf_tabs,
+                  (void **)&b->d_huf_info};
+    for (void **q : p) {
+        pool_free(ctx, *q);
+        *q = nullptr;
+    }
 }
 
 void szb_batch_destroy(szb_batch *b) {
@@ -885,6 +899,10 @@ static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_l
     CUDA_TRY(ctx, cudaEventRecord(ev_begin, ctx->stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_h2d, ev_begin, 0));
     int fail = SZB_OK;
+    const bool trace = getenv("SZB_TRACE") != nullptr;
+    double t_wait = 0, t_create = 0, t_launch = 0;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_loop0 = now();
     for (size_t ci = 0; ci < chunks.size(); ci++) {
         Chunk &c = chunks[ci];
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&c.up, cudaEventDisableTiming));
@@ -893,12 +911,17 @@ static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_l
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_src + c.src_lo, src + c.src_lo, (size_t)(c.src_hi - c.src_lo), cudaMemcpyHostToDevice, ctx->s_h2d));
         CUDA_TRY(ctx, cudaEventRecord(c.up, ctx->s_h2d));
         // descriptor tables of this chunk (walked by a worker), their upload, the kernels
+        double t0 = now();
         while (!walked[ci].load(std::memory_order_acquire)) std::this_thread::yield();
+        double t1 = now();
+        t_wait += t1 - t0;
         rc = c.walk_rc;
         if (!rc) {
             rc = szb_batch_create_from_tables(ctx, src_len, szb_walk_frames(c.walk), szb_walk_nframes(c.walk), szb_walk_blocks(c.walk),
                                               szb_walk_nblocks(c.walk), &c.batch);
         }
+        t0 = now();
+        t_create += t0 - t1;
         if (c.walk) {
             szb_walk_destroy(c.walk);
             c.walk = nullptr;
@@ -916,15 +939,21 @@ static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_l
             break;
         }
         CUDA_TRY(ctx, cudaEventRecord(c.done, ctx->stream));
+        batch_release_scratch(c.batch);
+        t_launch += now() - t0;
         // output of this chunk: D2H on the other copy stream
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_d2h, c.done, 0));
         if (c.dst_len) CUDA_TRY(ctx, cudaMemcpyAsync(dst + c.dst_lo, ctx->d_dst + c.dst_lo, (size_t)c.dst_len, cudaMemcpyDeviceToHost, ctx->s_d2h));
     }
     stop.store(true);
     for (auto &t : pool) t.join();
+    const double t_loop1 = now();
     cudaStreamSynchronize(ctx->s_h2d);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->s_d2h);
+    if (trace)
+        fprintf(stderr, "[szb] pipelined: %zu chunks, submit loop %.1f ms (walk wait %.1f, tables %.1f, launches %.1f), drain %.1f ms\n",
+                chunks.size(), t_loop1 - t_loop0, t_wait, t_create, t_launch, now() - t_loop1);
     *first_rc = SZB_OK;
     for (auto &c : chunks) {
         if (c.walk) szb_walk_destroy(c.walk);
