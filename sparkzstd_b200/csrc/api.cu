@@ -71,6 +71,7 @@ struct szb_batch {
     HufInfo *d_huf_info = nullptr;
     uint32_t *d_body_list = nullptr;
     uint32_t *d_exec_list = nullptr;
+    uint32_t n_long = 0;  // leading entries of exec_list that go to k_execute_pair
     uint64_t *d_out_size_init = nullptr;
     void *d_state = nullptr;  // one allocation: out_size | out_off | total | frame_out_off | frame_out_len | statuses
     uint64_t *d_out_size = nullptr, *d_out_off = nullptr, *d_total = nullptr, *d_frame_out_off = nullptr,
@@ -247,6 +248,13 @@ int szb_last_timing(szb_ctx *ctx, float *ms, int n) {
 void szb_free(void *p) { free(p); }
 
 // ---------------------------------------------------------------------------------------------
+// Frames with at least this many sequences (about 0.7 MiB of text) are executed by k_execute_pair, at most
+// kMaxLongFrames of them (16 per SM: half the warps an SM holds): with more long frames than that the SMs are full of
+// frames anyway and two warps per frame only cost (all 65 536 text frames as pairs: 10.2 -> 13.2 ms).
+// SZB_LONG_SEQS overrides the threshold (tests force every frame through the pair kernel with it).
+constexpr uint64_t kLongFrameSequences = 65536;
+constexpr uint32_t kMaxLongFrames = 2368;
+
 static int batch_upload_tables(szb_batch *b) {
     szb_ctx *ctx = b->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -284,6 +292,11 @@ static int batch_upload_tables(szb_batch *b) {
         b->exec_list.resize(nf);
         for (uint32_t f = 0; f < nf; f++) b->exec_list[f] = f;
         std::stable_sort(b->exec_list.begin(), b->exec_list.end(), [&](uint32_t x, uint32_t y) { return work[x] > work[y]; });
+        // Long frames finish last, and a frame is sequential: they get two warps each (k_execute_pair).
+        static const uint64_t long_seqs = getenv("SZB_LONG_SEQS") ? strtoull(getenv("SZB_LONG_SEQS"), nullptr, 10) : kLongFrameSequences;
+        uint32_t n_long = 0;
+        while (n_long < nf && n_long < kMaxLongFrames && work[b->exec_list[n_long]] >= long_seqs) n_long++;
+        b->n_long = n_long;
     }
     // descriptor tables: one allocation, one H2D copy
     size_t o_frames = 0;
@@ -569,8 +582,24 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
         ctx->launches++;
     }
     if (a.nframes && a.n_seq) {
-        k_execute<<<(a.nframes + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, s>>>(a);
-        ctx->launches++;
+        const uint32_t n_long = b->n_long, n_rest = a.nframes - n_long;
+        if (n_long) {  // beside the others, on the second stream
+            if (!ctx->s_lit) {
+                CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_lit, cudaStreamNonBlocking));
+                CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+                CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+            }
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, s));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_lit, ctx->ev_fork, 0));
+            k_execute_pair<<<n_long, 64, 0, ctx->s_lit>>>(a, 0, n_long);
+            ctx->launches++;
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->s_lit));
+        }
+        if (n_rest) {
+            k_execute<<<(n_rest + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, s>>>(a, n_long, n_rest);
+            ctx->launches++;
+        }
+        if (n_long) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
     CUDA_TRY(ctx, cudaGetLastError());

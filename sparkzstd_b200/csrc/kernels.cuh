@@ -1147,12 +1147,10 @@ struct ExecSmem {
     __align__(16) uint8_t grp[128];               // the bytes of the step in flight
 };
 
-struct ExecState {
+struct ExecState {  // the consumer's side
     uint64_t line;  // next line to produce (multiple of 128)
-    uint32_t prod;  // segments cover the output up to line + prod
     uint32_t head;  // output below line + head is in memory already (0 .. 128)
     uint32_t seen;  // segments that start below line + head
-    uint32_t nseg;  // segments appended so far
 };
 
 // Produces the bytes [lo, hi) of the line at st.line (positions relative to the line; kFull: all 128).
@@ -1239,11 +1237,10 @@ __device__ __forceinline__ void place_step(ExecSmem &sm, uint8_t *dst, ExecState
     __syncwarp();
 }
 
-// produce every complete line below line + limit (limit <= st.prod)
-__device__ __forceinline__ void exec_drain(ExecSmem &sm, uint8_t *dst, ExecState &st, uint32_t limit, uint32_t lane, uint32_t le_mask) {
-    uint32_t n = limit >> 7;
+// produce every complete line below the output position `limit` (segments must cover the output up to there)
+__device__ __forceinline__ void exec_drain(ExecSmem &sm, uint8_t *dst, ExecState &st, uint64_t limit, uint32_t lane, uint32_t le_mask) {
+    uint32_t n = (uint32_t)(limit - st.line) >> 7;
     if (n == 0) return;
-    st.prod -= n << 7;
     if (st.head) {  // the rest of a line that was flushed in part
         place_step<false>(sm, dst, st, st.head, 128, lane, le_mask);
         st.line += 128;
@@ -1255,19 +1252,70 @@ __device__ __forceinline__ void exec_drain(ExecSmem &sm, uint8_t *dst, ExecState
         st.line += 128;
     }
 }
-// produce everything the ring holds, the last, partial line included: everything below line + prod is then in memory
-__device__ __forceinline__ void exec_flush(ExecSmem &sm, uint8_t *dst, ExecState &st, uint32_t lane, uint32_t le_mask) {
-    exec_drain(sm, dst, st, st.prod, lane, le_mask);
-    if (st.prod > st.head) {
-        place_step<false>(sm, dst, st, st.head, st.prod, lane, le_mask);
-        st.head = st.prod;
+// produce everything up to `prod`, the last, partial line included: everything below prod is then in memory
+__device__ __forceinline__ void exec_flush(ExecSmem &sm, uint8_t *dst, ExecState &st, uint64_t prod, uint32_t lane, uint32_t le_mask) {
+    exec_drain(sm, dst, st, prod, lane, le_mask);
+    const uint32_t hi = (uint32_t)(prod - st.line);  // < 128
+    if (hi > st.head) {
+        place_step<false>(sm, dst, st, st.head, hi, lane, le_mask);
+        st.head = hi;
     }
 }
 // continue at another output position (everything flushed)
 __device__ __forceinline__ void exec_seek(ExecState &st, uint64_t pos) {
     st.line = pos & ~(uint64_t)127;
-    st.head = st.prod = (uint32_t)pos & 127;
+    st.head = (uint32_t)pos & 127;
 }
+
+// Where the producer's segments go.  InlineSink: the producing warp is the consumer too, and stays one append behind
+// so that the prefetches it issued have time to land.
+struct InlineSink {
+    ExecSmem &sm;
+    uint8_t *dst;
+    ExecState st;
+    uint32_t lane, le_mask;
+    __device__ __forceinline__ uint64_t line() const { return st.line; }
+    __device__ __forceinline__ void appended(uint64_t prev_prod, uint64_t) { exec_drain(sm, dst, st, prev_prod, lane, le_mask); }
+    __device__ __forceinline__ void drain(uint64_t prod) { exec_drain(sm, dst, st, prod, lane, le_mask); }
+    __device__ __forceinline__ void flush(uint64_t prod) { exec_flush(sm, dst, st, prod, lane, le_mask); }
+    __device__ __forceinline__ void seek(uint64_t pos) { exec_seek(st, pos); }
+    __device__ __forceinline__ void finish(uint64_t prod) { exec_flush(sm, dst, st, prod, lane, le_mask); }
+};
+
+// PairSink: a second warp of the CTA consumes (k_execute_pair).  The two warps meet at one __syncthreads per command;
+// a command is executed by the consumer while the producer works on the next round.
+enum : uint32_t { kCmdNop = 0, kCmdDrain = 1, kCmdFlush = 2, kCmdSeek = 3, kCmdExit = 4 };
+struct PairShared {
+    unsigned long long line[2];  // the consumer's st.line after command i, in slot i & 1
+    unsigned long long arg[2];
+    uint32_t cmd[2];
+};
+struct PairSink {
+    PairShared &sh;
+    uint32_t lane, it;
+    uint64_t seen_line;  // what the consumer had reached one command ago: a lower bound, which is all the producer needs
+    __device__ __forceinline__ uint64_t line() const { return seen_line; }
+    __device__ __forceinline__ void hand(uint32_t cmd, uint64_t arg) {
+        if (lane == 0) {
+            sh.cmd[it & 1] = cmd;
+            sh.arg[it & 1] = arg;
+        }
+        __syncthreads();  // command `it` starts; command it-1 is complete and published its line before this barrier
+        if (it) seen_line = sh.line[(it - 1) & 1];
+        it++;
+    }
+    __device__ __forceinline__ void appended(uint64_t, uint64_t prod) { hand(kCmdDrain, prod); }
+    __device__ __forceinline__ void drain(uint64_t prod) { hand(kCmdDrain, prod); }
+    __device__ __forceinline__ void flush(uint64_t prod) {  // returns when everything below prod is in memory
+        hand(kCmdFlush, prod);
+        hand(kCmdNop, 0);
+    }
+    __device__ __forceinline__ void seek(uint64_t pos) { hand(kCmdSeek, pos); }
+    __device__ __forceinline__ void finish(uint64_t prod) {
+        hand(kCmdFlush, prod);
+        hand(kCmdExit, 0);
+    }
+};
 
 // One thread per frame, before any output is written: the frame's verdict (the first failing
 // block decides, as in the sequential reference; then the header walk's verdict; then capacity)
@@ -1314,33 +1362,18 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute_bodies(DeviceBatch a) {
     }
 }
 
-// One warp per frame; blocks in order; 32 sequences per round (sequence_execution.go:14-63).
-#ifndef SZB_EXEC_MIN_CTAS
-#define SZB_EXEC_MIN_CTAS 8
-#endif
-__global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(DeviceBatch a) {
-    __shared__ ExecSmem smem[kWarpsPerCta];
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t slot = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    if (slot >= a.nframes) return;
-    const uint32_t f = a.exec_list[slot];
-    ExecSmem &sm = smem[threadIdx.x >> 5];
+// The producer half for one frame (status OK), one warp: blocks in order, 32 sequences per round
+// (sequence_execution.go:14-63); segments go to the ring in `sm`, the sink decides who consumes them and when.
+template <class Sink>
+__device__ __forceinline__ void produce_frame(const DeviceBatch &a, uint32_t f, ExecSmem &sm, Sink &sink, uint32_t lane) {
     const szb_frame_desc fr = a.frames[f];
     const uint32_t b0 = fr.first_block, nb = fr.nblocks;
     uint8_t *const dst = a.dst;
-
-    int err = a.frame_status[f];  // k_frame_verdict
-    if (err != SZB_OK) return;
+    int err = SZB_OK;
     const uint64_t frame_base = nb ? a.out_off[b0] : 0;
-    const uint32_t le_mask = 0xFFFFFFFFu >> (31 - lane);  // bits 0..lane
-    const uint32_t lt_mask = le_mask >> 1;                // bits 0..lane-1
-
-    for (uint32_t wd = lane; wd < kRingBits / 32; wd += 32) sm.bits[wd] = 0;
-    __syncwarp();
-    ExecState st;
-    exec_seek(st, frame_base);
-    st.seen = 0;
-    st.nseg = 0;
+    const uint32_t lt_mask = 0x7FFFFFFFu >> (31 - lane);  // bits 0..lane-1
+    uint64_t prod = frame_base;  // segments cover the output up to here
+    uint32_t nseg = 0;           // segments appended so far
 
     History hist{1, 4, 8};  // framedecompressor.go:48,59
     for (uint32_t bi = 0; bi < nb && err == SZB_OK; bi++) {
@@ -1349,9 +1382,10 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
         if (d.type != 2 || d.nseq == 0) continue;  // written by k_execute_bodies already
         const uint8_t *payload = a.src + d.src_off;
         uint64_t out_pos = a.out_off[b];
-        if (out_pos != st.line + st.prod) {  // blocks in between were written elsewhere
-            exec_flush(sm, dst, st, lane, le_mask);
-            exec_seek(st, out_pos);
+        if (out_pos != prod) {  // blocks in between were written elsewhere
+            sink.flush(prod);
+            sink.seek(out_pos);
+            prod = out_pos;
         }
         // Compressed: ExecuteSequences (sequence_execution.go:14-63)
         const bool lit_rle = d.lit_type == 1;
@@ -1465,7 +1499,8 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
             // --- the round's segments go to the ring, as many sequences at a time as the bitmap holds (normally all) ---
             uint32_t start = 0;
             while (start < cnt) {
-                const uint32_t out_rel = (uint32_t)(out_pos - st.line);
+                const uint64_t line = sink.line();
+                const uint32_t out_rel = (uint32_t)(out_pos - line);
                 const uint32_t my_rel = out_rel + excl_tot;  // my literal run, relative to the line being consumed
                 uint32_t nfit;
                 if (start == 0 && !lit_rle && out_rel + round_tot <= kSpanBytes) {
@@ -1477,7 +1512,7 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
                 }
                 if (nfit == 0) {
                     // one sequence longer than the ring: the whole warp on its literals, then on its match
-                    exec_flush(sm, dst, st, lane, le_mask);
+                    sink.flush(prod);
                     const uint32_t L = __shfl_sync(kFull, ll, start), ML = __shfl_sync(kFull, ml, start);
                     const uint32_t OFF = __shfl_sync(kFull, off, start);
                     const uint64_t D = out_pos + __shfl_sync(kFull, excl_tot, start);
@@ -1498,7 +1533,8 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
                         for (uint32_t k = lane; k < ML; k += 32) MD[k] = MS[k % OFF];
                     }
                     __syncwarp();
-                    exec_seek(st, D + L + ML);
+                    prod = D + L + ML;
+                    sink.seek(prod);
                     start++;
                     continue;
                 }
@@ -1506,8 +1542,8 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
                 const bool in = lane >= start && lane < end;
                 const uint32_t no_lit = __ballot_sync(kFull, in && ll == 0);
                 if (in) {
-                    uint32_t ord = st.nseg + 2 * (lane - start) - __popc(no_lit & lt_mask);
-                    const uint32_t bit0 = ((uint32_t)st.line & (kRingBits - 1)) + my_rel;  // my literal run in the bitmap
+                    uint32_t ord = nseg + 2 * (lane - start) - __popc(no_lit & lt_mask);
+                    const uint32_t bit0 = ((uint32_t)line & (kRingBits - 1)) + my_rel;  // my literal run in the bitmap
                     if (ll) {
                         // literal byte at output position p: lit[lit_pos + excl_ll + (p - my start)]; a run of RLE literals reads
                         // the first bytes of the fill row
@@ -1524,11 +1560,11 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(dst + (out_pos + excl_tot + ll - off)));
                     }
                 }
-                st.nseg += 2 * nfit - __popc(no_lit);
-                const uint32_t prev_prod = st.prod;
-                st.prod = __shfl_sync(kFull, my_rel + tot, end - 1);
+                nseg += 2 * nfit - __popc(no_lit);
+                const uint64_t prev_prod = prod;
+                prod = line + __shfl_sync(kFull, my_rel + tot, end - 1);
                 __syncwarp();
-                exec_drain(sm, dst, st, prev_prod, lane, le_mask);  // stays one append behind, so that the prefetches have time to land
+                sink.appended(prev_prod, prod);
                 start = end;
             }
             out_pos += round_tot;
@@ -1537,31 +1573,91 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
         if (err != SZB_OK) break;
         // trailing literals (sequence_execution.go:55-60, literals.go:411-420): one more segment, or a bulk copy
         const uint32_t rest = d.lit_regen - lit_pos;
-        if (rest && st.prod + rest <= kSpanBytes && !(lit_rle && rest > kConstRun)) {
+        if (rest && (prod - sink.line()) + rest <= kSpanBytes && !(lit_rle && rest > kConstRun)) {
             if (lane == 0) {
-                const uint32_t bit0 = ((uint32_t)st.line & (kRingBits - 1)) + st.prod;
-                sm.seg[st.nseg & (kSegRing - 1)] = reinterpret_cast<uintptr_t>(lit) + (lit_rle ? 0 : lit_pos) - out_pos;
-                atomicOr(&sm.bits[(bit0 >> 5) & (kRingBits / 32 - 1)], 1u << (bit0 & 31));
+                const uint32_t bit0 = (uint32_t)prod & (kRingBits - 1);
+                sm.seg[nseg & (kSegRing - 1)] = reinterpret_cast<uintptr_t>(lit) + (lit_rle ? 0 : lit_pos) - out_pos;
+                atomicOr(&sm.bits[bit0 >> 5], 1u << (bit0 & 31));
             }
-            st.nseg++;
-            st.prod += rest;
+            nseg++;
+            prod += rest;
             __syncwarp();
-            exec_drain(sm, dst, st, st.prod, lane, le_mask);
+            sink.drain(prod);
         } else if (rest) {
-            exec_flush(sm, dst, st, lane, le_mask);
+            sink.flush(prod);
             if (lit_rle)
                 warp_memset(dst + out_pos, lit[0], rest, lane);
             else
                 warp_memcpy(dst + out_pos, lit + lit_pos, rest, lane);
             __syncwarp();
-            exec_seek(st, out_pos + rest);
+            prod = out_pos + rest;
+            sink.seek(prod);
         }
     }
     // On an error the frame's output is void; what the ring still holds is written anyway (it is within the frame's range).
-    exec_flush(sm, dst, st, lane, le_mask);
+    sink.finish(prod);
     if (lane == 0 && err != SZB_OK) {  // failed while executing (bad offset, literals ran dry)
         a.frame_status[f] = err;
         a.frame_out_len[f] = 0;
+    }
+}
+
+// One warp per frame: it produces the segments and consumes them.  Frames exec_list[first_slot, first_slot + n_slots).
+#ifndef SZB_EXEC_MIN_CTAS
+#define SZB_EXEC_MIN_CTAS 8
+#endif
+__global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(DeviceBatch a, uint32_t first_slot, uint32_t n_slots) {
+    __shared__ ExecSmem smem[kWarpsPerCta];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t slot = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    if (slot >= n_slots) return;
+    const uint32_t f = a.exec_list[first_slot + slot];
+    if (a.frame_status[f] != SZB_OK) return;  // k_frame_verdict
+    ExecSmem &sm = smem[threadIdx.x >> 5];
+    for (uint32_t wd = lane; wd < kRingBits / 32; wd += 32) sm.bits[wd] = 0;
+    __syncwarp();
+    InlineSink sink{sm, a.dst, ExecState{}, lane, 0xFFFFFFFFu >> (31 - lane)};
+    const szb_frame_desc fr = a.frames[f];
+    exec_seek(sink.st, fr.nblocks ? a.out_off[fr.first_block] : 0);
+    sink.st.seen = 0;
+    produce_frame(a, f, sm, sink, lane);
+}
+
+// The few frames that are far longer than the rest finish last and then run almost alone: two warps per frame, one
+// producing segments, one consuming them (PairSink).  Twice the warps per frame is the wrong trade while the SMs are full
+// of frames, which is why only the longest frames take this path.
+__global__ void __launch_bounds__(64) k_execute_pair(DeviceBatch a, uint32_t first_slot, uint32_t n_slots) {
+    __shared__ ExecSmem sm;
+    __shared__ PairShared sh;
+    const uint32_t lane = threadIdx.x & 31;
+    if (blockIdx.x >= n_slots) return;
+    const uint32_t f = a.exec_list[first_slot + blockIdx.x];
+    if (a.frame_status[f] != SZB_OK) return;  // k_frame_verdict; both warps agree
+    const szb_frame_desc fr = a.frames[f];
+    const uint64_t frame_base = fr.nblocks ? a.out_off[fr.first_block] : 0;
+    for (uint32_t wd = threadIdx.x; wd < kRingBits / 32; wd += 64) sm.bits[wd] = 0;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        PairSink sink{sh, lane, 0, frame_base & ~(uint64_t)127};
+        produce_frame(a, f, sm, sink, lane);
+    } else {
+        const uint32_t le_mask = 0xFFFFFFFFu >> (31 - lane);
+        ExecState st;
+        exec_seek(st, frame_base);
+        st.seen = 0;
+        for (uint32_t it = 0;; it++) {
+            __syncthreads();
+            const uint32_t cmd = sh.cmd[it & 1];
+            const uint64_t arg = sh.arg[it & 1];
+            if (cmd == kCmdExit) break;
+            if (cmd == kCmdDrain)
+                exec_drain(sm, a.dst, st, arg, lane, le_mask);
+            else if (cmd == kCmdFlush)
+                exec_flush(sm, a.dst, st, arg, lane, le_mask);
+            else if (cmd == kCmdSeek)
+                exec_seek(st, arg);
+            if (lane == 0) sh.line[it & 1] = st.line;
+        }
     }
 }
 

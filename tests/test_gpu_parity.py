@@ -307,3 +307,38 @@ def test_kernels_were_launched(ctx):
     assert ctx.launch_count() > 0
     t = ctx.last_timing()
     assert t["total"] > 0
+
+
+def test_pair_kernel_on_every_frame(corpus, tmp_path):
+    """k_execute_pair (two warps per frame, normally only for frames with >= 65 536 sequences) forced onto every frame of the
+    corpus, the crafted frames and a text batch: same bytes.  The threshold is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    import textwrap
+
+    code = textwrap.dedent(
+        """
+        import hashlib, sys
+        sys.path.insert(0, "tests")
+        import crafted_frames
+        from tools import corpus as cg
+        from sparkzstd_b200.decompression import Context
+        ctx = Context(0)
+        gold = cg.golden_frames()
+        outs = ctx.decode_batch([d for _, d, _, _ in gold])
+        assert all(hashlib.sha256(o).hexdigest() == sha for o, (_, _, _, sha) in zip(outs, gold))
+        cs = crafted_frames.cases()
+        names = sorted(cs)
+        outs = ctx.decode_batch([cs[n][0] for n in names])
+        assert all(o == cs[n][1] for o, n in zip(outs, names))
+        t = cg.config2_text_frames(700)
+        outs = ctx.decode_batch([t.frame(i) for i in range(t.nframes)])
+        assert all(cg.hash_bytes(__import__("numpy").frombuffer(o, dtype="uint8")) == int(t.raw_hash[i]) for i, o in enumerate(outs))
+        print("pair ok", ctx.launch_count())
+        """
+    )
+    env = dict(os.environ, SZB_LONG_SEQS="1")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert res.returncode == 0 and "pair ok" in res.stdout, res.stdout + res.stderr
