@@ -1239,7 +1239,7 @@ __device__ __forceinline__ void place_step(ExecSmem &sm, uint8_t *dst, ExecState
 
 // produce every complete line below the output position `limit` (segments must cover the output up to there)
 __device__ __forceinline__ void exec_drain(ExecSmem &sm, uint8_t *dst, ExecState &st, uint64_t limit, uint32_t lane, uint32_t le_mask) {
-    uint32_t n = (uint32_t)(limit - st.line) >> 7;
+    uint32_t n = ((uint32_t)limit - (uint32_t)st.line) >> 7;  // limit - line < 2^32: the low words do
     if (n == 0) return;
     if (st.head) {  // the rest of a line that was flushed in part
         place_step<false>(sm, dst, st, st.head, 128, lane, le_mask);
@@ -1500,7 +1500,7 @@ __device__ __forceinline__ void produce_frame(const DeviceBatch &a, uint32_t f, 
             uint32_t start = 0;
             while (start < cnt) {
                 const uint64_t line = sink.line();
-                const uint32_t out_rel = (uint32_t)(out_pos - line);
+                const uint32_t out_rel = (uint32_t)out_pos - (uint32_t)line;  // < 2^32: the low words do
                 const uint32_t my_rel = out_rel + excl_tot;  // my literal run, relative to the line being consumed
                 uint32_t nfit;
                 if (start == 0 && !lit_rle && out_rel + round_tot <= kSpanBytes) {
