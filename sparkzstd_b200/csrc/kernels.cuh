@@ -21,6 +21,7 @@
 //                       then the output produced in address order, 128 bytes per step, every lane
 //                       fetching the source byte of its output byte (literal or match)
 //                       (decompression/sequence_execution.go:14-114, ringbuffer.go:197-277)
+//   k_execute_pair      the same for the few very long frames: a producer warp and a consumer warp per frame
 //   k_verify_checksums  optional XXH64 content checksum, one thread per frame
 //
 // All arithmetic is integer; there is no tensor-core work on this path.
