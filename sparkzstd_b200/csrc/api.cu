@@ -30,6 +30,7 @@ struct szb_ctx {
     std::string last_error;
     float timing[8] = {};
     uint64_t launches = 0;
+    int sm_count = 148;
     // grow-only staging for the host-pointer entry points
     uint8_t *d_src = nullptr;
     size_t d_src_cap = 0;
@@ -71,7 +72,13 @@ struct szb_batch {
     HufInfo *d_huf_info = nullptr;
     uint32_t *d_body_list = nullptr;
     uint32_t *d_exec_list = nullptr;
-    uint32_t n_long = 0;  // leading entries of exec_list that go to k_execute_pair
+    uint32_t n_long = 0;  // leading entries of exec_list: long frames (execute_long.cuh, else k_execute_pair)
+    std::vector<uint32_t> lb_block, lb_slot, long_first_lb;
+    std::vector<uint64_t> long_dbase;
+    bool long_jump = false;  // the block-parallel path is on for this batch
+    uint32_t *d_lb_block = nullptr, *d_lb_slot = nullptr, *d_long_first_lb = nullptr;
+    uint64_t *d_long_dbase = nullptr;
+    void *d_long = nullptr;  // one allocation: long_err | long_T | long_hist | dist
     uint64_t *d_out_size_init = nullptr;
     void *d_state = nullptr;  // one allocation: out_size | out_off | total | frame_out_off | frame_out_len | statuses
     uint64_t *d_out_size = nullptr, *d_out_off = nullptr, *d_total = nullptr, *d_frame_out_off = nullptr,
@@ -169,6 +176,7 @@ int szb_ctx_create(int device, void *stream, szb_ctx **out) {
         }
         ctx->own_stream = true;
     }
+    if (cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->sm_count <= 0) ctx->sm_count = 148;
     {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -293,10 +301,41 @@ static int batch_upload_tables(szb_batch *b) {
         for (uint32_t f = 0; f < nf; f++) b->exec_list[f] = f;
         std::stable_sort(b->exec_list.begin(), b->exec_list.end(), [&](uint32_t x, uint32_t y) { return work[x] > work[y]; });
         // Long frames finish last, and a frame is sequential: they get two warps each (k_execute_pair).
-        static const uint64_t long_seqs = getenv("SZB_LONG_SEQS") ? strtoull(getenv("SZB_LONG_SEQS"), nullptr, 10) : kLongFrameSequences;
+        const uint64_t long_seqs = getenv("SZB_LONG_SEQS") ? strtoull(getenv("SZB_LONG_SEQS"), nullptr, 10) : kLongFrameSequences;
         uint32_t n_long = 0;
-        while (n_long < nf && n_long < kMaxLongFrames && work[b->exec_list[n_long]] >= long_seqs) n_long++;
+        while (n_long < nf && n_long < kMaxLongFrames && work[b->exec_list[n_long]] >= long_seqs && work[b->exec_list[n_long]] > 0) n_long++;
         b->n_long = n_long;
+        // The block-parallel path (execute_long.cuh) wants every block of the long frames, and one distance cell per
+        // output byte: the host knows an upper bound (a Raw/RLE block regenerates Block_Size bytes, a compressed one at
+        // most Block_Maximum_Size = 128 KiB when the frame is valid; a frame that regenerates more stays on k_execute_pair).
+        const char *mode = getenv("SZB_LONG_MODE");
+        b->long_jump = n_long > 0 && !(mode && strcmp(mode, "pair") == 0);
+        b->long_first_lb.assign(1, 0);
+        b->long_dbase.assign(1, 0);
+        if (b->long_jump) {
+            uint64_t cells = 0;
+            for (uint32_t slot = 0; slot < n_long; slot++) {
+                const szb_frame_desc &fr = b->frames[b->exec_list[slot]];
+                uint64_t bound = 0;
+                for (uint32_t i = 0; i < fr.nblocks; i++) {
+                    const szb_block_desc &d = b->blocks[fr.first_block + i];
+                    b->lb_block.push_back(fr.first_block + i);
+                    b->lb_slot.push_back(slot);
+                    bound += d.type == 2 ? (d.nseq ? 128 * 1024 : d.lit_regen) : d.block_size;
+                }
+                cells += align_up(bound, kJumpTile);
+                b->long_first_lb.push_back((uint32_t)b->lb_block.size());
+                b->long_dbase.push_back(cells);
+            }
+            static const uint64_t max_cells = (getenv("SZB_LONG_MAX_GIB") ? strtoull(getenv("SZB_LONG_MAX_GIB"), nullptr, 10) : 64) << 28;
+            if (cells > max_cells) b->long_jump = false;  // 4 bytes per cell
+        }
+        if (!b->long_jump) {
+            b->lb_block.clear();
+            b->lb_slot.clear();
+            b->long_first_lb.assign(1, 0);
+            b->long_dbase.assign(1, 0);
+        }
     }
     // descriptor tables: one allocation, one H2D copy
     size_t o_frames = 0;
@@ -308,7 +347,11 @@ static int batch_upload_tables(szb_batch *b) {
     size_t o_body = align_up(o_slot + 4 * b->huf_slot.size(), 256);
     size_t o_exec = align_up(o_body + 4 * b->body_list.size(), 256);
     size_t o_init = align_up(o_exec + 4 * b->exec_list.size(), 256);
-    size_t total = align_up(o_init + 8 * (size_t)nb, 256) + 256;
+    size_t o_lbb = align_up(o_init + 8 * (size_t)nb, 256);
+    size_t o_lbs = align_up(o_lbb + 4 * b->lb_block.size(), 256);
+    size_t o_lfl = align_up(o_lbs + 4 * b->lb_slot.size(), 256);
+    size_t o_ldb = align_up(o_lfl + 4 * b->long_first_lb.size(), 256);
+    size_t total = align_up(o_ldb + 8 * b->long_dbase.size(), 256) + 256;
     std::vector<uint8_t> &stage = b->stage;
     stage.assign(total, 0);
     if (nf) memcpy(stage.data() + o_frames, b->frames.data(), sizeof(szb_frame_desc) * (size_t)nf);
@@ -320,6 +363,10 @@ static int batch_upload_tables(szb_batch *b) {
     if (!b->body_list.empty()) memcpy(stage.data() + o_body, b->body_list.data(), 4 * b->body_list.size());
     if (!b->exec_list.empty()) memcpy(stage.data() + o_exec, b->exec_list.data(), 4 * b->exec_list.size());
     if (nb) memcpy(stage.data() + o_init, out_size_init.data(), 8 * (size_t)nb);
+    if (!b->lb_block.empty()) memcpy(stage.data() + o_lbb, b->lb_block.data(), 4 * b->lb_block.size());
+    if (!b->lb_slot.empty()) memcpy(stage.data() + o_lbs, b->lb_slot.data(), 4 * b->lb_slot.size());
+    memcpy(stage.data() + o_lfl, b->long_first_lb.data(), 4 * b->long_first_lb.size());
+    memcpy(stage.data() + o_ldb, b->long_dbase.data(), 8 * b->long_dbase.size());
     CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_tables, total));
     CUDA_TRY(ctx, cudaMemcpyAsync(b->d_tables, stage.data(), total, cudaMemcpyHostToDevice, ctx->stream));
     uint8_t *base = (uint8_t *)b->d_tables;
@@ -332,6 +379,10 @@ static int batch_upload_tables(szb_batch *b) {
     b->d_body_list = (uint32_t *)(base + o_body);
     b->d_exec_list = (uint32_t *)(base + o_exec);
     b->d_out_size_init = (uint64_t *)(base + o_init);
+    b->d_lb_block = (uint32_t *)(base + o_lbb);
+    b->d_lb_slot = (uint32_t *)(base + o_lbs);
+    b->d_long_first_lb = (uint32_t *)(base + o_lfl);
+    b->d_long_dbase = (uint64_t *)(base + o_ldb);
     // mutable state
     size_t s_out_size = 0;
     size_t s_out_off = align_up(s_out_size + 8 * (size_t)nb, 256);
@@ -451,7 +502,7 @@ int szb_batch_create(szb_ctx *ctx, const uint8_t *h_src, size_t src_len, const u
 static void batch_release_scratch(szb_batch *b) {
     szb_ctx *ctx = b->ctx;
     void **p[] = {(void **)&b->d_litbuf, (void **)&b->d_seq, (void **)&b->d_seq_tabs, (void **)&b->d_seq_info, (void **)&b->d_huf_tabs,
-                  (void **)&b->d_huf_info};
+                  (void **)&b->d_huf_info, &b->d_long};
     for (void **q : p) {
         pool_free(ctx, *q);
         *q = nullptr;
@@ -470,6 +521,7 @@ void szb_batch_destroy(szb_batch *b) {
     pool_free(b->ctx, b->d_seq_info);
     pool_free(b->ctx, b->d_huf_tabs);
     pool_free(b->ctx, b->d_huf_info);
+    pool_free(b->ctx, b->d_long);
     delete b;
 }
 
@@ -514,6 +566,16 @@ static DeviceBatch make_args(szb_batch *b, const void *d_src, void *d_dst, size_
     a.exec_list = b->d_exec_list;
     a.body_list = b->d_body_list;
     a.n_body = (uint32_t)b->body_list.size();
+    a.n_long = b->n_long;
+    a.n_lb = (uint32_t)b->lb_block.size();
+    a.lb_block = b->d_lb_block;
+    a.lb_slot = b->d_lb_slot;
+    a.long_first_lb = b->d_long_first_lb;
+    a.long_dbase = b->d_long_dbase;
+    a.dist = nullptr;
+    a.long_T = nullptr;
+    a.long_hist = nullptr;
+    a.long_err = nullptr;
     return a;
 }
 
@@ -589,11 +651,49 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
                 CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
                 CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
             }
+            cudaStream_t sl = ctx->s_lit;
+            // scratch of the block-parallel path: error words | transfer functions | start histories | distance cells.
+            // Without it (allocation refused) every long frame stays on k_execute_pair.
+            if (b->long_jump && !b->d_long) {
+                const size_t n_lb = b->lb_block.size();
+                const size_t o_T = align_up(8 * (size_t)n_long, 256);
+                const size_t o_hist = align_up(o_T + 24 * n_lb, 256);
+                const size_t o_dist = align_up(o_hist + 12 * n_lb, 256);
+                const size_t bytes = o_dist + 4 * (size_t)b->long_dbase.back();
+                if (cudaMallocAsync(&b->d_long, bytes, s) != cudaSuccess) {
+                    cudaGetLastError();
+                    b->d_long = nullptr;
+                    b->long_jump = false;
+                }
+            }
+            if (b->long_jump) {
+                const size_t n_lb = b->lb_block.size();
+                const size_t o_T = align_up(8 * (size_t)n_long, 256);
+                const size_t o_hist = align_up(o_T + 24 * n_lb, 256);
+                const size_t o_dist = align_up(o_hist + 12 * n_lb, 256);
+                uint8_t *base = (uint8_t *)b->d_long;
+                a.long_err = (unsigned long long *)base;
+                a.long_T = (uint64_t *)(base + o_T);
+                a.long_hist = (uint32_t *)(base + o_hist);
+                a.dist = (uint32_t *)(base + o_dist);
+                CUDA_TRY(ctx, cudaMemsetAsync(a.long_err, 0xFF, 8 * (size_t)n_long, s));
+            }
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, s));
-            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_lit, ctx->ev_fork, 0));
-            k_execute_pair<<<n_long, 64, 0, ctx->s_lit>>>(a, 0, n_long);
+            CUDA_TRY(ctx, cudaStreamWaitEvent(sl, ctx->ev_fork, 0));
+            k_execute_pair<<<n_long, 64, 0, sl>>>(a, 0, n_long);  // the frames the block-parallel path does not take
             ctx->launches++;
-            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->s_lit));
+            if (b->long_jump) {
+                const uint32_t n_lb = a.n_lb;
+                k_long_hist<<<(n_lb + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, sl>>>(a);
+                k_long_compose<<<n_long, 32, 0, sl>>>(a);
+                k_long_emit<<<(n_lb + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, sl>>>(a);
+                const uint64_t tiles = b->long_dbase.back() / kJumpTile;
+                const uint64_t resident = (uint64_t)ctx->sm_count * (2048 / kJumpThreads);
+                k_long_jump<<<(unsigned)(tiles < resident ? (tiles ? tiles : 1) : resident), kJumpThreads, 0, sl>>>(a);
+                k_long_verdict<<<(n_long + 127) / 128, 128, 0, sl>>>(a);
+                ctx->launches += 5;
+            }
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, sl));
         }
         if (n_rest) {
             k_execute<<<(n_rest + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, s>>>(a, n_long, n_rest);

@@ -1,0 +1,74 @@
+// batch.cuh -- the argument block every kernel of the decode path takes (DeviceBatch) and the launch constants.
+// Plain structs: compiles for the host as well (tests/host_sim runs device code on the CPU).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/szb200.h"
+
+namespace szb {
+
+constexpr int kWarpsPerCta = 4;
+constexpr int kCtaThreads = kWarpsPerCta * 32;
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+
+constexpr int kSeqLanes = 21;             // blocks per warp in k_decode_sequences: 21 x 2.6 KB (tables + bit ring), 4 warps per SM
+constexpr uint32_t kTabSlotWords = 1280;  // LL 512 | ML 512 | OF 256
+
+struct SeqInfo {
+    uint8_t al_ll, al_of, al_ml, pad;
+    uint32_t stream_off;  // offset of the backward bitstream after the sequences-section header
+};
+
+struct HufInfo {
+    uint8_t max_bits, pad;
+    uint16_t tree_bytes;  // size of the tree description inside the origin block's literals section
+    int32_t status;
+};
+
+struct DeviceBatch {
+    const uint8_t *src;
+    const szb_block_desc *blocks;
+    const szb_frame_desc *frames;
+    uint32_t nblocks, nframes;
+    const uint32_t *huf_list;  // blocks with Huffman-coded literals
+    uint32_t n_huf;
+    const uint32_t *hufo_list; // blocks that carry a Huffman tree description (literals type Compressed)
+    uint32_t n_hufo;
+    const uint32_t *huf_slot;  // per huf_list entry: position of its origin block in hufo_list
+    uint16_t *huf_tabs;        // per hufo_list entry: 2^kMaxHufBits decode-table cells
+    HufInfo *huf_info;         // per hufo_list entry
+    const uint32_t *seq_list;  // blocks with nseq > 0
+    uint32_t n_seq;
+    uint8_t *litbuf;
+    uint32_t *seq_ll, *seq_ml, *seq_of;  // one allocation: seq_ml = seq_ll + seq_stride, seq_of = seq_ll + 2 * seq_stride
+    uint64_t seq_stride;
+    uint16_t *seq_tabs;     // per seq_list entry: LL(512) | ML(512) | OF(256) 16-bit decode-table cells
+    SeqInfo *seq_info;      // per seq_list entry
+    uint64_t *out_size;     // per block regenerated size (host-initialised for Raw/RLE/zero-sequence blocks)
+    uint64_t *out_off;      // per block exclusive prefix
+    int32_t *lit_status;    // per block
+    int32_t *seq_status;    // per block
+    uint64_t *total;        // [0] = total output bytes
+    const uint32_t *predef; // predefined LL(64) | OF(32) | ML(64) decode tables
+    const uint8_t *bytefill; // 256 rows of 256 equal bytes (row v holds v)
+    uint8_t *dst;
+    uint64_t dst_cap;
+    uint64_t *frame_out_off, *frame_out_len;
+    int32_t *frame_status;
+    const uint32_t *exec_list;  // frames in the order k_execute starts them (most sequences first)
+    const uint32_t *body_list;  // Raw / RLE / zero-sequence blocks: output independent of earlier output
+    uint32_t n_body;
+    // long frames: exec_list[0, n_long); their stage 4 is parallel over blocks and bytes (execute_long.cuh)
+    uint32_t n_long;
+    uint32_t n_lb;
+    const uint32_t *lb_block;       // all blocks of the long frames, frame after frame in block order
+    const uint32_t *lb_slot;        // per lb_block entry: its frame's position in exec_list
+    const uint32_t *long_first_lb;  // per long frame: its first lb_block entry (n_long + 1 entries)
+    const uint64_t *long_dbase;     // per long frame: its first distance cell (n_long + 1 entries, multiples of kJumpTile)
+    uint32_t *dist;                 // one distance cell per output byte of the long frames; nullptr: k_execute_pair takes them
+    uint64_t *long_T;               // per lb_block entry: the block's history transfer function (3 entries)
+    uint32_t *long_hist;            // per lb_block entry: the history the block starts with (3 entries)
+    unsigned long long *long_err;   // per long frame: the first error found while emitting (block << 40 | round << 8 | -code)
+};
+
+}  // namespace szb

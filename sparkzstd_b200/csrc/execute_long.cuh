@@ -1,0 +1,350 @@
+// execute_long.cuh -- stage 4 for LONG frames, parallel over the blocks and bytes of a frame (sm_100a).
+//
+// The reference executes a frame strictly in order: sequence after sequence through a ring buffer
+// (decompression/sequence_execution.go:14-63, ringbuffer.go:197-277), the repeat-offset history carried from block to
+// block (sequence_execution.go:65-114).  k_execute keeps that order inside a frame (one warp per frame) and is parallel
+// over frames; a frame of gigabytes then runs on one warp.  The kernels here remove the two things that are sequential:
+//
+//   k_long_hist     the HISTORY: every block is walked with a symbolic history (an entry is a constant, or "entry i of
+//                   the history the block started with, minus k") -- the block's transfer function;
+//   k_long_compose  one warp per frame composes the transfer functions in block order: the history every block starts with;
+//   k_long_emit     one warp per block, every block at once: offsets through the (now known) history, positions by
+//                   prefix sums; writes the literal bytes to their place and, for EVERY output byte, a DISTANCE cell:
+//                   0 for a literal byte, else how far back the byte's source lies (inside an overlapping match a
+//                   multiple of the offset, so that the source lies in front of the match: ringbuffer.go:236-262);
+//   k_long_jump     the COPY ORDER: one thread per output byte follows d[p] += d[p - d[p]] until p - d[p] is a literal
+//                   byte and copies it.  Cells are updated in place; whatever value a cell holds at any time points at
+//                   an ancestor of its byte, so no ordering between bytes, no flags and no waiting are needed -- bytes
+//                   handled earlier only shorten the walk of the ones handled later (tiles run in address order);
+//   k_long_verdict  errors found while emitting (bad offset, literals run dry) become the frame's status: the first
+//                   failing block and round decides, as in the sequential reference.
+//
+// Frames this path cannot take (more than 4 GiB - 1 of output, more output than the host's bound, no scratch memory)
+// stay on k_execute_pair; every kernel evaluates the same predicate (long_jump_ok).
+#pragma once
+// Included by kernels.cuh, inside namespace szb, after DeviceBatch and the stage-4 helpers.
+
+constexpr uint32_t kJumpTile = 1024;  // cells per tile of k_long_jump; every frame's cells start at a multiple of it
+constexpr unsigned long long kLongNoError = ~0ull;
+
+__device__ __forceinline__ bool long_jump_ok(const DeviceBatch &a, uint32_t slot) {
+    if (a.dist == nullptr) return false;
+    const uint32_t f = a.exec_list[slot];
+    if (a.frame_status[f] != SZB_OK) return false;
+    const uint64_t len = a.frame_out_len[f];
+    return len <= a.long_dbase[slot + 1] - a.long_dbase[slot] && len < 0xFFFFFFFFull;
+}
+
+// ---- history values: concrete (uint32_t) or symbolic (uint64_t) ----
+constexpr uint64_t kSymBit = 1ull << 63;
+__device__ __forceinline__ uint64_t sym_entry(uint32_t idx) { return kSymBit | ((uint64_t)idx << 32); }
+__device__ __forceinline__ uint32_t hist_dec1(uint32_t v) { return v - 1; }
+__device__ __forceinline__ uint64_t hist_dec1(uint64_t v) { return (v & kSymBit) ? v + 1 : (uint64_t)((uint32_t)v - 1u); }
+__device__ __forceinline__ uint32_t hist_apply(uint64_t t, uint32_t h0, uint32_t h1, uint32_t h2) {
+    if (!(t & kSymBit)) return (uint32_t)t;
+    const uint32_t idx = (uint32_t)(t >> 32) & 3;
+    return (idx == 0 ? h0 : (idx == 1 ? h1 : h2)) - (uint32_t)t;
+}
+
+template <class V>
+struct HistV {
+    V h0, h1, h2;
+};
+
+// sequence_execution.go:65-114 (the table in SURVEY.md A.9) for a repeat code (ofv 1..3)
+template <class V>
+__device__ __forceinline__ V next_repeat(HistV<V> &h, uint32_t ofv, bool ll_zero) {
+    const uint32_t idx = ofv - 1 + (ll_zero ? 1 : 0);  // 0: h0, 1: h1, 2: h2, 3: h0 - 1
+    if (idx == 0) return h.h0;
+    V off;
+    if (idx == 1) {
+        off = h.h1;
+        h.h1 = h.h0;
+        h.h0 = off;
+        return off;
+    }
+    off = idx == 2 ? h.h2 : hist_dec1(h.h0);
+    h.h2 = h.h1;
+    h.h1 = h.h0;
+    h.h0 = off;
+    return off;
+}
+
+// One round of up to 32 sequences (lane = sequence) through the history.  A sequence with a direct offset pushes it
+// whatever the history holds, so the walk goes from repeat code to repeat code and folds the direct runs in between.
+// Returns the lane's offset (of its own sequence).
+template <class V>
+__device__ __forceinline__ V walk_round(HistV<V> &hist, uint32_t ofv, uint32_t ll, bool act, uint32_t cnt, uint32_t lane) {
+    V off = (V)(ofv - 3);
+    uint32_t rm = __ballot_sync(kFull, act && ofv <= 3);
+    uint32_t p = 0;  // sequences [0, p) are folded into hist
+    for (;;) {
+        const uint32_t j = rm ? (uint32_t)__ffs(rm) - 1 : cnt;  // the next repeat code, or the end of the round
+        const uint32_t n = j - p;
+        if (n) {
+            const V o1 = (V)(__shfl_sync(kFull, ofv, j - 1) - 3);
+            const V o2 = (V)(__shfl_sync(kFull, ofv, n >= 2 ? j - 2 : 0) - 3);
+            const V o3 = (V)(__shfl_sync(kFull, ofv, n >= 3 ? j - 3 : 0) - 3);
+            if (n >= 3) {
+                hist = HistV<V>{o1, o2, o3};
+            } else if (n == 2) {
+                hist = HistV<V>{o1, o2, hist.h0};
+            } else {
+                hist = HistV<V>{o1, hist.h0, hist.h1};
+            }
+        }
+        if (j >= cnt) break;
+        const uint32_t v = __shfl_sync(kFull, ofv, j);
+        const uint32_t l = __shfl_sync(kFull, ll, j);
+        const V o = next_repeat(hist, v, l == 0);  // every lane tracks the same history
+        if (lane == j) off = o;
+        rm &= rm - 1;
+        p = j + 1;
+    }
+    return off;
+}
+
+// ---- k_long_hist: the transfer function of every block of the long frames ----
+__global__ void __launch_bounds__(kCtaThreads) k_long_hist(DeviceBatch a) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    if (w >= a.n_lb) return;
+    const uint32_t b = a.lb_block[w];
+    const szb_block_desc d = a.blocks[b];
+    HistV<uint64_t> h{sym_entry(0), sym_entry(1), sym_entry(2)};
+    if (d.type == 2 && d.nseq > 0 && a.frame_status[d.frame] == SZB_OK) {
+        const uint32_t nseq = d.nseq;
+        const uint32_t *tr = a.seq_ll + (d.seq_buf_off + lane);  // the arrays are padded to whole rounds
+        uint32_t ll = tr[0], ofv = tr[2 * a.seq_stride];
+        for (uint32_t base = 0; base < nseq; base += 32) {
+            const uint32_t cnt = nseq - base < 32 ? nseq - base : 32;
+            const bool act = lane < cnt;
+            const uint32_t c_ll = ll, c_ofv = act ? ofv : 4;
+            if (base + 32 < nseq) {  // the next round's loads are in flight during the walk
+                ll = tr[base + 32];
+                ofv = tr[base + 32 + 2 * a.seq_stride];
+            }
+            walk_round<uint64_t>(h, c_ofv, c_ll, act, cnt, lane);
+        }
+    }
+    if (lane == 0) {
+        a.long_T[3 * (uint64_t)w] = h.h0;
+        a.long_T[3 * (uint64_t)w + 1] = h.h1;
+        a.long_T[3 * (uint64_t)w + 2] = h.h2;
+    }
+}
+
+// ---- k_long_compose: the history each block starts with; one warp per long frame ----
+__global__ void __launch_bounds__(32) k_long_compose(DeviceBatch a) {
+    const uint32_t lane = threadIdx.x;
+    const uint32_t slot = blockIdx.x;
+    if (slot >= a.n_long) return;
+    const uint32_t first = a.long_first_lb[slot], end = a.long_first_lb[slot + 1];
+    uint32_t h0 = 1, h1 = 4, h2 = 8;  // framedecompressor.go:48,59
+    for (uint32_t base = first; base < end; base += 32) {
+        const uint32_t i = base + lane;
+        uint64_t t0 = sym_entry(0), t1 = sym_entry(1), t2 = sym_entry(2);
+        if (i < end) {
+            t0 = a.long_T[3 * (uint64_t)i];
+            t1 = a.long_T[3 * (uint64_t)i + 1];
+            t2 = a.long_T[3 * (uint64_t)i + 2];
+        }
+        const uint32_t cnt = end - base < 32 ? end - base : 32;
+        uint32_t m0 = 0, m1 = 0, m2 = 0;
+        for (uint32_t j = 0; j < cnt; j++) {
+            if (lane == j) {
+                m0 = h0;
+                m1 = h1;
+                m2 = h2;
+            }
+            const uint64_t u0 = __shfl_sync(kFull, t0, j), u1 = __shfl_sync(kFull, t1, j), u2 = __shfl_sync(kFull, t2, j);
+            const uint32_t n0 = hist_apply(u0, h0, h1, h2), n1 = hist_apply(u1, h0, h1, h2), n2 = hist_apply(u2, h0, h1, h2);
+            h0 = n0;
+            h1 = n1;
+            h2 = n2;
+        }
+        if (i < end) {
+            a.long_hist[3 * (uint64_t)i] = m0;
+            a.long_hist[3 * (uint64_t)i + 1] = m1;
+            a.long_hist[3 * (uint64_t)i + 2] = m2;
+        }
+    }
+}
+
+// ---- k_long_emit: literal bytes and distance cells of every block of the long frames; one warp per block ----
+__global__ void __launch_bounds__(kCtaThreads) k_long_emit(DeviceBatch a) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    if (w >= a.n_lb) return;
+    const uint32_t slot = a.lb_slot[w];
+    if (!long_jump_ok(a, slot)) return;
+    const uint32_t b = a.lb_block[w];
+    const szb_block_desc d = a.blocks[b];
+    const uint64_t frame_base = a.frame_out_off[d.frame];
+    uint64_t out_pos = a.out_off[b];
+    uint8_t *const dst = a.dst;
+    uint32_t *const cells = a.dist + a.long_dbase[slot];  // cell of the frame's first byte
+    const uint64_t fb0 = out_pos - frame_base;            // frame bytes in front of the block
+
+    if (d.type != 2 || d.nseq == 0) {
+        // Raw / RLE bodies and blocks without sequences: written by k_execute_bodies; every byte is a literal byte
+        const uint64_t n = a.out_size[b];
+        for (uint64_t i = lane; i < n; i += 32) cells[fb0 + i] = 0;
+        return;
+    }
+    const uint8_t *payload = a.src + d.src_off;
+    const bool lit_rle = d.lit_type == 1;
+    const uint32_t fill = lit_rle ? payload[d.lit_hdr_bytes] : 0;
+    const uint8_t *__restrict__ lit = d.lit_type == 0 ? payload + d.lit_hdr_bytes : a.litbuf + d.lit_buf_off;  // unused for RLE literals
+    const uint32_t nseq = d.nseq;
+    HistV<uint32_t> hist{a.long_hist[3 * (uint64_t)w], a.long_hist[3 * (uint64_t)w + 1], a.long_hist[3 * (uint64_t)w + 2]};
+    uint32_t lit_pos = 0;
+    uint64_t fb = fb0;  // frame bytes in front of the round
+    int err = SZB_OK;
+    uint32_t err_base = 0;
+    const uint32_t *tr = a.seq_ll + (d.seq_buf_off + lane);
+    uint32_t n_ll = tr[0], n_ml = tr[a.seq_stride], n_ofv = tr[2 * a.seq_stride];
+    for (uint32_t base = 0; base < nseq; base += 32) {
+        const uint32_t cnt = nseq - base < 32 ? nseq - base : 32;
+        const bool act = lane < cnt;
+        const uint32_t ll = act ? n_ll : 0, ml = act ? n_ml : 0, ofv = act ? n_ofv : 4;
+        if (base + 32 < nseq) {
+            n_ll = tr[base + 32];
+            n_ml = tr[base + 32 + a.seq_stride];
+            n_ofv = tr[base + 32 + 2 * a.seq_stride];
+        }
+        const uint32_t off = walk_round<uint32_t>(hist, ofv, ll, act, cnt, lane);
+        // positions: prefix sums over the round (a sequence is < 2^18 bytes: the sums fit 32 bits)
+        const uint32_t tot = ll + ml;
+        uint32_t incl_ll = ll, incl_tot = tot;
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            const uint32_t t1 = __shfl_up_sync(kFull, incl_ll, dlt);
+            const uint32_t t2 = __shfl_up_sync(kFull, incl_tot, dlt);
+            if ((int)lane >= dlt) {
+                incl_ll += t1;
+                incl_tot += t2;
+            }
+        }
+        const uint32_t round_ll = __shfl_sync(kFull, incl_ll, 31);
+        const uint32_t round_tot = __shfl_sync(kFull, incl_tot, 31);
+        if ((uint64_t)lit_pos + round_ll > d.lit_regen) {
+            // literals.go:398-409 Read runs dry / sequence_execution.go:26-28; RLE literals: GetRest panics
+            err = lit_rle ? SZB_ERR_PANIC : SZB_ERR_DIDNT_COPY_ALL_LITERAL_BYTES;
+            err_base = base;
+            break;
+        }
+        const uint32_t excl_tot = incl_tot - tot, excl_ll = incl_ll - ll;
+        // every match must lie inside the frame (ringbuffer.go:203-214); a match length of 0 cannot come out of stage 3
+        if (__any_sync(kFull, act && ((uint64_t)off > fb + excl_tot + ll || off == 0 || ml == 0))) {
+            err = SZB_ERR_CANT_REPEAT_BYTES;
+            err_base = base;
+            break;
+        }
+        // every byte of the round: its sequence by binary search over the inclusive sums (lanes past cnt repeat the last sum)
+        for (uint32_t x0 = 0; x0 < round_tot; x0 += 32) {
+            const uint32_t x = x0 + lane;
+            uint32_t j = 0;
+#pragma unroll
+            for (uint32_t step = 16; step; step >>= 1) {
+                const uint32_t t = __shfl_sync(kFull, incl_tot, j + step - 1);
+                if (t <= x) j += step;
+            }
+            const uint32_t s_excl = __shfl_sync(kFull, excl_tot, j);
+            const uint32_t s_ll = __shfl_sync(kFull, ll, j);
+            const uint32_t s_off = __shfl_sync(kFull, off, j);
+            const uint32_t s_lit = __shfl_sync(kFull, excl_ll, j);
+            if (x < round_tot) {
+                const uint32_t k = x - s_excl;
+                uint32_t cell = 0;
+                if (k < s_ll) {
+                    dst[out_pos + x] = lit_rle ? (uint8_t)fill : lit[lit_pos + s_lit + k];
+                } else {
+                    const uint32_t m = k - s_ll;
+                    cell = m < s_off ? s_off : s_off * (m / s_off + 1);
+                }
+                cells[fb + x] = cell;
+            }
+        }
+        out_pos += round_tot;
+        fb += round_tot;
+        lit_pos += round_ll;
+    }
+    if (err != SZB_OK) {
+        if (lane == 0) atomicMin(&a.long_err[slot], ((unsigned long long)w << 40) | ((unsigned long long)err_base << 8) | (uint32_t)(-err));
+        return;
+    }
+    // trailing literals (sequence_execution.go:55-60, literals.go:411-420)
+    const uint32_t rest = d.lit_regen - lit_pos;
+    for (uint32_t i = lane; i < rest; i += 32) {
+        dst[out_pos + i] = lit_rle ? (uint8_t)fill : lit[lit_pos + i];
+        cells[fb + i] = 0;
+    }
+}
+
+// ---- k_long_jump: every match byte finds its literal byte ----
+constexpr int kJumpThreads = 256;
+__global__ void __launch_bounds__(kJumpThreads) k_long_jump(DeviceBatch a) {
+    const uint64_t total = a.long_dbase[a.n_long];
+    const uint32_t tid = threadIdx.x;
+    for (uint64_t c0 = (uint64_t)blockIdx.x * kJumpTile; c0 < total; c0 += (uint64_t)gridDim.x * kJumpTile) {
+        // the frame of the tile: the last slot whose cells start at or before c0
+        uint32_t lo = 0, hi = a.n_long;  // invariant: dbase[lo] <= c0 < dbase[hi]
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (a.long_dbase[mid] <= c0)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const uint32_t slot = lo;
+        if (!long_jump_ok(a, slot) || a.long_err[slot] != kLongNoError) continue;
+        const uint32_t f = a.exec_list[slot];
+        const uint64_t len = a.frame_out_len[f];
+        const uint64_t rel0 = c0 - a.long_dbase[slot];
+        if (rel0 >= len) continue;
+        uint32_t *const cells = a.dist + a.long_dbase[slot];
+        uint8_t *const out = a.dst + a.frame_out_off[f];
+        uint32_t dj[4], first[4];
+        uint32_t open = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const uint64_t rel = rel0 + c * kJumpThreads + tid;
+            dj[c] = rel < len ? __ldcg(cells + rel) : 0;
+            first[c] = dj[c];
+            if (dj[c]) open |= 1u << c;
+        }
+        while (open) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                if (open & (1u << c)) {
+                    const uint64_t rel = rel0 + c * kJumpThreads + tid;
+                    const uint32_t e = __ldcg(cells + (rel - dj[c]));
+                    if (e)
+                        dj[c] += e;
+                    else
+                        open &= ~(1u << c);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            if (first[c]) {
+                const uint64_t rel = rel0 + c * kJumpThreads + tid;
+                if (dj[c] != first[c]) __stcg(cells + rel, dj[c]);  // later bytes reach the literal in one step
+                out[rel] = out[rel - dj[c]];
+            }
+        }
+    }
+}
+
+// ---- k_long_verdict: one thread per long frame ----
+__global__ void k_long_verdict(DeviceBatch a) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= a.n_long) return;
+    const unsigned long long e = a.long_err[slot];
+    if (e == kLongNoError) return;
+    const uint32_t f = a.exec_list[slot];
+    a.frame_status[f] = -(int32_t)(e & 0xFF);
+    a.frame_out_len[f] = 0;
+}
+

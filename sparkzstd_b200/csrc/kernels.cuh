@@ -21,74 +21,27 @@
 //                       then the output produced in address order, 128 bytes per step, every lane
 //                       fetching the source byte of its output byte (literal or match)
 //                       (decompression/sequence_execution.go:14-114, ringbuffer.go:197-277)
-//   k_execute_pair      the same for the few very long frames: a producer warp and a consumer warp per frame
+//   k_execute_pair      the same with a producer warp and a consumer warp per frame: the long frames the
+//                       block-parallel path cannot take
+//   k_long_hist / k_long_compose / k_long_emit / k_long_jump / k_long_verdict  (execute_long.cuh)
+//                       stage 4 of LONG frames, parallel over their blocks and bytes: repeat-offset history by
+//                       composing per-block transfer functions, then one distance cell per output byte resolved
+//                       by in-place pointer jumping
 //   k_verify_checksums  optional XXH64 content checksum, one thread per frame
 //
 // All arithmetic is integer; there is no tensor-core work on this path.
 #pragma once
 #include <cuda_runtime.h>
 
+#include "batch.cuh"
 #include "huffman.cuh"
 #include "sequences.cuh"
 
 namespace szb {
 
-constexpr int kWarpsPerCta = 4;
-constexpr int kCtaThreads = kWarpsPerCta * 32;
-constexpr uint32_t kFull = 0xFFFFFFFFu;
-
 #ifndef SZB_SERIAL_TABLES
 #define SZB_SERIAL_TABLES 0
 #endif
-
-constexpr int kSeqLanes = 21;             // blocks per warp in k_decode_sequences: 21 x 2.6 KB (tables + bit ring), 4 warps per SM
-constexpr uint32_t kTabSlotWords = 1280;  // LL 512 | ML 512 | OF 256
-
-struct SeqInfo {
-    uint8_t al_ll, al_of, al_ml, pad;
-    uint32_t stream_off;  // offset of the backward bitstream after the sequences-section header
-};
-
-struct HufInfo {
-    uint8_t max_bits, pad;
-    uint16_t tree_bytes;  // size of the tree description inside the origin block's literals section
-    int32_t status;
-};
-
-struct DeviceBatch {
-    const uint8_t *src;
-    const szb_block_desc *blocks;
-    const szb_frame_desc *frames;
-    uint32_t nblocks, nframes;
-    const uint32_t *huf_list;  // blocks with Huffman-coded literals
-    uint32_t n_huf;
-    const uint32_t *hufo_list; // blocks that carry a Huffman tree description (literals type Compressed)
-    uint32_t n_hufo;
-    const uint32_t *huf_slot;  // per huf_list entry: position of its origin block in hufo_list
-    uint16_t *huf_tabs;        // per hufo_list entry: 2^kMaxHufBits decode-table cells
-    HufInfo *huf_info;         // per hufo_list entry
-    const uint32_t *seq_list;  // blocks with nseq > 0
-    uint32_t n_seq;
-    uint8_t *litbuf;
-    uint32_t *seq_ll, *seq_ml, *seq_of;  // one allocation: seq_ml = seq_ll + seq_stride, seq_of = seq_ll + 2 * seq_stride
-    uint64_t seq_stride;
-    uint16_t *seq_tabs;     // per seq_list entry: LL(512) | ML(512) | OF(256) 16-bit decode-table cells
-    SeqInfo *seq_info;      // per seq_list entry
-    uint64_t *out_size;     // per block regenerated size (host-initialised for Raw/RLE/zero-sequence blocks)
-    uint64_t *out_off;      // per block exclusive prefix
-    int32_t *lit_status;    // per block
-    int32_t *seq_status;    // per block
-    uint64_t *total;        // [0] = total output bytes
-    const uint32_t *predef; // predefined LL(64) | OF(32) | ML(64) decode tables
-    const uint8_t *bytefill; // 256 rows of 256 equal bytes (row v holds v)
-    uint8_t *dst;
-    uint64_t dst_cap;
-    uint64_t *frame_out_off, *frame_out_len;
-    int32_t *frame_status;
-    const uint32_t *exec_list;  // frames in the order k_execute starts them (most sequences first)
-    const uint32_t *body_list;  // Raw / RLE / zero-sequence blocks: output independent of earlier output
-    uint32_t n_body;
-};
 
 __device__ __forceinline__ int warp_first_error(int rc) {
     uint32_t bad = __ballot_sync(kFull, rc != 0);
@@ -1603,6 +1556,8 @@ __device__ __forceinline__ void produce_frame(const DeviceBatch &a, uint32_t f, 
     }
 }
 
+#include "execute_long.cuh"
+
 // One warp per frame: it produces the segments and consumes them.  Frames exec_list[first_slot, first_slot + n_slots).
 #ifndef SZB_EXEC_MIN_CTAS
 #define SZB_EXEC_MIN_CTAS 8
@@ -1634,6 +1589,7 @@ __global__ void __launch_bounds__(64) k_execute_pair(DeviceBatch a, uint32_t fir
     if (blockIdx.x >= n_slots) return;
     const uint32_t f = a.exec_list[first_slot + blockIdx.x];
     if (a.frame_status[f] != SZB_OK) return;  // k_frame_verdict; both warps agree
+    if (long_jump_ok(a, first_slot + blockIdx.x)) return;  // taken by the block-parallel path (execute_long.cuh)
     const szb_frame_desc fr = a.frames[f];
     const uint64_t frame_base = fr.nblocks ? a.out_off[fr.first_block] : 0;
     for (uint32_t wd = threadIdx.x; wd < kRingBits / 32; wd += 64) sm.bits[wd] = 0;

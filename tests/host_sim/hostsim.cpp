@@ -2,15 +2,26 @@
 // (bits.cuh, fse.cuh, huffman.cuh, sequences.cuh -- the code a single lane executes) on the CPU,
 // driven by the product's own header walker, so that `pytest -m "not gpu"` can check them
 // against the oracle without a GPU.  The warp-cooperative parts (table builds with ballots,
-// k_execute) only run on the device and are covered by the -m gpu tests.
+// k_execute) only run on the device and are covered by the -m gpu tests -- except the block-parallel stage 4 of long
+// frames (execute_long.cuh), whose kernels run here lane by lane on an emulated warp (warpsim.h).
 // This file is never linked into libszb200.so.
 #include <cstdint>
 #include <cstring>
 #include <vector>
 
+#include <algorithm>
+#include <random>
+
+#include "warpsim.h"
+
 #include "../../include/szb200.h"
+#include "../../sparkzstd_b200/csrc/batch.cuh"
 #include "../../sparkzstd_b200/csrc/huffman.cuh"
 #include "../../sparkzstd_b200/csrc/sequences.cuh"
+
+namespace szb {
+#include "../../sparkzstd_b200/csrc/execute_long.cuh"
+}
 
 using namespace szb;
 
@@ -230,6 +241,178 @@ int hostsim_decode_frame(const uint8_t *src, size_t len, uint8_t *out, size_t ca
     szb_walk_destroy(w);
     *out_len = pos;
     return rc;
+}
+
+
+// Decodes ONE frame the way the product does when the frame is LONG: walker, serial device functions for stages 1-3, the
+// body blocks as k_execute_bodies writes them, then the kernels of execute_long.cuh on an emulated warp.
+// order: 0 = CTAs in launch order, 1 = reversed (the worst case for k_long_jump), >= 2 = shuffled with that seed.
+// With two_frames the same frame is decoded twice in one batch (two long slots) and both copies must agree.
+int hostsim_decode_frame_long(const uint8_t *src, size_t len, uint8_t *out, size_t cap, size_t *out_len, int order, int two_frames) {
+    uint64_t off = 0, flen = len;
+    szb_walk *w = nullptr;
+    *out_len = 0;
+    int rc = szb_walk_create(src, len, &off, &flen, 1, &w);
+    if (rc) return rc;
+    const szb_frame_desc fr0 = szb_walk_frames(w)[0];
+    const uint32_t nb1 = szb_walk_nblocks(w);
+    if (fr0.status != SZB_OK || fr0.nblocks != nb1) {
+        szb_walk_destroy(w);
+        return fr0.status ? fr0.status : SZB_ERR_INVALID_ARGUMENT;
+    }
+    const uint32_t copies = two_frames ? 2 : 1;
+    const uint32_t nb = nb1 * copies;
+    std::vector<szb_block_desc> blocks(nb);
+    std::vector<szb_frame_desc> frames(copies, fr0);
+    uint64_t lit_bytes = 0, seqs = 0;
+    for (uint32_t b = 0; b < nb1; b++) {
+        const szb_block_desc &d = szb_walk_blocks(w)[b];
+        if (d.type == 2 && d.lit_type >= 2) lit_bytes = std::max<uint64_t>(lit_bytes, d.lit_buf_off + ((d.lit_regen + 15) & ~15u));
+        if (d.type == 2) seqs = std::max<uint64_t>(seqs, d.seq_buf_off + ((d.nseq + 31) & ~31u));
+    }
+    for (uint32_t c = 0; c < copies; c++) {
+        frames[c].first_block = c * nb1;
+        for (uint32_t b = 0; b < nb1; b++) {
+            szb_block_desc d = szb_walk_blocks(w)[b];
+            d.frame = c;
+            d.lit_buf_off += c * lit_bytes;
+            d.seq_buf_off += c * seqs;
+            if (d.huf_origin != SZB_NONE) d.huf_origin += c * nb1;
+            if (d.ll_origin != SZB_NONE) d.ll_origin += c * nb1;
+            if (d.of_origin != SZB_NONE) d.of_origin += c * nb1;
+            if (d.ml_origin != SZB_NONE) d.ml_origin += c * nb1;
+            blocks[c * nb1 + b] = d;
+        }
+    }
+    szb_walk_destroy(w);
+    // stages 1-3 with the serial device functions
+    const uint64_t stride = seqs * copies + 32;
+    std::vector<uint8_t> litbuf(lit_bytes * copies + 16, 0xEE);
+    std::vector<uint32_t> seq(3 * stride, 0xDEADBEEFu);  // padding lanes hold garbage, as on the device
+    std::vector<uint64_t> out_size(nb), out_off(nb);
+    std::vector<uint32_t> ll, ml, of;
+    for (uint32_t b = 0; b < nb; b++) {
+        const szb_block_desc &d = blocks[b];
+        out_size[b] = d.type == 2 ? d.lit_regen : d.block_size;
+        if (d.type != 2) continue;
+        if (d.lit_type >= 2) {
+            rc = huffman_block(src, blocks.data(), b, litbuf.data() + d.lit_buf_off);
+            if (rc) return rc;
+        }
+        if (d.nseq) {
+            rc = sequences_block(src, blocks.data(), b, ll, ml, of);
+            if (rc) return rc;
+            for (uint32_t i = 0; i < d.nseq; i++) {
+                seq[d.seq_buf_off + i] = ll[i];
+                seq[stride + d.seq_buf_off + i] = ml[i];
+                seq[2 * stride + d.seq_buf_off + i] = of[i];
+                out_size[b] += ml[i];
+            }
+        }
+    }
+    uint64_t total = 0;
+    for (uint32_t b = 0; b < nb; b++) {
+        out_off[b] = total;
+        total += out_size[b];
+    }
+    if (total > cap) return SZB_ERR_DST_TOO_SMALL;
+    std::vector<uint64_t> frame_out_off(copies), frame_out_len(copies);
+    std::vector<int32_t> frame_status(copies, SZB_OK);
+    for (uint32_t c = 0; c < copies; c++) {
+        frame_out_off[c] = out_off[c * nb1];
+        frame_out_len[c] = total / copies;
+    }
+    // k_execute_bodies
+    for (uint32_t b = 0; b < nb; b++) {
+        const szb_block_desc &d = blocks[b];
+        const uint8_t *payload = src + d.src_off;
+        uint8_t *o = out + out_off[b];
+        if (d.type == 0) memcpy(o, payload, d.block_size);
+        else if (d.type == 1) memset(o, payload[0], d.block_size);
+        else if (d.nseq == 0) {
+            if (d.lit_type == 1) memset(o, payload[d.lit_hdr_bytes], d.lit_regen);
+            else memcpy(o, d.lit_type == 0 ? payload + d.lit_hdr_bytes : litbuf.data() + d.lit_buf_off, d.lit_regen);
+        }
+    }
+    // the long-frame tables, as batch_upload_tables (api.cu) builds them
+    std::vector<uint32_t> exec_list(copies), lb_block, lb_slot, long_first_lb(1, 0);
+    std::vector<uint64_t> long_dbase(1, 0);
+    for (uint32_t c = 0; c < copies; c++) exec_list[c] = copies - 1 - c;  // slots need not be in frame order
+    for (uint32_t slot = 0; slot < copies; slot++) {
+        const szb_frame_desc &fr = frames[exec_list[slot]];
+        uint64_t bound = 0;
+        for (uint32_t i = 0; i < fr.nblocks; i++) {
+            const szb_block_desc &d = blocks[fr.first_block + i];
+            lb_block.push_back(fr.first_block + i);
+            lb_slot.push_back(slot);
+            bound += d.type == 2 ? (d.nseq ? 128 * 1024 : d.lit_regen) : d.block_size;
+        }
+        long_dbase.push_back(long_dbase.back() + (bound + kJumpTile - 1) / kJumpTile * kJumpTile);
+        long_first_lb.push_back((uint32_t)lb_block.size());
+    }
+    const uint32_t n_lb = (uint32_t)lb_block.size();
+    std::vector<uint32_t> dist(long_dbase.back(), 0xCDCDCDCDu), long_hist(3 * (size_t)n_lb + 3);
+    std::vector<uint64_t> long_T(3 * (size_t)n_lb + 3);
+    std::vector<unsigned long long> long_err(copies, kLongNoError);
+    DeviceBatch a{};
+    a.src = src;
+    a.blocks = blocks.data();
+    a.frames = frames.data();
+    a.nblocks = nb;
+    a.nframes = copies;
+    a.litbuf = litbuf.data();
+    a.seq_ll = seq.data();
+    a.seq_ml = seq.data() + stride;
+    a.seq_of = seq.data() + 2 * stride;
+    a.seq_stride = stride;
+    a.out_size = out_size.data();
+    a.out_off = out_off.data();
+    a.dst = out;
+    a.dst_cap = cap;
+    a.frame_out_off = frame_out_off.data();
+    a.frame_out_len = frame_out_len.data();
+    a.frame_status = frame_status.data();
+    a.exec_list = exec_list.data();
+    a.n_long = copies;
+    a.n_lb = n_lb;
+    a.lb_block = lb_block.data();
+    a.lb_slot = lb_slot.data();
+    a.long_first_lb = long_first_lb.data();
+    a.long_dbase = long_dbase.data();
+    a.dist = dist.data();
+    a.long_T = long_T.data();
+    a.long_hist = long_hist.data();
+    a.long_err = long_err.data();
+
+    auto cta_order = [&](unsigned grid) {
+        std::vector<unsigned> o(grid);
+        for (unsigned i = 0; i < grid; i++) o[i] = i;
+        if (order == 1) std::reverse(o.begin(), o.end());
+        if (order >= 2) std::shuffle(o.begin(), o.end(), std::mt19937(order));
+        return o;
+    };
+    const unsigned g_blocks = (n_lb + kWarpsPerCta - 1) / kWarpsPerCta;
+    {
+        auto o = cta_order(g_blocks);
+        warpsim::launch(g_blocks, kCtaThreads, [&] { k_long_hist(a); }, &o);
+    }
+    warpsim::launch(copies, 32, [&] { k_long_compose(a); });
+    {
+        auto o = cta_order(g_blocks);
+        warpsim::launch(g_blocks, kCtaThreads, [&] { k_long_emit(a); }, &o);
+    }
+    {
+        const unsigned tiles = (unsigned)(long_dbase.back() / kJumpTile);
+        const unsigned grid = order == 0 ? std::max(1u, tiles / 3) : std::max(1u, tiles);  // order 0 also takes the grid-stride loop
+        auto o = cta_order(grid);
+        warpsim::launch(grid, kJumpThreads, [&] { k_long_jump(a); }, &o);
+    }
+    warpsim::launch(1, 128, [&] { k_long_verdict(a); });
+    for (uint32_t c = 0; c < copies; c++)
+        if (frame_status[c] != SZB_OK) return frame_status[c];
+    if (copies == 2 && memcmp(out, out + total / 2, total / 2) != 0) return SZB_ERR_INVALID_ARGUMENT;
+    *out_len = total / copies;
+    return SZB_OK;
 }
 
 }  // extern "C"

@@ -309,9 +309,12 @@ def test_kernels_were_launched(ctx):
     assert t["total"] > 0
 
 
-def test_pair_kernel_on_every_frame(corpus, tmp_path):
-    """k_execute_pair (two warps per frame, normally only for frames with >= 65 536 sequences) forced onto every frame of the
-    corpus, the crafted frames and a text batch: same bytes.  The threshold is read once per process, hence the subprocess."""
+@pytest.mark.parametrize("mode", ["jump", "pair"])
+def test_long_frame_paths_on_every_frame(corpus, tmp_path, mode):
+    """The two stage-4 paths for LONG frames (normally frames with >= 65 536 sequences) forced onto every frame: the
+    block-parallel kernels of execute_long.cuh ("jump") and k_execute_pair ("pair").  Corpus, crafted frames, a text batch,
+    a streamed multi-block frame and the mixed corpus: same bytes; bit-flipped payloads: same statuses and bytes as the
+    one-warp-per-frame path.  Run in a subprocess so that a hang cannot take the test session with it."""
     import os
     import subprocess
     import sys
@@ -319,10 +322,12 @@ def test_pair_kernel_on_every_frame(corpus, tmp_path):
 
     code = textwrap.dedent(
         """
-        import hashlib, sys
+        import hashlib, os, sys
+        import numpy as np
         sys.path.insert(0, "tests")
         import crafted_frames
         from tools import corpus as cg
+        from oracle import pyszo
         from sparkzstd_b200.decompression import Context
         ctx = Context(0)
         gold = cg.golden_frames()
@@ -334,11 +339,43 @@ def test_pair_kernel_on_every_frame(corpus, tmp_path):
         assert all(o == cs[n][1] for o, n in zip(outs, names))
         t = cg.config2_text_frames(700)
         outs = ctx.decode_batch([t.frame(i) for i in range(t.nframes)])
-        assert all(cg.hash_bytes(__import__("numpy").frombuffer(o, dtype="uint8")) == int(t.raw_hash[i]) for i, o in enumerate(outs))
-        print("pair ok", ctx.launch_count())
+        assert all(cg.hash_bytes(np.frombuffer(o, dtype="uint8")) == int(t.raw_hash[i]) for i, o in enumerate(outs))
+        for c in (cg.config3_single_frame(12 << 20, window_log=20), cg.config5_mixed(24 << 20)):
+            frames = [c.frame(i) for i in range(c.nframes)]
+            outs = ctx.decode_batch(frames)
+            assert all(o == pyszo.decode_frame(f) for f, o in zip(frames, outs)), c.name
+        # bit flips: statuses and bytes must not depend on the path
+        rng = np.random.default_rng(5)
+        frames = []
+        for name, data, size, _ in gold[:80]:
+            if len(data) < 40:
+                continue
+            buf = bytearray(data)
+            for _ in range(2):
+                p = int(rng.integers(12, len(buf) - 4))
+                buf[p] ^= 1 << int(rng.integers(0, 8))
+            frames.append(bytes(buf))
+        src = np.frombuffer(b"".join(frames) + bytes(64), dtype=np.uint8)
+        lens = np.array([len(f) for f in frames], dtype=np.uint64)
+        offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64)
+        res = []
+        for thr in ("1", "4000000000"):
+            os.environ["SZB_LONG_SEQS"] = thr
+            dst = np.zeros(64 << 20, dtype=np.uint8)
+            out_off, out_len, status = ctx.decode_batch_into(src, offs, lens, dst)
+            res.append((np.array(out_off), np.array(out_len), np.array(status), dst))
+        a, b = res
+        assert (a[2] == b[2]).all(), (a[2], b[2])
+        assert (a[1] == b[1]).all()
+        for i in range(len(frames)):
+            if a[2][i] == 0:
+                o, l = int(a[0][i]), int(a[1][i])
+                o2 = int(b[0][i])
+                assert (a[3][o:o + l] == b[3][o2:o2 + l]).all(), i
+        print("long ok", ctx.launch_count(), int((a[2] != 0).sum()), "of", len(frames), "fail")
         """
     )
-    env = dict(os.environ, SZB_LONG_SEQS="1")
+    env = dict(os.environ, SZB_LONG_SEQS="1", SZB_LONG_MODE=mode)
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300,
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    assert res.returncode == 0 and "pair ok" in res.stdout, res.stdout + res.stderr
+    assert res.returncode == 0 and "long ok" in res.stdout, res.stdout + res.stderr

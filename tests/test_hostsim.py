@@ -20,7 +20,7 @@ SIM = os.path.join(ROOT, "tests", "host_sim")
 def sim():
     lib = os.path.join(SIM, "libhostsim.so")
     srcs = [os.path.join(SIM, "hostsim.cpp"), os.path.join(ROOT, "sparkzstd_b200", "csrc", "walker.cpp")]
-    deps = srcs + [os.path.join(ROOT, "sparkzstd_b200", "csrc", f) for f in ("bits.cuh", "fse.cuh", "huffman.cuh", "sequences.cuh")]
+    deps = srcs + [os.path.join(SIM, "warpsim.h")] + [os.path.join(ROOT, "sparkzstd_b200", "csrc", f) for f in ("bits.cuh", "fse.cuh", "huffman.cuh", "sequences.cuh", "batch.cuh", "execute_long.cuh")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", lib, *srcs], check=True)
     L = C.CDLL(lib)
@@ -56,3 +56,55 @@ def test_serial_device_code_error_paths(sim, corpus):
     assert rc == -32
     rc, _ = _decode(sim, b"\0\0\0\0" + data[4:], size)
     assert rc == -1
+
+
+# ---- the block-parallel stage 4 of long frames (execute_long.cuh) on an emulated warp (warpsim.h) ----
+def _decode_long(L, data: bytes, cap: int, order: int, two: int):
+    L.hostsim_decode_frame_long.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_int, C.c_int]
+    out = np.empty(2 * cap + 16, dtype=np.uint8)
+    n = C.c_size_t()
+    rc = L.hostsim_decode_frame_long(data, len(data), out.ctypes.data, 2 * cap + 16, C.byref(n), order, two)
+    return rc, out[: n.value].tobytes()
+
+
+def test_long_frame_kernels_decode_golden_frames(sim, corpus):
+    done = 0
+    for k, (name, data, size, sha) in enumerate(corpus):
+        if size > 40_000:
+            continue
+        order = k % 4 if k % 4 < 2 else 1000 + k
+        rc, out = _decode_long(sim, data, size, order, k % 2)
+        assert rc == 0 and len(out) == size and hashlib.sha256(out).hexdigest() == sha, (name, order)
+        done += 1
+    assert done >= 20
+
+
+def test_long_frame_kernels_match_oracle_on_synthetic_shapes(sim):
+    for c in (cg.config2_text_frames(2), cg.config3_single_frame(1 << 19, 20), cg.config5_mixed(1 << 20, with_golden=False)):
+        for i in range(min(c.nframes, 6)):
+            f = c.frame(i)
+            want = pyszo.decode_frame(f)
+            if len(want) > 600_000:
+                continue
+            rc, out = _decode_long(sim, f, len(want), 1 if i % 2 else 77 + i, 0)
+            assert rc == 0 and out == want, (c.name, i)
+
+
+def test_long_frame_kernels_on_crafted_frames(sim):
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import crafted_frames as crafted
+
+    for k, (name, (frame, expected)) in enumerate(sorted(crafted.cases().items())):
+        rc, out = _decode_long(sim, frame, len(expected), k % 3, k % 2)
+        assert rc == 0 and out == expected, name
+    # a match that reaches in front of the frame: the first failing round decides (ringbuffer.go:203-214)
+    seed = bytes(range(200)) * 5
+    frame, _ = crafted.frame(seed, "raw", bytes(50), 10, 50, 900)
+    cut = frame[:9] + crafted._block_header(0, 0, 10) + seed[:10] + frame[9 + 3 + len(seed):]
+    with pytest.raises(pyszo.OracleError) as e:
+        pyszo.decode_frame(cut)
+    assert e.value.code == -30
+    rc, _ = _decode_long(sim, cut, 4096, 0, 0)
+    assert rc == -30
