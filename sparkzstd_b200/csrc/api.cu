@@ -262,6 +262,7 @@ void szb_free(void *p) { free(p); }
 // SZB_LONG_SEQS overrides the threshold (tests force every frame through the pair kernel with it).
 constexpr uint64_t kLongFrameSequences = 65536;
 constexpr uint32_t kMaxLongFrames = 2368;
+constexpr double kPairGBps = 0.26, kJumpGBps = 16.0;  // measured: profiles/r01d_bench_single256m_1gpu.json, r01e_bench_single256m_1gpu.json
 
 static int batch_upload_tables(szb_batch *b) {
     szb_ctx *ctx = b->ctx;
@@ -329,6 +330,17 @@ static int batch_upload_tables(szb_batch *b) {
             }
             static const uint64_t max_cells = (getenv("SZB_LONG_MAX_GIB") ? strtoull(getenv("SZB_LONG_MAX_GIB"), nullptr, 10) : 64) << 28;
             if (cells > max_cells) b->long_jump = false;  // 4 bytes per cell
+            // Which path is faster depends on the batch.  k_execute_pair runs every long frame at kPairGBps on its own two
+            // warps, all frames side by side (up to 16 per SM): its time is the longest frame's.  The block-parallel path
+            // works on all bytes of all long frames at kJumpGBps together: its time is the sum.  A few huge frames: jump;
+            // thousands of 2 MiB frames: pair.  SZB_LONG_MODE=jump|pair overrides.
+            if (b->long_jump && !(mode && strcmp(mode, "jump") == 0)) {
+                uint64_t longest = 0;
+                for (uint32_t slot = 0; slot < n_long; slot++) longest = std::max(longest, b->long_dbase[slot + 1] - b->long_dbase[slot]);
+                const uint64_t waves = (n_long + (uint64_t)ctx->sm_count * 16 - 1) / ((uint64_t)ctx->sm_count * 16);
+                const double t_pair = (double)longest * (double)waves / kPairGBps, t_jump = (double)cells / kJumpGBps;
+                if (t_pair <= t_jump) b->long_jump = false;
+            }
         }
         if (!b->long_jump) {
             b->lb_block.clear();

@@ -13,9 +13,10 @@
 //                   0 for a literal byte, else how far back the byte's source lies (inside an overlapping match a
 //                   multiple of the offset, so that the source lies in front of the match: ringbuffer.go:236-262);
 //   k_long_jump     the COPY ORDER: one thread per output byte follows d[p] += d[p - d[p]] until p - d[p] is a literal
-//                   byte and copies it.  Cells are updated in place; whatever value a cell holds at any time points at
-//                   an ancestor of its byte, so no ordering between bytes, no flags and no waiting are needed -- bytes
-//                   handled earlier only shorten the walk of the ones handled later (tiles run in address order);
+//                   byte and copies it.  Cells are updated in place after every step; whatever value a cell holds at
+//                   any time points at an ancestor of its byte, so no ordering between bytes, no flags and no waiting
+//                   are needed -- every byte in flight shortens the walk of the bytes that hang on it (pointer doubling),
+//                   and bytes handled earlier have their literal one step away (tiles run in address order);
 //   k_long_verdict  errors found while emitting (bad offset, literals run dry) become the frame's status: the first
 //                   failing block and round decides, as in the sequential reference.
 //
@@ -240,7 +241,11 @@ __global__ void __launch_bounds__(kCtaThreads) k_long_emit(DeviceBatch a) {
             err_base = base;
             break;
         }
-        // every byte of the round: its sequence by binary search over the inclusive sums (lanes past cnt repeat the last sum)
+        // Every byte of the round, 32 consecutive bytes per step in address order: its sequence by binary search over the
+        // inclusive sums (lanes past cnt repeat the last sum).  A source inside the block that an EARLIER step (or round)
+        // of this warp emitted has its cell in memory already, and that cell is resolved as far as the block allows:
+        // adding it makes this cell point at a literal byte of the block or in front of the block, so that the chains
+        // k_long_jump still has to follow go from block to block instead of from match to match.
         for (uint32_t x0 = 0; x0 < round_tot; x0 += 32) {
             const uint32_t x = x0 + lane;
             uint32_t j = 0;
@@ -253,6 +258,7 @@ __global__ void __launch_bounds__(kCtaThreads) k_long_emit(DeviceBatch a) {
             const uint32_t s_ll = __shfl_sync(kFull, ll, j);
             const uint32_t s_off = __shfl_sync(kFull, off, j);
             const uint32_t s_lit = __shfl_sync(kFull, excl_ll, j);
+            __syncwarp();  // the cells of the steps before this one are in memory
             if (x < round_tot) {
                 const uint32_t k = x - s_excl;
                 uint32_t cell = 0;
@@ -261,6 +267,8 @@ __global__ void __launch_bounds__(kCtaThreads) k_long_emit(DeviceBatch a) {
                 } else {
                     const uint32_t m = k - s_ll;
                     cell = m < s_off ? s_off : s_off * (m / s_off + 1);
+                    const uint64_t me = fb + x;  // my byte, counted from the frame's start
+                    if (cell <= me - fb0 && cell > lane) cell += __ldcg(cells + (me - cell));  // in the block, below this step
                 }
                 cells[fb + x] = cell;
             }
@@ -319,10 +327,12 @@ __global__ void __launch_bounds__(kJumpThreads) k_long_jump(DeviceBatch a) {
                 if (open & (1u << c)) {
                     const uint64_t rel = rel0 + c * kJumpThreads + tid;
                     const uint32_t e = __ldcg(cells + (rel - dj[c]));
-                    if (e)
+                    if (e) {
                         dj[c] += e;
-                    else
+                        __stcg(cells + rel, dj[c]);  // bytes that hang on this one skip what it has skipped
+                    } else {
                         open &= ~(1u << c);
+                    }
                 }
             }
         }
@@ -330,7 +340,6 @@ __global__ void __launch_bounds__(kJumpThreads) k_long_jump(DeviceBatch a) {
         for (int c = 0; c < 4; c++) {
             if (first[c]) {
                 const uint64_t rel = rel0 + c * kJumpThreads + tid;
-                if (dj[c] != first[c]) __stcg(cells + rel, dj[c]);  // later bytes reach the literal in one step
                 out[rel] = out[rel - dj[c]];
             }
         }

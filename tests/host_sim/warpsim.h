@@ -131,6 +131,7 @@ inline uint64_t __shfl_sync(uint32_t, uint64_t v, uint32_t src) { return warpsim
 inline uint32_t __shfl_up_sync(uint32_t, uint32_t v, uint32_t d) { return (uint32_t)warpsim::collective(warpsim::OP_SHFL_UP, v, d); }
 inline uint32_t __ballot_sync(uint32_t, bool p) { return (uint32_t)warpsim::collective(warpsim::OP_BALLOT, p, 0); }
 inline bool __any_sync(uint32_t, bool p) { return warpsim::collective(warpsim::OP_BALLOT, p, 0) != 0; }
+inline void __syncwarp() { warpsim::collective(warpsim::OP_BALLOT, 0, 0); }
 inline int __ffs(uint32_t v) { return __builtin_ffs((int)v); }
 inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 inline uint32_t __ldcg(const uint32_t *p) { return *(const volatile uint32_t *)p; }
