@@ -700,7 +700,7 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
                 k_long_compose<<<n_long, 32, 0, sl>>>(a);
                 k_long_emit<<<(n_lb + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, sl>>>(a);
                 const uint64_t tiles = b->long_dbase.back() / kJumpTile;
-                const uint64_t resident = (uint64_t)ctx->sm_count * (2048 / kJumpThreads);
+                const uint64_t resident = (uint64_t)ctx->sm_count * SZB_JUMP_CTAS_PER_SM;
                 k_long_jump<<<(unsigned)(tiles < resident ? (tiles ? tiles : 1) : resident), kJumpThreads, 0, sl>>>(a);
                 k_long_verdict<<<(n_long + 127) / 128, 128, 0, sl>>>(a);
                 ctx->launches += 5;
