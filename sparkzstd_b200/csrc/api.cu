@@ -648,7 +648,7 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
     cudaStream_t s = ctx->stream;
     DeviceBatch a = make_args(b, d_src, d_dst, dst_cap);
     if (a.nframes) {
-        k_frame_verdict<<<(a.nframes + 127) / 128, 128, 0, s>>>(a);
+        k_frame_verdict<<<(a.nframes + 3) / 4, 128, 0, s>>>(a);
         ctx->launches++;
     }
     if (a.n_body) {

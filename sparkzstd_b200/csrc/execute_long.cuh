@@ -31,6 +31,9 @@
 #ifndef SZB_JUMP_LD
 #define SZB_JUMP_LD 1  // 1 = k_long_jump follows cells through L1 (a stale cell is still an ancestor): 9.6 -> 6.9 ms on one 256 MiB frame
 #endif
+#ifndef SZB_EMIT_CTAS
+#define SZB_EMIT_CTAS 8  // CTAs per SM k_long_emit is compiled for (64 registers)
+#endif
 #ifndef SZB_JUMP_CTAS_PER_SM
 #define SZB_JUMP_CTAS_PER_SM 8
 #endif
@@ -172,45 +175,65 @@ __global__ void __launch_bounds__(kCtaThreads) k_long_hist(DeviceBatch a) {
     }
 }
 
+// an entry of a LATER transfer function over the entries (a0, a1, a2) of the function before it
+__device__ __forceinline__ uint64_t sym_compose(uint64_t e, uint64_t a0, uint64_t a1, uint64_t a2) {
+    if (!(e & kSymBit)) return e;
+    const uint32_t idx = (uint32_t)(e >> 32) & 3;
+    const uint64_t base = idx == 0 ? a0 : (idx == 1 ? a1 : a2);
+    if (base & kSymBit) return base + (uint32_t)e;  // "entry j minus m" minus k
+    return (uint64_t)((uint32_t)base - (uint32_t)e);
+}
+
 // ---- k_long_compose: the history each block starts with; one warp per long frame ----
+// Transfer functions compose associatively: 32 blocks per step by a warp scan, the history carried from step to step.
 __global__ void __launch_bounds__(32) k_long_compose(DeviceBatch a) {
     const uint32_t lane = threadIdx.x;
     const uint32_t slot = blockIdx.x;
     if (slot >= a.n_long) return;
     const uint32_t first = a.long_first_lb[slot], end = a.long_first_lb[slot + 1];
     uint32_t h0 = 1, h1 = 4, h2 = 8;  // framedecompressor.go:48,59
+    uint64_t n0 = sym_entry(0), n1 = sym_entry(1), n2 = sym_entry(2);
+    if (first + lane < end) {
+        n0 = a.long_T[3 * (uint64_t)(first + lane)];
+        n1 = a.long_T[3 * (uint64_t)(first + lane) + 1];
+        n2 = a.long_T[3 * (uint64_t)(first + lane) + 2];
+    }
     for (uint32_t base = first; base < end; base += 32) {
         const uint32_t i = base + lane;
-        uint64_t t0 = sym_entry(0), t1 = sym_entry(1), t2 = sym_entry(2);
-        if (i < end) {
-            t0 = a.long_T[3 * (uint64_t)i];
-            t1 = a.long_T[3 * (uint64_t)i + 1];
-            t2 = a.long_T[3 * (uint64_t)i + 2];
+        uint64_t t0 = n0, t1 = n1, t2 = n2;  // blocks past the end hold the identity
+        n0 = sym_entry(0), n1 = sym_entry(1), n2 = sym_entry(2);
+        if (i + 32 < end) {  // the next step's functions are on their way during the scan
+            n0 = a.long_T[3 * (uint64_t)(i + 32)];
+            n1 = a.long_T[3 * (uint64_t)(i + 32) + 1];
+            n2 = a.long_T[3 * (uint64_t)(i + 32) + 2];
         }
-        const uint32_t cnt = end - base < 32 ? end - base : 32;
-        uint32_t m0 = 0, m1 = 0, m2 = 0;
-        for (uint32_t j = 0; j < cnt; j++) {
-            if (lane == j) {
-                m0 = h0;
-                m1 = h1;
-                m2 = h2;
+        // inclusive scan: lane j ends up with the function of blocks base .. base + j
+        for (uint32_t dlt = 1; dlt < 32; dlt <<= 1) {
+            const uint64_t g0 = __shfl_up_sync(kFull, t0, dlt), g1 = __shfl_up_sync(kFull, t1, dlt), g2 = __shfl_up_sync(kFull, t2, dlt);
+            if (lane >= dlt) {
+                t0 = sym_compose(t0, g0, g1, g2);
+                t1 = sym_compose(t1, g0, g1, g2);
+                t2 = sym_compose(t2, g0, g1, g2);
             }
-            const uint64_t u0 = __shfl_sync(kFull, t0, j), u1 = __shfl_sync(kFull, t1, j), u2 = __shfl_sync(kFull, t2, j);
-            const uint32_t n0 = hist_apply(u0, h0, h1, h2), n1 = hist_apply(u1, h0, h1, h2), n2 = hist_apply(u2, h0, h1, h2);
-            h0 = n0;
-            h1 = n1;
-            h2 = n2;
         }
+        // a block starts with what the blocks before it leave behind
+        uint64_t e0 = __shfl_up_sync(kFull, t0, 1), e1 = __shfl_up_sync(kFull, t1, 1), e2 = __shfl_up_sync(kFull, t2, 1);
+        if (lane == 0) e0 = sym_entry(0), e1 = sym_entry(1), e2 = sym_entry(2);
         if (i < end) {
-            a.long_hist[3 * (uint64_t)i] = m0;
-            a.long_hist[3 * (uint64_t)i + 1] = m1;
-            a.long_hist[3 * (uint64_t)i + 2] = m2;
+            a.long_hist[3 * (uint64_t)i] = hist_apply(e0, h0, h1, h2);
+            a.long_hist[3 * (uint64_t)i + 1] = hist_apply(e1, h0, h1, h2);
+            a.long_hist[3 * (uint64_t)i + 2] = hist_apply(e2, h0, h1, h2);
         }
+        const uint64_t l0 = __shfl_sync(kFull, t0, 31), l1 = __shfl_sync(kFull, t1, 31), l2 = __shfl_sync(kFull, t2, 31);
+        const uint32_t c0 = hist_apply(l0, h0, h1, h2), c1 = hist_apply(l1, h0, h1, h2), c2 = hist_apply(l2, h0, h1, h2);
+        h0 = c0;
+        h1 = c1;
+        h2 = c2;
     }
 }
 
 // ---- k_long_emit: literal bytes and distance cells of every block of the long frames; one warp per block ----
-__global__ void __launch_bounds__(kCtaThreads) k_long_emit(DeviceBatch a) {
+__global__ void __launch_bounds__(kCtaThreads, SZB_EMIT_CTAS) k_long_emit(DeviceBatch a) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     if (w >= a.n_lb) return;
@@ -348,11 +371,14 @@ __global__ void __launch_bounds__(kJumpThreads) k_long_jump(DeviceBatch a) {
         if (rel0 >= len) continue;
         uint32_t *const cells = a.dist + a.long_dbase[slot];
         uint8_t *const out = a.dst + a.frame_out_off[f];
+        // positions inside the frame fit 32 bits (long_jump_ok), and so does the whole tile: rel0 is a multiple of the
+        // tile and below len <= 2^32
+        const uint32_t r0 = (uint32_t)rel0 + tid;
         uint32_t dj[kJumpChains], first[kJumpChains];
         uint32_t open = 0;
 #pragma unroll
         for (int c = 0; c < kJumpChains; c++) {
-            const uint64_t rel = rel0 + c * kJumpThreads + tid;
+            const uint32_t rel = r0 + c * kJumpThreads;
             dj[c] = rel < len ? __ldcg(cells + rel) : 0;
             first[c] = dj[c];
             if (dj[c]) open |= 1u << c;
@@ -361,7 +387,7 @@ __global__ void __launch_bounds__(kJumpThreads) k_long_jump(DeviceBatch a) {
 #pragma unroll
             for (int c = 0; c < kJumpChains; c++) {
                 if (open & (1u << c)) {
-                    const uint64_t rel = rel0 + c * kJumpThreads + tid;
+                    const uint32_t rel = r0 + c * kJumpThreads;
                     const uint32_t e = jump_ld(cells + (rel - dj[c]));
                     if (e) {
                         dj[c] += e;
@@ -375,7 +401,7 @@ __global__ void __launch_bounds__(kJumpThreads) k_long_jump(DeviceBatch a) {
 #pragma unroll
         for (int c = 0; c < kJumpChains; c++) {
             if (first[c]) {
-                const uint64_t rel = rel0 + c * kJumpThreads + tid;
+                const uint32_t rel = r0 + c * kJumpThreads;
                 out[rel] = out[rel - dj[c]];
             }
         }

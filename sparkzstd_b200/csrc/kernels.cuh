@@ -1271,19 +1271,26 @@ struct PairSink {
     }
 };
 
-// One thread per frame, before any output is written: the frame's verdict (the first failing
+// One warp per frame, before any output is written: the frame's verdict (the first failing
 // block decides, as in the sequential reference; then the header walk's verdict; then capacity)
 // and its placement in dst.
 __global__ void k_frame_verdict(DeviceBatch a) {
-    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per frame: a frame may have 10^5 blocks
     if (f >= a.nframes) return;
     const szb_frame_desc fr = a.frames[f];
     const uint32_t b0 = fr.first_block, nb = fr.nblocks;
     int err = SZB_OK;
-    for (uint32_t i = 0; i < nb && err == SZB_OK; i++) {
-        const int ls = a.lit_status[b0 + i], ss = a.seq_status[b0 + i];
-        if ((ls | ss) != 0) err = ls ? ls : ss;
+    for (uint32_t i0 = 0; i0 < nb; i0 += 32) {
+        int e = SZB_OK;
+        if (i0 + lane < nb) {
+            const int ls = a.lit_status[b0 + i0 + lane], ss = a.seq_status[b0 + i0 + lane];
+            if ((ls | ss) != 0) e = ls ? ls : ss;
+        }
+        err = warp_first_error(e);
+        if (err != SZB_OK) break;
     }
+    if (lane != 0) return;
     if (err == SZB_OK) err = fr.status;  // blocks after a failing header are absent from the table
     if (err == SZB_OK && a.total[0] > a.dst_cap) err = SZB_ERR_DST_TOO_SMALL;
     const uint64_t frame_base = nb ? a.out_off[b0] : 0;

@@ -415,4 +415,38 @@ int hostsim_decode_frame_long(const uint8_t *src, size_t len, uint8_t *out, size
     return SZB_OK;
 }
 
+
+// k_long_compose alone: random transfer functions for `nblocks` blocks of one frame; the warp scan must give every block
+// the history that applying the functions one after the other gives.  Returns the number of mismatching blocks.
+int hostsim_compose_selftest(uint32_t nblocks, uint32_t seed) {
+    std::mt19937 rng(seed);
+    std::vector<uint64_t> T(3 * (size_t)nblocks);
+    for (auto &t : T) {
+        const uint32_t kind = rng() % 4;
+        if (kind == 0) t = (uint64_t)(1 + rng() % 100000);            // a constant
+        else t = sym_entry(rng() % 3) + (kind == 1 ? 0 : rng() % 5);  // entry i, minus 0..4
+    }
+    for (uint32_t b = 0; b < nblocks; b += 7)                          // some blocks without sequences: the identity
+        for (int k = 0; k < 3; k++) T[3 * (size_t)b + k] = sym_entry(k);
+    std::vector<uint32_t> want(3 * (size_t)nblocks), got(3 * (size_t)nblocks, 0);
+    uint32_t h[3] = {1, 4, 8};
+    for (uint32_t b = 0; b < nblocks; b++) {
+        for (int k = 0; k < 3; k++) want[3 * (size_t)b + k] = h[k];
+        const uint32_t n0 = hist_apply(T[3 * (size_t)b], h[0], h[1], h[2]), n1 = hist_apply(T[3 * (size_t)b + 1], h[0], h[1], h[2]),
+                       n2 = hist_apply(T[3 * (size_t)b + 2], h[0], h[1], h[2]);
+        h[0] = n0, h[1] = n1, h[2] = n2;
+    }
+    const uint32_t first_lb[2] = {0, nblocks};
+    DeviceBatch a{};
+    a.n_long = 1;
+    a.long_first_lb = first_lb;
+    a.long_T = T.data();
+    a.long_hist = got.data();
+    warpsim::launch(1, 32, [&] { k_long_compose(a); });
+    int bad = 0;
+    for (uint32_t b = 0; b < nblocks; b++)
+        if (memcmp(&want[3 * (size_t)b], &got[3 * (size_t)b], 12) != 0) bad++;
+    return bad;
+}
+
 }  // extern "C"

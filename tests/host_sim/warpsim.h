@@ -129,6 +129,7 @@ inline uint32_t __shfl_sync(uint32_t, uint32_t v, uint32_t src) { return (uint32
 inline int __shfl_sync(uint32_t, int v, uint32_t src) { return (int)warpsim::collective(warpsim::OP_SHFL, (uint32_t)v, src); }
 inline uint64_t __shfl_sync(uint32_t, uint64_t v, uint32_t src) { return warpsim::collective(warpsim::OP_SHFL, v, src); }
 inline uint32_t __shfl_up_sync(uint32_t, uint32_t v, uint32_t d) { return (uint32_t)warpsim::collective(warpsim::OP_SHFL_UP, v, d); }
+inline uint64_t __shfl_up_sync(uint32_t, uint64_t v, uint32_t d) { return warpsim::collective(warpsim::OP_SHFL_UP, v, d); }
 inline uint32_t __ballot_sync(uint32_t, bool p) { return (uint32_t)warpsim::collective(warpsim::OP_BALLOT, p, 0); }
 inline bool __any_sync(uint32_t, bool p) { return warpsim::collective(warpsim::OP_BALLOT, p, 0) != 0; }
 inline void __syncwarp() { warpsim::collective(warpsim::OP_BALLOT, 0, 0); }

@@ -108,3 +108,9 @@ def test_long_frame_kernels_on_crafted_frames(sim):
     assert e.value.code == -30
     rc, _ = _decode_long(sim, cut, 4096, 0, 0)
     assert rc == -30
+
+
+@pytest.mark.parametrize("nblocks", [1, 31, 32, 33, 64, 100, 1000])
+def test_long_frame_history_scan(sim, nblocks):
+    sim.hostsim_compose_selftest.argtypes = [C.c_uint32, C.c_uint32]
+    assert sim.hostsim_compose_selftest(nblocks, 1234 + nblocks) == 0
