@@ -588,6 +588,7 @@ static DeviceBatch make_args(szb_batch *b, const void *d_src, void *d_dst, size_
     a.long_T = nullptr;
     a.long_hist = nullptr;
     a.long_err = nullptr;
+    a.long_ticket = nullptr;
     return a;
 }
 
@@ -668,7 +669,7 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
             // Without it (allocation refused) every long frame stays on k_execute_pair.
             if (b->long_jump && !b->d_long) {
                 const size_t n_lb = b->lb_block.size();
-                const size_t o_T = align_up(8 * (size_t)n_long, 256);
+                const size_t o_T = align_up(8 * (size_t)n_long + 8, 256);
                 const size_t o_hist = align_up(o_T + 24 * n_lb, 256);
                 const size_t o_dist = align_up(o_hist + 12 * n_lb, 256);
                 const size_t bytes = o_dist + 4 * (size_t)b->long_dbase.back();
@@ -680,7 +681,7 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
             }
             if (b->long_jump) {
                 const size_t n_lb = b->lb_block.size();
-                const size_t o_T = align_up(8 * (size_t)n_long, 256);
+                const size_t o_T = align_up(8 * (size_t)n_long + 8, 256);
                 const size_t o_hist = align_up(o_T + 24 * n_lb, 256);
                 const size_t o_dist = align_up(o_hist + 12 * n_lb, 256);
                 uint8_t *base = (uint8_t *)b->d_long;
@@ -688,7 +689,9 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
                 a.long_T = (uint64_t *)(base + o_T);
                 a.long_hist = (uint32_t *)(base + o_hist);
                 a.dist = (uint32_t *)(base + o_dist);
+                a.long_ticket = a.long_err + n_long;
                 CUDA_TRY(ctx, cudaMemsetAsync(a.long_err, 0xFF, 8 * (size_t)n_long, s));
+                CUDA_TRY(ctx, cudaMemsetAsync(a.long_ticket, 0, 8, s));
             }
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, s));
             CUDA_TRY(ctx, cudaStreamWaitEvent(sl, ctx->ev_fork, 0));
@@ -699,7 +702,7 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
                 k_long_hist<<<(n_lb + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, sl>>>(a);
                 k_long_compose<<<n_long, 32, 0, sl>>>(a);
                 k_long_emit<<<(n_lb + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, sl>>>(a);
-                const uint64_t tiles = b->long_dbase.back() / kJumpTile;
+                const uint64_t tiles = (b->long_dbase.back() / kJumpTile + kJumpThreads / 32 - 1) / (kJumpThreads / 32);  // a tile per warp
                 const uint64_t resident = (uint64_t)ctx->sm_count * SZB_JUMP_CTAS_PER_SM;
                 k_long_jump<<<(unsigned)(tiles < resident ? (tiles ? tiles : 1) : resident), kJumpThreads, 0, sl>>>(a);
                 k_long_verdict<<<(n_long + 127) / 128, 128, 0, sl>>>(a);

@@ -68,6 +68,7 @@ struct DeviceBatch {
     uint32_t *dist;                 // one distance cell per output byte of the long frames; nullptr: k_execute_pair takes them
     uint64_t *long_T;               // per lb_block entry: the block's history transfer function (3 entries)
     uint32_t *long_hist;            // per lb_block entry: the history the block starts with (3 entries)
+    unsigned long long *long_ticket;  // k_long_jump hands out its tiles in address order
     unsigned long long *long_err;   // per long frame: the first error found while emitting (block << 40 | round << 8 | -code)
 };
 

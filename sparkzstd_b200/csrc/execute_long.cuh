@@ -65,7 +65,7 @@ __device__ __forceinline__ uint32_t jump_ld(const uint32_t *p) {
 #endif
 constexpr int kJumpThreads = 256;
 constexpr int kJumpChains = SZB_JUMP_CHAINS;  // bytes (independent walks in flight) per thread of k_long_jump
-constexpr uint32_t kJumpTile = kJumpThreads * kJumpChains;  // cells per tile; every frame's cells start at a multiple of it
+constexpr uint32_t kJumpTile = 1024;  // cells per ticket of k_long_jump; every frame's cells start at a multiple of it
 constexpr unsigned long long kLongNoError = ~0ull;
 
 __device__ __forceinline__ bool long_jump_ok(const DeviceBatch &a, uint32_t slot) {
@@ -350,10 +350,19 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EMIT_CTAS) k_long_emit(Device
 }
 
 // ---- k_long_jump: every match byte finds its literal byte ----
-__global__ void __launch_bounds__(kJumpThreads) k_long_jump(DeviceBatch a) {
+// Tiles of kJumpTile cells are handed out in address order from a ticket counter, one tile per warp at a time: whatever
+// the number of resident warps (or the kernels running beside this one), the tiles in flight are the lowest unfinished
+// ones, so that a walk leaves the region in flight after a few steps and lands on a finished cell.  (A static
+// tile-to-CTA map loses that as soon as one CTA of the grid is not resident: 6.8 -> 10.2 ms on one 256 MiB frame.)
+__global__ void __launch_bounds__(kJumpThreads, 8) k_long_jump(DeviceBatch a) {
     const uint64_t total = a.long_dbase[a.n_long];
-    const uint32_t tid = threadIdx.x;
-    for (uint64_t c0 = (uint64_t)blockIdx.x * kJumpTile; c0 < total; c0 += (uint64_t)gridDim.x * kJumpTile) {
+    const uint32_t lane = threadIdx.x & 31;
+    unsigned long long next = 0;
+    if (lane == 0) next = atomicAdd(a.long_ticket, 1ull);
+    for (;;) {
+        const uint64_t c0 = __shfl_sync(kFull, next, 0) * kJumpTile;
+        if (c0 >= total) break;
+        if (lane == 0) next = atomicAdd(a.long_ticket, 1ull);  // the next tile's ticket is on its way meanwhile
         // the frame of the tile: the last slot whose cells start at or before c0
         uint32_t lo = 0, hi = a.n_long;  // invariant: dbase[lo] <= c0 < dbase[hi]
         while (hi - lo > 1) {
@@ -373,36 +382,39 @@ __global__ void __launch_bounds__(kJumpThreads) k_long_jump(DeviceBatch a) {
         uint8_t *const out = a.dst + a.frame_out_off[f];
         // positions inside the frame fit 32 bits (long_jump_ok), and so does the whole tile: rel0 is a multiple of the
         // tile and below len <= 2^32
-        const uint32_t r0 = (uint32_t)rel0 + tid;
-        uint32_t dj[kJumpChains], first[kJumpChains];
-        uint32_t open = 0;
-#pragma unroll
-        for (int c = 0; c < kJumpChains; c++) {
-            const uint32_t rel = r0 + c * kJumpThreads;
-            dj[c] = rel < len ? __ldcg(cells + rel) : 0;
-            first[c] = dj[c];
-            if (dj[c]) open |= 1u << c;
-        }
-        while (open) {
+        for (uint32_t sub = 0; sub < kJumpTile; sub += 32 * kJumpChains) {
+            const uint32_t r0 = (uint32_t)rel0 + sub + lane;
+            if (r0 - lane >= len) break;
+            uint32_t dj[kJumpChains], first[kJumpChains];
+            uint32_t open = 0;
 #pragma unroll
             for (int c = 0; c < kJumpChains; c++) {
-                if (open & (1u << c)) {
-                    const uint32_t rel = r0 + c * kJumpThreads;
-                    const uint32_t e = jump_ld(cells + (rel - dj[c]));
-                    if (e) {
-                        dj[c] += e;
-                        __stcg(cells + rel, dj[c]);  // bytes that hang on this one skip what it has skipped
-                    } else {
-                        open &= ~(1u << c);
+                const uint32_t rel = r0 + c * 32;
+                dj[c] = rel < len ? __ldcg(cells + rel) : 0;
+                first[c] = dj[c];
+                if (dj[c]) open |= 1u << c;
+            }
+            while (open) {
+#pragma unroll
+                for (int c = 0; c < kJumpChains; c++) {
+                    if (open & (1u << c)) {
+                        const uint32_t rel = r0 + c * 32;
+                        const uint32_t e = jump_ld(cells + (rel - dj[c]));
+                        if (e) {
+                            dj[c] += e;
+                            __stcg(cells + rel, dj[c]);  // bytes that hang on this one skip what it has skipped
+                        } else {
+                            open &= ~(1u << c);
+                        }
                     }
                 }
             }
-        }
 #pragma unroll
-        for (int c = 0; c < kJumpChains; c++) {
-            if (first[c]) {
-                const uint32_t rel = r0 + c * kJumpThreads;
-                out[rel] = out[rel - dj[c]];
+            for (int c = 0; c < kJumpChains; c++) {
+                if (first[c]) {
+                    const uint32_t rel = r0 + c * 32;
+                    out[rel] = out[rel - dj[c]];
+                }
             }
         }
     }

@@ -354,6 +354,7 @@ int hostsim_decode_frame_long(const uint8_t *src, size_t len, uint8_t *out, size
     std::vector<uint32_t> dist(long_dbase.back(), 0xCDCDCDCDu), long_hist(3 * (size_t)n_lb + 3);
     std::vector<uint64_t> long_T(3 * (size_t)n_lb + 3);
     std::vector<unsigned long long> long_err(copies, kLongNoError);
+    unsigned long long ticket = 0;
     DeviceBatch a{};
     a.src = src;
     a.blocks = blocks.data();
@@ -383,6 +384,7 @@ int hostsim_decode_frame_long(const uint8_t *src, size_t len, uint8_t *out, size
     a.long_T = long_T.data();
     a.long_hist = long_hist.data();
     a.long_err = long_err.data();
+    a.long_ticket = &ticket;
 
     auto cta_order = [&](unsigned grid) {
         std::vector<unsigned> o(grid);
@@ -403,7 +405,7 @@ int hostsim_decode_frame_long(const uint8_t *src, size_t len, uint8_t *out, size
     }
     {
         const unsigned tiles = (unsigned)(long_dbase.back() / kJumpTile);
-        const unsigned grid = order == 0 ? std::max(1u, tiles / 3) : std::max(1u, tiles);  // order 0 also takes the grid-stride loop
+        const unsigned grid = order == 0 ? std::max(1u, tiles / 24) : std::max(1u, tiles / 8 + 1);  // order 0: several tiles per warp
         auto o = cta_order(grid);
         warpsim::launch(grid, kJumpThreads, [&] { k_long_jump(a); }, &o);
     }

@@ -125,11 +125,10 @@ using warpsim::blockIdx;
 using warpsim::gridDim;
 using warpsim::threadIdx;
 
-inline uint32_t __shfl_sync(uint32_t, uint32_t v, uint32_t src) { return (uint32_t)warpsim::collective(warpsim::OP_SHFL, v, src); }
-inline int __shfl_sync(uint32_t, int v, uint32_t src) { return (int)warpsim::collective(warpsim::OP_SHFL, (uint32_t)v, src); }
-inline uint64_t __shfl_sync(uint32_t, uint64_t v, uint32_t src) { return warpsim::collective(warpsim::OP_SHFL, v, src); }
-inline uint32_t __shfl_up_sync(uint32_t, uint32_t v, uint32_t d) { return (uint32_t)warpsim::collective(warpsim::OP_SHFL_UP, v, d); }
-inline uint64_t __shfl_up_sync(uint32_t, uint64_t v, uint32_t d) { return warpsim::collective(warpsim::OP_SHFL_UP, v, d); }
+template <class T, class S>
+inline T __shfl_sync(uint32_t, T v, S src) { return (T)warpsim::collective(warpsim::OP_SHFL, (uint64_t)v, (uint32_t)src); }
+template <class T, class S>
+inline T __shfl_up_sync(uint32_t, T v, S d) { return (T)warpsim::collective(warpsim::OP_SHFL_UP, (uint64_t)v, (uint32_t)d); }
 inline uint32_t __ballot_sync(uint32_t, bool p) { return (uint32_t)warpsim::collective(warpsim::OP_BALLOT, p, 0); }
 inline bool __any_sync(uint32_t, bool p) { return warpsim::collective(warpsim::OP_BALLOT, p, 0) != 0; }
 inline void __syncwarp() { warpsim::collective(warpsim::OP_BALLOT, 0, 0); }
@@ -137,6 +136,11 @@ inline int __ffs(uint32_t v) { return __builtin_ffs((int)v); }
 inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 inline uint32_t __ldcg(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 inline void __stcg(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
+    const unsigned long long old = *p;
+    *p = old + v;
+    return old;
+}
 inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) {
     const unsigned long long old = *p;
     if (v < old) *p = v;
