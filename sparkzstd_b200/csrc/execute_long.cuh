@@ -61,7 +61,7 @@ __device__ __forceinline__ uint32_t jump_ld(const uint32_t *p) {
 #endif
 }
 #ifndef SZB_JUMP_CHAINS
-#define SZB_JUMP_CHAINS 4
+#define SZB_JUMP_CHAINS 8  // 8: 3-4 % faster than 4 (profiles/README.md, r01k)
 #endif
 constexpr int kJumpThreads = 256;
 constexpr int kJumpChains = SZB_JUMP_CHAINS;  // bytes (independent walks in flight) per thread of k_long_jump
