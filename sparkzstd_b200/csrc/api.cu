@@ -262,7 +262,9 @@ void szb_free(void *p) { free(p); }
 // SZB_LONG_SEQS overrides the threshold (tests force every frame through the pair kernel with it).
 constexpr uint64_t kLongFrameSequences = 65536;
 constexpr uint32_t kMaxLongFrames = 2368;
-constexpr double kPairGBps = 0.26, kJumpGBps = 16.0;  // measured: profiles/r01d_bench_single256m_1gpu.json, r01e_bench_single256m_1gpu.json
+// measured on text-like frames: k_execute_pair 0.26 GB/s per frame at 10.7 bytes per sequence (profiles/r01d_bench_single256m_1gpu.json);
+// the block-parallel path 38-49 GB/s over everything it is given (profiles/r01k_bench_single*.json)
+constexpr double kPairSeqPerMs = 24000.0, kJumpCellsPerMs = 40e6;
 
 static int batch_upload_tables(szb_batch *b) {
     szb_ctx *ctx = b->ctx;
@@ -330,15 +332,15 @@ static int batch_upload_tables(szb_batch *b) {
             }
             static const uint64_t max_cells = (getenv("SZB_LONG_MAX_GIB") ? strtoull(getenv("SZB_LONG_MAX_GIB"), nullptr, 10) : 64) << 28;
             if (cells > max_cells) b->long_jump = false;  // 4 bytes per cell
-            // Which path is faster depends on the batch.  k_execute_pair runs every long frame at kPairGBps on its own two
-            // warps, all frames side by side (up to 16 per SM): its time is the longest frame's.  The block-parallel path
-            // works on all bytes of all long frames at kJumpGBps together: its time is the sum.  A few huge frames: jump;
-            // thousands of 2 MiB frames: pair.  SZB_LONG_MODE=jump|pair overrides.
+            // Which path is faster depends on the batch.  k_execute_pair runs every long frame on its own two warps at
+            // kPairSeqPerMs sequences per millisecond, all frames side by side (up to 16 per SM): its time is that of the
+            // frame with the most sequences.  The block-parallel path works on all cells of all long frames together at
+            // kJumpCellsPerMs: its time follows the sum.  A few huge frames: jump; thousands of 2 MiB frames: pair.
+            // SZB_LONG_MODE=jump|pair overrides.
             if (b->long_jump && !(mode && strcmp(mode, "jump") == 0)) {
-                uint64_t longest = 0;
-                for (uint32_t slot = 0; slot < n_long; slot++) longest = std::max(longest, b->long_dbase[slot + 1] - b->long_dbase[slot]);
+                const uint64_t most = work[b->exec_list[0]];  // exec_list is sorted by sequences, most first
                 const uint64_t waves = (n_long + (uint64_t)ctx->sm_count * 16 - 1) / ((uint64_t)ctx->sm_count * 16);
-                const double t_pair = (double)longest * (double)waves / kPairGBps, t_jump = (double)cells / kJumpGBps;
+                const double t_pair = (double)most * (double)waves / kPairSeqPerMs, t_jump = (double)cells / kJumpCellsPerMs;
                 if (t_pair <= t_jump) b->long_jump = false;
             }
         }
