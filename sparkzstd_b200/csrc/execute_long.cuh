@@ -65,7 +65,11 @@ __device__ __forceinline__ uint32_t jump_ld(const uint32_t *p) {
 #endif
 constexpr int kJumpThreads = 256;
 constexpr int kJumpChains = SZB_JUMP_CHAINS;  // bytes (independent walks in flight) per thread of k_long_jump
-constexpr uint32_t kJumpTile = 1024;  // cells per ticket of k_long_jump; every frame's cells start at a multiple of it
+#ifndef SZB_JUMP_TILE
+#define SZB_JUMP_TILE 1024
+#endif
+constexpr uint32_t kJumpTile = SZB_JUMP_TILE;  // cells per ticket of k_long_jump; every frame's cells start at a multiple of it
+static_assert(kJumpTile % (32 * kJumpChains) == 0, "a tile is a whole number of warp steps");
 constexpr unsigned long long kLongNoError = ~0ull;
 
 __device__ __forceinline__ bool long_jump_ok(const DeviceBatch &a, uint32_t slot) {

@@ -85,9 +85,10 @@ def _raw_or_rle_literals_header(ltype, regen):
     return bytes([((regen & 15) << 4) | (3 << 2) | ltype, (regen >> 4) & 255, regen >> 12])
 
 
-def frame(seed_bytes: bytes, lit_kind: str, literals: bytes, ll: int, ml: int, offset: int):
+def frame(seed_bytes: bytes, lit_kind: str, literals: bytes, ll: int, ml: int, offset: int, oversize: bool = False):
     """-> (frame bytes, expected output).  lit_kind 'rle': every literal is literals[0] and len(literals) is the
-    regenerated size; 'raw': literals as given.  One sequence (ll, ml, offset), the rest are trailing literals."""
+    regenerated size; 'raw': literals as given.  One sequence (ll, ml, offset), the rest are trailing literals.
+    oversize: allow a block that regenerates more than Block_Maximum_Size (the reference does not check it)."""
     regen = len(literals)
     assert ll <= regen and offset >= 4  # offsets 1..3 would be repeat codes
     if lit_kind == "rle":
@@ -104,7 +105,7 @@ def frame(seed_bytes: bytes, lit_kind: str, literals: bytes, ll: int, ml: int, o
         out.append(out[-offset])
     out += literals[ll:]
     total = len(out)
-    assert regen + ml <= 128 * 1024
+    assert regen + ml <= 128 * 1024 or oversize
     hdr = bytes([0x28, 0xB5, 0x2F, 0xFD, 0xA0]) + total.to_bytes(4, "little")  # single segment, 4-byte content size
     blocks = _block_header(0, 0, len(seed_bytes)) + seed_bytes + _block_header(1, 2, len(body)) + body
     return hdr + blocks, bytes(out)
@@ -131,3 +132,13 @@ def cases(seed: int = 7):
     out["match_127_off_4"] = frame(seed_bytes, "raw", rnd(300), 200, 127, 4)
     out["match_128_off_129"] = frame(seed_bytes, "raw", rnd(300), 131, 128, 129)
     return out
+
+
+def oversize_block_case(seed: int = 11):
+    """(frame, expected): the compressed block regenerates 20 + 131 074 bytes, more than Block_Maximum_Size (128 KiB).
+    The reference decodes it (no check); the block-parallel long-frame path sizes its scratch for 128 KiB per block and
+    must hand the frame to k_execute_pair."""
+    rng = np.random.default_rng(seed)
+    seed_bytes = rng.integers(0, 256, 1024, dtype=np.uint8).tobytes()
+    return frame(seed_bytes, "raw", rng.integers(0, 256, 20, dtype=np.uint8).tobytes(), 7, 131074, 900, oversize=True)
+

@@ -410,6 +410,16 @@ int hostsim_decode_frame_long(const uint8_t *src, size_t len, uint8_t *out, size
         warpsim::launch(grid, kJumpThreads, [&] { k_long_jump(a); }, &o);
     }
     warpsim::launch(1, 128, [&] { k_long_verdict(a); });
+    {   // a frame beyond its scratch bound is not this path's: no kernel may have touched its cells (returns 1)
+        bool skipped = false;
+        for (uint32_t slot = 0; slot < copies; slot++) {
+            if (frame_out_len[exec_list[slot]] <= long_dbase[slot + 1] - long_dbase[slot]) continue;
+            skipped = true;
+            for (uint64_t i = long_dbase[slot]; i < long_dbase[slot + 1]; i++)
+                if (dist[i] != 0xCDCDCDCDu) return SZB_ERR_INVALID_ARGUMENT;
+        }
+        if (skipped) return 1;
+    }
     for (uint32_t c = 0; c < copies; c++)
         if (frame_status[c] != SZB_OK) return frame_status[c];
     if (copies == 2 && memcmp(out, out + total / 2, total / 2) != 0) return SZB_ERR_INVALID_ARGUMENT;

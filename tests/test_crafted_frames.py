@@ -25,6 +25,12 @@ def test_oracle_decodes_crafted_frame(name):
     assert blk.nseq == 1 and blk.modes == (0, 0, 0)
 
 
+def test_oracle_decodes_oversize_block():
+    frame, expected = crafted.oversize_block_case()
+    assert len(expected) == 1024 + 20 + 131074
+    assert pyszo.decode_frame(frame) == expected
+
+
 @pytest.mark.gpu
 def test_gpu_decodes_crafted_frames_in_one_batch():
     from sparkzstd_b200.decompression import Context
@@ -40,5 +46,7 @@ def test_gpu_decodes_crafted_frames_in_one_batch():
         many = [cs[names[(i * 5) % len(names)]] for i in range(256)]
         outs = ctx.decode_batch([f for f, _ in many])
         assert all(o == e for o, (_, e) in zip(outs, many))
+        f, e = crafted.oversize_block_case()
+        assert ctx.decode_batch([f, cs[names[0]][0], f]) == [e, cs[names[0]][1], e]
     finally:
         ctx.close()

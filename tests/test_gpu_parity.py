@@ -337,6 +337,10 @@ def test_long_frame_paths_on_every_frame(corpus, tmp_path, mode):
         names = sorted(cs)
         outs = ctx.decode_batch([cs[n][0] for n in names])
         assert all(o == cs[n][1] for o, n in zip(outs, names))
+        # a block that regenerates more than 128 KiB: beyond the scratch bound of the block-parallel path, which must
+        # leave that frame (and only that one) to k_execute_pair
+        f, e = crafted_frames.oversize_block_case()
+        assert ctx.decode_batch([f, cs[names[0]][0], f]) == [e, cs[names[0]][1], e]
         t = cg.config2_text_frames(700)
         outs = ctx.decode_batch([t.frame(i) for i in range(t.nframes)])
         assert all(cg.hash_bytes(np.frombuffer(o, dtype="uint8")) == int(t.raw_hash[i]) for i, o in enumerate(outs))

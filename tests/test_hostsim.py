@@ -108,6 +108,10 @@ def test_long_frame_kernels_on_crafted_frames(sim):
     assert e.value.code == -30
     rc, _ = _decode_long(sim, cut, 4096, 0, 0)
     assert rc == -30
+    # a block that regenerates more than 128 KiB is beyond the path's scratch bound: every kernel must leave the frame alone
+    big, expected = crafted.oversize_block_case()
+    rc, _ = _decode_long(sim, big, len(expected), 0, 1)
+    assert rc == 1
 
 
 @pytest.mark.parametrize("nblocks", [1, 31, 32, 33, 64, 100, 1000])
