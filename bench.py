@@ -372,7 +372,9 @@ def main():
         "pipeline": {"algorithmic_bytes": C_bytes + D + M, "C": C_bytes, "D": D, "M": M, "achieved": pipe_ach, "frac": pipe_ach / peak,
                      "frac_of_8TBps_nominal": pipe_ach / 8000.0},
         "stages_ms": {k: v["ms"] for k, v in kernels.items()},
-        "stages_note": "k_huffman_literals and k_sequences run side by side on two streams; each is measured from the start of the step",
+        "stages_note": "k_huffman_literals and k_sequences run side by side on two streams; each is measured from the start of the step; "
+                       "k_execute is all of stage 4: k_frame_verdict, k_execute_bodies, k_execute and, for frames with >= 65 536 sequences, "
+                       "k_execute_pair or the block-parallel kernels k_long_* (execute_long.cuh), whichever the host picked for the batch",
     }
 
     cpu = None
