@@ -72,4 +72,13 @@ struct DeviceBatch {
     unsigned long long *long_err;   // per long frame: the first error found while emitting (block << 40 | round << 8 | -code)
 };
 
+#if defined(__CUDACC__) || defined(SZB_WARPSIM)  // device code, or the host-side warp emulator of tests/host_sim
+// the first lane's non-zero code, 0 when every lane is fine
+__device__ __forceinline__ int warp_first_error(int rc) {
+    uint32_t bad = __ballot_sync(kFull, rc != 0);
+    if (!bad) return 0;
+    return __shfl_sync(kFull, rc, __ffs(bad) - 1);
+}
+#endif
+
 }  // namespace szb

@@ -43,11 +43,6 @@ namespace szb {
 #define SZB_SERIAL_TABLES 0
 #endif
 
-__device__ __forceinline__ int warp_first_error(int rc) {
-    uint32_t bad = __ballot_sync(kFull, rc != 0);
-    if (!bad) return 0;
-    return __shfl_sync(kFull, rc, __ffs(bad) - 1);
-}
 
 // ---------------------------------------------------------------------------------------------
 // Builds one FSE decode table into `table` from `ts`.  Lane 0 parses, the warp builds.

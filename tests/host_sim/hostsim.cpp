@@ -1,9 +1,9 @@
-// hostsim.cpp -- TEST INFRASTRUCTURE: runs the *serial* device functions of the CUDA path
-// (bits.cuh, fse.cuh, huffman.cuh, sequences.cuh -- the code a single lane executes) on the CPU,
-// driven by the product's own header walker, so that `pytest -m "not gpu"` can check them
-// against the oracle without a GPU.  The warp-cooperative parts (table builds with ballots,
-// k_execute) only run on the device and are covered by the -m gpu tests -- except the block-parallel stage 4 of long
-// frames (execute_long.cuh), whose kernels run here lane by lane on an emulated warp (warpsim.h).
+// hostsim.cpp -- TEST INFRASTRUCTURE: runs the device code of the CUDA path on the CPU, driven by the product's own header
+// walker, so that `pytest -m "not gpu"` can check it against the oracle without a GPU:
+//   * stages 1-3: the *serial* device functions (bits.cuh, fse.cuh, huffman.cuh, sequences.cuh -- the code a single lane
+//     executes).  Their warp-cooperative wrappers (table builds with ballots, cp.async bit rings) only run on the device and
+//     are covered by the -m gpu tests;
+//   * stage 4: the kernels themselves (execute.cuh, execute_long.cuh), thread by thread on an emulated CTA (warpsim.h).
 // This file is never linked into libszb200.so.
 #include <cstdint>
 #include <cstring>
@@ -20,7 +20,7 @@
 #include "../../sparkzstd_b200/csrc/sequences.cuh"
 
 namespace szb {
-#include "../../sparkzstd_b200/csrc/execute_long.cuh"
+#include "../../sparkzstd_b200/csrc/execute.cuh"  // stage 4, execute_long.cuh included
 }
 
 using namespace szb;
@@ -244,11 +244,15 @@ int hostsim_decode_frame(const uint8_t *src, size_t len, uint8_t *out, size_t ca
 }
 
 
-// Decodes ONE frame the way the product does when the frame is LONG: walker, serial device functions for stages 1-3, the
-// body blocks as k_execute_bodies writes them, then the kernels of execute_long.cuh on an emulated warp.
+// Decodes ONE frame with the product's own stage 4 on an emulated CTA (warpsim.h): walker, the serial device functions for
+// stages 1-3, then the kernels of execute.cuh exactly as launch_execute (api.cu) queues them -- k_scan_blocks,
+// k_frame_verdict, k_execute_bodies and, by `path`,
+//   0: k_execute (one warp per frame)   1: k_execute_pair (producer warp + consumer warp)
+//   2: the block-parallel kernels of execute_long.cuh, with k_execute_pair launched beside them as the fallback.
 // order: 0 = CTAs in launch order, 1 = reversed (the worst case for k_long_jump), >= 2 = shuffled with that seed.
-// With two_frames the same frame is decoded twice in one batch (two long slots) and both copies must agree.
-int hostsim_decode_frame_long(const uint8_t *src, size_t len, uint8_t *out, size_t cap, size_t *out_len, int order, int two_frames) {
+// With two_frames the same frame is decoded twice in one batch and both copies must agree.
+// Returns the frame's status; 1 when path 2 left the frame to its fallback (and the fallback decoded it).
+int hostsim_stage4(const uint8_t *src, size_t len, uint8_t *out, size_t cap, size_t *out_len, int path, int order, int two_frames) {
     uint64_t off = 0, flen = len;
     szb_walk *w = nullptr;
     *out_len = 0;
@@ -287,13 +291,15 @@ int hostsim_decode_frame_long(const uint8_t *src, size_t len, uint8_t *out, size
     szb_walk_destroy(w);
     // stages 1-3 with the serial device functions
     const uint64_t stride = seqs * copies + 32;
-    std::vector<uint8_t> litbuf(lit_bytes * copies + 16, 0xEE);
+    std::vector<uint8_t> litbuf(lit_bytes * copies + 512, 0xEE);
     std::vector<uint32_t> seq(3 * stride, 0xDEADBEEFu);  // padding lanes hold garbage, as on the device
-    std::vector<uint64_t> out_size(nb), out_off(nb);
-    std::vector<uint32_t> ll, ml, of;
+    std::vector<uint64_t> out_size(nb), out_off(nb, ~0ull);
+    std::vector<int32_t> lit_status(nb, SZB_OK), seq_status(nb, SZB_OK);
+    std::vector<uint32_t> ll, ml, of, body_list;
     for (uint32_t b = 0; b < nb; b++) {
         const szb_block_desc &d = blocks[b];
         out_size[b] = d.type == 2 ? d.lit_regen : d.block_size;
+        if ((d.type != 2 && d.block_size > 0) || (d.type == 2 && d.nseq == 0 && d.lit_regen > 0)) body_list.push_back(b);  // api.cu
         if (d.type != 2) continue;
         if (d.lit_type >= 2) {
             rc = huffman_block(src, blocks.data(), b, litbuf.data() + d.lit_buf_off);
@@ -310,48 +316,33 @@ int hostsim_decode_frame_long(const uint8_t *src, size_t len, uint8_t *out, size
             }
         }
     }
-    uint64_t total = 0;
-    for (uint32_t b = 0; b < nb; b++) {
-        out_off[b] = total;
-        total += out_size[b];
-    }
+    uint64_t total = 0, dev_total = 0;
+    for (uint32_t b = 0; b < nb; b++) total += out_size[b];
     if (total > cap) return SZB_ERR_DST_TOO_SMALL;
-    std::vector<uint64_t> frame_out_off(copies), frame_out_len(copies);
-    std::vector<int32_t> frame_status(copies, SZB_OK);
-    for (uint32_t c = 0; c < copies; c++) {
-        frame_out_off[c] = out_off[c * nb1];
-        frame_out_len[c] = total / copies;
-    }
-    // k_execute_bodies
-    for (uint32_t b = 0; b < nb; b++) {
-        const szb_block_desc &d = blocks[b];
-        const uint8_t *payload = src + d.src_off;
-        uint8_t *o = out + out_off[b];
-        if (d.type == 0) memcpy(o, payload, d.block_size);
-        else if (d.type == 1) memset(o, payload[0], d.block_size);
-        else if (d.nseq == 0) {
-            if (d.lit_type == 1) memset(o, payload[d.lit_hdr_bytes], d.lit_regen);
-            else memcpy(o, d.lit_type == 0 ? payload + d.lit_hdr_bytes : litbuf.data() + d.lit_buf_off, d.lit_regen);
-        }
-    }
+    std::vector<uint64_t> frame_out_off(copies, ~0ull), frame_out_len(copies, ~0ull);
+    std::vector<int32_t> frame_status(copies, -99);
+    std::vector<uint8_t> bytefill(256 * 256);
+    for (int v = 0; v < 256; v++) memset(bytefill.data() + 256 * v, v, 256);
     // the long-frame tables, as batch_upload_tables (api.cu) builds them
     std::vector<uint32_t> exec_list(copies), lb_block, lb_slot, long_first_lb(1, 0);
     std::vector<uint64_t> long_dbase(1, 0);
     for (uint32_t c = 0; c < copies; c++) exec_list[c] = copies - 1 - c;  // slots need not be in frame order
-    for (uint32_t slot = 0; slot < copies; slot++) {
-        const szb_frame_desc &fr = frames[exec_list[slot]];
-        uint64_t bound = 0;
-        for (uint32_t i = 0; i < fr.nblocks; i++) {
-            const szb_block_desc &d = blocks[fr.first_block + i];
-            lb_block.push_back(fr.first_block + i);
-            lb_slot.push_back(slot);
-            bound += d.type == 2 ? (d.nseq ? 128 * 1024 : d.lit_regen) : d.block_size;
+    if (path == 2) {
+        for (uint32_t slot = 0; slot < copies; slot++) {
+            const szb_frame_desc &fr = frames[exec_list[slot]];
+            uint64_t bound = 0;
+            for (uint32_t i = 0; i < fr.nblocks; i++) {
+                const szb_block_desc &d = blocks[fr.first_block + i];
+                lb_block.push_back(fr.first_block + i);
+                lb_slot.push_back(slot);
+                bound += d.type == 2 ? (d.nseq ? 128 * 1024 : d.lit_regen) : d.block_size;
+            }
+            long_dbase.push_back(long_dbase.back() + (bound + kJumpTile - 1) / kJumpTile * kJumpTile);
+            long_first_lb.push_back((uint32_t)lb_block.size());
         }
-        long_dbase.push_back(long_dbase.back() + (bound + kJumpTile - 1) / kJumpTile * kJumpTile);
-        long_first_lb.push_back((uint32_t)lb_block.size());
     }
     const uint32_t n_lb = (uint32_t)lb_block.size();
-    std::vector<uint32_t> dist(long_dbase.back(), 0xCDCDCDCDu), long_hist(3 * (size_t)n_lb + 3);
+    std::vector<uint32_t> dist(long_dbase.back() + 1, 0xCDCDCDCDu), long_hist(3 * (size_t)n_lb + 3);
     std::vector<uint64_t> long_T(3 * (size_t)n_lb + 3);
     std::vector<unsigned long long> long_err(copies, kLongNoError);
     unsigned long long ticket = 0;
@@ -368,19 +359,25 @@ int hostsim_decode_frame_long(const uint8_t *src, size_t len, uint8_t *out, size
     a.seq_stride = stride;
     a.out_size = out_size.data();
     a.out_off = out_off.data();
+    a.lit_status = lit_status.data();
+    a.seq_status = seq_status.data();
+    a.total = &dev_total;
+    a.bytefill = bytefill.data();
     a.dst = out;
     a.dst_cap = cap;
     a.frame_out_off = frame_out_off.data();
     a.frame_out_len = frame_out_len.data();
     a.frame_status = frame_status.data();
     a.exec_list = exec_list.data();
-    a.n_long = copies;
+    a.body_list = body_list.data();
+    a.n_body = (uint32_t)body_list.size();
+    a.n_long = path == 0 ? 0 : copies;
     a.n_lb = n_lb;
     a.lb_block = lb_block.data();
     a.lb_slot = lb_slot.data();
     a.long_first_lb = long_first_lb.data();
     a.long_dbase = long_dbase.data();
-    a.dist = dist.data();
+    a.dist = path == 2 ? dist.data() : nullptr;
     a.long_T = long_T.data();
     a.long_hist = long_hist.data();
     a.long_err = long_err.data();
@@ -393,38 +390,55 @@ int hostsim_decode_frame_long(const uint8_t *src, size_t len, uint8_t *out, size
         if (order >= 2) std::shuffle(o.begin(), o.end(), std::mt19937(order));
         return o;
     };
-    const unsigned g_blocks = (n_lb + kWarpsPerCta - 1) / kWarpsPerCta;
-    {
-        auto o = cta_order(g_blocks);
-        warpsim::launch(g_blocks, kCtaThreads, [&] { k_long_hist(a); }, &o);
+    // launch_entropy's last kernel, then launch_execute (api.cu)
+    warpsim::launch(1, kScanThreads, [&] { k_scan_blocks(a); });
+    if (dev_total != total) return SZB_ERR_INVALID_ARGUMENT;
+    warpsim::launch((copies + 3) / 4, 128, [&] { k_frame_verdict(a); });
+    if (a.n_body) {
+        const unsigned g = (a.n_body + kWarpsPerCta - 1) / kWarpsPerCta;
+        auto o = cta_order(g);
+        warpsim::launch(g, kCtaThreads, [&] { k_execute_bodies(a); }, &o);
     }
-    warpsim::launch(copies, 32, [&] { k_long_compose(a); });
-    {
-        auto o = cta_order(g_blocks);
-        warpsim::launch(g_blocks, kCtaThreads, [&] { k_long_emit(a); }, &o);
+    bool fallback = false;
+    if (path == 0) {
+        warpsim::launch((copies + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, [&] { k_execute(a, 0, copies); });
+    } else {
+        warpsim::launch(copies, 64, [&] { k_execute_pair(a, 0, copies); });
     }
-    {
-        const unsigned tiles = (unsigned)(long_dbase.back() / kJumpTile);
-        const unsigned grid = order == 0 ? std::max(1u, tiles / 24) : std::max(1u, tiles / 8 + 1);  // order 0: several tiles per warp
-        auto o = cta_order(grid);
-        warpsim::launch(grid, kJumpThreads, [&] { k_long_jump(a); }, &o);
-    }
-    warpsim::launch(1, 128, [&] { k_long_verdict(a); });
-    {   // a frame beyond its scratch bound is not this path's: no kernel may have touched its cells (returns 1)
-        bool skipped = false;
+    if (path == 2) {
+        const unsigned g_blocks = (n_lb + kWarpsPerCta - 1) / kWarpsPerCta;
+        {
+            auto o = cta_order(g_blocks);
+            warpsim::launch(g_blocks, kCtaThreads, [&] { k_long_hist(a); }, &o);
+        }
+        warpsim::launch(copies, 32, [&] { k_long_compose(a); });
+        {
+            auto o = cta_order(g_blocks);
+            warpsim::launch(g_blocks, kCtaThreads, [&] { k_long_emit(a); }, &o);
+        }
+        {
+            const unsigned tiles = (unsigned)(long_dbase.back() / kJumpTile);
+            const unsigned grid = order == 0 ? std::max(1u, tiles / 24) : std::max(1u, tiles / 8 + 1);  // order 0: several tiles per warp
+            auto o = cta_order(grid);
+            warpsim::launch(grid, kJumpThreads, [&] { k_long_jump(a); }, &o);
+        }
+        warpsim::launch(1, 128, [&] { k_long_verdict(a); });
+        // a frame beyond its scratch bound is not this path's: no kernel of it may have touched the frame's cells
         for (uint32_t slot = 0; slot < copies; slot++) {
+            if (frame_status[exec_list[slot]] != SZB_OK) continue;
             if (frame_out_len[exec_list[slot]] <= long_dbase[slot + 1] - long_dbase[slot]) continue;
-            skipped = true;
+            fallback = true;
             for (uint64_t i = long_dbase[slot]; i < long_dbase[slot + 1]; i++)
                 if (dist[i] != 0xCDCDCDCDu) return SZB_ERR_INVALID_ARGUMENT;
         }
-        if (skipped) return 1;
     }
     for (uint32_t c = 0; c < copies; c++)
         if (frame_status[c] != SZB_OK) return frame_status[c];
+    for (uint32_t c = 0; c < copies; c++)
+        if (frame_out_off[c] != c * (total / copies) || frame_out_len[c] != total / copies) return SZB_ERR_INVALID_ARGUMENT;
     if (copies == 2 && memcmp(out, out + total / 2, total / 2) != 0) return SZB_ERR_INVALID_ARGUMENT;
     *out_len = total / copies;
-    return SZB_OK;
+    return fallback ? 1 : SZB_OK;
 }
 
 

@@ -1,6 +1,7 @@
-"""The serial device functions of the CUDA path (bits.cuh, fse.cuh, huffman.cuh, sequences.cuh: the code
-one lane runs) compiled for the host and driven by the product's header walker, checked against the
-golden corpus and the oracle.  tests/host_sim/hostsim.cpp is test infrastructure only."""
+"""Device code of the CUDA path compiled for the host and driven by the product's header walker, checked against the
+golden corpus and the oracle: the serial device functions of stages 1-3 (bits.cuh, fse.cuh, huffman.cuh, sequences.cuh:
+the code one lane runs) and the kernels of stage 4 (execute.cuh, execute_long.cuh) on an emulated CTA (warpsim.h).
+tests/host_sim/ is test infrastructure only."""
 import ctypes as C
 import hashlib
 import os
@@ -20,7 +21,7 @@ SIM = os.path.join(ROOT, "tests", "host_sim")
 def sim():
     lib = os.path.join(SIM, "libhostsim.so")
     srcs = [os.path.join(SIM, "hostsim.cpp"), os.path.join(ROOT, "sparkzstd_b200", "csrc", "walker.cpp")]
-    deps = srcs + [os.path.join(SIM, "warpsim.h")] + [os.path.join(ROOT, "sparkzstd_b200", "csrc", f) for f in ("bits.cuh", "fse.cuh", "huffman.cuh", "sequences.cuh", "batch.cuh", "execute_long.cuh")]
+    deps = srcs + [os.path.join(SIM, "warpsim.h")] + [os.path.join(ROOT, "sparkzstd_b200", "csrc", f) for f in ("bits.cuh", "fse.cuh", "huffman.cuh", "sequences.cuh", "batch.cuh", "execute.cuh", "execute_long.cuh")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", lib, *srcs], check=True)
     L = C.CDLL(lib)
@@ -59,12 +60,19 @@ def test_serial_device_code_error_paths(sim, corpus):
 
 
 # ---- the block-parallel stage 4 of long frames (execute_long.cuh) on an emulated warp (warpsim.h) ----
-def _decode_long(L, data: bytes, cap: int, order: int, two: int):
-    L.hostsim_decode_frame_long.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_int, C.c_int]
-    out = np.empty(2 * cap + 16, dtype=np.uint8)
+K_EXECUTE, K_EXECUTE_PAIR, K_LONG = 0, 1, 2
+
+
+def _stage4(L, data: bytes, cap: int, path: int, order: int, two: int):
+    L.hostsim_stage4.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int]
+    out = np.empty(2 * cap + 256, dtype=np.uint8)
     n = C.c_size_t()
-    rc = L.hostsim_decode_frame_long(data, len(data), out.ctypes.data, 2 * cap + 16, C.byref(n), order, two)
+    rc = L.hostsim_stage4(data, len(data), out.ctypes.data, 2 * cap + 16, C.byref(n), path, order, two)
     return rc, out[: n.value].tobytes()
+
+
+def _decode_long(L, data: bytes, cap: int, order: int, two: int):
+    return _stage4(L, data, cap, K_LONG, order, two)
 
 
 def test_long_frame_kernels_decode_golden_frames(sim, corpus):
@@ -110,11 +118,45 @@ def test_long_frame_kernels_on_crafted_frames(sim):
     assert rc == -30
     # a block that regenerates more than 128 KiB is beyond the path's scratch bound: every kernel must leave the frame alone
     big, expected = crafted.oversize_block_case()
-    rc, _ = _decode_long(sim, big, len(expected), 0, 1)
-    assert rc == 1
+    rc, out = _decode_long(sim, big, len(expected), 0, 1)
+    assert rc == 1 and out == expected  # 1: left to k_execute_pair, which decoded it
 
 
 @pytest.mark.parametrize("nblocks", [1, 31, 32, 33, 64, 100, 1000])
 def test_long_frame_history_scan(sim, nblocks):
     sim.hostsim_compose_selftest.argtypes = [C.c_uint32, C.c_uint32]
     assert sim.hostsim_compose_selftest(nblocks, 1234 + nblocks) == 0
+
+
+# ---- k_execute and k_execute_pair themselves (execute.cuh), with k_scan_blocks / k_frame_verdict / k_execute_bodies ----
+@pytest.mark.parametrize("path", [K_EXECUTE, K_EXECUTE_PAIR])
+def test_execute_kernels_decode_golden_frames(sim, corpus, path):
+    done = 0
+    for k, (name, data, size, sha) in enumerate(corpus):
+        if size > 60_000:
+            continue
+        rc, out = _stage4(sim, data, size, path, 0, k % 2)
+        assert rc == 0 and len(out) == size and hashlib.sha256(out).hexdigest() == sha, (name, path)
+        done += 1
+    assert done >= 20
+
+
+@pytest.mark.parametrize("path", [K_EXECUTE, K_EXECUTE_PAIR])
+def test_execute_kernels_on_crafted_and_synthetic_frames(sim, path):
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import crafted_frames as crafted
+
+    for k, (name, (frame, expected)) in enumerate(sorted(crafted.cases().items())):
+        rc, out = _stage4(sim, frame, len(expected), path, 0, k % 2)
+        assert rc == 0 and out == expected, name
+    big, expected = crafted.oversize_block_case()
+    rc, out = _stage4(sim, big, len(expected), path, 0, 0)
+    assert rc == 0 and out == expected
+    for c in (cg.config2_text_frames(2), cg.config3_single_frame(1 << 19, 20)):
+        for i in range(min(c.nframes, 2)):
+            f = c.frame(i)
+            want = pyszo.decode_frame(f)
+            rc, out = _stage4(sim, f, len(want), path, 0, 0)
+            assert rc == 0 and out == want, (c.name, i)
