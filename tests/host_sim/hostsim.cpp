@@ -251,8 +251,11 @@ int hostsim_decode_frame(const uint8_t *src, size_t len, uint8_t *out, size_t ca
 //   2: the block-parallel kernels of execute_long.cuh, with k_execute_pair launched beside them as the fallback.
 // order: 0 = CTAs in launch order, 1 = reversed (the worst case for k_long_jump), >= 2 = shuffled with that seed.
 // With two_frames the same frame is decoded twice in one batch and both copies must agree.
+// verify_checksum: 1 = also run k_verify_checksums; 2 = then flip an output byte and expect the mismatch (returns 3; 2 when the
+// frame carries no checksum).
 // Returns the frame's status; 1 when path 2 left the frame to its fallback (and the fallback decoded it).
-int hostsim_stage4(const uint8_t *src, size_t len, uint8_t *out, size_t cap, size_t *out_len, int path, int order, int two_frames) {
+int hostsim_stage4(const uint8_t *src, size_t len, uint8_t *out, size_t cap, size_t *out_len, int path, int order, int two_frames,
+                   int verify_checksum) {
     uint64_t off = 0, flen = len;
     szb_walk *w = nullptr;
     *out_len = 0;
@@ -434,6 +437,18 @@ int hostsim_stage4(const uint8_t *src, size_t len, uint8_t *out, size_t cap, siz
     }
     for (uint32_t c = 0; c < copies; c++)
         if (frame_status[c] != SZB_OK) return frame_status[c];
+    if (verify_checksum) {  // SZB_FLAG_VERIFY_CHECKSUM: XXH64 of the output against the frame's trailer
+        warpsim::launch((copies + 63) / 64, 64, [&] { k_verify_checksums(a); });
+        for (uint32_t c = 0; c < copies; c++)
+            if (frame_status[c] != SZB_OK) return frame_status[c];
+        if (verify_checksum == 2) {  // and a flipped output byte must be noticed
+            if (!fr0.checksum_valid || total == 0) return 2;
+            out[total / copies / 2] ^= 0x40;
+            warpsim::launch((copies + 63) / 64, 64, [&] { k_verify_checksums(a); });
+            out[total / copies / 2] ^= 0x40;
+            return frame_status[0] == SZB_ERR_CHECKSUM_MISMATCH && frame_out_len[0] == 0 ? 3 : SZB_ERR_INVALID_ARGUMENT;
+        }
+    }
     for (uint32_t c = 0; c < copies; c++)
         if (frame_out_off[c] != c * (total / copies) || frame_out_len[c] != total / copies) return SZB_ERR_INVALID_ARGUMENT;
     if (copies == 2 && memcmp(out, out + total / 2, total / 2) != 0) return SZB_ERR_INVALID_ARGUMENT;

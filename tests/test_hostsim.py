@@ -63,11 +63,11 @@ def test_serial_device_code_error_paths(sim, corpus):
 K_EXECUTE, K_EXECUTE_PAIR, K_LONG = 0, 1, 2
 
 
-def _stage4(L, data: bytes, cap: int, path: int, order: int, two: int):
-    L.hostsim_stage4.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int]
+def _stage4(L, data: bytes, cap: int, path: int, order: int, two: int, checksum: int = 0):
+    L.hostsim_stage4.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int, C.c_int]
     out = np.empty(2 * cap + 256, dtype=np.uint8)
     n = C.c_size_t()
-    rc = L.hostsim_stage4(data, len(data), out.ctypes.data, 2 * cap + 16, C.byref(n), path, order, two)
+    rc = L.hostsim_stage4(data, len(data), out.ctypes.data, 2 * cap + 16, C.byref(n), path, order, two, checksum)
     return rc, out[: n.value].tobytes()
 
 
@@ -135,10 +135,21 @@ def test_execute_kernels_decode_golden_frames(sim, corpus, path):
     for k, (name, data, size, sha) in enumerate(corpus):
         if size > 60_000:
             continue
-        rc, out = _stage4(sim, data, size, path, 0, k % 2)
+        rc, out = _stage4(sim, data, size, path, 0, k % 2, 1)  # the golden frames carry content checksums: verified too
         assert rc == 0 and len(out) == size and hashlib.sha256(out).hexdigest() == sha, (name, path)
         done += 1
     assert done >= 20
+
+
+def test_checksum_kernel_notices_a_flipped_byte(sim, corpus):
+    seen = 0
+    for name, data, size, _ in corpus[:40]:
+        if not (0 < size <= 60_000):
+            continue
+        rc, _ = _stage4(sim, data, size, K_EXECUTE, 0, 0, 2)
+        assert rc in (2, 3), name  # 3: mismatch reported; 2: the frame has no checksum
+        seen += rc == 3
+    assert seen >= 5
 
 
 @pytest.mark.parametrize("path", [K_EXECUTE, K_EXECUTE_PAIR])
