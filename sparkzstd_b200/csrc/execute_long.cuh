@@ -34,8 +34,11 @@
 #ifndef SZB_EMIT_CTAS
 #define SZB_EMIT_CTAS 8  // CTAs per SM k_long_emit is compiled for (64 registers)
 #endif
+#ifndef SZB_JUMP_BATCHED
+#define SZB_JUMP_BATCHED 1  // 1 = the loads of a thread's walks are issued together (predicated), then consumed; 0 = a branch per walk
+#endif
 #ifndef SZB_JUMP_CTAS_PER_SM
-#define SZB_JUMP_CTAS_PER_SM 8
+#define SZB_JUMP_CTAS_PER_SM 5  // 8 walks per thread need ~48 registers: 5 CTAs of 256 threads, 10 240 loads in flight per SM
 #endif
 __device__ __forceinline__ uint32_t ld_ca(const uint32_t *p) {
 #if defined(__CUDA_ARCH__)
@@ -51,6 +54,30 @@ __device__ __forceinline__ uint32_t emit_ld(const uint32_t *p) {
     return ld_ca(p);
 #else
     return __ldcg(p);
+#endif
+}
+// Predicated loads: the load is issued only where `on`, without a branch, so that the loads of a thread's independent
+// walks leave back to back (a branch per walk makes the compiler wait for each load before it issues the next).
+__device__ __forceinline__ uint32_t jump_ld_if(const uint32_t *p, uint32_t on) {
+#if defined(__CUDA_ARCH__)
+    uint32_t v;
+#if SZB_JUMP_LD
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.u32 %0, 0;\n\t@q ld.global.ca.u32 %0, [%1];\n\t}" : "=r"(v) : "l"(p), "r"(on) : "memory");
+#else
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.u32 %0, 0;\n\t@q ld.global.cg.u32 %0, [%1];\n\t}" : "=r"(v) : "l"(p), "r"(on) : "memory");
+#endif
+    return v;
+#else
+    return on ? *p : 0;
+#endif
+}
+__device__ __forceinline__ uint32_t ld_u8_if(const uint8_t *p, uint32_t on) {
+#if defined(__CUDA_ARCH__)
+    uint32_t v;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.u32 %0, 0;\n\t@q ld.global.u8 %0, [%1];\n\t}" : "=r"(v) : "l"(p), "r"(on) : "memory");
+    return v;
+#else
+    return on ? *p : 0;
 #endif
 }
 __device__ __forceinline__ uint32_t jump_ld(const uint32_t *p) {
@@ -358,7 +385,7 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EMIT_CTAS) k_long_emit(Device
 // the number of resident warps (or the kernels running beside this one), the tiles in flight are the lowest unfinished
 // ones, so that a walk leaves the region in flight after a few steps and lands on a finished cell.  (A static
 // tile-to-CTA map loses that as soon as one CTA of the grid is not resident: 6.8 -> 10.2 ms on one 256 MiB frame.)
-__global__ void __launch_bounds__(kJumpThreads, 8) k_long_jump(DeviceBatch a) {
+__global__ void __launch_bounds__(kJumpThreads, SZB_JUMP_CTAS_PER_SM) k_long_jump(DeviceBatch a) {
     const uint64_t total = a.long_dbase[a.n_long];
     const uint32_t lane = threadIdx.x & 31;
     unsigned long long next = 0;
@@ -389,15 +416,37 @@ __global__ void __launch_bounds__(kJumpThreads, 8) k_long_jump(DeviceBatch a) {
         for (uint32_t sub = 0; sub < kJumpTile; sub += 32 * kJumpChains) {
             const uint32_t r0 = (uint32_t)rel0 + sub + lane;
             if (r0 - lane >= len) break;
-            uint32_t dj[kJumpChains], first[kJumpChains];
+            uint32_t dj[kJumpChains];
             uint32_t open = 0;
 #pragma unroll
             for (int c = 0; c < kJumpChains; c++) {
                 const uint32_t rel = r0 + c * 32;
                 dj[c] = rel < len ? __ldcg(cells + rel) : 0;
-                first[c] = dj[c];
                 if (dj[c]) open |= 1u << c;
             }
+            const uint32_t moved = open;  // the match bytes among mine
+#if SZB_JUMP_BATCHED
+            while (open) {
+                uint32_t e[kJumpChains];
+#pragma unroll
+                for (int c = 0; c < kJumpChains; c++) e[c] = jump_ld_if(cells + (r0 + c * 32 - dj[c]), open & (1u << c));  // all in flight
+#pragma unroll
+                for (int c = 0; c < kJumpChains; c++) {
+                    if (e[c]) {
+                        dj[c] += e[c];
+                        __stcg(cells + (r0 + c * 32), dj[c]);  // bytes that hang on this one skip what it has skipped
+                    } else {
+                        open &= ~(1u << c);  // reached a literal (or was not walking)
+                    }
+                }
+            }
+            uint32_t v[kJumpChains];
+#pragma unroll
+            for (int c = 0; c < kJumpChains; c++) v[c] = ld_u8_if(out + (r0 + c * 32 - dj[c]), moved & (1u << c));
+#pragma unroll
+            for (int c = 0; c < kJumpChains; c++)
+                if (moved & (1u << c)) out[r0 + c * 32] = (uint8_t)v[c];
+#else
             while (open) {
 #pragma unroll
                 for (int c = 0; c < kJumpChains; c++) {
@@ -415,11 +464,12 @@ __global__ void __launch_bounds__(kJumpThreads, 8) k_long_jump(DeviceBatch a) {
             }
 #pragma unroll
             for (int c = 0; c < kJumpChains; c++) {
-                if (first[c]) {
+                if (moved & (1u << c)) {
                     const uint32_t rel = r0 + c * 32;
                     out[rel] = out[rel - dj[c]];
                 }
             }
+#endif
         }
     }
 }
