@@ -37,6 +37,9 @@
 #ifndef SZB_JUMP_BATCHED
 #define SZB_JUMP_BATCHED 1  // 1 = the loads of a thread's walks are issued together (predicated), then consumed; 0 = a branch per walk
 #endif
+#ifndef SZB_JUMP_REFILL
+#define SZB_JUMP_REFILL 0  // experiment, see k_long_jump
+#endif
 #ifndef SZB_JUMP_CTAS_PER_SM
 #define SZB_JUMP_CTAS_PER_SM 5  // 8 walks per thread need ~48 registers: 5 CTAs of 256 threads, 10 240 loads in flight per SM
 #endif
@@ -413,6 +416,62 @@ __global__ void __launch_bounds__(kJumpThreads, SZB_JUMP_CTAS_PER_SM) k_long_jum
         uint8_t *const out = a.dst + a.frame_out_off[f];
         // positions inside the frame fit 32 bits (long_jump_ok), and so does the whole tile: rel0 is a multiple of the
         // tile and below len <= 2^32
+#if SZB_JUMP_REFILL
+        // EXPERIMENT (not measured yet): a lane owns the bytes lane, lane + 32, ... of the tile and keeps kJumpChains walks
+        // going; a walk that ends hands its slot to the lane's next byte at once, instead of the lane idling until the
+        // slowest walk of the warp's step is over (with one step per 32 x kJumpChains bytes, 14 of 32 lanes are busy on
+        // average).  A walk starts at distance 0, so that its first load is the byte's own cell; the bytes are copied in a
+        // second, fully batched pass over the (now final) cells.
+        {
+            const uint32_t base = (uint32_t)rel0 + lane;
+            const uint64_t left = len - rel0;  // > 0
+            const uint32_t span = left < kJumpTile ? (uint32_t)left : kJumpTile;
+            const uint32_t n_own = lane < span ? (span - lane + 31) / 32 : 0;
+            uint32_t pos[kJumpChains], dj[kJumpChains];
+            uint32_t act = 0, nexti = 0;
+#pragma unroll
+            for (int c = 0; c < kJumpChains; c++) {
+                pos[c] = base;
+                dj[c] = 0;
+                if (nexti < n_own) {
+                    pos[c] = base + 32 * nexti++;
+                    act |= 1u << c;
+                }
+            }
+            while (act) {
+                uint32_t e[kJumpChains];
+#pragma unroll
+                for (int c = 0; c < kJumpChains; c++) e[c] = jump_ld_if(cells + (pos[c] - dj[c]), act & (1u << c));
+#pragma unroll
+                for (int c = 0; c < kJumpChains; c++) {
+                    if (!(act & (1u << c))) continue;
+                    if (e[c]) {
+                        if (dj[c]) {
+                            dj[c] += e[c];
+                            __stcg(cells + pos[c], dj[c]);
+                        } else {
+                            dj[c] = e[c];  // that was the byte's own cell
+                        }
+                    } else if (nexti < n_own) {  // a literal byte, or a walk that reached one: the cell holds the distance
+                        pos[c] = base + 32 * nexti++;
+                        dj[c] = 0;
+                    } else {
+                        act &= ~(1u << c);
+                    }
+                }
+            }
+            for (uint32_t i0 = 0; i0 < n_own; i0 += kJumpChains) {
+                uint32_t d[kJumpChains], v[kJumpChains];
+#pragma unroll
+                for (int c = 0; c < kJumpChains; c++) d[c] = i0 + c < n_own ? __ldcg(cells + (base + 32 * (i0 + c))) : 0;
+#pragma unroll
+                for (int c = 0; c < kJumpChains; c++) v[c] = ld_u8_if(out + (base + 32 * (i0 + c) - d[c]), d[c]);
+#pragma unroll
+                for (int c = 0; c < kJumpChains; c++)
+                    if (d[c]) out[base + 32 * (i0 + c)] = (uint8_t)v[c];
+            }
+        }
+#else
         for (uint32_t sub = 0; sub < kJumpTile; sub += 32 * kJumpChains) {
             const uint32_t r0 = (uint32_t)rel0 + sub + lane;
             if (r0 - lane >= len) break;
@@ -471,6 +530,7 @@ __global__ void __launch_bounds__(kJumpThreads, SZB_JUMP_CTAS_PER_SM) k_long_jum
             }
 #endif
         }
+#endif
     }
 }
 
