@@ -264,7 +264,8 @@ constexpr uint64_t kLongFrameSequences = 65536;
 constexpr uint32_t kMaxLongFrames = 2368;
 // measured on text-like frames: k_execute_pair 0.26 GB/s per frame at 10.7 bytes per sequence (profiles/r01d_bench_single256m_1gpu.json);
 // the block-parallel path 38-49 GB/s over everything it is given (profiles/r01k_bench_single*.json)
-constexpr double kPairSeqPerMs = 24000.0, kJumpCellsPerMs = 40e6;
+// (one warp of k_long_emit needs ~3 ms for a 128 KiB block whatever the number of blocks: r01l_long_ncu_full_summary.txt)
+constexpr double kPairSeqPerMs = 24000.0, kJumpCellsPerMs = 40e6, kJumpFloorMs = 3.0;
 
 static int batch_upload_tables(szb_batch *b) {
     szb_ctx *ctx = b->ctx;
@@ -340,7 +341,7 @@ static int batch_upload_tables(szb_batch *b) {
             if (b->long_jump && !(mode && strcmp(mode, "jump") == 0)) {
                 const uint64_t most = work[b->exec_list[0]];  // exec_list is sorted by sequences, most first
                 const uint64_t waves = (n_long + (uint64_t)ctx->sm_count * 16 - 1) / ((uint64_t)ctx->sm_count * 16);
-                const double t_pair = (double)most * (double)waves / kPairSeqPerMs, t_jump = (double)cells / kJumpCellsPerMs;
+                const double t_pair = (double)most * (double)waves / kPairSeqPerMs, t_jump = kJumpFloorMs + (double)cells / kJumpCellsPerMs;
                 if (t_pair <= t_jump) b->long_jump = false;
             }
         }
