@@ -329,6 +329,10 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EMIT_CTAS) k_long_emit(Device
             break;
         }
         const uint32_t excl_tot = incl_tot - tot, excl_ll = incl_ll - ll;
+        if (!lit_rle && lane < 4) {  // the literals of the next rounds are on their way to L1 while this round is emitted
+            const uint32_t ahead = lit_pos + round_ll + 128 * lane;
+            if (ahead < d.lit_regen) SZB_PREFETCH_L1(lit + ahead);
+        }
         // every match must lie inside the frame (ringbuffer.go:203-214); a match length of 0 cannot come out of stage 3
         if (__any_sync(kFull, act && ((uint64_t)off > fb + excl_tot + ll || off == 0 || ml == 0))) {
             err = SZB_ERR_CANT_REPEAT_BYTES;
