@@ -17,6 +17,7 @@
 
 #include "../../include/szb200.h"
 #include "kernels.cuh"
+#include "long_tables.h"
 
 using namespace szb;
 
@@ -73,12 +74,13 @@ struct szb_batch {
     uint32_t *d_body_list = nullptr;
     uint32_t *d_exec_list = nullptr;
     uint32_t n_long = 0;  // leading entries of exec_list: long frames (execute_long.cuh, else k_execute_pair)
-    std::vector<uint32_t> lb_block, lb_slot, long_first_lb;
-    std::vector<uint64_t> long_dbase;
+    LongTables lt;            // index tables of the block-parallel path (long_tables.h)
+    uint32_t long_slice = 0;  // sequences per slice of a block (0: the whole block)
     bool long_jump = false;  // the block-parallel path is on for this batch
-    uint32_t *d_lb_block = nullptr, *d_lb_slot = nullptr, *d_long_first_lb = nullptr;
+    uint32_t *d_lb_block = nullptr, *d_lb_slot = nullptr, *d_long_first_lb = nullptr, *d_ls_lb = nullptr, *d_ls_seq0 = nullptr,
+             *d_lb_first_ls = nullptr;
     uint64_t *d_long_dbase = nullptr;
-    void *d_long = nullptr;  // one allocation: long_err | long_T | long_hist | dist
+    void *d_long = nullptr;  // one allocation: long_err, long_ticket | long_T | long_hist | ls_T | ls_sum | dist
     uint64_t *d_out_size_init = nullptr;
     void *d_state = nullptr;  // one allocation: out_size | out_off | total | frame_out_off | frame_out_len | statuses
     uint64_t *d_out_size = nullptr, *d_out_off = nullptr, *d_total = nullptr, *d_frame_out_off = nullptr,
@@ -314,23 +316,15 @@ static int batch_upload_tables(szb_batch *b) {
         // most Block_Maximum_Size = 128 KiB when the frame is valid; a frame that regenerates more stays on k_execute_pair).
         const char *mode = getenv("SZB_LONG_MODE");
         b->long_jump = n_long > 0 && !(mode && strcmp(mode, "pair") == 0);
-        b->long_first_lb.assign(1, 0);
-        b->long_dbase.assign(1, 0);
+        b->lt.clear();
         if (b->long_jump) {
-            uint64_t cells = 0;
-            for (uint32_t slot = 0; slot < n_long; slot++) {
-                const szb_frame_desc &fr = b->frames[b->exec_list[slot]];
-                uint64_t bound = 0;
-                for (uint32_t i = 0; i < fr.nblocks; i++) {
-                    const szb_block_desc &d = b->blocks[fr.first_block + i];
-                    b->lb_block.push_back(fr.first_block + i);
-                    b->lb_slot.push_back(slot);
-                    bound += d.type == 2 ? (d.nseq ? 128 * 1024 : d.lit_regen) : d.block_size;
-                }
-                cells += align_up(bound, kJumpTile);
-                b->long_first_lb.push_back((uint32_t)b->lb_block.size());
-                b->long_dbase.push_back(cells);
-            }
+            // SZB_LONG_SLICE (sequences, rounded up to whole rounds; default 0 = one warp per block): k_long_hist and k_long_emit
+            // run one warp per slice -- more, shorter warps for frames of few blocks -- at the price of cells that are only
+            // resolved inside a slice when they leave k_long_emit.  Not measured yet.
+            const uint32_t slice = getenv("SZB_LONG_SLICE") ? (uint32_t)((strtoul(getenv("SZB_LONG_SLICE"), nullptr, 10) + 31) / 32 * 32) : 0;
+            b->long_slice = slice;
+            build_long_tables(b->frames.data(), b->blocks.data(), b->exec_list.data(), n_long, slice, kJumpTile, b->lt);
+            const uint64_t cells = b->lt.long_dbase.back();
             static const uint64_t max_cells = (getenv("SZB_LONG_MAX_GIB") ? strtoull(getenv("SZB_LONG_MAX_GIB"), nullptr, 10) : 64) << 28;
             if (cells > max_cells) b->long_jump = false;  // 4 bytes per cell
             // Which path is faster depends on the batch.  k_execute_pair runs every long frame on its own two warps at
@@ -345,12 +339,7 @@ static int batch_upload_tables(szb_batch *b) {
                 if (t_pair <= t_jump) b->long_jump = false;
             }
         }
-        if (!b->long_jump) {
-            b->lb_block.clear();
-            b->lb_slot.clear();
-            b->long_first_lb.assign(1, 0);
-            b->long_dbase.assign(1, 0);
-        }
+        if (!b->long_jump) b->lt.clear();
     }
     // descriptor tables: one allocation, one H2D copy
     size_t o_frames = 0;
@@ -363,10 +352,14 @@ static int batch_upload_tables(szb_batch *b) {
     size_t o_exec = align_up(o_body + 4 * b->body_list.size(), 256);
     size_t o_init = align_up(o_exec + 4 * b->exec_list.size(), 256);
     size_t o_lbb = align_up(o_init + 8 * (size_t)nb, 256);
-    size_t o_lbs = align_up(o_lbb + 4 * b->lb_block.size(), 256);
-    size_t o_lfl = align_up(o_lbs + 4 * b->lb_slot.size(), 256);
-    size_t o_ldb = align_up(o_lfl + 4 * b->long_first_lb.size(), 256);
-    size_t total = align_up(o_ldb + 8 * b->long_dbase.size(), 256) + 256;
+    const LongTables &lt = b->lt;
+    size_t o_lbs = align_up(o_lbb + 4 * lt.lb_block.size(), 256);
+    size_t o_lfl = align_up(o_lbs + 4 * lt.lb_slot.size(), 256);
+    size_t o_ldb = align_up(o_lfl + 4 * lt.long_first_lb.size(), 256);
+    size_t o_lsl = align_up(o_ldb + 8 * lt.long_dbase.size(), 256);
+    size_t o_lss = align_up(o_lsl + 4 * lt.ls_lb.size(), 256);
+    size_t o_lfs = align_up(o_lss + 4 * lt.ls_seq0.size(), 256);
+    size_t total = align_up(o_lfs + 4 * lt.lb_first_ls.size(), 256) + 256;
     std::vector<uint8_t> &stage = b->stage;
     stage.assign(total, 0);
     if (nf) memcpy(stage.data() + o_frames, b->frames.data(), sizeof(szb_frame_desc) * (size_t)nf);
@@ -378,10 +371,13 @@ static int batch_upload_tables(szb_batch *b) {
     if (!b->body_list.empty()) memcpy(stage.data() + o_body, b->body_list.data(), 4 * b->body_list.size());
     if (!b->exec_list.empty()) memcpy(stage.data() + o_exec, b->exec_list.data(), 4 * b->exec_list.size());
     if (nb) memcpy(stage.data() + o_init, out_size_init.data(), 8 * (size_t)nb);
-    if (!b->lb_block.empty()) memcpy(stage.data() + o_lbb, b->lb_block.data(), 4 * b->lb_block.size());
-    if (!b->lb_slot.empty()) memcpy(stage.data() + o_lbs, b->lb_slot.data(), 4 * b->lb_slot.size());
-    memcpy(stage.data() + o_lfl, b->long_first_lb.data(), 4 * b->long_first_lb.size());
-    memcpy(stage.data() + o_ldb, b->long_dbase.data(), 8 * b->long_dbase.size());
+    if (!lt.lb_block.empty()) memcpy(stage.data() + o_lbb, lt.lb_block.data(), 4 * lt.lb_block.size());
+    if (!lt.lb_slot.empty()) memcpy(stage.data() + o_lbs, lt.lb_slot.data(), 4 * lt.lb_slot.size());
+    memcpy(stage.data() + o_lfl, lt.long_first_lb.data(), 4 * lt.long_first_lb.size());
+    memcpy(stage.data() + o_ldb, lt.long_dbase.data(), 8 * lt.long_dbase.size());
+    if (!lt.ls_lb.empty()) memcpy(stage.data() + o_lsl, lt.ls_lb.data(), 4 * lt.ls_lb.size());
+    if (!lt.ls_seq0.empty()) memcpy(stage.data() + o_lss, lt.ls_seq0.data(), 4 * lt.ls_seq0.size());
+    memcpy(stage.data() + o_lfs, lt.lb_first_ls.data(), 4 * lt.lb_first_ls.size());
     CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_tables, total));
     CUDA_TRY(ctx, cudaMemcpyAsync(b->d_tables, stage.data(), total, cudaMemcpyHostToDevice, ctx->stream));
     uint8_t *base = (uint8_t *)b->d_tables;
@@ -398,6 +394,9 @@ static int batch_upload_tables(szb_batch *b) {
     b->d_lb_slot = (uint32_t *)(base + o_lbs);
     b->d_long_first_lb = (uint32_t *)(base + o_lfl);
     b->d_long_dbase = (uint64_t *)(base + o_ldb);
+    b->d_ls_lb = (uint32_t *)(base + o_lsl);
+    b->d_ls_seq0 = (uint32_t *)(base + o_lss);
+    b->d_lb_first_ls = (uint32_t *)(base + o_lfs);
     // mutable state
     size_t s_out_size = 0;
     size_t s_out_off = align_up(s_out_size + 8 * (size_t)nb, 256);
@@ -582,7 +581,14 @@ static DeviceBatch make_args(szb_batch *b, const void *d_src, void *d_dst, size_
     a.body_list = b->d_body_list;
     a.n_body = (uint32_t)b->body_list.size();
     a.n_long = b->n_long;
-    a.n_lb = (uint32_t)b->lb_block.size();
+    a.n_lb = (uint32_t)b->lt.lb_block.size();
+    a.n_ls = (uint32_t)b->lt.ls_lb.size();
+    a.long_slice = b->long_slice;
+    a.ls_lb = b->d_ls_lb;
+    a.ls_seq0 = b->d_ls_seq0;
+    a.lb_first_ls = b->d_lb_first_ls;
+    a.ls_T = nullptr;
+    a.ls_sum = nullptr;
     a.lb_block = b->d_lb_block;
     a.lb_slot = b->d_lb_slot;
     a.long_first_lb = b->d_long_first_lb;
@@ -670,12 +676,14 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
             cudaStream_t sl = ctx->s_lit;
             // scratch of the block-parallel path: error words | transfer functions | start histories | distance cells.
             // Without it (allocation refused) every long frame stays on k_execute_pair.
+            const size_t n_lb = b->lt.lb_block.size(), n_ls = b->lt.ls_lb.size();
+            const size_t o_T = align_up(8 * (size_t)n_long + 8, 256);
+            const size_t o_hist = align_up(o_T + 24 * n_lb, 256);
+            const size_t o_lsT = align_up(o_hist + 12 * n_lb, 256);
+            const size_t o_lsum = align_up(o_lsT + 24 * n_ls, 256);
+            const size_t o_dist = align_up(o_lsum + 16 * n_ls, 256);
             if (b->long_jump && !b->d_long) {
-                const size_t n_lb = b->lb_block.size();
-                const size_t o_T = align_up(8 * (size_t)n_long + 8, 256);
-                const size_t o_hist = align_up(o_T + 24 * n_lb, 256);
-                const size_t o_dist = align_up(o_hist + 12 * n_lb, 256);
-                const size_t bytes = o_dist + 4 * (size_t)b->long_dbase.back();
+                const size_t bytes = o_dist + 4 * (size_t)b->lt.long_dbase.back();
                 if (cudaMallocAsync(&b->d_long, bytes, s) != cudaSuccess) {
                     cudaGetLastError();
                     b->d_long = nullptr;
@@ -683,14 +691,12 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
                 }
             }
             if (b->long_jump) {
-                const size_t n_lb = b->lb_block.size();
-                const size_t o_T = align_up(8 * (size_t)n_long + 8, 256);
-                const size_t o_hist = align_up(o_T + 24 * n_lb, 256);
-                const size_t o_dist = align_up(o_hist + 12 * n_lb, 256);
                 uint8_t *base = (uint8_t *)b->d_long;
                 a.long_err = (unsigned long long *)base;
                 a.long_T = (uint64_t *)(base + o_T);
                 a.long_hist = (uint32_t *)(base + o_hist);
+                a.ls_T = (uint64_t *)(base + o_lsT);
+                a.ls_sum = (uint64_t *)(base + o_lsum);
                 a.dist = (uint32_t *)(base + o_dist);
                 a.long_ticket = a.long_err + n_long;
                 CUDA_TRY(ctx, cudaMemsetAsync(a.long_err, 0xFF, 8 * (size_t)n_long, s));
@@ -701,15 +707,16 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
             k_execute_pair<<<n_long, 64, 0, sl>>>(a, 0, n_long);  // the frames the block-parallel path does not take
             ctx->launches++;
             if (b->long_jump) {
-                const uint32_t n_lb = a.n_lb;
-                k_long_hist<<<(n_lb + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, sl>>>(a);
+                const uint32_t g_lb = (a.n_lb + kWarpsPerCta - 1) / kWarpsPerCta, g_ls = (a.n_ls + kWarpsPerCta - 1) / kWarpsPerCta;
+                k_long_hist<<<g_ls, kCtaThreads, 0, sl>>>(a);
+                k_long_blockscan<<<g_lb, kCtaThreads, 0, sl>>>(a);
                 k_long_compose<<<n_long, 32, 0, sl>>>(a);
-                k_long_emit<<<(n_lb + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, sl>>>(a);
-                const uint64_t tiles = (b->long_dbase.back() / kJumpTile + kJumpThreads / 32 - 1) / (kJumpThreads / 32);  // a tile per warp
+                k_long_emit<<<g_ls, kCtaThreads, 0, sl>>>(a);
+                const uint64_t tiles = (b->lt.long_dbase.back() / kJumpTile + kJumpThreads / 32 - 1) / (kJumpThreads / 32);  // a tile per warp
                 const uint64_t resident = (uint64_t)ctx->sm_count * SZB_JUMP_CTAS_PER_SM;
                 k_long_jump<<<(unsigned)(tiles < resident ? (tiles ? tiles : 1) : resident), kJumpThreads, 0, sl>>>(a);
                 k_long_verdict<<<(n_long + 127) / 128, 128, 0, sl>>>(a);
-                ctx->launches += 5;
+                ctx->launches += 6;
             }
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, sl));
         }

@@ -65,6 +65,15 @@ struct DeviceBatch {
     const uint32_t *lb_slot;        // per lb_block entry: its frame's position in exec_list
     const uint32_t *long_first_lb;  // per long frame: its first lb_block entry (n_long + 1 entries)
     const uint64_t *long_dbase;     // per long frame: its first distance cell (n_long + 1 entries, multiples of kJumpTile)
+    uint32_t n_ls;                  // SLICES of those blocks: k_long_hist and k_long_emit run one warp per slice
+    uint32_t long_slice;            // sequences per slice (a multiple of 32); 0: every block is one slice
+    const uint32_t *ls_lb;          // per slice: its block's lb_block entry
+    const uint32_t *ls_seq0;        // per slice: its first sequence in the block
+    const uint32_t *lb_first_ls;    // per lb_block entry: its first slice (n_lb + 1 entries)
+    uint64_t *ls_T;                 // per slice: its history transfer function (3 entries); after k_long_blockscan: the function
+                                    // from the block's start to the slice's start
+    uint64_t *ls_sum;               // per slice: sum of literal lengths, sum of literal + match lengths; after k_long_blockscan:
+                                    // the exclusive prefixes within the block
     uint32_t *dist;                 // one distance cell per output byte of the long frames; nullptr: k_execute_pair takes them
     uint64_t *long_T;               // per lb_block entry: the block's history transfer function (3 entries)
     uint32_t *long_hist;            // per lb_block entry: the history the block starts with (3 entries)

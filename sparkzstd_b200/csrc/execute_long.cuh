@@ -179,33 +179,49 @@ __device__ __forceinline__ V walk_round(HistV<V> &hist, uint32_t ofv, uint32_t l
     return off;
 }
 
-// ---- k_long_hist: the transfer function of every block of the long frames ----
+// ---- k_long_hist: the transfer function and the length sums of every SLICE of the long frames' blocks; one warp each ----
+// A slice is a run of DeviceBatch::long_slice sequences of one block (the whole block when long_slice is 0).
+__device__ __forceinline__ uint32_t slice_end(const DeviceBatch &a, uint32_t seq0, uint32_t nseq) {
+    return a.long_slice && nseq - seq0 > a.long_slice ? seq0 + a.long_slice : nseq;
+}
 __global__ void __launch_bounds__(kCtaThreads) k_long_hist(DeviceBatch a) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    if (w >= a.n_lb) return;
-    const uint32_t b = a.lb_block[w];
+    if (w >= a.n_ls) return;
+    const uint32_t b = a.lb_block[a.ls_lb[w]];
     const szb_block_desc d = a.blocks[b];
     HistV<uint64_t> h{sym_entry(0), sym_entry(1), sym_entry(2)};
+    uint64_t sum_ll = 0, sum_tot = 0;  // this lane's share
     if (d.type == 2 && d.nseq > 0 && a.frame_status[d.frame] == SZB_OK) {
-        const uint32_t nseq = d.nseq;
+        const uint32_t seq0 = a.ls_seq0[w], seq1 = slice_end(a, seq0, d.nseq);
         const uint32_t *tr = a.seq_ll + (d.seq_buf_off + lane);  // the arrays are padded to whole rounds
-        uint32_t ll = tr[0], ofv = tr[2 * a.seq_stride];
-        for (uint32_t base = 0; base < nseq; base += 32) {
-            const uint32_t cnt = nseq - base < 32 ? nseq - base : 32;
+        uint32_t ll = tr[seq0], ml = tr[seq0 + a.seq_stride], ofv = tr[seq0 + 2 * a.seq_stride];
+        for (uint32_t base = seq0; base < seq1; base += 32) {
+            const uint32_t cnt = seq1 - base < 32 ? seq1 - base : 32;
             const bool act = lane < cnt;
             const uint32_t c_ll = ll, c_ofv = act ? ofv : 4;
-            if (base + 32 < nseq) {  // the next round's loads are in flight during the walk
+            if (act) {
+                sum_ll += ll;
+                sum_tot += (uint64_t)ll + ml;
+            }
+            if (base + 32 < seq1) {  // the next round's loads are in flight during the walk
                 ll = tr[base + 32];
+                ml = tr[base + 32 + a.seq_stride];
                 ofv = tr[base + 32 + 2 * a.seq_stride];
             }
             walk_round<uint64_t>(h, c_ofv, c_ll, act, cnt, lane);
         }
     }
+    for (int dlt = 16; dlt; dlt >>= 1) {
+        sum_ll += __shfl_xor_sync(kFull, sum_ll, dlt);
+        sum_tot += __shfl_xor_sync(kFull, sum_tot, dlt);
+    }
     if (lane == 0) {
-        a.long_T[3 * (uint64_t)w] = h.h0;
-        a.long_T[3 * (uint64_t)w + 1] = h.h1;
-        a.long_T[3 * (uint64_t)w + 2] = h.h2;
+        a.ls_T[3 * (uint64_t)w] = h.h0;
+        a.ls_T[3 * (uint64_t)w + 1] = h.h1;
+        a.ls_T[3 * (uint64_t)w + 2] = h.h2;
+        a.ls_sum[2 * (uint64_t)w] = sum_ll;
+        a.ls_sum[2 * (uint64_t)w + 1] = sum_tot;
     }
 }
 
@@ -216,6 +232,62 @@ __device__ __forceinline__ uint64_t sym_compose(uint64_t e, uint64_t a0, uint64_
     const uint64_t base = idx == 0 ? a0 : (idx == 1 ? a1 : a2);
     if (base & kSymBit) return base + (uint32_t)e;  // "entry j minus m" minus k
     return (uint64_t)((uint32_t)base - (uint32_t)e);
+}
+
+// ---- k_long_blockscan: one warp per block: the slices' functions and sums scanned in slice order ----
+// Afterwards a slice's entry holds what lies between the block's start and its own: the composed transfer function and the
+// literal / output bytes in front of it; long_T gets the block's whole function (what k_long_compose scans over the frame).
+__global__ void __launch_bounds__(kCtaThreads) k_long_blockscan(DeviceBatch a) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lb = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    if (lb >= a.n_lb) return;
+    const uint32_t first = a.lb_first_ls[lb], end = a.lb_first_ls[lb + 1];
+    uint64_t c0 = sym_entry(0), c1 = sym_entry(1), c2 = sym_entry(2);  // everything before this step, as a function of the block's start
+    uint64_t cs_ll = 0, cs_tot = 0;
+    for (uint32_t base = first; base < end; base += 32) {
+        const uint32_t i = base + lane;
+        uint64_t t0 = sym_entry(0), t1 = sym_entry(1), t2 = sym_entry(2), s_ll = 0, s_tot = 0;
+        if (i < end) {
+            t0 = a.ls_T[3 * (uint64_t)i];
+            t1 = a.ls_T[3 * (uint64_t)i + 1];
+            t2 = a.ls_T[3 * (uint64_t)i + 2];
+            s_ll = a.ls_sum[2 * (uint64_t)i];
+            s_tot = a.ls_sum[2 * (uint64_t)i + 1];
+        }
+        for (uint32_t dlt = 1; dlt < 32; dlt <<= 1) {  // inclusive scans
+            const uint64_t g0 = __shfl_up_sync(kFull, t0, dlt), g1 = __shfl_up_sync(kFull, t1, dlt), g2 = __shfl_up_sync(kFull, t2, dlt);
+            const uint64_t u_ll = __shfl_up_sync(kFull, s_ll, dlt), u_tot = __shfl_up_sync(kFull, s_tot, dlt);
+            if (lane >= dlt) {
+                t0 = sym_compose(t0, g0, g1, g2);
+                t1 = sym_compose(t1, g0, g1, g2);
+                t2 = sym_compose(t2, g0, g1, g2);
+                s_ll += u_ll;
+                s_tot += u_tot;
+            }
+        }
+        uint64_t e0 = __shfl_up_sync(kFull, t0, 1), e1 = __shfl_up_sync(kFull, t1, 1), e2 = __shfl_up_sync(kFull, t2, 1);
+        uint64_t x_ll = __shfl_up_sync(kFull, s_ll, 1), x_tot = __shfl_up_sync(kFull, s_tot, 1);
+        if (lane == 0) e0 = sym_entry(0), e1 = sym_entry(1), e2 = sym_entry(2), x_ll = 0, x_tot = 0;
+        if (i < end) {
+            a.ls_T[3 * (uint64_t)i] = sym_compose(e0, c0, c1, c2);
+            a.ls_T[3 * (uint64_t)i + 1] = sym_compose(e1, c0, c1, c2);
+            a.ls_T[3 * (uint64_t)i + 2] = sym_compose(e2, c0, c1, c2);
+            a.ls_sum[2 * (uint64_t)i] = cs_ll + x_ll;
+            a.ls_sum[2 * (uint64_t)i + 1] = cs_tot + x_tot;
+        }
+        const uint64_t l0 = __shfl_sync(kFull, t0, 31), l1 = __shfl_sync(kFull, t1, 31), l2 = __shfl_sync(kFull, t2, 31);
+        const uint64_t n0 = sym_compose(l0, c0, c1, c2), n1 = sym_compose(l1, c0, c1, c2), n2 = sym_compose(l2, c0, c1, c2);
+        c0 = n0;
+        c1 = n1;
+        c2 = n2;
+        cs_ll += __shfl_sync(kFull, s_ll, 31);
+        cs_tot += __shfl_sync(kFull, s_tot, 31);
+    }
+    if (lane == 0) {
+        a.long_T[3 * (uint64_t)lb] = c0;
+        a.long_T[3 * (uint64_t)lb + 1] = c1;
+        a.long_T[3 * (uint64_t)lb + 2] = c2;
+    }
 }
 
 // ---- k_long_compose: the history each block starts with; one warp per long frame ----
@@ -266,25 +338,24 @@ __global__ void __launch_bounds__(32) k_long_compose(DeviceBatch a) {
     }
 }
 
-// ---- k_long_emit: literal bytes and distance cells of every block of the long frames; one warp per block ----
+// ---- k_long_emit: literal bytes and distance cells of every slice of the long frames' blocks; one warp per slice ----
 __global__ void __launch_bounds__(kCtaThreads, SZB_EMIT_CTAS) k_long_emit(DeviceBatch a) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    if (w >= a.n_lb) return;
-    const uint32_t slot = a.lb_slot[w];
+    if (w >= a.n_ls) return;
+    const uint32_t lb = a.ls_lb[w];
+    const uint32_t slot = a.lb_slot[lb];
     if (!long_jump_ok(a, slot)) return;
-    const uint32_t b = a.lb_block[w];
+    const uint32_t b = a.lb_block[lb];
     const szb_block_desc d = a.blocks[b];
     const uint64_t frame_base = a.frame_out_off[d.frame];
-    uint64_t out_pos = a.out_off[b];
     uint8_t *const dst = a.dst;
     uint32_t *const cells = a.dist + a.long_dbase[slot];  // cell of the frame's first byte
-    const uint64_t fb0 = out_pos - frame_base;            // frame bytes in front of the block
 
     if (d.type != 2 || d.nseq == 0) {
         // Raw / RLE bodies and blocks without sequences: written by k_execute_bodies; every byte is a literal byte
-        const uint64_t n = a.out_size[b];
-        for (uint64_t i = lane; i < n; i += 32) cells[fb0 + i] = 0;
+        const uint64_t n = a.out_size[b], at = a.out_off[b] - frame_base;
+        for (uint64_t i = lane; i < n; i += 32) cells[at + i] = 0;
         return;
     }
     const uint8_t *payload = a.src + d.src_off;
@@ -292,18 +363,32 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EMIT_CTAS) k_long_emit(Device
     const uint32_t fill = lit_rle ? payload[d.lit_hdr_bytes] : 0;
     const uint8_t *__restrict__ lit = d.lit_type == 0 ? payload + d.lit_hdr_bytes : a.litbuf + d.lit_buf_off;  // unused for RLE literals
     const uint32_t nseq = d.nseq;
-    HistV<uint32_t> hist{a.long_hist[3 * (uint64_t)w], a.long_hist[3 * (uint64_t)w + 1], a.long_hist[3 * (uint64_t)w + 2]};
-    uint32_t lit_pos = 0;
-    uint64_t fb = fb0;  // frame bytes in front of the round
+    const uint32_t seq0 = a.ls_seq0[w], seq1 = slice_end(a, seq0, nseq);
+    // what the slices of the block in front of this one leave behind (k_long_blockscan), from what the block starts with (k_long_compose)
+    const uint32_t b0 = a.long_hist[3 * (uint64_t)lb], b1 = a.long_hist[3 * (uint64_t)lb + 1], b2 = a.long_hist[3 * (uint64_t)lb + 2];
+    HistV<uint32_t> hist{hist_apply(a.ls_T[3 * (uint64_t)w], b0, b1, b2), hist_apply(a.ls_T[3 * (uint64_t)w + 1], b0, b1, b2),
+                         hist_apply(a.ls_T[3 * (uint64_t)w + 2], b0, b1, b2)};
+    const uint64_t lit_before = a.ls_sum[2 * (uint64_t)w], out_before = a.ls_sum[2 * (uint64_t)w + 1];
     int err = SZB_OK;
     uint32_t err_base = 0;
+    if (lit_before > d.lit_regen) {
+        // an earlier slice of the block runs out of literals (and says so with a smaller key): nothing of this one may be emitted
+        if (lane == 0)
+            atomicMin(&a.long_err[slot], ((unsigned long long)lb << 40) | ((unsigned long long)seq0 << 8) |
+                                             (uint32_t)(-(lit_rle ? SZB_ERR_PANIC : SZB_ERR_DIDNT_COPY_ALL_LITERAL_BYTES)));
+        return;
+    }
+    uint32_t lit_pos = (uint32_t)lit_before;
+    uint64_t out_pos = a.out_off[b] + out_before;
+    const uint64_t fb0 = out_pos - frame_base;  // frame bytes in front of the slice
+    uint64_t fb = fb0;                          // frame bytes in front of the round
     const uint32_t *tr = a.seq_ll + (d.seq_buf_off + lane);
-    uint32_t n_ll = tr[0], n_ml = tr[a.seq_stride], n_ofv = tr[2 * a.seq_stride];
-    for (uint32_t base = 0; base < nseq; base += 32) {
-        const uint32_t cnt = nseq - base < 32 ? nseq - base : 32;
+    uint32_t n_ll = tr[seq0], n_ml = tr[seq0 + a.seq_stride], n_ofv = tr[seq0 + 2 * a.seq_stride];
+    for (uint32_t base = seq0; base < seq1; base += 32) {
+        const uint32_t cnt = seq1 - base < 32 ? seq1 - base : 32;
         const bool act = lane < cnt;
         const uint32_t ll = act ? n_ll : 0, ml = act ? n_ml : 0, ofv = act ? n_ofv : 4;
-        if (base + 32 < nseq) {
+        if (base + 32 < seq1) {
             n_ll = tr[base + 32];
             n_ml = tr[base + 32 + a.seq_stride];
             n_ofv = tr[base + 32 + 2 * a.seq_stride];
@@ -366,7 +451,7 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EMIT_CTAS) k_long_emit(Device
                     const uint32_t m = k - s_ll;
                     cell = m < s_off ? s_off : s_off * (m / s_off + 1);
                     const uint64_t me = fb + x;  // my byte, counted from the frame's start
-                    if (cell <= me - fb0 && cell > lane) cell += emit_ld(cells + (me - cell));  // in the block, below this step
+                    if (cell <= me - fb0 && cell > lane) cell += emit_ld(cells + (me - cell));  // in the slice, below this step
                 }
                 cells[fb + x] = cell;
             }
@@ -376,10 +461,11 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EMIT_CTAS) k_long_emit(Device
         lit_pos += round_ll;
     }
     if (err != SZB_OK) {
-        if (lane == 0) atomicMin(&a.long_err[slot], ((unsigned long long)w << 40) | ((unsigned long long)err_base << 8) | (uint32_t)(-err));
+        if (lane == 0) atomicMin(&a.long_err[slot], ((unsigned long long)lb << 40) | ((unsigned long long)err_base << 8) | (uint32_t)(-err));
         return;
     }
-    // trailing literals (sequence_execution.go:55-60, literals.go:411-420)
+    if (seq1 != nseq) return;
+    // trailing literals (sequence_execution.go:55-60, literals.go:411-420): after the block's last sequence
     const uint32_t rest = d.lit_regen - lit_pos;
     for (uint32_t i = lane; i < rest; i += 32) {
         dst[out_pos + i] = lit_rle ? (uint8_t)fill : lit[lit_pos + i];

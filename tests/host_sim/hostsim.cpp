@@ -16,6 +16,7 @@
 
 #include "../../include/szb200.h"
 #include "../../sparkzstd_b200/csrc/batch.cuh"
+#include "../../sparkzstd_b200/csrc/long_tables.h"
 #include "../../sparkzstd_b200/csrc/huffman.cuh"
 #include "../../sparkzstd_b200/csrc/sequences.cuh"
 
@@ -326,27 +327,18 @@ int hostsim_stage4(const uint8_t *src, size_t len, uint8_t *out, size_t cap, siz
     std::vector<int32_t> frame_status(copies, -99);
     std::vector<uint8_t> bytefill(256 * 256);
     for (int v = 0; v < 256; v++) memset(bytefill.data() + 256 * v, v, 256);
-    // the long-frame tables, as batch_upload_tables (api.cu) builds them
-    std::vector<uint32_t> exec_list(copies), lb_block, lb_slot, long_first_lb(1, 0);
-    std::vector<uint64_t> long_dbase(1, 0);
+    // the long-frame tables, as batch_upload_tables (api.cu) builds them (SZB_LONG_SLICE as there)
+    std::vector<uint32_t> exec_list(copies);
     for (uint32_t c = 0; c < copies; c++) exec_list[c] = copies - 1 - c;  // slots need not be in frame order
-    if (path == 2) {
-        for (uint32_t slot = 0; slot < copies; slot++) {
-            const szb_frame_desc &fr = frames[exec_list[slot]];
-            uint64_t bound = 0;
-            for (uint32_t i = 0; i < fr.nblocks; i++) {
-                const szb_block_desc &d = blocks[fr.first_block + i];
-                lb_block.push_back(fr.first_block + i);
-                lb_slot.push_back(slot);
-                bound += d.type == 2 ? (d.nseq ? 128 * 1024 : d.lit_regen) : d.block_size;
-            }
-            long_dbase.push_back(long_dbase.back() + (bound + kJumpTile - 1) / kJumpTile * kJumpTile);
-            long_first_lb.push_back((uint32_t)lb_block.size());
-        }
-    }
+    const uint32_t slice = getenv("SZB_LONG_SLICE") ? (uint32_t)((strtoul(getenv("SZB_LONG_SLICE"), nullptr, 10) + 31) / 32 * 32) : 0;
+    LongTables lt;
+    lt.clear();
+    if (path == 2) build_long_tables(frames.data(), blocks.data(), exec_list.data(), copies, slice, kJumpTile, lt);
+    const std::vector<uint32_t> &lb_block = lt.lb_block, &lb_slot = lt.lb_slot, &long_first_lb = lt.long_first_lb;
+    const std::vector<uint64_t> &long_dbase = lt.long_dbase;
     const uint32_t n_lb = (uint32_t)lb_block.size();
     std::vector<uint32_t> dist(long_dbase.back() + 1, 0xCDCDCDCDu), long_hist(3 * (size_t)n_lb + 3);
-    std::vector<uint64_t> long_T(3 * (size_t)n_lb + 3);
+    std::vector<uint64_t> long_T(3 * (size_t)n_lb + 3), ls_T(3 * lt.ls_lb.size() + 3, 0xABABABABABABABABull), ls_sum(2 * lt.ls_lb.size() + 2);
     std::vector<unsigned long long> long_err(copies, kLongNoError);
     unsigned long long ticket = 0;
     DeviceBatch a{};
@@ -385,6 +377,13 @@ int hostsim_stage4(const uint8_t *src, size_t len, uint8_t *out, size_t cap, siz
     a.long_hist = long_hist.data();
     a.long_err = long_err.data();
     a.long_ticket = &ticket;
+    a.n_ls = (uint32_t)lt.ls_lb.size();
+    a.long_slice = slice;
+    a.ls_lb = lt.ls_lb.data();
+    a.ls_seq0 = lt.ls_seq0.data();
+    a.lb_first_ls = lt.lb_first_ls.data();
+    a.ls_T = ls_T.data();
+    a.ls_sum = ls_sum.data();
 
     auto cta_order = [&](unsigned grid) {
         std::vector<unsigned> o(grid);
@@ -409,15 +408,19 @@ int hostsim_stage4(const uint8_t *src, size_t len, uint8_t *out, size_t cap, siz
         warpsim::launch(copies, 64, [&] { k_execute_pair(a, 0, copies); });
     }
     if (path == 2) {
-        const unsigned g_blocks = (n_lb + kWarpsPerCta - 1) / kWarpsPerCta;
+        const unsigned g_blocks = (n_lb + kWarpsPerCta - 1) / kWarpsPerCta, g_slices = (a.n_ls + kWarpsPerCta - 1) / kWarpsPerCta;
+        {
+            auto o = cta_order(g_slices);
+            warpsim::launch(g_slices, kCtaThreads, [&] { k_long_hist(a); }, &o);
+        }
         {
             auto o = cta_order(g_blocks);
-            warpsim::launch(g_blocks, kCtaThreads, [&] { k_long_hist(a); }, &o);
+            warpsim::launch(g_blocks, kCtaThreads, [&] { k_long_blockscan(a); }, &o);
         }
         warpsim::launch(copies, 32, [&] { k_long_compose(a); });
         {
-            auto o = cta_order(g_blocks);
-            warpsim::launch(g_blocks, kCtaThreads, [&] { k_long_emit(a); }, &o);
+            auto o = cta_order(g_slices);
+            warpsim::launch(g_slices, kCtaThreads, [&] { k_long_emit(a); }, &o);
         }
         {
             const unsigned tiles = (unsigned)(long_dbase.back() / kJumpTile);

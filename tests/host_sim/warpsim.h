@@ -180,6 +180,8 @@ template <class T, class S>
 inline T __shfl_sync(uint32_t, T v, S src) { return (T)warpsim::collective(warpsim::OP_SHFL, (uint64_t)v, (uint32_t)src); }
 template <class T, class S>
 inline T __shfl_up_sync(uint32_t, T v, S d) { return (T)warpsim::collective(warpsim::OP_SHFL_UP, (uint64_t)v, (uint32_t)d); }
+template <class T>
+inline T __shfl_xor_sync(uint32_t, T v, int mask) { return (T)warpsim::collective(warpsim::OP_SHFL, (uint64_t)v, (uint32_t)((warpsim::cur & 31) ^ mask)); }
 inline uint32_t __ballot_sync(uint32_t, bool p) { return (uint32_t)warpsim::collective(warpsim::OP_BALLOT, p, 0); }
 inline bool __any_sync(uint32_t, bool p) { return warpsim::collective(warpsim::OP_BALLOT, p, 0) != 0; }
 inline uint32_t __reduce_max_sync(uint32_t, uint32_t v) { return (uint32_t)warpsim::collective(warpsim::OP_REDUCE_MAX, v, 0); }

@@ -231,3 +231,49 @@ def test_long_frame_kernels_refill_variant(sim_refill, corpus):
     want = pyszo.decode_frame(f)
     rc, out = _stage4(sim_refill, f, len(want), K_LONG, 1, 0)
     assert rc == 0 and out == want
+
+
+@pytest.mark.parametrize("slice_seqs", [32, 96, 1024])
+def test_long_frame_kernels_with_sliced_blocks(sim, corpus, slice_seqs, monkeypatch):
+    """SZB_LONG_SLICE: k_long_hist / k_long_emit run one warp per slice of a block (k_long_blockscan gives every slice the
+    history and the positions it starts with).  Same bytes, same statuses."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import crafted_frames as crafted
+
+    monkeypatch.setenv("SZB_LONG_SLICE", str(slice_seqs))
+    done = 0
+    for k, (name, data, size, sha) in enumerate(corpus):
+        if size > (30_000 if slice_seqs < 1024 else 120_000):
+            continue
+        rc, out = _stage4(sim, data, size, K_LONG, [0, 1, 500 + k][k % 3], k % 2, 1)
+        assert rc == 0 and len(out) == size and hashlib.sha256(out).hexdigest() == sha, (name, slice_seqs)
+        done += 1
+    assert done >= 20
+    for k, (name, (frame, expected)) in enumerate(sorted(crafted.cases().items())):
+        rc, out = _stage4(sim, frame, len(expected), K_LONG, k % 3, 0)
+        assert rc == 0 and out == expected, name
+    f = cg.config3_single_frame(1 << 19, 20).frame(0)  # several blocks of ~12 000 sequences, matches across blocks
+    want = pyszo.decode_frame(f)
+    rc, out = _stage4(sim, f, len(want), K_LONG, 1, 0)
+    assert rc == 0 and out == want
+    if slice_seqs != 32:
+        return
+    # errors: the first failing round decides, whichever slice finds it
+    rng = np.random.default_rng(11)
+    small = [(n, d, s) for n, d, s, _ in corpus if 200 <= s <= 12_000 and len(d) >= 60]
+    errors = 0
+    for k in range(240):
+        name, data, size = small[k % len(small)]
+        buf = bytearray(data)
+        for _ in range(1 + k % 3):
+            p = int(rng.integers(10, len(buf) - 4))
+            buf[p] ^= 1 << int(rng.integers(0, 8))
+        frame = bytes(buf)
+        cap = size * 4 + 4096
+        a = _stage4(sim, frame, cap, K_EXECUTE, 0, 0)
+        b = _stage4(sim, frame, cap, K_LONG, k % 2, 0)
+        assert a == b, (name, k, a[0], b[0])
+        errors += a[0] in (-28, -30, -33)
+    assert errors >= 1
