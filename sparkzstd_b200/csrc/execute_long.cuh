@@ -5,10 +5,13 @@
 // block (sequence_execution.go:65-114).  k_execute keeps that order inside a frame (one warp per frame) and is parallel
 // over frames; a frame of gigabytes then runs on one warp.  The kernels here remove the two things that are sequential:
 //
-//   k_long_hist     the HISTORY: every block is walked with a symbolic history (an entry is a constant, or "entry i of
-//                   the history the block started with, minus k") -- the block's transfer function;
-//   k_long_compose  one warp per frame composes the transfer functions in block order: the history every block starts with;
-//   k_long_emit     one warp per block, every block at once: offsets through the (now known) history, positions by
+//   k_long_hist     the HISTORY: every block (or SLICE of a block: DeviceBatch::long_slice sequences, one warp each) is walked
+//                   with a symbolic history (an entry is a constant, or "entry i of the history the slice started with, minus
+//                   k") -- its transfer function; the sums of its literal and match lengths come out of the same walk;
+//   k_long_blockscan  one warp per block scans the functions and sums of the block's slices: what lies between the block's
+//                   start and every slice, and the block's whole function;
+//   k_long_compose  one warp per frame composes the blocks' functions in block order: the history every block starts with;
+//   k_long_emit     one warp per slice, every slice at once: offsets through the (now known) history, positions by
 //                   prefix sums; writes the literal bytes to their place and, for EVERY output byte, a DISTANCE cell:
 //                   0 for a literal byte, else how far back the byte's source lies (inside an overlapping match a
 //                   multiple of the offset, so that the source lies in front of the match: ringbuffer.go:236-262);
