@@ -215,7 +215,8 @@ int szb_batch_read_block_results(szb_batch *b, uint64_t *out_size, int32_t *stat
 
 /* Device-event timings of the last szb_batch_run / decode call, milliseconds:
  * [0] total, [1] Huffman literals, [2] FSE tables + sequences, [3] offset scan, [4] execution,
- * [5] H2D, [6] D2H, [7] the FSE table construction share of [2].  [1] and [2] are both measured from the
+ * [5] H2D, [6] D2H, [7] the FSE table construction share of [2], [8] the share of [4] spent resolving offsets and
+ * positions (k_resolve).  [1] and [2] are both measured from the
  * start of the step: the two chains run side by side on two streams.  Returns how many entries were written. */
 int szb_last_timing(szb_ctx *ctx, float *ms, int n);
 /* Kernel launches issued by the library since the context was created. */

@@ -25,11 +25,11 @@ struct szb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    cudaEvent_t ev[11] = {};
+    cudaEvent_t ev[13] = {};
     uint32_t *d_predef = nullptr;
     uint8_t *d_bytefill = nullptr;  // 256 rows of 256 equal bytes: the source of RLE literal runs (kernels.cuh, stage 4)
     std::string last_error;
-    float timing[8] = {};
+    float timing[10] = {};
     uint64_t launches = 0;
     int sm_count = 148;
     // grow-only staging for the host-pointer entry points
@@ -74,6 +74,7 @@ struct szb_batch {
     uint32_t *d_body_list = nullptr;
     uint32_t *d_exec_list = nullptr;
     uint32_t n_long = 0;  // leading entries of exec_list: long frames (execute_long.cuh, else k_execute_pair)
+    uint32_t n_noplace = 0;  // leading entries of exec_list that k_resolve / k_place leave to the other kernels
     LongTables lt;            // index tables of the block-parallel path (long_tables.h)
     uint32_t long_slice = 0;  // sequences per slice of a block (0: the whole block)
     bool long_jump = false;  // the block-parallel path is on for this batch
@@ -91,6 +92,13 @@ struct szb_batch {
     uint32_t *d_seq = nullptr;  // ll | ml | of
     uint16_t *d_seq_tabs = nullptr;  // FSE decode-table arena, kTabSlotWords 16-bit cells per block with sequences
     SeqInfo *d_seq_info = nullptr;
+    // frames one warp executes (place.cuh)
+    bool place = false;
+    std::vector<uint64_t> rec_off;
+    uint64_t rec_entries = 0, bm_bound = 0, bm_words = 0;
+    uint64_t *d_rec_off = nullptr;
+    void *d_place = nullptr;  // one allocation: rec | bm
+    int32_t *d_place_state = nullptr;
     bool entropy_done = false;
 };
 
@@ -250,7 +258,7 @@ uint64_t szb_launch_count(szb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int szb_last_timing(szb_ctx *ctx, float *ms, int n) {
     if (!ctx || !ms) return 0;
-    int k = n < 8 ? n : 8;
+    int k = n < 10 ? n : 10;
     for (int i = 0; i < k; i++) ms[i] = ctx->timing[i];
     return k;
 }
@@ -268,6 +276,11 @@ constexpr uint32_t kMaxLongFrames = 2368;
 // the block-parallel path 38-49 GB/s over everything it is given (profiles/r01k_bench_single*.json)
 // (one warp of k_long_emit needs ~3 ms for a 128 KiB block whatever the number of blocks: r01l_long_ncu_full_summary.txt)
 constexpr double kPairSeqPerMs = 24000.0, kJumpCellsPerMs = 40e6, kJumpFloorMs = 3.0;
+constexpr uint64_t kPlaceMaxSeqs = 16384;  // per frame, for k_resolve / k_place (place.cuh)
+#ifndef SZB_DEFAULT_EXEC_PLACE
+#define SZB_DEFAULT_EXEC_PLACE 0
+#endif
+constexpr bool kDefaultExecPlace = SZB_DEFAULT_EXEC_PLACE != 0;
 
 static int batch_upload_tables(szb_batch *b) {
     szb_ctx *ctx = b->ctx;
@@ -341,6 +354,47 @@ static int batch_upload_tables(szb_batch *b) {
         }
         if (!b->long_jump) b->lt.clear();
     }
+    // k_resolve / k_place (place.cuh): one entry per segment, one bitmap over the output positions.  The host
+    // only knows an upper bound of the output: a Raw/RLE block regenerates Block_Size bytes, a compressed one at most
+    // Block_Maximum_Size when the frame is valid, a frame that declares its content size no more than that; when the
+    // frames regenerate more, k_execute takes them (place_on).
+    {
+        const char *em = getenv("SZB_EXEC");
+        // k_resolve walks a frame with one lane: frames of more than kPlaceMaxSeqs sequences stay with k_execute
+        // (exec_list is sorted by sequences, most first)
+        const uint64_t max_seqs = getenv("SZB_PLACE_MAX_SEQS") ? strtoull(getenv("SZB_PLACE_MAX_SEQS"), nullptr, 10) : kPlaceMaxSeqs;
+        b->n_noplace = b->n_long;
+        {
+            std::vector<uint64_t> work(nf ? nf : 1, 0);
+            for (uint32_t i : b->seq_list) work[b->blocks[i].frame] += b->blocks[i].nseq;
+            while (b->n_noplace < nf && work[b->exec_list[b->n_noplace]] > max_seqs) b->n_noplace++;
+        }
+        // SZB_EXEC=place|legacy picks stage 4 for the frames one warp executes; the default is what measured faster on the
+        // headline workload (profiles/README.md, r02)
+        const bool want_place = em ? strcmp(em, "place") == 0 : kDefaultExecPlace;
+        b->place = want_place && nf > b->n_noplace;
+        b->rec_off.assign(nb ? nb : 1, 0);
+        uint64_t entries = 0, bound = 0;
+        if (b->place) {
+            for (uint32_t f = 0; f < nf; f++) {
+                const szb_frame_desc &fr = b->frames[f];
+                uint64_t fb = 0;
+                for (uint32_t i = fr.first_block; i < fr.first_block + fr.nblocks; i++) {
+                    const szb_block_desc &d = b->blocks[i];
+                    fb += d.type != 2 ? d.block_size : (d.nseq ? 128u * 1024u : d.lit_regen);
+                    if (d.type == 2 && d.nseq) {
+                        b->rec_off[i] = entries;
+                        entries += ((2 * (uint64_t)d.nseq + 1 + 3) & ~3ull) + 4;  // two segments per sequence + the literals after the last
+                    }
+                }
+                if (fr.has_content_size && fr.content_size < fb) fb = fr.content_size;
+                bound += fb;
+            }
+        }
+        b->rec_entries = entries + 64;
+        b->bm_bound = bound;
+        b->bm_words = ((bound + 256) / 32 + 4ull * nf + 64 + 3) & ~3ull;  // a line's four words are one 16-byte load
+    }
     // descriptor tables: one allocation, one H2D copy
     size_t o_frames = 0;
     size_t o_blocks = align_up(o_frames + sizeof(szb_frame_desc) * (size_t)nf, 256);
@@ -359,7 +413,8 @@ static int batch_upload_tables(szb_batch *b) {
     size_t o_lsl = align_up(o_ldb + 8 * lt.long_dbase.size(), 256);
     size_t o_lss = align_up(o_lsl + 4 * lt.ls_lb.size(), 256);
     size_t o_lfs = align_up(o_lss + 4 * lt.ls_seq0.size(), 256);
-    size_t total = align_up(o_lfs + 4 * lt.lb_first_ls.size(), 256) + 256;
+    size_t o_rec = align_up(o_lfs + 4 * lt.lb_first_ls.size(), 256);
+    size_t total = align_up(o_rec + 8 * (size_t)(nb ? nb : 1), 256) + 256;
     std::vector<uint8_t> &stage = b->stage;
     stage.assign(total, 0);
     if (nf) memcpy(stage.data() + o_frames, b->frames.data(), sizeof(szb_frame_desc) * (size_t)nf);
@@ -378,6 +433,7 @@ static int batch_upload_tables(szb_batch *b) {
     if (!lt.ls_lb.empty()) memcpy(stage.data() + o_lsl, lt.ls_lb.data(), 4 * lt.ls_lb.size());
     if (!lt.ls_seq0.empty()) memcpy(stage.data() + o_lss, lt.ls_seq0.data(), 4 * lt.ls_seq0.size());
     memcpy(stage.data() + o_lfs, lt.lb_first_ls.data(), 4 * lt.lb_first_ls.size());
+    memcpy(stage.data() + o_rec, b->rec_off.data(), 8 * b->rec_off.size());
     CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_tables, total));
     CUDA_TRY(ctx, cudaMemcpyAsync(b->d_tables, stage.data(), total, cudaMemcpyHostToDevice, ctx->stream));
     uint8_t *base = (uint8_t *)b->d_tables;
@@ -397,6 +453,7 @@ static int batch_upload_tables(szb_batch *b) {
     b->d_ls_lb = (uint32_t *)(base + o_lsl);
     b->d_ls_seq0 = (uint32_t *)(base + o_lss);
     b->d_lb_first_ls = (uint32_t *)(base + o_lfs);
+    b->d_rec_off = (uint64_t *)(base + o_rec);
     // mutable state
     size_t s_out_size = 0;
     size_t s_out_off = align_up(s_out_size + 8 * (size_t)nb, 256);
@@ -407,8 +464,9 @@ static int batch_upload_tables(szb_batch *b) {
     size_t s_lit = s_status;
     size_t s_seqs = s_lit + 4 * (size_t)nb;
     size_t s_fst = s_seqs + 4 * (size_t)nb;
-    b->status_bytes = 4 * (2 * (size_t)nb + (size_t)nf);
-    size_t s_end = align_up(s_fst + 4 * (size_t)nf, 256) + 256;
+    size_t s_pst = s_fst + 4 * (size_t)nf;
+    b->status_bytes = 4 * (2 * (size_t)nb + 2 * (size_t)nf);
+    size_t s_end = align_up(s_pst + 4 * (size_t)nf, 256) + 256;
     CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_state, s_end));
     CUDA_TRY(ctx, cudaMemsetAsync(b->d_state, 0, s_end, ctx->stream));
     base = (uint8_t *)b->d_state;
@@ -420,6 +478,7 @@ static int batch_upload_tables(szb_batch *b) {
     b->d_lit_status = (int32_t *)(base + s_lit);
     b->d_seq_status = (int32_t *)(base + s_seqs);
     b->d_frame_status = (int32_t *)(base + s_fst);
+    b->d_place_state = (int32_t *)(base + s_pst);
     // scratch arenas
     CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_litbuf, (size_t)b->literal_bytes + 256));
     CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_seq, (size_t)(b->sequences * 3 + 64) * 4));
@@ -427,6 +486,7 @@ static int batch_upload_tables(szb_batch *b) {
     CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_seq_info, (b->seq_list.size() + 1) * sizeof(SeqInfo)));
     CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_huf_tabs, (b->hufo_list.size() + 1) * (size_t)(2u << kMaxHufBits)));
     CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_huf_info, (b->hufo_list.size() + 1) * sizeof(HufInfo)));
+    if (b->place) CUDA_TRY(ctx, pool_alloc(ctx, &b->d_place, 4 * (size_t)(b->rec_entries + b->bm_words) + 256));
     return SZB_OK;
 }
 
@@ -516,7 +576,7 @@ int szb_batch_create(szb_ctx *ctx, const uint8_t *h_src, size_t src_len, const u
 static void batch_release_scratch(szb_batch *b) {
     szb_ctx *ctx = b->ctx;
     void **p[] = {(void **)&b->d_litbuf, (void **)&b->d_seq, (void **)&b->d_seq_tabs, (void **)&b->d_seq_info, (void **)&b->d_huf_tabs,
-                  (void **)&b->d_huf_info, &b->d_long};
+                  (void **)&b->d_huf_info, &b->d_long, &b->d_place};
     for (void **q : p) {
         pool_free(ctx, *q);
         *q = nullptr;
@@ -536,6 +596,7 @@ void szb_batch_destroy(szb_batch *b) {
     pool_free(b->ctx, b->d_huf_tabs);
     pool_free(b->ctx, b->d_huf_info);
     pool_free(b->ctx, b->d_long);
+    pool_free(b->ctx, b->d_place);
     delete b;
 }
 
@@ -598,6 +659,12 @@ static DeviceBatch make_args(szb_batch *b, const void *d_src, void *d_dst, size_
     a.long_hist = nullptr;
     a.long_err = nullptr;
     a.long_ticket = nullptr;
+    a.rec = b->place && b->d_place ? (uint32_t *)b->d_place : nullptr;
+    a.rec_off = b->d_rec_off;
+    a.bm = a.rec ? a.rec + b->rec_entries : nullptr;
+    a.bm_bound = b->bm_bound;
+    a.place_state = a.rec ? b->d_place_state : nullptr;
+    a.n_noplace = b->n_noplace;
     return a;
 }
 
@@ -657,6 +724,12 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     DeviceBatch a = make_args(b, d_src, d_dst, dst_cap);
+    if (a.nframes && a.rec) {  // place.cuh: every frame k_place will execute, walked in order by one lane
+        k_place_zero<<<ctx->sm_count * 8, 256, 0, s>>>(a);
+        k_resolve<<<(a.nframes + kResolveWarps * 32 - 1) / (kResolveWarps * 32), kResolveWarps * 32, 0, s>>>(a);
+        ctx->launches += 2;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[11], s));
     if (a.nframes) {
         k_frame_verdict<<<(a.nframes + 3) / 4, 128, 0, s>>>(a);
         ctx->launches++;
@@ -720,7 +793,12 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
             }
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, sl));
         }
-        if (n_rest) {
+        if (a.rec) {
+            const uint32_t n_place = a.nframes - b->n_noplace;
+            k_place<<<(n_place + kPlaceWarps - 1) / kPlaceWarps, kPlaceWarps * 32, 0, s>>>(a, b->n_noplace, n_place);
+            ctx->launches++;
+        }
+        if (n_rest) {  // with k_place on: only the frames it could not take (place_on)
             k_execute<<<(n_rest + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, s>>>(a, n_long, n_rest);
             ctx->launches++;
         }
@@ -747,6 +825,8 @@ static int collect_timing(szb_ctx *ctx) {
     ctx->timing[4] = t;
     CUDA_TRY(ctx, cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[7]));
     ctx->timing[7] = t;  // table construction share of [2]
+    CUDA_TRY(ctx, cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[11]));
+    ctx->timing[8] = t;  // k_resolve's share of [4]
     return SZB_OK;
 }
 

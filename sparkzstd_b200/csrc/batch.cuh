@@ -79,6 +79,16 @@ struct DeviceBatch {
     uint32_t *long_hist;            // per lb_block entry: the history the block starts with (3 entries)
     unsigned long long *long_ticket;  // k_long_jump hands out its tiles in address order
     unsigned long long *long_err;   // per long frame: the first error found while emitting (block << 40 | round << 8 | -code)
+    // frames one warp executes (place.cuh): k_resolve -> k_place; nullptr: k_execute takes them all
+    uint32_t *rec;                  // per block with sequences, at rec_off[block]: one entry per segment (literal run or match) in
+                                    // output order: a match's offset (through the repeat history), or bit 31 | the match bytes
+                                    // of the block in front of the literal run
+    const uint64_t *rec_off;        // per block: its first entry in rec (multiples of 4)
+    uint32_t *bm;                   // bitmap over output positions: a segment starts here
+    uint64_t bm_bound;              // output bytes the bitmap was sized for (the host's upper bound)
+    int32_t *place_state;           // per frame: 0 = k_place executes it, < 0 = the error k_resolve found, 1 = k_execute's
+    uint32_t n_noplace;             // exec_list[0, n_noplace): the long frames and the frames with too many sequences for one lane
+                                    // of k_resolve to walk (k_execute's)
 };
 
 #if defined(__CUDACC__) || defined(SZB_WARPSIM)  // device code, or the host-side warp emulator of tests/host_sim

@@ -179,8 +179,8 @@ struct ExecState {  // the consumer's side
     uint32_t seen;  // segments that start below line + head
 };
 
-// Produces the bytes [lo, hi) of the line at st.line (positions relative to the line; kFull: all 128).
-template <bool kFull>
+// Produces the bytes [lo, hi) of the line at st.line (positions relative to the line; kWhole: all 128).
+template <bool kWhole>
 __device__ __forceinline__ void place_step(ExecSmem &sm, uint8_t *dst, ExecState &st, uint32_t lo, uint32_t hi, uint32_t lane,
                                            uint32_t le_mask) {
     uint32_t *bw = &sm.bits[(uint32_t)(st.line >> 5) & (kRingBits / 32 - 1)];
@@ -198,7 +198,7 @@ __device__ __forceinline__ void place_step(ExecSmem &sm, uint8_t *dst, ExecState
         const uint32_t rel = (c << 5) + lane;
         const uint32_t ord = last + __popc(m[c] & le_mask);  // the last segment that starts at or before my byte
         last += __popc(m[c]);
-        const bool live = kFull || (rel >= lo && rel < hi);
+        const bool live = kWhole || (rel >= lo && rel < hi);
         const uint64_t src = sm.seg[ord & (kSegRing - 1)] + my_pos + (c << 5);
         // Sources in [low_addr, my own address) repeat a byte of this step that is not in memory yet.  Only a match can
         // point there, and a line does not straddle a 4 GiB boundary: compare the low words, then the high ones.
@@ -252,7 +252,7 @@ __device__ __forceinline__ void place_step(ExecSmem &sm, uint8_t *dst, ExecState
     const uint32_t wrel = lane << 2;
     const uint32_t word = reinterpret_cast<const uint32_t *>(sm.grp)[lane];
     uint8_t *out = dst + st.line;
-    if (kFull || (wrel >= lo && wrel + 4 <= hi)) {
+    if (kWhole || (wrel >= lo && wrel + 4 <= hi)) {
         *reinterpret_cast<uint32_t *>(out + wrel) = word;
     } else {
 #pragma unroll
@@ -353,14 +353,20 @@ __global__ void k_frame_verdict(DeviceBatch a) {
     const szb_frame_desc fr = a.frames[f];
     const uint32_t b0 = fr.first_block, nb = fr.nblocks;
     int err = SZB_OK;
-    for (uint32_t i0 = 0; i0 < nb; i0 += 32) {
-        int e = SZB_OK;
-        if (i0 + lane < nb) {
-            const int ls = a.lit_status[b0 + i0 + lane], ss = a.seq_status[b0 + i0 + lane];
-            if ((ls | ss) != 0) e = ls ? ls : ss;
+    // k_resolve walked the frame in order (place.cuh): its verdict covers the blocks' entropy stages and the execution
+    const int ps = a.place_state ? a.place_state[f] : 1;
+    if (ps <= 0) {
+        err = ps;
+    } else {
+        for (uint32_t i0 = 0; i0 < nb; i0 += 32) {
+            int e = SZB_OK;
+            if (i0 + lane < nb) {
+                const int ls = a.lit_status[b0 + i0 + lane], ss = a.seq_status[b0 + i0 + lane];
+                if ((ls | ss) != 0) e = ls ? ls : ss;
+            }
+            err = warp_first_error(e);
+            if (err != SZB_OK) break;
         }
-        err = warp_first_error(e);
-        if (err != SZB_OK) break;
     }
     if (lane != 0) return;
     if (err == SZB_OK) err = fr.status;  // blocks after a failing header are absent from the table
@@ -636,6 +642,7 @@ __device__ __forceinline__ void produce_frame(const DeviceBatch &a, uint32_t f, 
 }
 
 #include "execute_long.cuh"
+#include "place.cuh"
 
 // One warp per frame: it produces the segments and consumes them.  Frames exec_list[first_slot, first_slot + n_slots).
 #ifndef SZB_EXEC_MIN_CTAS
@@ -648,6 +655,7 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
     if (slot >= n_slots) return;
     const uint32_t f = a.exec_list[first_slot + slot];
     if (a.frame_status[f] != SZB_OK) return;  // k_frame_verdict
+    if (a.place_state && a.place_state[f] != 1) return;  // k_place executes it (place.cuh)
     ExecSmem &sm = smem[threadIdx.x >> 5];
     for (uint32_t wd = lane; wd < kRingBits / 32; wd += 32) sm.bits[wd] = 0;
     __syncwarp();

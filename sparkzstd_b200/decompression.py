@@ -99,9 +99,9 @@ class Context:
         return int(self._L.szb_launch_count(self._h))
 
     def last_timing(self) -> dict:
-        ms = (C.c_float * 8)()
-        self._L.szb_last_timing(self._h, ms, 8)
-        keys = ("total", "huffman_literals", "sequences", "scan", "execute", "h2d", "d2h", "seq_tables")
+        ms = (C.c_float * 10)()
+        self._L.szb_last_timing(self._h, ms, 10)
+        keys = ("total", "huffman_literals", "sequences", "scan", "execute", "h2d", "d2h", "seq_tables", "resolve")
         return dict(zip(keys, [float(x) for x in ms]))
 
     def _raise(self, rc: int):

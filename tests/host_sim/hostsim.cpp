@@ -167,6 +167,9 @@ int sequences_block(const uint8_t *src, const szb_block_desc *blocks, uint32_t b
 }  // namespace
 
 extern "C" {
+int hostsim_stage4_at(const uint8_t *src, size_t len, uint8_t *out, size_t cap, size_t *out_len, int path, int order, int two_frames,
+                      int verify_checksum, int *exec_err);
+
 
 // Decodes ONE frame with walker + serial device functions + a plain serial executor.
 // Optional per-block capture: lit_out (concatenated Huffman-decoded literals, block order).
@@ -250,6 +253,9 @@ int hostsim_decode_frame(const uint8_t *src, size_t len, uint8_t *out, size_t ca
 // k_frame_verdict, k_execute_bodies and, by `path`,
 //   0: k_execute (one warp per frame)   1: k_execute_pair (producer warp + consumer warp)
 //   2: the block-parallel kernels of execute_long.cuh, with k_execute_pair launched beside them as the fallback.
+//   3: k_resolve + k_place (place.cuh), with k_execute launched behind them as the fallback, as launch_execute does;
+//      4: the same with bitmaps too small for the output, so that every frame falls back to k_execute.
+//      (lines are aligned to memory, not to the output: callers also pass an `out` that is not 128-byte aligned)
 // order: 0 = CTAs in launch order, 1 = reversed (the worst case for k_long_jump), >= 2 = shuffled with that seed.
 // With two_frames the same frame is decoded twice in one batch and both copies must agree.
 // verify_checksum: 1 = also run k_verify_checksums; 2 = then flip an output byte and expect the mismatch (returns 3; 2 when the
@@ -257,6 +263,13 @@ int hostsim_decode_frame(const uint8_t *src, size_t len, uint8_t *out, size_t ca
 // Returns the frame's status; 1 when path 2 left the frame to its fallback (and the fallback decoded it).
 int hostsim_stage4(const uint8_t *src, size_t len, uint8_t *out, size_t cap, size_t *out_len, int path, int order, int two_frames,
                    int verify_checksum) {
+    return hostsim_stage4_at(src, len, out, cap, out_len, path, order, two_frames, verify_checksum, nullptr);
+}
+
+// The same; exec_err (when given) receives the status the frame ends with even when it is an error (statuses are compared
+// with the oracle's codes).
+int hostsim_stage4_at(const uint8_t *src, size_t len, uint8_t *out, size_t cap, size_t *out_len, int path, int order, int two_frames,
+                      int verify_checksum, int *exec_err) {
     uint64_t off = 0, flen = len;
     szb_walk *w = nullptr;
     *out_len = 0;
@@ -384,6 +397,35 @@ int hostsim_stage4(const uint8_t *src, size_t len, uint8_t *out, size_t cap, siz
     a.lb_first_ls = lt.lb_first_ls.data();
     a.ls_T = ls_T.data();
     a.ls_sum = ls_sum.data();
+    // place.cuh, as batch_upload_tables / make_args (api.cu)
+    std::vector<uint64_t> rec_off(nb ? nb : 1, 0);
+    uint64_t rec_entries = 0, bm_bound = 0;
+    for (uint32_t c = 0; c < copies; c++) {
+        uint64_t fbound = 0;
+        for (uint32_t i = c * nb1; i < (c + 1) * nb1; i++) {
+            const szb_block_desc &d = blocks[i];
+            fbound += d.type != 2 ? d.block_size : (d.nseq ? 128u * 1024u : d.lit_regen);
+            if (d.type == 2 && d.nseq) {
+                rec_off[i] = rec_entries;
+                rec_entries += ((2 * (uint64_t)d.nseq + 1 + 3) & ~3ull) + 4;
+            }
+        }
+        if (fr0.has_content_size && fr0.content_size < fbound) fbound = fr0.content_size;
+        bm_bound += fbound;
+    }
+    if (path == 4) bm_bound = total ? total - 1 : 0;
+    rec_entries += 64;
+    const uint64_t bm_words = ((bm_bound + 256) / 32 + 4ull * copies + 64 + 3) & ~3ull;
+    std::vector<uint32_t> place_mem(rec_entries + bm_words, 0xA5A5A5A5u);
+    std::vector<int32_t> place_state(copies, -77);
+    if (path == 3 || path == 4) {
+        a.rec = place_mem.data();
+        a.rec_off = rec_off.data();
+        a.bm = a.rec + rec_entries;
+        a.bm_bound = bm_bound;
+        a.place_state = place_state.data();
+        a.n_long = 0;
+    }
 
     auto cta_order = [&](unsigned grid) {
         std::vector<unsigned> o(grid);
@@ -395,6 +437,10 @@ int hostsim_stage4(const uint8_t *src, size_t len, uint8_t *out, size_t cap, siz
     // launch_entropy's last kernel, then launch_execute (api.cu)
     warpsim::launch(1, kScanThreads, [&] { k_scan_blocks(a); });
     if (dev_total != total) return SZB_ERR_INVALID_ARGUMENT;
+    if (a.rec) {
+        warpsim::launch(3, 256, [&] { k_place_zero(a); });
+        warpsim::launch((copies + kResolveWarps * 32 - 1) / (kResolveWarps * 32), kResolveWarps * 32, [&] { k_resolve(a); });
+    }
     warpsim::launch((copies + 3) / 4, 128, [&] { k_frame_verdict(a); });
     if (a.n_body) {
         const unsigned g = (a.n_body + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -402,7 +448,12 @@ int hostsim_stage4(const uint8_t *src, size_t len, uint8_t *out, size_t cap, siz
         warpsim::launch(g, kCtaThreads, [&] { k_execute_bodies(a); }, &o);
     }
     bool fallback = false;
-    if (path == 0) {
+    if (path == 3 || path == 4) {
+        for (uint32_t c = 0; c < copies; c++)
+            if (place_state[c] != (total > bm_bound ? kPlaceFallback : (frame_status[c] == SZB_ERR_DST_TOO_SMALL ? 0 : frame_status[c]))) return SZB_ERR_INVALID_ARGUMENT;
+        warpsim::launch((copies + kPlaceWarps - 1) / kPlaceWarps, kPlaceWarps * 32, [&] { k_place(a, 0, copies); });
+        warpsim::launch((copies + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, [&] { k_execute(a, 0, copies); });
+    } else if (path == 0) {
         warpsim::launch((copies + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, [&] { k_execute(a, 0, copies); });
     } else {
         warpsim::launch(copies, 64, [&] { k_execute_pair(a, 0, copies); });
@@ -438,6 +489,7 @@ int hostsim_stage4(const uint8_t *src, size_t len, uint8_t *out, size_t cap, siz
                 if (dist[i] != 0xCDCDCDCDu) return SZB_ERR_INVALID_ARGUMENT;
         }
     }
+    if (exec_err) *exec_err = frame_status[0];
     for (uint32_t c = 0; c < copies; c++)
         if (frame_status[c] != SZB_OK) return frame_status[c];
     if (verify_checksum) {  // SZB_FLAG_VERIFY_CHECKSUM: XXH64 of the output against the frame's trailer

@@ -30,6 +30,10 @@
 struct alignas(16) uint4 {
     uint32_t x, y, z, w;
 };
+struct alignas(8) uint2 {
+    uint32_t x, y;
+};
+inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 
 namespace warpsim {
@@ -187,6 +191,12 @@ inline bool __any_sync(uint32_t, bool p) { return warpsim::collective(warpsim::O
 inline uint32_t __reduce_max_sync(uint32_t, uint32_t v) { return (uint32_t)warpsim::collective(warpsim::OP_REDUCE_MAX, v, 0); }
 inline void __syncwarp() { warpsim::collective(warpsim::OP_BALLOT, 0, 0); }
 inline void __syncthreads() { warpsim::collective(warpsim::OP_CTA_BARRIER, 0, 0); }
+inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
+    const uint64_t t = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((t >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+    return r;
+}
 inline int __ffs(uint32_t v) { return __builtin_ffs((int)v); }
 inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t shift) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (shift & 31)); }

@@ -12,6 +12,14 @@ from tools import corpus as cg
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["legacy", "place"])
+def stage4_path(request, monkeypatch):
+    """Every test runs twice: stage 4 of the frames one warp executes by k_execute, and by k_resolve + k_place
+    (SZB_EXEC is read when a batch's tables are built)."""
+    monkeypatch.setenv("SZB_EXEC", request.param)
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def ctx():
     from sparkzstd_b200.decompression import Context

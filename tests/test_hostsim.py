@@ -20,7 +20,7 @@ SIM = os.path.join(ROOT, "tests", "host_sim")
 def _build_sim(lib_name, defines=()):
     lib = os.path.join(SIM, lib_name)
     srcs = [os.path.join(SIM, "hostsim.cpp"), os.path.join(ROOT, "sparkzstd_b200", "csrc", "walker.cpp")]
-    deps = srcs + [os.path.join(SIM, "warpsim.h")] + [os.path.join(ROOT, "sparkzstd_b200", "csrc", f) for f in ("bits.cuh", "fse.cuh", "huffman.cuh", "sequences.cuh", "batch.cuh", "execute.cuh", "execute_long.cuh")]
+    deps = srcs + [os.path.join(SIM, "warpsim.h")] + [os.path.join(ROOT, "sparkzstd_b200", "csrc", f) for f in ("bits.cuh", "fse.cuh", "huffman.cuh", "sequences.cuh", "batch.cuh", "execute.cuh", "execute_long.cuh", "place.cuh")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", *[f"-D{d}" for d in defines], "-o", lib, *srcs], check=True)
     L = C.CDLL(lib)
@@ -130,6 +130,92 @@ def test_long_frame_kernels_on_crafted_frames(sim):
     big, expected = crafted.oversize_block_case()
     rc, out = _decode_long(sim, big, len(expected), 0, 1)
     assert rc == 1 and out == expected  # 1: left to k_execute_pair, which decoded it
+
+
+# ---- k_resolve + k_place (place.cuh): one lane per frame resolves, one warp per frame places ----
+K_PLACE, K_PLACE_FALLBACK = 3, 4
+
+
+def _stage4_at(L, data: bytes, cap: int, path: int, two: int, checksum: int = 0, mis: int = 0):
+    """`mis`: the output starts that many bytes into a 128-byte aligned allocation (lines are lines of memory)."""
+    L.hostsim_stage4_at.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.POINTER(C.c_int)]
+    raw = np.empty(2 * cap + 512, dtype=np.uint8)
+    base = (-raw.ctypes.data) % 128 + mis
+    out = raw[base:]
+    n = C.c_size_t()
+    err = C.c_int(1)  # stays 1 when the frame fails before stage 4
+    rc = L.hostsim_stage4_at(data, len(data), out.ctypes.data, 2 * cap + 16, C.byref(n), path, 0, two, checksum, C.byref(err))
+    _stage4_at.exec_status = err.value
+    return rc, out[: n.value].tobytes()
+
+
+def test_place_kernels_decode_golden_frames(sim, corpus):
+    done = 0
+    for k, (name, data, size, sha) in enumerate(corpus):
+        if size > 60_000:
+            continue
+        rc, out = _stage4_at(sim, data, size, K_PLACE, k % 2, 1, (k * 37) % 128)
+        assert rc == 0 and len(out) == size and hashlib.sha256(out).hexdigest() == sha, name
+        done += 1
+    assert done >= 20
+    for k, (name, data, size, sha) in enumerate(corpus[:30]):  # bitmaps too small: every frame is left to k_execute
+        if not (0 < size <= 30_000):
+            continue
+        rc, out = _stage4_at(sim, data, size, K_PLACE_FALLBACK, k % 2, 0, (k * 11) % 128)
+        assert rc == 0 and hashlib.sha256(out).hexdigest() == sha, name
+
+
+def test_place_kernels_on_crafted_and_synthetic_frames(sim):
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import crafted_frames as crafted
+
+    for k, (name, (frame, expected)) in enumerate(sorted(crafted.cases().items())):
+        for mis in (0, 1 + (k * 29) % 127):
+            rc, out = _stage4_at(sim, frame, len(expected), K_PLACE, k % 2, 0, mis)
+            assert rc == 0 and out == expected, (name, mis)
+    big, expected = crafted.oversize_block_case()  # more output than the host's bound: k_execute's
+    rc, out = _stage4_at(sim, big, len(expected), K_PLACE, 0, 0, 5)
+    assert rc == 0 and out == expected
+    for c in (cg.config2_text_frames(3), cg.config3_single_frame(1 << 19, 20), cg.config5_mixed(1 << 20, with_golden=False)):
+        for i in range(min(c.nframes, 4)):
+            f = c.frame(i)
+            want = pyszo.decode_frame(f)
+            if len(want) > 600_000:
+                continue
+            rc, out = _stage4_at(sim, f, len(want), K_PLACE, i % 2, 0, (i * 53) % 128)
+            assert rc == 0 and out == want, (c.name, i)
+
+
+def test_place_kernels_report_the_oracles_errors(sim, corpus):
+    """k_resolve walks a frame in the reference's order, so a corrupted frame ends with the reference's error (the oracle's code),
+    not just with some error: bit flips in small golden frames; whatever still decodes must decode to the oracle's bytes."""
+    rng = np.random.default_rng(5)
+    small = [(n, d, s) for n, d, s, _ in corpus if 200 <= s <= 12_000 and len(d) >= 60]
+    same_bytes = same_code = 0
+    for k in range(400):
+        name, data, size = small[k % len(small)]
+        buf = bytearray(data)
+        for _ in range(1 + k % 3):
+            p = int(rng.integers(10, len(buf) - 4))
+            buf[p] ^= 1 << int(rng.integers(0, 8))
+        frame = bytes(buf)
+        want, code = None, 0
+        try:
+            want = pyszo.decode_frame(frame)
+        except pyszo.OracleError as e:
+            code = e.code
+        cap = max(size, len(want) if want is not None else 0, 1) * 4 + 4096
+        rc, out = _stage4_at(sim, frame, cap, K_PLACE, k % 2, 0, (k * 7) % 128)
+        if want is not None and rc == 0:
+            assert out == want, (name, k)
+            same_bytes += 1
+        elif _stage4_at.exec_status < 0:  # found while executing (stages 1-3 were fine)
+            assert rc == _stage4_at.exec_status == code, (name, k, rc, code)
+            same_code += 1
+    assert same_bytes >= 60 and same_code >= 3
 
 
 @pytest.mark.parametrize("nblocks", [1, 31, 32, 33, 64, 100, 1000])
