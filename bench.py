@@ -185,6 +185,32 @@ def cpu_reference_arm(args, c, rank, world):
     }
 
 
+def ncu_traffic(workload: str, nframes: int, stage_name: str):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels of one stage, from the newest
+    profiles/*_ncu_traffic.json -- written by scripts/ncu_traffic.py from an `ncu --set full` capture of this command and stamped
+    with the commit it was taken on.  None when no capture of this workload and size exists."""
+    import glob
+
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_traffic.json"))):
+        try:
+            with open(f) as fh:
+                d = json.load(fh)
+        except (OSError, ValueError):
+            continue
+        if d.get("workload") == workload and int(d.get("frames", -1)) == int(nframes):
+            best = (f, d)
+    if best is None:
+        return None, None
+    f, d = best
+    names = d.get("stages", {}).get(stage_name, [])
+    tot = sum(d["kernels"][k]["dram_read"] + d["kernels"][k]["dram_write"] for k in names if k in d["kernels"])
+    if not tot:
+        return None, None
+    return float(tot), (f"{os.path.relpath(f, ROOT)} (commit {d.get('commit', '?')}): dram__bytes_read.sum + dram__bytes_write.sum "
+                        f"per launch of {', '.join(k for k in names if k in d['kernels'])}")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -349,32 +375,37 @@ def main():
         return 0
 
     peak, peak_src = measured_peak()
-    # roofline for the dominant kernel (largest share of the step)
+    # Roofline.  ALGORITHMIC bytes only: what a stage must read and write whatever its implementation --
+    # intermediate traffic (sequence arrays, literal buffers, segment lists) lowers the achievable fraction, it does not count.
+    #   stage 2 (Huffman literals): compressed literal bytes read + regenerated literal bytes written
+    #   stage 3 (FSE sequences):    sequences-section bytes read (everything of the compressed blocks that is not literals)
+    #   stage 4 (execution):        D + M: decompressed bytes written + match-source bytes read
+    # The headline is the PIPELINE fraction (C + D + M) / t_step; `frac` is the same for the stage that takes longest.
     kernels = {
         "k_huffman_literals": {"ms": stage["huffman_literals"], "bytes": lit_comp + lit_huf},
-        "k_sequences": {"ms": stage["sequences"], "bytes": (C_bytes - lit_comp) + 12 * nseq},
+        "k_sequences": {"ms": stage["sequences"], "bytes": C_bytes - lit_comp},
         "k_scan_blocks": {"ms": stage["scan"], "bytes": 16 * len(blocks)},
-        "k_execute": {"ms": stage["execute"], "bytes": D + M + lit_huf + 12 * nseq},
+        "k_execute": {"ms": stage["execute"], "bytes": D + M},
     }
-    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of one ncu --set full capture of this very
-    # command, profiles/r01c_ncu_full_summary.txt; only the default workload at its default size was captured.
-    ncu_traffic = {}
-    if args.workload == "text" and c.nframes == 65536:
-        ncu_traffic = {"k_execute": 21.316e9 + 4.339e9, "k_sequences": 1.236e9 + 4.687e9, "k_huffman_literals": 0.812e9 + 0.996e9}
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
     dom_ach = kernels[dom]["bytes"] / max(kernels[dom]["ms"], 1e-6) / 1e6
     pipe_ach = (C_bytes + D + M) / (ms_step * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(args.workload, c.nframes, dom)
     roofline = {
-        "bound": "hbm", "kernel": dom, "achieved": dom_ach, "peak": peak, "unit": "GB/s", "frac": dom_ach / peak, "traffic": ncu_traffic.get(dom),
-        "traffic_unit": "bytes per launch, ncu dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01c_ncu_full_summary.txt)",
-        "peak_source": peak_src,
-        "kernel_bytes": "bytes this kernel must read+write per launch (DESIGN.md section 5)",
+        "bound": "hbm", "kernel": dom, "achieved": dom_ach, "peak": peak, "unit": "GB/s", "frac": dom_ach / peak, "traffic": traffic,
+        "traffic_source": traffic_src, "peak_source": peak_src,
+        "kernel_bytes": "algorithmic bytes of that stage per launch (SURVEY.md 8d; DESIGN.md section 4): stage 4 D + M, stage 3 the "
+                        "sequences sections, stage 2 compressed + regenerated literals",
+        "headline": "pipeline.frac",
         "pipeline": {"algorithmic_bytes": C_bytes + D + M, "C": C_bytes, "D": D, "M": M, "achieved": pipe_ach, "frac": pipe_ach / peak,
                      "frac_of_8TBps_nominal": pipe_ach / 8000.0},
         "stages_ms": {k: v["ms"] for k, v in kernels.items()},
+        "stage4_ms": {"k_resolve": stage.get("resolve", 0.0), "rest": stage["execute"] - stage.get("resolve", 0.0)},
+        "stage4_path": os.environ.get("SZB_EXEC", "default"),
         "stages_note": "k_huffman_literals and k_sequences run side by side on two streams; each is measured from the start of the step; "
-                       "k_execute is all of stage 4: k_frame_verdict, k_execute_bodies, k_execute and, for frames with >= 65 536 sequences, "
-                       "k_execute_pair or the block-parallel kernels k_long_* (execute_long.cuh), whichever the host picked for the batch",
+                       "k_execute is all of stage 4: (k_place_zero, k_resolve,) k_frame_verdict, k_execute_bodies, k_execute or k_place and, "
+                       "for frames with >= 65 536 sequences, k_execute_pair or the block-parallel kernels k_long_* (execute_long.cuh), "
+                       "whichever the host picked for the batch",
     }
 
     cpu = None

@@ -175,6 +175,18 @@ int szb_decode_batch(szb_ctx *ctx, const uint8_t *src, size_t src_len, const uin
                      const uint64_t *frame_len, uint32_t nframes, uint8_t *dst, size_t dst_cap, uint64_t *out_off,
                      uint64_t *out_len, int32_t *status, uint32_t flags);
 
+/* A `.zst` stream as the zstd tools write it: frames back to back, skippable frames (magic 0x184D2A5?) in between,
+ * a content checksum after a frame when its header says so.  The frames are discovered by the header walk, decoded as one
+ * batch and written back to back into dst (so dst holds the stream's content).  out_off/out_len/status (each max_frames
+ * long, host; any may be NULL) receive every frame's placement and result; *nframes_out the number of frames found.
+ * SZB_ERR_INVALID_ARGUMENT when the stream holds more than max_frames frames and per-frame arrays were given;
+ * trailing bytes that are no frame end the walk with that frame's error (SZB_ERR_WRONG_MAGICNUMBER).
+ * NOT a reference behaviour: the reference decodes exactly one frame per reader (framedecompressor.go:130-150) and knows no
+ * skippable frames; SURVEY.md section 8f-1. */
+int szb_decode_stream(szb_ctx *ctx, const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap, uint64_t *out_off,
+                      uint64_t *out_len, int32_t *status, uint32_t max_frames, uint32_t *nframes_out, uint64_t *total_out,
+                      uint32_t flags);
+
 /* Descriptor-level entry: what the Go walker feeds.  d_src / d_dst are DEVICE pointers,
  * frames / blocks are HOST tables (copied before return).  replaces: DecodeNextBlockContent +
  * ExecuteSequences + the Raw/RLE bodies of DecodeNextBlock (framedecompressor.go:93-126,

@@ -22,6 +22,8 @@ def main(argv=None) -> int:
     ap.add_argument("files", nargs="+", help="X.zst files; X is used as the expected output when present")
     ap.add_argument("--verify-checksum", action="store_true", help="also verify the content checksum (not done by the reference)")
     ap.add_argument("-o", "--output-dir", help="write decoded files here")
+    ap.add_argument("--stream", action="store_true", help="treat every file as a zstd stream: concatenated frames, skippable frames "
+                    "(szb_decode_stream; the reference decodes exactly one frame per file)")
     args = ap.parse_args(argv)
 
     from . import decompression as D
@@ -34,22 +36,26 @@ def main(argv=None) -> int:
     for path in args.files:
         t0 = time.perf_counter()
         try:
-            with open(path, "rb") as f:
-                comp.Reset(f)
-                chunks = []
-                while True:
-                    c = comp.Read(1 << 20)
-                    if not c:
-                        break
-                    chunks.append(c)
-            out = b"".join(chunks)
-            if args.verify_checksum:
-                data = np.fromfile(path, dtype=np.uint8)
-                dst = np.empty(max(len(out), 1), dtype=np.uint8)
-                _, _, st = ctx.decode_batch_into(np.concatenate([data, np.zeros(8, np.uint8)]), np.array([0], np.uint64),
-                                                 np.array([len(data)], np.uint64), dst, verify_checksum=True)
-                if st[0] != 0:
-                    raise D.error_for(int(st[0]))
+            if args.stream:
+                with open(path, "rb") as f:
+                    out = ctx.decode_stream(f.read(), verify_checksum=args.verify_checksum)
+            else:
+                with open(path, "rb") as f:
+                    comp.Reset(f)
+                    chunks = []
+                    while True:
+                        c = comp.Read(1 << 20)
+                        if not c:
+                            break
+                        chunks.append(c)
+                out = b"".join(chunks)
+                if args.verify_checksum:
+                    data = np.fromfile(path, dtype=np.uint8)
+                    dst = np.empty(max(len(out), 1), dtype=np.uint8)
+                    _, _, st = ctx.decode_batch_into(np.concatenate([data, np.zeros(8, np.uint8)]), np.array([0], np.uint64),
+                                                     np.array([len(data)], np.uint64), dst, verify_checksum=True)
+                    if st[0] != 0:
+                        raise D.error_for(int(st[0]))
         except Exception as e:  # the reference prints the error and goes on to the next file
             failed += 1
             print(f"{path}: ERROR {e}")

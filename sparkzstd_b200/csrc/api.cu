@@ -1244,6 +1244,37 @@ int szb_decode_batch(szb_ctx *ctx, const uint8_t *src, size_t src_len, const uin
     return rc;
 }
 
+int szb_decode_stream(szb_ctx *ctx, const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap, uint64_t *out_off,
+                      uint64_t *out_len, int32_t *status, uint32_t max_frames, uint32_t *nframes_out, uint64_t *total_out,
+                      uint32_t flags) {
+    if (!ctx || (!src && src_len) || (!dst && dst_cap)) return SZB_ERR_INVALID_ARGUMENT;
+    if (flags & SZB_FLAG_SRC_DEVICE) return SZB_ERR_INVALID_ARGUMENT;  // the header walk needs host bytes
+    if (nframes_out) *nframes_out = 0;
+    if (total_out) *total_out = 0;
+    szb_batch *b = nullptr;
+    int rc = szb_batch_create(ctx, src, src_len, nullptr, nullptr, 0, &b);  // frame boundaries from the walk
+    if (rc) return rc;
+    const uint32_t n = b->nframes;
+    if (nframes_out) *nframes_out = n;
+    if ((out_off || out_len || status) && n > max_frames) {
+        szb_batch_destroy(b);
+        return SZB_ERR_INVALID_ARGUMENT;
+    }
+    std::vector<uint64_t> off(n ? n : 1), len(n ? n : 1);
+    std::vector<int32_t> st(n ? n : 1, 0);
+    rc = decode_tables(ctx, b, src, src_len, dst, dst_cap, off.data(), len.data(), st.data(), flags);
+    uint64_t total = 0;
+    for (uint32_t f = 0; f < n; f++) {
+        if (out_off) out_off[f] = off[f];
+        if (out_len) out_len[f] = len[f];
+        if (status) status[f] = st[f];
+        if (st[f] == SZB_OK && off[f] + len[f] > total) total = off[f] + len[f];
+    }
+    if (total_out) *total_out = total;
+    szb_batch_destroy(b);
+    return rc;
+}
+
 int szb_decode_blocks(szb_ctx *ctx, const void *d_src, size_t src_len, const szb_frame_desc *frames, uint32_t nframes,
                       const szb_block_desc *blocks, uint32_t nblocks, void *d_dst, size_t dst_cap, uint64_t *out_off,
                       uint64_t *out_len, int32_t *status) {

@@ -127,6 +127,34 @@ class Context:
             self._raise(rc)
         return out_off, out_len, status
 
+    def decode_stream(self, data: bytes, verify_checksum: bool = False) -> bytes:
+        """szb_decode_stream: a `.zst` stream as the zstd tools write it -- frames back to back, skippable frames in between,
+        content checksums -- decoded as one batch; returns the stream's content.  (The reference handles one frame per reader.)"""
+        src = np.frombuffer(bytes(data) + b"\0" * 16, dtype=np.uint8)
+        with Walk(src[: len(data)]) as w:
+            frames = w.frames()
+            known = w.known_output_size()
+        n = len(frames)
+        bad = [f.status for f in frames if f.status != 0]
+        if bad:
+            self._raise(int(bad[0]))
+        if known is None:  # a streamed frame's size is in no header: the entropy stages tell
+            fo = np.array([f.src_off for f in frames], dtype=np.uint64)
+            fl = np.array([f.src_len for f in frames], dtype=np.uint64)
+            known = self.output_size(src, fo, fl) if n else 0
+        dst = np.empty(max(int(known), 1), dtype=np.uint8)
+        out_off = np.zeros(max(n, 1), dtype=np.uint64)
+        out_len = np.zeros(max(n, 1), dtype=np.uint64)
+        status = np.zeros(max(n, 1), dtype=np.int32)
+        found = C.c_uint32()
+        total = C.c_uint64()
+        rc = self._L.szb_decode_stream(self._h, src.ctypes.data, len(data), dst.ctypes.data, dst.nbytes, out_off.ctypes.data,
+                                       out_len.ctypes.data, status.ctypes.data, max(n, 1), C.byref(found), C.byref(total),
+                                       4 if verify_checksum else 0)
+        if rc != 0:
+            self._raise(rc)
+        return dst[: total.value].tobytes()
+
     def decode_batch(self, frames: Sequence[bytes], capacity: Optional[int] = None) -> List[bytes]:
         """Decodes independent frames; raises the first frame's error (like a loop of Decompress())."""
         if not frames:

@@ -16,13 +16,16 @@ def pytest_configure(config):
 
 
 def _cuda_device_present() -> bool:
-    try:
-        from sparkzstd_b200.decompression import Context
+    """False only when the engine itself says there is no device (-67); a missing or broken libszb200.so still fails loudly."""
+    from sparkzstd_b200.decompression import Context, SzbError
 
+    try:
         Context(0).close()
         return True
-    except Exception:
-        return False
+    except SzbError as e:
+        if getattr(e, "code", None) == -67:
+            return False
+        raise
 
 
 def pytest_collection_modifyitems(config, items):
