@@ -25,9 +25,94 @@ type Error int
 
 func (e Error) Error() string { return C.GoString(C.szb_strerror(C.int(e))) }
 
-// FrameDesc and BlockDesc mirror szb_frame_desc / szb_block_desc byte for byte.
-type FrameDesc = C.szb_frame_desc
-type BlockDesc = C.szb_block_desc
+// FrameDesc and BlockDesc mirror szb_frame_desc / szb_block_desc (include/szb200.h) byte for byte.  They are PLAIN Go structs
+// with exported fields on purpose: a cgo type (C.szb_frame_desc) is private to the package that names it -- another package can
+// neither touch its lower-case fields nor mix its own C.uint64_t with this package's -- so package structure fills these and this
+// package hands them to C as unsafe.Pointer.  The layout is pinned three times: static_asserts on every offset in
+// csrc/abi_layout.h (compile time, C side), init() below against szb_abi_layout() (load time, Go side), and
+// tests/test_abi_and_walker.py (the ctypes mirror).  Go lays out uint64/uint32/uint8 fields in declaration order with natural
+// alignment, exactly like the C compiler does for this field order.
+type FrameDesc struct {
+	SrcOff         uint64 // offset of the frame's magic number inside src
+	SrcLen         uint64 // bytes from the magic to the end of the last block
+	WindowSize     uint64 // frame.go:28-36
+	ContentSize    uint64 // frame.go:49-61, or ContentSizeUnknown
+	DictionaryID   uint64 // frame.go:38-47
+	FirstBlock     uint32
+	NBlocks        uint32
+	Checksum       uint32
+	Status         int32
+	Descriptor     uint8
+	SingleSegment  uint8
+	HasChecksum    uint8
+	HasContentSize uint8
+	ChecksumValid  uint32
+}
+
+type BlockDesc struct {
+	SrcOff      uint64 // offset inside src of the block payload (after the 3-byte header)
+	LitBufOff   uint64
+	SeqBufOff   uint64
+	BlockSize   uint32
+	Frame       uint32
+	LitRegen    uint32
+	LitComp     uint32
+	NSeq        uint32
+	SeqOff      uint32
+	HufOrigin   uint32
+	LLOrigin    uint32
+	OFOrigin    uint32
+	MLOrigin    uint32
+	Type        uint8
+	Last        uint8
+	LitType     uint8
+	LitStreams  uint8
+	LitHdrBytes uint8
+	SeqHdrBytes uint8
+	SeqModes    uint8
+	Pad         uint8
+	Pad2        uint32
+}
+
+const ContentSizeUnknown = ^uint64(0)
+const None = uint32(0xFFFFFFFF) // SZB_NONE
+
+// layout() lists sizeof and every field offset in the order szb_abi_layout() (include/szb200.h) reports them.
+func layout() []uint32 {
+	var f FrameDesc
+	var b BlockDesc
+	return []uint32{
+		uint32(unsafe.Sizeof(f)),
+		uint32(unsafe.Offsetof(f.SrcOff)), uint32(unsafe.Offsetof(f.SrcLen)), uint32(unsafe.Offsetof(f.WindowSize)),
+		uint32(unsafe.Offsetof(f.ContentSize)), uint32(unsafe.Offsetof(f.DictionaryID)), uint32(unsafe.Offsetof(f.FirstBlock)),
+		uint32(unsafe.Offsetof(f.NBlocks)), uint32(unsafe.Offsetof(f.Checksum)), uint32(unsafe.Offsetof(f.Status)),
+		uint32(unsafe.Offsetof(f.Descriptor)), uint32(unsafe.Offsetof(f.SingleSegment)), uint32(unsafe.Offsetof(f.HasChecksum)),
+		uint32(unsafe.Offsetof(f.HasContentSize)), uint32(unsafe.Offsetof(f.ChecksumValid)),
+		uint32(unsafe.Sizeof(b)),
+		uint32(unsafe.Offsetof(b.SrcOff)), uint32(unsafe.Offsetof(b.LitBufOff)), uint32(unsafe.Offsetof(b.SeqBufOff)),
+		uint32(unsafe.Offsetof(b.BlockSize)), uint32(unsafe.Offsetof(b.Frame)), uint32(unsafe.Offsetof(b.LitRegen)),
+		uint32(unsafe.Offsetof(b.LitComp)), uint32(unsafe.Offsetof(b.NSeq)), uint32(unsafe.Offsetof(b.SeqOff)),
+		uint32(unsafe.Offsetof(b.HufOrigin)), uint32(unsafe.Offsetof(b.LLOrigin)), uint32(unsafe.Offsetof(b.OFOrigin)),
+		uint32(unsafe.Offsetof(b.MLOrigin)), uint32(unsafe.Offsetof(b.Type)), uint32(unsafe.Offsetof(b.Last)),
+		uint32(unsafe.Offsetof(b.LitType)), uint32(unsafe.Offsetof(b.LitStreams)), uint32(unsafe.Offsetof(b.LitHdrBytes)),
+		uint32(unsafe.Offsetof(b.SeqHdrBytes)), uint32(unsafe.Offsetof(b.SeqModes)),
+	}
+}
+
+// A binding whose structs drifted from the header must not run: the device would read garbage tables.
+func init() {
+	want := layout()
+	got := make([]C.uint32_t, len(want)+8)
+	n := int(C.szb_abi_layout(&got[0], C.uint32_t(len(got))))
+	if n != len(want) {
+		panic("szb200: szb_abi_layout reports another number of fields than this binding mirrors")
+	}
+	for i := range want {
+		if uint32(got[i]) != want[i] {
+			panic("szb200: FrameDesc/BlockDesc do not match szb_frame_desc/szb_block_desc (include/szb200.h)")
+		}
+	}
+}
 
 // Ctx is one CUDA stream plus scratch arenas on one GPU.  Not goroutine-safe: one per goroutine,
 // exactly like a reference FrameDecompressor.
@@ -104,16 +189,17 @@ func (c *Ctx) DecodeBatch(src []byte, off, length []uint64, dst []byte, flags ui
 // (package structure) emitted.
 func (c *Ctx) DecodeBlocks(dSrc unsafe.Pointer, srcLen int, frames []FrameDesc, blocks []BlockDesc, dDst unsafe.Pointer, dstCap int) (outOff, outLen []uint64, status []int32, err error) {
 	n := len(frames)
+	if n == 0 {
+		return nil, nil, nil, nil
+	}
 	outOff = make([]uint64, n)
 	outLen = make([]uint64, n)
 	status = make([]int32, n)
-	var fp *FrameDesc
-	var bp *BlockDesc
-	if n > 0 {
-		fp = &frames[0]
-	}
+	// the tables are host memory the library copies before it returns; they hold no Go pointers
+	fp := (*C.szb_frame_desc)(unsafe.Pointer(&frames[0]))
+	var bp *C.szb_block_desc
 	if len(blocks) > 0 {
-		bp = &blocks[0]
+		bp = (*C.szb_block_desc)(unsafe.Pointer(&blocks[0]))
 	}
 	rc := C.szb_decode_blocks(c.p, dSrc, C.size_t(srcLen), fp, C.uint32_t(n), bp, C.uint32_t(len(blocks)), dDst, C.size_t(dstCap),
 		(*C.uint64_t)(unsafe.Pointer(&outOff[0])), (*C.uint64_t)(unsafe.Pointer(&outLen[0])), (*C.int32_t)(unsafe.Pointer(&status[0])))

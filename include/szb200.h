@@ -128,6 +128,12 @@ typedef struct szb_block_desc {
     uint32_t _pad2;
 } szb_block_desc;
 
+/* The layout of the two structs above, for bindings that mirror them instead of including this header (the Go structs of
+ * go/szb200, the ctypes mirror): sizeof(szb_frame_desc), the offset of each of its fields in declaration order (src_off ..
+ * checksum_valid), sizeof(szb_block_desc), the offset of each of its fields (src_off .. seq_modes; the padding is not
+ * listed).  Writes at most cap values, returns how many there are (36).  A binding compares them with its own when it loads. */
+uint32_t szb_abi_layout(uint32_t *out, uint32_t cap);
+
 typedef struct szb_walk szb_walk;
 
 /* Walks the headers of nframes frames.  frame_off/frame_len give each frame's extent inside

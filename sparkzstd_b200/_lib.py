@@ -72,6 +72,7 @@ SYMBOLS = [
     ("szb_walk_known_output_size", C.c_uint64, [_P]),
     ("szb_ctx_create", C.c_int, [C.c_int, _P, C.POINTER(_P)]),
     ("szb_ctx_destroy", None, [_P]),
+    ("szb_abi_layout", C.c_uint32, [_P, C.c_uint32]),
     ("szb_ctx_stream", _P, [_P]),
     ("szb_ctx_last_error", C.c_char_p, [_P]),
     ("szb_decode_batch", C.c_int, [_P, _P, C.c_size_t, _P, _P, C.c_uint32, _P, C.c_size_t, _P, _P, _P, C.c_uint32]),

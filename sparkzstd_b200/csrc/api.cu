@@ -94,6 +94,7 @@ struct szb_batch {
     SeqInfo *d_seq_info = nullptr;
     // frames one warp executes (place.cuh)
     bool place = false;
+    bool exec2 = false;      // k_execute2 (exec2.cuh) for the frames one warp executes
     std::vector<uint64_t> rec_off;
     uint64_t rec_entries = 0, bm_bound = 0, bm_words = 0;
     uint64_t *d_rec_off = nullptr;
@@ -373,6 +374,8 @@ static int batch_upload_tables(szb_batch *b) {
         // headline workload (profiles/README.md, r02)
         const bool want_place = em ? strcmp(em, "place") == 0 : kDefaultExecPlace;
         b->place = want_place && nf > b->n_noplace;
+        // SZB_EXEC=legacy: k_execute for every frame; exec2 (the default): k_execute2, k_execute for frames of 2 GiB and more
+        b->exec2 = !b->place && !(em && strcmp(em, "legacy") == 0);
         b->rec_off.assign(nb ? nb : 1, 0);
         uint64_t entries = 0, bound = 0;
         if (b->place) {
@@ -665,6 +668,7 @@ static DeviceBatch make_args(szb_batch *b, const void *d_src, void *d_dst, size_
     a.bm_bound = b->bm_bound;
     a.place_state = a.rec ? b->d_place_state : nullptr;
     a.n_noplace = b->n_noplace;
+    a.exec2 = b->exec2 ? 1u : 0u;
     return a;
 }
 
@@ -798,7 +802,25 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
             k_place<<<(n_place + kPlaceWarps - 1) / kPlaceWarps, kPlaceWarps * 32, 0, s>>>(a, b->n_noplace, n_place);
             ctx->launches++;
         }
-        if (n_rest) {  // with k_place on: only the frames it could not take (place_on)
+        if (n_rest && a.exec2) {  // exec2.cuh: every frame of the range that regenerates less than 2 GiB
+            // SZB_X2_CTAS_PER_SM=N (experiments): dynamic shared memory nobody uses caps the CTAs an SM holds, i.e. the frames in
+            // flight and with them the output that wants to stay in L2
+            static const int cap_ctas = getenv("SZB_X2_CTAS_PER_SM") ? atoi(getenv("SZB_X2_CTAS_PER_SM")) : 0;
+            size_t pad = 0;
+            if (cap_ctas > 0) {
+                const size_t per = (size_t)227 * 1024 / (size_t)cap_ctas;
+                const size_t own = sizeof(X2Smem) * kX2Warps + 1024;
+                pad = per > own ? per - own : 0;
+                static bool once = false;
+                if (!once) {
+                    once = true;
+                    cudaFuncSetAttribute(k_execute2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+                }
+            }
+            k_execute2<<<(n_rest + kX2Warps - 1) / kX2Warps, kX2Warps * 32, pad, s>>>(a, n_long, n_rest);
+            ctx->launches++;
+        }
+        if (n_rest) {  // with k_place or k_execute2 on: only the frames they could not take (place_on, x2_takes)
             k_execute<<<(n_rest + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, s>>>(a, n_long, n_rest);
             ctx->launches++;
         }
@@ -1072,7 +1094,6 @@ static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_l
         c.f0 = f;
         c.src_lo = ~0ull;
         uint64_t bytes = 0, dpos = 0;
-        for (uint32_t g = 0; g < f; g++) (void)g;
         while (f < nframes && (bytes < kChunkBytes || f == c.f0)) {
             c.src_lo = frame_off[f] < c.src_lo ? frame_off[f] : c.src_lo;
             c.src_hi = frame_off[f] + frame_len[f] > c.src_hi ? frame_off[f] + frame_len[f] : c.src_hi;
@@ -1108,8 +1129,13 @@ static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_l
             walked[i].store(1, std::memory_order_release);
         }
     };
+    // SZB_WALK_THREADS caps the workers (one process per GPU on a shared host: cores / ranks; bench.py sets it)
     unsigned nthreads = std::thread::hardware_concurrency();
     nthreads = nthreads < 2 ? 1 : (nthreads > 8 ? 8 : nthreads - 1);
+    if (const char *wt = getenv("SZB_WALK_THREADS")) {
+        const unsigned cap = (unsigned)strtoul(wt, nullptr, 10);
+        if (cap >= 1 && cap < nthreads) nthreads = cap;
+    }
     if (nthreads > chunks.size()) nthreads = (unsigned)chunks.size();
     std::vector<std::thread> pool;
     try {
@@ -1137,13 +1163,22 @@ static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_l
     double t_wait = 0, t_create = 0, t_launch = 0;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_loop0 = now();
+#define CUDA_BRK(expr)                                                                    \
+    {                                                                                     \
+        const cudaError_t e__ = (expr);                                                   \
+        if (e__ != cudaSuccess) {                                                         \
+            ctx->last_error = std::string(#expr) + ": " + cudaGetErrorString(e__);        \
+            fail = SZB_ERR_CUDA;                                                          \
+            break;                                                                        \
+        }                                                                                 \
+    }
     for (size_t ci = 0; ci < chunks.size(); ci++) {
         Chunk &c = chunks[ci];
-        CUDA_TRY(ctx, cudaEventCreateWithFlags(&c.up, cudaEventDisableTiming));
-        CUDA_TRY(ctx, cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+        CUDA_BRK(cudaEventCreateWithFlags(&c.up, cudaEventDisableTiming));
+        CUDA_BRK(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
         // compressed bytes of this chunk: H2D on the copy stream
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_src + c.src_lo, src + c.src_lo, (size_t)(c.src_hi - c.src_lo), cudaMemcpyHostToDevice, ctx->s_h2d));
-        CUDA_TRY(ctx, cudaEventRecord(c.up, ctx->s_h2d));
+        CUDA_BRK(cudaMemcpyAsync(ctx->d_src + c.src_lo, src + c.src_lo, (size_t)(c.src_hi - c.src_lo), cudaMemcpyHostToDevice, ctx->s_h2d));
+        CUDA_BRK(cudaEventRecord(c.up, ctx->s_h2d));
         // descriptor tables of this chunk (walked by a worker), their upload, the kernels
         double t0 = now();
         while (!walked[ci].load(std::memory_order_acquire)) std::this_thread::yield();
@@ -1164,7 +1199,7 @@ static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_l
             fail = rc;
             break;
         }
-        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, c.up, 0));
+        CUDA_BRK(cudaStreamWaitEvent(ctx->stream, c.up, 0));
         rc = launch_entropy(c.batch, ctx->d_src);
         if (!rc) rc = launch_execute(c.batch, ctx->d_src, ctx->d_dst + c.dst_lo, (size_t)(total - c.dst_lo));
         if (!rc && verify) rc = szb_batch_verify_checksums(c.batch, ctx->d_dst + c.dst_lo);
@@ -1172,13 +1207,14 @@ static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_l
             fail = rc;
             break;
         }
-        CUDA_TRY(ctx, cudaEventRecord(c.done, ctx->stream));
+        CUDA_BRK(cudaEventRecord(c.done, ctx->stream));
         batch_release_scratch(c.batch);
         t_launch += now() - t0;
         // output of this chunk: D2H on the other copy stream
-        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_d2h, c.done, 0));
-        if (c.dst_len) CUDA_TRY(ctx, cudaMemcpyAsync(dst + c.dst_lo, ctx->d_dst + c.dst_lo, (size_t)c.dst_len, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        CUDA_BRK(cudaStreamWaitEvent(ctx->s_d2h, c.done, 0));
+        if (c.dst_len) CUDA_BRK(cudaMemcpyAsync(dst + c.dst_lo, ctx->d_dst + c.dst_lo, (size_t)c.dst_len, cudaMemcpyDeviceToHost, ctx->s_d2h));
     }
+#undef CUDA_BRK
     stop.store(true);
     for (auto &t : pool) t.join();
     const double t_loop1 = now();
@@ -1198,7 +1234,15 @@ static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_l
             cudaMemcpy(st.data(), c.batch->d_frame_status, 4 * (size_t)n, cudaMemcpyDeviceToHost);
             cudaMemcpy(off.data(), c.batch->d_frame_out_off, 8 * (size_t)n, cudaMemcpyDeviceToHost);
             cudaMemcpy(len.data(), c.batch->d_frame_out_len, 8 * (size_t)n, cudaMemcpyDeviceToHost);
+            // The chunk was placed and copied back by the sizes its frame headers declare.  Every frame, failed or not, must
+            // start where those sizes put it and the chunk must end where they end it: a failed frame whose blocks regenerate
+            // another size would otherwise shift its (valid) neighbours past what was copied back.
+            uint64_t d_total = 0, expect = 0;
+            cudaMemcpy(&d_total, c.batch->d_total, 8, cudaMemcpyDeviceToHost);
+            if (d_total != c.dst_len) fail = SZB_ERR_CORRUPT_SIZES;
             for (uint32_t i = 0; i < n; i++) {
+                if (off[i] != expect) fail = SZB_ERR_CORRUPT_SIZES;
+                expect += fcs[c.f0 + i];
                 if (status) status[c.f0 + i] = st[i];
                 if (out_off) out_off[c.f0 + i] = c.dst_lo + off[i];
                 if (out_len) out_len[c.f0 + i] = st[i] == SZB_OK ? len[i] : 0;

@@ -79,6 +79,7 @@ struct DeviceBatch {
     uint32_t *long_hist;            // per lb_block entry: the history the block starts with (3 entries)
     unsigned long long *long_ticket;  // k_long_jump hands out its tiles in address order
     unsigned long long *long_err;   // per long frame: the first error found while emitting (block << 40 | round << 8 | -code)
+    uint32_t exec2;                 // non-zero: k_execute2 (exec2.cuh) executes the frames one warp executes; 0: k_execute
     // frames one warp executes (place.cuh): k_resolve -> k_place; nullptr: k_execute takes them all
     uint32_t *rec;                  // per block with sequences, at rec_off[block]: one entry per segment (literal run or match) in
                                     // output order: a match's offset (through the repeat history), or bit 31 | the match bytes

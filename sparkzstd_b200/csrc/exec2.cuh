@@ -1,0 +1,437 @@
+// exec2.cuh -- stage 4 for the frames one warp executes, second generation (sm_100a): k_execute2.
+// Included by execute.cuh inside namespace szb.  Plain CUDA C++ (tests/host_sim runs it on an emulated CTA).
+//
+// replaces: decompression/sequence_execution.go:14-114 (ExecuteSequences, nextOffset) and ringbuffer.go:197-277 (match copy)
+//
+// The shape is k_execute's (execute.cuh): a producer half that turns 32 sequences per round into SEGMENTS (a literal run or a
+// match: a contiguous piece of output with a contiguous source), and a consumer half that makes the output in address order,
+// one aligned 128-byte line per step, lane i making bytes i, 32+i, 64+i, 96+i.  What changed is the arithmetic, because
+// k_execute is bound by instruction issue (profiles/r02_*: 267 warp instructions per line, 170 of them in the consumer):
+//
+//   * positions are 32-bit "q positions", counted from the 128-byte aligned address at or below the frame's first byte,
+//     so a line of output is a line of memory; a frame that regenerates 2 GiB or more stays with k_execute;
+//   * a segment is ONE 32-bit entry: a match's offset (through the repeat history), or bit 31 | the difference between a
+//     literal byte's q position and its index into the block's literals.  For both, `q - (entry & 0x7FFFFFFF)` is the index of
+//     the source byte -- into the output for a match, into the literals for a literal run -- and "the source is a byte of
+//     this very step" is one unsigned compare of the entry against the byte's place in the line (a literal entry is huge);
+//   * the line leaves as four 32-byte stores (one byte per lane each), no transposition through shared memory; bytes that
+//     repeat bytes of the same step take them from the lane that holds them: earlier 32-byte chunks with one shuffle of the
+//     packed bytes, the own chunk by pointer jumping over shuffles;
+//   * the block's literals have ONE base address, so the consumer is brought up to date at every block boundary (a partial
+//     line per block).
+//
+// Shared memory per warp: 256 entries + a 4096-position bitmap = 1.5 KB (k_execute: 2.7 KB).
+#pragma once
+
+constexpr uint32_t kX2Bits = 4096;             // output positions the bitmap covers
+constexpr uint32_t kX2Span = kX2Bits - 256;    // a round may reach this far past the line being consumed
+constexpr uint32_t kX2Ring = 256;              // >= 2 x 64 segments of two rounds + the segments of a partial line (<= 64) + 1
+constexpr uint32_t kX2ConstRun = 256;          // RLE literal runs up to this long are segments (source: a row of DeviceBatch::bytefill)
+constexpr uint32_t kX2Lit = 0x80000000u;
+constexpr uint64_t kX2MaxFrame = 0x7FFF0000ull;  // frames that regenerate this much or more are k_execute's
+
+struct X2Smem {
+    uint32_t seg[kX2Ring];                         // per segment: match offset, or kX2Lit | (q position - literal index)
+    __align__(16) uint32_t bits[kX2Bits / 32];     // bit q % kX2Bits set: a segment starts at q
+};
+
+struct X2State {
+    uint8_t *qb;         // q position 0
+    const uint8_t *lit;  // the literals of the block being executed
+    uint32_t line;       // next line to produce (q position, multiple of 128)
+    uint32_t head;       // output below line + head is in memory already (0 .. 128)
+    uint32_t seen;       // segments that start below line + head
+};
+
+// every kernel evaluates the same predicate: does k_execute2 take frame f (status OK)?
+__device__ __forceinline__ bool x2_takes(const DeviceBatch &a, uint32_t f) { return a.exec2 != 0 && a.frame_out_len[f] < kX2MaxFrame; }
+
+// Produces the bytes [lo, hi) of the line at st.line (positions relative to the line; kWhole: all 128).
+template <bool kWhole>
+__device__ __forceinline__ void x2_step(X2Smem &sm, X2State &st, uint32_t lo, uint32_t hi, uint32_t lane, uint32_t le_mask) {
+    uint32_t *bw = &sm.bits[(st.line >> 5) & (kX2Bits / 32 - 1)];
+    const uint4 m4 = *reinterpret_cast<const uint4 *>(bw);
+    const uint32_t m[4] = {m4.x, m4.y, m4.z, m4.w};
+    const uint32_t q0 = st.line + lane;  // q position of my byte of chunk 0
+    uint32_t last = st.seen - 1;         // the last segment that starts below the chunk
+    uint32_t v[4], so[4];
+    bool ing[4];
+    // every byte of the line finds its segment and issues its load
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const uint32_t rel = (c << 5) + lane;
+        const uint32_t ord = last + __popc(m[c] & le_mask);  // the last segment that starts at or before my byte
+        last += __popc(m[c]);
+        const uint32_t e = sm.seg[ord & (kX2Ring - 1)];
+        const bool live = kWhole || (rel >= lo && rel < hi);
+        const uint32_t idx = q0 + (c << 5) - (e & ~kX2Lit);
+        // A match whose offset does not reach below the step's first byte repeats a byte of this step that is not in memory yet.
+        ing[c] = live && e <= rel - lo;
+        so[c] = rel - e;  // its place in the line
+        const uint8_t *p = ((int32_t)e < 0 ? st.lit : st.qb) + idx;
+        v[c] = 0;
+        if (live && !ing[c]) v[c] = *p;
+    }
+    st.seen = last + 1;
+    if (__any_sync(kFull, ing[0] | ing[1] | ing[2] | ing[3])) {
+        uint32_t W = 0;  // the bytes of the chunks done so far, chunk k in bits 8k..8k+7
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            uint32_t open = __ballot_sync(kFull, ing[c]);
+            if (open) {
+                bool unres = ing[c];
+                uint32_t par = so[c] & 31;
+                if (c > 0) {
+                    const uint32_t t = __shfl_sync(kFull, W, par);
+                    if (unres && (so[c] >> 5) < (uint32_t)c) {
+                        v[c] = (t >> ((so[c] >> 5) << 3)) & 0xFF;
+                        unres = false;
+                    }
+                    open = __ballot_sync(kFull, unres);
+                }
+                while (open) {  // the own chunk: chains of in-chunk sources halve every round
+                    const uint32_t pv = __shfl_sync(kFull, v[c], par);
+                    const uint32_t pp = __shfl_sync(kFull, par, par);
+                    if (unres) {
+                        if (!((open >> par) & 1)) {
+                            v[c] = pv;
+                            unres = false;
+                        } else {
+                            par = pp;
+                        }
+                    }
+                    open = __ballot_sync(kFull, unres);
+                }
+            }
+            W |= v[c] << (c << 3);
+        }
+    }
+    // out: four 32-byte rows, one byte per lane each
+    uint8_t *out = st.qb + q0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const uint32_t rel = (c << 5) + lane;
+        if (kWhole || (rel >= lo && rel < hi)) out[c << 5] = (uint8_t)v[c];
+    }
+    if (lane < 4) bw[lane] = 0;  // the bitmap is a ring: leave it clean for the next lap
+    __syncwarp();
+}
+
+// produce every complete line below the q position `limit` (segments must cover the output up to there)
+__device__ __forceinline__ void x2_drain(X2Smem &sm, X2State &st, uint32_t limit, uint32_t lane, uint32_t le_mask) {
+    uint32_t n = (limit - st.line) >> 7;
+    if (n == 0) return;
+    if (st.head) {  // the rest of a line that was flushed in part
+        x2_step<false>(sm, st, st.head, 128, lane, le_mask);
+        st.line += 128;
+        st.head = 0;
+        n--;
+    }
+    for (; n; n--) {
+        x2_step<true>(sm, st, 0, 128, lane, le_mask);
+        st.line += 128;
+    }
+}
+// produce everything up to `prod`, the last, partial line included: everything below prod is then in memory
+__device__ __forceinline__ void x2_flush(X2Smem &sm, X2State &st, uint32_t prod, uint32_t lane, uint32_t le_mask) {
+    x2_drain(sm, st, prod, lane, le_mask);
+    const uint32_t hi = prod - st.line;  // < 128
+    if (hi > st.head) {
+        x2_step<false>(sm, st, st.head, hi, lane, le_mask);
+        st.head = hi;
+    }
+}
+// The same out of line, for the places a frame passes rarely (block starts, sequences longer than the ring, the frame's end):
+// one inlined copy of the step per hot call site keeps the kernel inside the instruction cache.
+__device__ __noinline__ X2State x2_drain_cold(X2Smem &sm, X2State st, uint32_t limit, uint32_t lane, uint32_t le_mask) {
+    x2_drain(sm, st, limit, lane, le_mask);
+    return st;
+}
+__device__ __noinline__ X2State x2_flush_cold(X2Smem &sm, X2State st, uint32_t prod, uint32_t lane, uint32_t le_mask) {
+    st = x2_drain_cold(sm, st, prod, lane, le_mask);
+    const uint32_t hi = prod - st.line;  // < 128
+    if (hi > st.head) {
+        x2_step<false>(sm, st, st.head, hi, lane, le_mask);
+        st.head = hi;
+    }
+    return st;
+}
+// continue at another q position (everything flushed)
+__device__ __forceinline__ void x2_seek(X2State &st, uint32_t q) {
+    st.line = q & ~127u;
+    st.head = q & 127u;
+}
+
+// One frame (status OK, taken by x2_takes), one warp: blocks in order, 32 sequences per round (sequence_execution.go:14-63).
+__device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Smem &sm, uint32_t lane) {
+    const szb_frame_desc fr = a.frames[f];
+    const uint32_t b0 = fr.first_block, nb = fr.nblocks;
+    if (nb == 0) return;
+    int err = SZB_OK;
+    const uint64_t frame_base = a.out_off[b0];
+    const uint32_t le_mask = 0xFFFFFFFFu >> (31 - lane);  // bits 0..lane
+    const uint32_t lt_mask = le_mask >> 1;                // bits 0..lane-1
+    X2State st;
+    uint32_t mis;  // q position of the frame's first byte
+    {
+        uint8_t *first = a.dst + frame_base;
+        mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 127);
+        st.qb = first - mis;
+        st.lit = nullptr;
+        st.seen = 0;
+        x2_seek(st, mis);
+    }
+    uint32_t prod = mis;  // segments cover the output up to this q position
+    uint32_t nseg = 0;    // segments appended so far
+
+    History hist{1, 4, 8};  // framedecompressor.go:48,59
+    for (uint32_t bi = 0; bi < nb && err == SZB_OK; bi++) {
+        const uint32_t b = b0 + bi;
+        const szb_block_desc d = a.blocks[b];
+        if (d.type != 2 || d.nseq == 0) continue;  // written by k_execute_bodies already
+        const uint8_t *payload = a.src + d.src_off;
+        uint32_t qpos = mis + (uint32_t)(a.out_off[b] - frame_base);
+        // the consumer is brought up to date at every block start: the literals' base address changes, and blocks in between
+        // may have been written elsewhere
+        st = x2_flush_cold(sm, st, prod, lane, le_mask);
+        if (qpos != prod) {
+            x2_seek(st, qpos);
+            prod = qpos;
+        }
+        // Compressed: ExecuteSequences (sequence_execution.go:14-63)
+        const bool lit_rle = d.lit_type == 1;
+        // RLE literals: every literal byte is payload[lit_hdr_bytes]; runs read it from that byte's row of the fill table
+        const uint8_t *lit = lit_rle ? a.bytefill + 256 * (uint32_t)payload[d.lit_hdr_bytes]
+                                     : (d.lit_type == 0 ? payload + d.lit_hdr_bytes : a.litbuf + d.lit_buf_off);
+        st.lit = lit;
+        const uint32_t nseq = d.nseq;
+        uint32_t lit_pos = 0;
+        const uint32_t *const seqp = a.seq_ll + d.seq_buf_off;
+        // the triples are prefetched to L1 two rounds ahead (one line per array and round): lanes 0..2 take one array each
+        const uint32_t *const my_seq = seqp + (lane < 3 ? lane : 0) * a.seq_stride;
+        if (lane < 3) {
+            SZB_PREFETCH_L1(my_seq);
+            if (nseq > 32) SZB_PREFETCH_L1(my_seq + 32);
+        }
+        for (uint32_t base = 0; base < nseq; base += 32) {
+            const uint32_t cnt = nseq - base < 32 ? nseq - base : 32;
+            const bool act = lane < cnt;
+            const uint32_t *const tr = seqp + (base + lane);  // the arrays are padded to whole rounds: no bounds needed
+            uint32_t ll = tr[0], ml = tr[a.seq_stride], ofv = tr[2 * a.seq_stride];
+            if (!act) {
+                ll = 0;
+                ml = 0;
+                ofv = 4;
+            }
+            if (!lit_rle && lane == 0) SZB_PREFETCH_L1(lit + lit_pos + 256);
+            if (lane < 3 && base + 64 < nseq) SZB_PREFETCH_L1(my_seq + base + 64);
+
+            // --- offsets through the 3-entry history (nextOffset): the walk jumps from repeat code to repeat code, the run of
+            // direct sequences in between is folded in at once (its last three offsets are the new history) ---
+            uint32_t off = ofv - 3;
+            {
+                uint32_t rm = __ballot_sync(kFull, act && ofv <= 3);
+                uint32_t p = 0;  // sequences [0, p) are folded into hist
+                for (;;) {
+                    const uint32_t j = rm ? (uint32_t)__ffs(rm) - 1 : cnt;  // the next repeat code, or the end of the round
+                    const uint32_t n = j - p;
+                    if (n) {
+                        const uint32_t o1 = __shfl_sync(kFull, off, j - 1);
+                        const uint32_t o2 = __shfl_sync(kFull, off, n >= 2 ? j - 2 : 0);
+                        const uint32_t o3 = __shfl_sync(kFull, off, n >= 3 ? j - 3 : 0);
+                        if (n >= 3) {
+                            hist = History{o1, o2, o3};
+                        } else if (n == 2) {
+                            hist = History{o1, o2, hist.h0};
+                        } else {
+                            hist = History{o1, hist.h0, hist.h1};
+                        }
+                    }
+                    if (j >= cnt) break;
+                    const uint32_t v = __shfl_sync(kFull, ofv, j);
+                    const uint32_t l = __shfl_sync(kFull, ll, j);
+                    const uint32_t o = next_offset(hist, v, l == 0);  // every lane tracks the same history
+                    if (lane == j) off = o;
+                    rm &= rm - 1;
+                    p = j + 1;
+                }
+            }
+
+            // --- positions: prefix sums over the round ---
+            const uint32_t tot = ll + ml;
+            uint32_t incl_ll, incl_tot;
+            if (__reduce_max_sync(kFull, tot) < 2048) {
+                // both sums stay below 2^16: one scan over (literals | literals + match << 16)
+                uint32_t x = ll | (tot << 16);
+                for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                    const uint32_t t = __shfl_up_sync(kFull, x, dlt);
+                    if ((int)lane >= dlt) x += t;
+                }
+                incl_ll = x & 0xFFFF;
+                incl_tot = x >> 16;
+            } else {
+                incl_ll = ll;
+                incl_tot = tot;
+                for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                    const uint32_t t1 = __shfl_up_sync(kFull, incl_ll, dlt);
+                    const uint32_t t2 = __shfl_up_sync(kFull, incl_tot, dlt);
+                    if ((int)lane >= dlt) {
+                        incl_ll += t1;
+                        incl_tot += t2;
+                    }
+                }
+            }
+            const uint32_t round_ll = __shfl_sync(kFull, incl_ll, 31);
+            const uint32_t round_tot = __shfl_sync(kFull, incl_tot, 31);
+            if ((uint64_t)lit_pos + round_ll > d.lit_regen) {
+                // literals.go:398-409 Read runs dry / sequence_execution.go:26-28; RLE literals: GetRest panics
+                err = lit_rle ? SZB_ERR_PANIC : SZB_ERR_DIDNT_COPY_ALL_LITERAL_BYTES;
+                break;
+            }
+            const uint32_t excl_tot = incl_tot - tot;  // my literal run starts at qpos + excl_tot
+            const uint32_t excl_ll = incl_ll - ll;     // and reads the literals from lit_pos + excl_ll
+            // (positions stay below the frame's length, which is the sum stage 3 made of the same numbers: once the literals are
+            // known not to run dry, literals + matches of the block so far <= lit_regen + the block's match bytes = out_size)
+            {
+                // every match must lie inside the frame (ringbuffer.go:203-214); a match length of 0 cannot come out of
+                // stage 3 (ML codes start at 3, predefined.go:36-50) and would break the segment count below
+                const uint32_t fb = qpos - mis;  // frame bytes in front of the round
+                const bool bad = off > fb + excl_tot + ll;
+                if (__any_sync(kFull, act && (bad || off == 0 || ml == 0))) {
+                    err = SZB_ERR_CANT_REPEAT_BYTES;
+                    break;
+                }
+            }
+
+            // --- the round's segments go to the ring, as many sequences at a time as the bitmap holds (normally all) ---
+            uint32_t start = 0;
+            while (start < cnt) {
+                uint32_t out_rel = qpos - st.line;
+                if (out_rel + round_tot > kX2Span && prod - st.line >= 128) {
+                    // rounds of long sequences: the consumer catches up before the round is cut into pieces
+                    st = x2_drain_cold(sm, st, prod, lane, le_mask);
+                    out_rel = qpos - st.line;
+                }
+                const uint32_t my_rel = out_rel + excl_tot;  // my literal run, relative to the line being consumed
+                uint32_t nfit;
+                if (start == 0 && !lit_rle && out_rel + round_tot <= kX2Span) {
+                    nfit = cnt;  // the usual case: the whole round fits the ring
+                } else {
+                    const bool fits = my_rel + tot <= kX2Span && !(lit_rle && ll > kX2ConstRun);
+                    const uint32_t fitmask = __ballot_sync(kFull, fits && lane < cnt) >> start;
+                    nfit = fitmask == (0xFFFFFFFFu >> start) ? 32 - start : __ffs(~fitmask) - 1;  // leading fits
+                }
+                if (nfit == 0) {
+                    // one sequence longer than the ring: the whole warp on its literals, then on its match
+                    st = x2_flush_cold(sm, st, prod, lane, le_mask);
+                    const uint32_t L = __shfl_sync(kFull, ll, start), ML = __shfl_sync(kFull, ml, start);
+                    const uint32_t OFF = __shfl_sync(kFull, off, start);
+                    const uint32_t Dq = qpos + __shfl_sync(kFull, excl_tot, start);
+                    uint8_t *D = st.qb + Dq;
+                    if (lit_rle)
+                        warp_memset(D, lit[0], L, lane);
+                    else
+                        warp_memcpy(D, lit + lit_pos + __shfl_sync(kFull, excl_ll, start), L, lane);
+                    __syncwarp();
+                    uint8_t *MD = D + L;
+                    const uint8_t *MS = MD - OFF;
+                    if (OFF >= 32) {
+                        for (uint32_t k0 = 0; k0 < ML; k0 += 32) {
+                            const uint32_t k = k0 + lane;
+                            if (k < ML) MD[k] = MS[k];
+                            __syncwarp();
+                        }
+                    } else if (ML) {  // overlapping: periodic extension of the OFF bytes before the match
+                        for (uint32_t k = lane; k < ML; k += 32) MD[k] = MS[k % OFF];
+                    }
+                    __syncwarp();
+                    prod = Dq + L + ML;
+                    x2_seek(st, prod);
+                    start++;
+                    continue;
+                }
+                const uint32_t end = start + nfit;
+                const bool in = lane >= start && lane < end;
+                const uint32_t no_lit = __ballot_sync(kFull, in && ll == 0);
+                if (in) {
+                    uint32_t ord = nseg + 2 * (lane - start) - __popc(no_lit & lt_mask);
+                    const uint32_t q_lit = qpos + excl_tot;  // my literal run
+                    if (ll) {
+                        // literal byte at q: lit[lit_pos + excl_ll + (q - q_lit)]; a run of RLE literals reads the first bytes of the fill row
+                        sm.seg[ord & (kX2Ring - 1)] = kX2Lit | (q_lit - (lit_rle ? 0u : lit_pos + excl_ll));
+                        atomicOr(&sm.bits[(q_lit >> 5) & (kX2Bits / 32 - 1)], 1u << (q_lit & 31));
+                        ord++;
+                    }
+                    {
+                        const uint32_t q_m = q_lit + ll;
+                        sm.seg[ord & (kX2Ring - 1)] = off;
+                        atomicOr(&sm.bits[(q_m >> 5) & (kX2Bits / 32 - 1)], 1u << (q_m & 31));
+                        // the consumer gets here about a round later: have the source on its way to L1
+                        SZB_PREFETCH_L1(st.qb + (q_m - off));
+                    }
+                }
+                nseg += 2 * nfit - __popc(no_lit);
+                const uint32_t prev_prod = prod;
+                prod = st.line + __shfl_sync(kFull, my_rel + tot, end - 1);
+                __syncwarp();
+                x2_drain(sm, st, prev_prod, lane, le_mask);  // one append behind: the prefetches have time to land
+                start = end;
+            }
+            qpos += round_tot;
+            lit_pos += round_ll;
+        }
+        if (err != SZB_OK) break;
+        // trailing literals (sequence_execution.go:55-60, literals.go:411-420): one more segment, or a bulk copy
+        const uint32_t rest = d.lit_regen - lit_pos;
+        if (rest && (prod - st.line) + rest <= kX2Span && !(lit_rle && rest > kX2ConstRun)) {
+            if (lane == 0) {
+                sm.seg[nseg & (kX2Ring - 1)] = kX2Lit | (qpos - (lit_rle ? 0u : lit_pos));
+                atomicOr(&sm.bits[(prod >> 5) & (kX2Bits / 32 - 1)], 1u << (prod & 31));
+            }
+            nseg++;
+            prod += rest;
+            __syncwarp();
+            st = x2_drain_cold(sm, st, prod, lane, le_mask);
+        } else if (rest) {
+            st = x2_flush_cold(sm, st, prod, lane, le_mask);
+            if (lit_rle)
+                warp_memset(st.qb + qpos, lit[0], rest, lane);
+            else
+                warp_memcpy(st.qb + qpos, lit + lit_pos, rest, lane);
+            __syncwarp();
+            prod = qpos + rest;
+            x2_seek(st, prod);
+        }
+    }
+    // On an error the frame's output is void; what the ring still holds is written anyway (it is within the frame's range).
+    st = x2_flush_cold(sm, st, prod, lane, le_mask);
+    if (lane == 0 && err != SZB_OK) {  // failed while executing (bad offset, literals ran dry)
+        a.frame_status[f] = err;
+        a.frame_out_len[f] = 0;
+    }
+}
+
+// One warp per frame.  Frames exec_list[first_slot, first_slot + n_slots) that x2_takes; k_execute takes the others.
+// ONE warp per CTA (r02i, 65 536 text frames: 9.0 ms against 10.5 ms with four): a CTA's registers and shared memory come back
+// when its frame ends instead of when the longest of four frames ends, and the warp's shared memory sits at a constant address.
+// 32 CTAs per SM is what the register file holds at 64 registers anyway.
+#ifndef SZB_EXEC2_WARPS
+#define SZB_EXEC2_WARPS 1
+#endif
+#ifndef SZB_EXEC2_MIN_CTAS
+#define SZB_EXEC2_MIN_CTAS 32
+#endif
+constexpr int kX2Warps = SZB_EXEC2_WARPS;
+__global__ void __launch_bounds__(kX2Warps * 32, SZB_EXEC2_MIN_CTAS) k_execute2(DeviceBatch a, uint32_t first_slot, uint32_t n_slots) {
+    __shared__ X2Smem smem[kX2Warps];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t slot = blockIdx.x * kX2Warps + (threadIdx.x >> 5);
+    if (slot >= n_slots) return;
+    const uint32_t f = a.exec_list[first_slot + slot];
+    if (a.frame_status[f] != SZB_OK) return;  // k_frame_verdict
+    if (!x2_takes(a, f)) return;              // k_execute's
+    X2Smem &sm = smem[threadIdx.x >> 5];
+    for (uint32_t wd = lane; wd < kX2Bits / 32; wd += 32) sm.bits[wd] = 0;
+    __syncwarp();
+    x2_frame(a, f, sm, lane);
+}

@@ -643,6 +643,7 @@ __device__ __forceinline__ void produce_frame(const DeviceBatch &a, uint32_t f, 
 
 #include "execute_long.cuh"
 #include "place.cuh"
+#include "exec2.cuh"
 
 // One warp per frame: it produces the segments and consumes them.  Frames exec_list[first_slot, first_slot + n_slots).
 #ifndef SZB_EXEC_MIN_CTAS
@@ -656,6 +657,7 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
     const uint32_t f = a.exec_list[first_slot + slot];
     if (a.frame_status[f] != SZB_OK) return;  // k_frame_verdict
     if (a.place_state && a.place_state[f] != 1) return;  // k_place executes it (place.cuh)
+    if (x2_takes(a, f)) return;                          // k_execute2 executes it (exec2.cuh)
     ExecSmem &sm = smem[threadIdx.x >> 5];
     for (uint32_t wd = lane; wd < kRingBits / 32; wd += 32) sm.bits[wd] = 0;
     __syncwarp();

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/szb200.h"
+#include "abi_layout.h"
 
 struct szb_walk {
     std::vector<szb_frame_desc> frames;
@@ -226,6 +227,8 @@ void walk_frame(szb_walk &w, const uint8_t *src, uint64_t off, uint64_t len, uin
 }  // namespace
 
 extern "C" {
+
+uint32_t szb_abi_layout(uint32_t *out, uint32_t cap) { return szb_abi_layout_impl(out, out ? cap : 0); }
 
 int szb_walk_create(const uint8_t *src, size_t src_len, const uint64_t *frame_off, const uint64_t *frame_len,
                     uint32_t nframes, szb_walk **out) {

@@ -255,6 +255,7 @@ int hostsim_decode_frame(const uint8_t *src, size_t len, uint8_t *out, size_t ca
 //   2: the block-parallel kernels of execute_long.cuh, with k_execute_pair launched beside them as the fallback.
 //   3: k_resolve + k_place (place.cuh), with k_execute launched behind them as the fallback, as launch_execute does;
 //      4: the same with bitmaps too small for the output, so that every frame falls back to k_execute.
+//   5: k_execute2 (exec2.cuh), with k_execute launched behind it as launch_execute does.
 //      (lines are aligned to memory, not to the output: callers also pass an `out` that is not 128-byte aligned)
 // order: 0 = CTAs in launch order, 1 = reversed (the worst case for k_long_jump), >= 2 = shuffled with that seed.
 // With two_frames the same frame is decoded twice in one batch and both copies must agree.
@@ -379,7 +380,8 @@ int hostsim_stage4_at(const uint8_t *src, size_t len, uint8_t *out, size_t cap, 
     a.exec_list = exec_list.data();
     a.body_list = body_list.data();
     a.n_body = (uint32_t)body_list.size();
-    a.n_long = path == 0 ? 0 : copies;
+    a.n_long = (path == 0 || path == 5) ? 0 : copies;
+    a.exec2 = path == 5 ? 1 : 0;
     a.n_lb = n_lb;
     a.lb_block = lb_block.data();
     a.lb_slot = lb_slot.data();
@@ -452,6 +454,9 @@ int hostsim_stage4_at(const uint8_t *src, size_t len, uint8_t *out, size_t cap, 
         for (uint32_t c = 0; c < copies; c++)
             if (place_state[c] != (total > bm_bound ? kPlaceFallback : (frame_status[c] == SZB_ERR_DST_TOO_SMALL ? 0 : frame_status[c]))) return SZB_ERR_INVALID_ARGUMENT;
         warpsim::launch((copies + kPlaceWarps - 1) / kPlaceWarps, kPlaceWarps * 32, [&] { k_place(a, 0, copies); });
+        warpsim::launch((copies + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, [&] { k_execute(a, 0, copies); });
+    } else if (path == 5) {  // k_execute2 (exec2.cuh), with k_execute launched behind it for the frames it does not take
+        warpsim::launch((copies + kX2Warps - 1) / kX2Warps, kX2Warps * 32, [&] { k_execute2(a, 0, copies); });
         warpsim::launch((copies + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, [&] { k_execute(a, 0, copies); });
     } else if (path == 0) {
         warpsim::launch((copies + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, [&] { k_execute(a, 0, copies); });

@@ -36,6 +36,48 @@ def test_struct_layouts_match_the_header():
 
     assert C.sizeof(FrameDesc) == 64
     assert C.sizeof(BlockDesc) == 80
+    # szb_abi_layout(): what the library was compiled with -- the ctypes mirror must agree field by field ...
+    import sparkzstd_b200
+
+    L = sparkzstd_b200.load()
+    buf = (C.c_uint32 * 64)()
+    n = L.szb_abi_layout(buf, 64)
+    got = list(buf[:n])
+    ff = [f[0] for f in FrameDesc._fields_]
+    bf = [f[0] for f in BlockDesc._fields_ if not f[0].startswith("_pad")]
+    want = [C.sizeof(FrameDesc)] + [getattr(FrameDesc, f).offset for f in ff] + [C.sizeof(BlockDesc)] + [getattr(BlockDesc, f).offset for f in bf]
+    assert n == len(want) == 36 and got == want
+    # ... and so must the Go mirror (go/szb200/szb200.go: plain structs with exported fields, same order, same widths; Go
+    # aligns every field naturally, as the C compiler does): recompute its layout from the declaration
+    import os
+    import re
+
+    go = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "go", "szb200", "szb200.go")).read()
+    width = {"uint64": 8, "uint32": 4, "int32": 4, "uint8": 1}
+
+    def go_layout(name):
+        body = re.search(r"type %s struct \{(.*?)\n\}" % name, go, re.S).group(1)
+        off, offs, align = 0, [], 1
+        for line in body.splitlines():
+            m = re.match(r"\s*(\w+)\s+(uint64|uint32|int32|uint8)\b", line)
+            if not m:
+                continue
+            w = width[m.group(2)]
+            off = (off + w - 1) // w * w
+            offs.append((m.group(1), off))
+            off += w
+            align = max(align, w)
+        return (off + align - 1) // align * align, offs
+
+    fsize, foffs = go_layout("FrameDesc")
+    bsize, boffs = go_layout("BlockDesc")
+    boffs = [o for o in boffs if not o[0].startswith("Pad")]
+    assert [fsize] + [o for _, o in foffs] + [bsize] + [o for _, o in boffs] == got
+    # same field order by name (snake_case <-> CamelCase)
+    camel = lambda s: "".join(p.upper() if p in ("ll", "of", "ml", "id") else p.capitalize() for p in s.split("_"))
+    fix = {"Nblocks": "NBlocks", "Nseq": "NSeq"}
+    assert [fix.get(camel(f), camel(f)) for f in ff] == [n_ for n_, _ in foffs]
+    assert [fix.get(camel(f), camel(f)) for f in bf] == [n_ for n_, _ in boffs]
 
 
 def test_no_cpu_fallback_without_a_device():

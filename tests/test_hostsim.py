@@ -20,7 +20,7 @@ SIM = os.path.join(ROOT, "tests", "host_sim")
 def _build_sim(lib_name, defines=()):
     lib = os.path.join(SIM, lib_name)
     srcs = [os.path.join(SIM, "hostsim.cpp"), os.path.join(ROOT, "sparkzstd_b200", "csrc", "walker.cpp")]
-    deps = srcs + [os.path.join(SIM, "warpsim.h")] + [os.path.join(ROOT, "sparkzstd_b200", "csrc", f) for f in ("bits.cuh", "fse.cuh", "huffman.cuh", "sequences.cuh", "batch.cuh", "execute.cuh", "execute_long.cuh", "place.cuh")]
+    deps = srcs + [os.path.join(SIM, "warpsim.h")] + [os.path.join(ROOT, "sparkzstd_b200", "csrc", f) for f in ("bits.cuh", "fse.cuh", "huffman.cuh", "sequences.cuh", "batch.cuh", "execute.cuh", "execute_long.cuh", "place.cuh", "exec2.cuh")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", *[f"-D{d}" for d in defines], "-o", lib, *srcs], check=True)
     L = C.CDLL(lib)
@@ -216,6 +216,75 @@ def test_place_kernels_report_the_oracles_errors(sim, corpus):
             assert rc == _stage4_at.exec_status == code, (name, k, rc, code)
             same_code += 1
     assert same_bytes >= 60 and same_code >= 3
+
+
+# ---- k_execute2 (exec2.cuh): 32-bit positions and entries, lines of memory, four 32-byte rows per line ----
+K_EXECUTE2 = 5
+
+
+def test_execute2_decodes_golden_frames(sim, corpus):
+    done = 0
+    for k, (name, data, size, sha) in enumerate(corpus):
+        if size > 60_000:
+            continue
+        rc, out = _stage4_at(sim, data, size, K_EXECUTE2, k % 2, 1, (k * 37) % 128)
+        assert rc == 0 and len(out) == size and hashlib.sha256(out).hexdigest() == sha, name
+        done += 1
+    assert done >= 20
+
+
+def test_execute2_on_crafted_and_synthetic_frames(sim):
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import crafted_frames as crafted
+
+    for k, (name, (frame, expected)) in enumerate(sorted(crafted.cases().items())):
+        for mis in (0, 1 + (k * 29) % 127):
+            rc, out = _stage4_at(sim, frame, len(expected), K_EXECUTE2, k % 2, 0, mis)
+            assert rc == 0 and out == expected, (name, mis)
+    big, expected = crafted.oversize_block_case()
+    rc, out = _stage4_at(sim, big, len(expected), K_EXECUTE2, 0, 0, 5)
+    assert rc == 0 and out == expected
+    for c in (cg.config2_text_frames(3), cg.config3_single_frame(1 << 19, 20), cg.config5_mixed(1 << 20, with_golden=False)):
+        for i in range(min(c.nframes, 4)):
+            f = c.frame(i)
+            want = pyszo.decode_frame(f)
+            if len(want) > 600_000:
+                continue
+            rc, out = _stage4_at(sim, f, len(want), K_EXECUTE2, i % 2, 0, (i * 53) % 128)
+            assert rc == 0 and out == want, (c.name, i)
+
+
+def test_execute2_agrees_with_execute_on_corrupted_frames(sim, corpus):
+    """Bit flips in small golden frames: k_execute2 must end like k_execute (status and bytes), and with the oracle's bytes
+    whenever the oracle still decodes the frame."""
+    rng = np.random.default_rng(23)
+    small = [(n, d, s) for n, d, s, _ in corpus if 200 <= s <= 12_000 and len(d) >= 60]
+    ok = errs = 0
+    for k in range(300):
+        name, data, size = small[k % len(small)]
+        buf = bytearray(data)
+        for _ in range(1 + k % 3):
+            p = int(rng.integers(10, len(buf) - 4))
+            buf[p] ^= 1 << int(rng.integers(0, 8))
+        frame = bytes(buf)
+        try:
+            want = pyszo.decode_frame(frame)
+        except pyszo.OracleError:
+            want = None
+        cap = max(size, len(want) if want is not None else 0, 1) * 4 + 4096
+        a = _stage4_at(sim, frame, cap, K_EXECUTE, k % 2, 0, (k * 7) % 128)
+        b = _stage4_at(sim, frame, cap, K_EXECUTE2, k % 2, 0, (k * 7) % 128)
+        assert a[0] == b[0], (name, k, a[0], b[0])
+        if a[0] == 0:
+            assert a[1] == b[1], (name, k)
+            if want is not None:
+                assert b[1] == want, (name, k)
+                ok += 1
+        else:
+            errs += 1
+    assert ok >= 60 and errs >= 20
 
 
 @pytest.mark.parametrize("nblocks", [1, 31, 32, 33, 64, 100, 1000])
