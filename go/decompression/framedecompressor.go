@@ -30,10 +30,11 @@ type FrameDecompressor struct {
 	target io.Writer
 	ctx    *szb200.Ctx
 
-	data    []byte // the whole compressed frame: the GPU decodes frames, not blocks
-	out     []byte
-	written int
-	walk    *structure.Walk
+	data      []byte // the whole compressed frame: the GPU decodes frames, not blocks
+	out       []byte
+	decodeErr error // what decodeFrame found; sticky, like a failed reference decoder
+	written   int
+	walk      *structure.Walk
 
 	CurrentBlock  structure.Block
 	PreviousBlock structure.Block
@@ -54,7 +55,7 @@ func NewFrameDecompressor(s io.Reader, t io.Writer) *FrameDecompressor {
 func (fd *FrameDecompressor) Reset(newsource io.Reader, newtarget io.Writer) {
 	fd.source = bufio.NewReader(newsource)
 	fd.target = newtarget
-	fd.data, fd.out, fd.walk = nil, nil, nil
+	fd.data, fd.out, fd.walk, fd.decodeErr = nil, nil, nil, nil
 	fd.written = 0
 	fd.CurrentBlock = structure.Block{}
 	fd.PreviousBlock = structure.Block{}
@@ -114,9 +115,57 @@ func (fd *FrameDecompressor) DecodeNextBlockHeader() error {
 	return nil
 }
 
-// DecodeNextBlock mirrors framedecompressor.go:198-244.  The first call decodes the whole frame on
-// the GPU (DecodeNextBlockContent + ExecuteSequences for every block, in four kernel stages); later
-// calls only advance the block cursor.
+// decodeFrame runs the four GPU stages over the whole frame, once.  The device decodes frames, not blocks: the entropy
+// stages of all blocks run side by side and stage 4 needs every block's size before it can place the first byte.
+func (fd *FrameDecompressor) decodeFrame() error {
+	if fd.out != nil || fd.decodeErr != nil {
+		return fd.decodeErr
+	}
+	if fd.ctx == nil {
+		c, err := szb200.NewCtx(0)
+		if err != nil {
+			return err
+		}
+		fd.ctx = c
+	}
+	out, _, err := fd.ctx.DecompressFrame(fd.data)
+	if err != nil {
+		fd.decodeErr = translate(err)
+		return fd.decodeErr
+	}
+	if out == nil {
+		out = []byte{}
+	}
+	fd.out = out
+	return nil
+}
+
+// DecodeNextBlockContent mirrors framedecompressor.go:93-126: the literals and sequences sections of the CURRENT block
+// (a Compressed block whose header DecodeNextBlockHeader has read).  The section headers were walked with the frame
+// (structure.WalkFrame), so a block whose sections do not add up to Block_Size has already failed with ErrCorruptSizes in
+// DecodeFrameHeader -- earlier than the reference reports it, with the same error value.  The entropy decode itself happens
+// for all blocks at once on the first call; later calls return what that decode found.
+func (fd *FrameDecompressor) DecodeNextBlockContent() error {
+	if fd.walk == nil {
+		return io.ErrUnexpectedEOF
+	}
+	if fd.CurrentBlock.Header.Type != structure.BlockTypeCompressed {
+		return nil // the reference only calls it for Compressed blocks (framedecompressor.go:219-222)
+	}
+	return fd.decodeFrame()
+}
+
+// ExecuteSequences mirrors sequence_execution.go:14-63 for a caller that steps through a frame itself: after it returns nil
+// the CURRENT block's output exists.  Stage 4 of every block ran inside decodeFrame (one warp per frame walks the blocks in
+// order, exactly the reference's order), so per block there is nothing left to do but report that decode's verdict: an
+// error found while executing (ErrDidntCopyAllLiteralBytes, a match reaching before the frame) is returned here as the
+// reference returns it.
+func (fd *FrameDecompressor) ExecuteSequences() error {
+	return fd.decodeFrame()
+}
+
+// DecodeNextBlock mirrors framedecompressor.go:198-244: header, then for a Compressed block DecodeNextBlockContent +
+// ExecuteSequences; Raw and RLE bodies are written by the same GPU pass (k_execute_bodies).
 func (fd *FrameDecompressor) DecodeNextBlock() error {
 	if fd.CurrentBlock.Header.LastBlock {
 		return ErrOutOfBlocks
@@ -124,21 +173,15 @@ func (fd *FrameDecompressor) DecodeNextBlock() error {
 	if err := fd.DecodeNextBlockHeader(); err != nil {
 		return err
 	}
-	if fd.out == nil {
-		if fd.ctx == nil {
-			c, err := szb200.NewCtx(0)
-			if err != nil {
-				return err
-			}
-			fd.ctx = c
+	switch fd.CurrentBlock.Header.Type {
+	case structure.BlockTypeCompressed:
+		if err := fd.DecodeNextBlockContent(); err != nil {
+			return err
 		}
-		out, _, err := fd.ctx.DecompressFrame(fd.data)
-		if err != nil {
-			return translate(err)
-		}
-		fd.out = out
+		return fd.ExecuteSequences()
+	default:
+		return fd.decodeFrame()
 	}
-	return nil
 }
 
 // Decompress mirrors framedecompressor.go:153-170.

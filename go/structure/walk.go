@@ -72,7 +72,7 @@ func ErrorForCode(code int) (error, bool) {
 }
 
 func BlockFromDesc(d *szb200.BlockDesc) Block {
-	return Block{Header: BlockHeader{LastBlock: d.last != 0, Type: BlockType(d._type), BlockSize: uint64(d.block_size)}}
+	return Block{Header: BlockHeader{LastBlock: d.Last != 0, Type: BlockType(d.Type), BlockSize: uint64(d.BlockSize)}}
 }
 
 // WalkFrame walks the frame at src[0:] (framedecompressor.go:130-150, :306-374, :270-303;
@@ -120,15 +120,15 @@ func WalkFrame(src []byte) (*Walk, error) {
 		return nil, io.ErrUnexpectedEOF
 	}
 	f := &w.Frame
-	f.descriptor = C_uint8(fhd)
-	f.content_size = ^C_uint64(0)
+	f.Descriptor = uint8(fhd)
+	f.ContentSize = ^uint64(0)
 	if single {
-		f.single_segment = 1
+		f.SingleSegment = 1
 	} else {
 		wd := src[pos]
 		pos++
 		base := uint64(1) << (10 + (wd >> 3))
-		f.window_size = C_uint64(base + (base/8)*uint64(wd&7))
+		f.WindowSize = uint64(base + (base/8)*uint64(wd&7))
 	}
 	pos += dictBytes
 	if fcsBytes > 0 {
@@ -140,10 +140,10 @@ func WalkFrame(src []byte) (*Walk, error) {
 			v += 256
 		}
 		pos += fcsBytes
-		f.content_size = C_uint64(v)
-		f.has_content_size = 1
+		f.ContentSize = uint64(v)
+		f.HasContentSize = 1
 		if single {
-			f.window_size = C_uint64(v)
+			f.WindowSize = uint64(v)
 		}
 	}
 	carryHuf, carryLL, carryOF, carryML := uint32(none), uint32(none), uint32(none), uint32(none)
@@ -197,15 +197,15 @@ func WalkFrame(src []byte) (*Walk, error) {
 		}
 		w.Blocks = append(w.Blocks, d)
 	}
-	f.src_len = C_uint64(pos)
-	f.nblocks = C_uint32(len(w.Blocks))
+	f.SrcLen = uint64(pos)
+	f.NBlocks = uint32(len(w.Blocks))
 	// The reference leaves the optional content checksum unread (frame.go:105-108).  It is recorded so that
 	// szb200.FlagVerifyChecksum can have the GPU check it; src_len stays "up to the end of the last block".
 	if (fhd>>2)&1 == 1 {
-		f.has_checksum = 1
+		f.HasChecksum = 1
 		if w.Err == nil && need(4) {
-			f.checksum = C_uint32(uint32(src[pos]) | uint32(src[pos+1])<<8 | uint32(src[pos+2])<<16 | uint32(src[pos+3])<<24)
-			f.checksum_valid = 1
+			f.Checksum = uint32(uint32(src[pos]) | uint32(src[pos+1])<<8 | uint32(src[pos+2])<<16 | uint32(src[pos+3])<<24)
+			f.ChecksumValid = 1
 		}
 	}
 	return w, nil

@@ -1,9 +1,7 @@
 package structure
 
-/*
-#include "../../include/szb200.h"
-*/
-import "C"
+// No cgo in this package: the descriptor rows are the plain Go structs of package szb200 (exported fields, layout checked
+// against the C header when that package loads), so nothing here depends on C types.
 
 import (
 	"io"
@@ -11,18 +9,14 @@ import (
 	"github.com/killingspark/sparkzstd/szb200"
 )
 
-type C_uint8 = C.uint8_t
-type C_uint32 = C.uint32_t
-type C_uint64 = C.uint64_t
-
 func setBlock(d *szb200.BlockDesc, payloadOff int, size uint32, btype byte, last bool) {
-	d.src_off = C.uint64_t(payloadOff)
-	d.block_size = C.uint32_t(size)
-	d._type = C.uint8_t(btype)
+	d.SrcOff = uint64(payloadOff)
+	d.BlockSize = uint32(size)
+	d.Type = uint8(btype)
 	if last {
-		d.last = 1
+		d.Last = 1
 	}
-	d.huf_origin, d.ll_origin, d.of_origin, d.ml_origin = none, none, none, none
+	d.HufOrigin, d.LLOrigin, d.OFOrigin, d.MLOrigin = none, none, none, none
 }
 
 // parseCompressed fills the literals / sequences header fields and resolves the origin blocks of
@@ -87,21 +81,21 @@ func parseCompressed(d *szb200.BlockDesc, b []byte, self uint32, carryHuf, carry
 	if regen > 128*1024 || comp > 128*1024 {
 		return errPanic
 	}
-	d.lit_type, d.lit_streams, d.lit_hdr_bytes = C.uint8_t(litType), C.uint8_t(streams), C.uint8_t(need)
-	d.lit_regen, d.lit_comp = C.uint32_t(regen), C.uint32_t(comp)
+	d.LitType, d.LitStreams, d.LitHdrBytes = uint8(litType), uint8(streams), uint8(need)
+	d.LitRegen, d.LitComp = uint32(regen), uint32(comp)
 	if litType == 3 {
 		if *carryHuf == none {
 			return ErrNoHuffTableToCarryOver
 		}
-		d.huf_origin = C.uint32_t(*carryHuf)
+		d.HufOrigin = uint32(*carryHuf)
 	} else if litType == 2 {
-		d.huf_origin = C.uint32_t(self)
+		d.HufOrigin = uint32(self)
 	}
 	litTotal := need + int(comp)
 	if litTotal > len(b) {
 		return io.ErrUnexpectedEOF
 	}
-	d.seq_off = C.uint32_t(litTotal)
+	d.SeqOff = uint32(litTotal)
 	s := b[litTotal:]
 	if len(s) < 1 {
 		return io.ErrUnexpectedEOF
@@ -126,17 +120,23 @@ func parseCompressed(d *szb200.BlockDesc, b []byte, self uint32, carryHuf, carry
 		nseq = uint32(s[1]) + uint32(s[2])<<8 + 0x7F00
 	}
 	if s[0] == 0 {
-		d.seq_hdr_bytes = 1
+		d.SeqHdrBytes = 1
 		if litTotal+1 != len(b) {
 			return ErrCorruptSizes
 		}
+	} else if nseq == 0 {
+		// A two- or three-byte count that says zero (0x80 0x00): the reference (sequences.go:395-400 short-circuits on the
+		// first byte only) goes on to decode tables and a stream of no sequences.  Both walkers agree on ONE answer instead:
+		// the section is not the single zero byte, so the sizes do not add up (walker.cpp; DESIGN.md section 2).  The carry
+		// origins are left alone: a block without sequences defines no tables.
+		return ErrCorruptSizes
 	} else {
 		if len(s) < nb+1 {
 			return io.ErrUnexpectedEOF
 		}
-		d.nseq = C.uint32_t(nseq)
-		d.seq_modes = C.uint8_t(s[nb])
-		d.seq_hdr_bytes = C.uint8_t(nb + 1)
+		d.NSeq = uint32(nseq)
+		d.SeqModes = uint8(s[nb])
+		d.SeqHdrBytes = uint8(nb + 1)
 		modes := s[nb]
 		pick := func(mode byte, carry *uint32, missing error) (uint32, error) {
 			if mode == 3 {
@@ -159,15 +159,15 @@ func parseCompressed(d *szb200.BlockDesc, b []byte, self uint32, carryHuf, carry
 		if err != nil {
 			return err
 		}
-		d.ll_origin, d.of_origin, d.ml_origin = C.uint32_t(ll), C.uint32_t(of), C.uint32_t(ml)
+		d.LLOrigin, d.OFOrigin, d.MLOrigin = uint32(ll), uint32(of), uint32(ml)
 		*carryLL, *carryOF, *carryML = ll, of, ml
 	}
 	if litType >= 2 {
-		*carryHuf = uint32(d.huf_origin)
-		d.lit_buf_off = C.uint64_t(*litBytes)
+		*carryHuf = uint32(d.HufOrigin)
+		d.LitBufOff = uint64(*litBytes)
 		*litBytes += (uint64(regen) + 15) &^ 15
 	}
-	d.seq_buf_off = C.uint64_t(*seqs)
-	*seqs += (uint64(d.nseq) + 31) &^ 31
+	d.SeqBufOff = uint64(*seqs)
+	*seqs += (uint64(d.NSeq) + 31) &^ 31
 	return nil
 }

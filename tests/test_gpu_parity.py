@@ -329,6 +329,35 @@ def test_content_checksums_verify_on_the_gpu(ctx, corpus):
     assert not st3.any()
 
 
+def test_concatenated_and_skippable_stream_through_the_decode_entry(ctx, corpus, tmp_path):
+    """szb_decode_stream (not a reference behaviour: the reference decodes one frame per reader and knows no
+    skippable frames): frames back to back with skippable frames in between and content checksums after each -- the stream's
+    content is the concatenation of what the oracle decodes frame by frame."""
+    picks = [corpus[i] for i in (0, 3, 7, 11, 19, 23)]
+    skip = lambda k, body: (0x184D2A50 + k).to_bytes(4, "little") + len(body).to_bytes(4, "little") + body
+    blob = skip(0, b"") + picks[0][1] + skip(5, b"metadata") + picks[1][1] + picks[2][1] + skip(15, bytes(300)) + picks[3][1] + picks[4][1] + picks[5][1]
+    want = b"".join(pyszo.decode_frame(d) for _, d, _, _ in picks)
+    assert ctx.decode_stream(blob) == want
+    assert ctx.decode_stream(blob, verify_checksum=True) == want  # every golden frame carries its XXH64
+    assert ctx.decode_stream(b"") == b"" and ctx.decode_stream(skip(1, b"only a skippable frame")) == b""
+    # a flipped content byte of the third frame: the checksum of that frame no longer matches
+    bad = bytearray(blob)
+    at = len(skip(0, b"")) + len(picks[0][1]) + len(skip(5, b"metadata")) + len(picks[1][1]) + len(picks[2][1]) - 5
+    bad[at] ^= 0xFF
+    with pytest.raises(Exception):
+        ctx.decode_stream(bytes(bad), verify_checksum=True)
+    # trailing garbage is no frame: the walk ends with its error
+    with pytest.raises(Exception):
+        ctx.decode_stream(blob + b"\x01\x02\x03\x04\x05\x06")
+    # the CLI's --stream mode writes the stream's content
+    from sparkzstd_b200 import cli
+
+    f = tmp_path / "many.zst"
+    f.write_bytes(blob)
+    (tmp_path / "many").write_bytes(want)
+    assert cli.main(["--stream", str(f)]) == 0
+
+
 def test_cli_compares_with_originals(ctx, corpus, tmp_path):
     """cmd/sparkzstd equivalent: decode X.zst, compare with X (main.go:46-111)."""
     from sparkzstd_b200 import cli
