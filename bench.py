@@ -124,6 +124,9 @@ def build_corpus(args, rank: int):
         c = cg.config4_literal_heavy(n, 1 << 20, base_seed=cg.BASE_SEED + 10_000_000 + rank * n)
     elif args.workload == "single":
         c = cg.config3_single_frame(args.frames * args.frame_size, 23, seed=cg.BASE_SEED + 20_000_000 + rank)
+    elif args.scaling == "strong":
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        c = cg.config5_mixed(args.total_bytes, seed=cg.BASE_SEED + 30_000_000, shard=(rank, world))
     else:
         c = cg.config5_mixed(args.frames * args.frame_size, seed=cg.BASE_SEED + 30_000_000 + rank)
     log(f"[rank {rank}] corpus '{c.name}': {c.nframes} frames, C={c.compressed_bytes} D={c.decompressed_bytes} in {time.time() - t0:.1f}s")
@@ -220,6 +223,10 @@ def main():
     ap.add_argument("--workload", default="text", choices=["text", "literal", "single", "mixed"])
     ap.add_argument("--frames", type=int, default=65536, help="frames per GPU (text) / size multiplier for other workloads")
     ap.add_argument("--frame-size", type=int, default=65536)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong (mixed workload only): ONE corpus of --total-bytes, frame-sharded over the ranks by szb_shard_frames "
+                         "(configs[4] as BASELINE.json words it); weak: every rank decodes its own corpus")
+    ap.add_argument("--total-bytes", type=int, default=16 << 30, help="decompressed size of the whole corpus for --scaling strong")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
@@ -229,6 +236,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.scaling == "strong" and args.workload != "mixed":
+        raise SystemExit("--scaling strong is the frame-sharded mixed corpus (configs[4]): use --workload mixed")
+    # one process per GPU on a shared host: the library's host-side workers (header walks, staging copies) get cores / ranks
+    os.environ.setdefault("SZB_WALK_THREADS", str(max(1, min(8, (os.cpu_count() or 8) // max(world, 1) - 1))))
     # exactly ONE JSON line may reach stdout: libraries (NCCL prints its version on stdout) get stderr
     sys.stdout.flush()
     json_out = os.fdopen(os.dup(1), "w")
@@ -318,7 +329,7 @@ def main():
                 cov["of_modes"][(b.seq_modes >> 4) & 3] += 1
                 cov["ml_modes"][(b.seq_modes >> 2) & 3] += 1
     cov["legend"] = "block types Raw/RLE/Compressed; literal types Raw/RLE/Compressed/Treeless; modes Predefined/RLE/FSE/Repeat"
-    if args.workload == "mixed":
+    if args.workload == "mixed" and args.scaling == "weak":
         assert all(cov["block_types"]) and all(cov["literal_types"]) and all(cov["ll_modes"]) and all(cov["of_modes"]) and \
             all(cov["ml_modes"]), f"the mixed corpus misses a format path: {cov}"
 
@@ -340,6 +351,12 @@ def main():
         dist.all_reduce(tot)
     ms_step_max = float(t.item())
     D_all, C_all, M_all = [float(x) for x in tot.tolist()]
+    shards = None
+    if world > 1:  # what every rank had to do and how long it took: the imbalance a strong-scaling split leaves
+        mine = torch.tensor([float(D), ms_step], dtype=torch.float64, device=f"cuda:{local_rank}")
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        shards = {"decompressed_bytes": [int(e[0].item()) for e in every], "ms_per_step": [float(e[1].item()) for e in every]}
     value = D_all / (ms_step_max * 1e-3) / 1e9
 
     # ---- e2e: host buffers through the C-ABI batch call, copies inside the timed region ----
@@ -415,13 +432,14 @@ def main():
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "ms_per_step": ms_step_max, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
         "config": {"workload": c.meta.get("workload", c.name), "frames_per_gpu": c.nframes, "blocks_per_gpu": len(blocks),
                    "sequences_per_gpu": nseq, "compressed_bytes_per_gpu": C_bytes, "decompressed_bytes_per_gpu": D,
                    "parallelism": f"frame-sharded x{world}, no collective",
                    "l2": "inputs (compressed + scratch + output, > 5 GB) are larger than the 126 MB L2; no flush needed",
-                   "header_walk_s": walk_s, "format_coverage_per_gpu": cov, "numa_node_rank0": numa},
+                   "header_walk_s": walk_s, "format_coverage_per_gpu": cov, "numa_node_rank0": numa,
+                   "shards": shards, "shard_plan": c.meta.get("shard")},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "verified": verified,
     }

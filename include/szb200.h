@@ -66,7 +66,8 @@ enum {
     SZB_ERR_CUDA = -65,
     SZB_ERR_INVALID_ARGUMENT = -66,
     SZB_ERR_NO_DEVICE = -67,
-    SZB_ERR_CHECKSUM_MISMATCH = -68 /* only when SZB_FLAG_VERIFY_CHECKSUM is set (not a reference behaviour) */
+    SZB_ERR_CHECKSUM_MISMATCH = -68, /* only when SZB_FLAG_VERIFY_CHECKSUM is set (not a reference behaviour) */
+    SZB_ERR_IO = -69                 /* a read / write callback of szb_decompress_reader failed */
 };
 
 /* replaces: the Go `error` values' Error() strings */
@@ -134,6 +135,14 @@ typedef struct szb_block_desc {
  * listed).  Writes at most cap values, returns how many there are (36).  A binding compares them with its own when it loads. */
 uint32_t szb_abi_layout(uint32_t *out, uint32_t cap);
 
+/* Multi-GPU host split: frames are independent, so G GPUs decode a partition of the frame list, one process
+ * (one szb_ctx) per GPU, no data-path collective.  weight[i] is frame i's cost (its content size when the header declares it,
+ * else a multiple of its compressed size); shard_of[i] receives the shard (0 .. nshards-1) of frame i, shard_load[r]
+ * (optional) the summed weight of shard r.  Greedy longest-processing-time binning; deterministic: every rank computes the
+ * same partition from the same weights.  The reference decodes one frame per FrameDecompressor on one core
+ * (cmd/sparkzstd/main.go:22-40 loops over files); this is the batch counterpart of that loop across devices. */
+int szb_shard_frames(const uint64_t *weight, uint32_t nframes, uint32_t nshards, uint32_t *shard_of, uint64_t *shard_load);
+
 typedef struct szb_walk szb_walk;
 
 /* Walks the headers of nframes frames.  frame_off/frame_len give each frame's extent inside
@@ -197,9 +206,31 @@ int szb_decode_stream(szb_ctx *ctx, const uint8_t *src, size_t src_len, uint8_t 
  * frames / blocks are HOST tables (copied before return).  replaces: DecodeNextBlockContent +
  * ExecuteSequences + the Raw/RLE bodies of DecodeNextBlock (framedecompressor.go:93-126,
  * :198-244; sequence_execution.go:14-63) for every block of every frame. */
+/* DEVICE SOURCE BUFFERS (d_src here, in szb_batch_decode_entropy / szb_batch_execute / szb_batch_run, and src with
+ * SZB_FLAG_SRC_DEVICE): the bit readers fetch whole aligned 16-byte chunks, so d_src must be 16-byte aligned and at least 16
+ * bytes past src_len must be readable (their content does not matter).  A misaligned pointer is SZB_ERR_INVALID_ARGUMENT; the
+ * padding cannot be checked and is the caller's to provide (cudaMalloc'd buffers of src_len + 16 bytes satisfy both). */
 int szb_decode_blocks(szb_ctx *ctx, const void *d_src, size_t src_len, const szb_frame_desc *frames, uint32_t nframes,
                       const szb_block_desc *blocks, uint32_t nblocks, void *d_dst, size_t dst_cap, uint64_t *out_off,
                       uint64_t *out_len, int32_t *status);
+
+/* Streaming single-frame entry: what NewFrameDecompressor(source, target).Decompress() and FrameReader.Read do, with the
+ * transfers overlapped instead of read-all / decode / write-all.  `read` is source.Read: it fills buf with up to cap bytes and
+ * returns how many (0 = end of input, < 0 = error); `write` is target.Write: it takes n decoded bytes and returns 0 (non-zero
+ * aborts).  Input pieces are staged through pinned memory and travel to the device while the next piece is being read; the
+ * frame is decoded once its last byte is on the device (stage 4 needs every block's size); the output comes back in pieces,
+ * piece k+1 and k+2 on the link while `write` consumes piece k -- so a reader sees its first bytes one piece after the
+ * decode, not after the whole device-to-host copy.  Like the reference's bufio.Reader the source is read to its end, the
+ * frame's own extent is reported through in_used (checksum excluded).  Both callbacks run on the calling thread.
+ * replaces: FrameDecompressor.Decompress (framedecompressor.go:153-170) with its io.Reader source and io.Writer target, and
+ * the read loop of FrameReader.Read (framereader.go:51-109).  SZB_FLAG_VERIFY_CHECKSUM is honoured. */
+typedef int64_t (*szb_read_fn)(void *user, uint8_t *buf, size_t cap);
+typedef int (*szb_write_fn)(void *user, const uint8_t *buf, size_t n);
+int szb_decompress_reader(szb_ctx *ctx, szb_read_fn read, void *read_user, szb_write_fn write, void *write_user,
+                          uint64_t *in_used, uint64_t *out_total, uint32_t flags);
+/* The header row (window size, content size, number of blocks, walk status ...) of the frame szb_decompress_reader decoded
+ * last on this context: what FrameDecompressor.BlockCounter and the reference's frame-header fields are filled from. */
+int szb_ctx_last_frame(szb_ctx *ctx, szb_frame_desc *out);
 
 /* ---- staged batch object (size-then-decode, resident inputs, timing) ------------------ */
 typedef struct szb_batch szb_batch;

@@ -73,10 +73,13 @@ SYMBOLS = [
     ("szb_ctx_create", C.c_int, [C.c_int, _P, C.POINTER(_P)]),
     ("szb_ctx_destroy", None, [_P]),
     ("szb_abi_layout", C.c_uint32, [_P, C.c_uint32]),
+    ("szb_shard_frames", C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P]),
     ("szb_ctx_stream", _P, [_P]),
     ("szb_ctx_last_error", C.c_char_p, [_P]),
     ("szb_decode_batch", C.c_int, [_P, _P, C.c_size_t, _P, _P, C.c_uint32, _P, C.c_size_t, _P, _P, _P, C.c_uint32]),
     ("szb_decode_stream", C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t, _P, _P, _P, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_uint32]),
+    ("szb_ctx_last_frame", C.c_int, [_P, _P]),
+    ("szb_decompress_reader", C.c_int, [_P, _P, _P, _P, _P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint32]),
     ("szb_decode_blocks", C.c_int, [_P, _P, C.c_size_t, _P, C.c_uint32, _P, C.c_uint32, _P, C.c_size_t, _P, _P, _P]),
     ("szb_batch_create", C.c_int, [_P, _P, C.c_size_t, _P, _P, C.c_uint32, C.POINTER(_P)]),
     ("szb_batch_create_from_tables", C.c_int, [_P, C.c_size_t, _P, C.c_uint32, _P, C.c_uint32, C.POINTER(_P)]),

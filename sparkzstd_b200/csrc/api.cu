@@ -9,7 +9,11 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -41,6 +45,13 @@ struct szb_ctx {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaStream_t s_lit = nullptr;          // the literal chain runs beside the sequence chain (they meet at stage 4)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // Pinned staging for callers whose buffers are pageable (a Go slice, a Python bytes object): the copy engines only run
+    // asynchronously from / to page-locked memory.  Two rings of kPinBytes slots, allocated on first use.
+    static constexpr int kPinIn = 2, kPinOut = 3;
+    static constexpr size_t kPinBytes = (size_t)32 << 20;
+    szb_frame_desc last_frame = {};  // the header row of the frame szb_decompress_reader decoded last
+    uint8_t *pin_in[kPinIn] = {}, *pin_out[kPinOut] = {};
+    cudaEvent_t pin_in_ev[kPinIn] = {}, pin_out_ev[kPinOut] = {};
 };
 
 static cudaError_t pool_alloc(szb_ctx *ctx, void **p, size_t bytes);
@@ -119,6 +130,7 @@ const char *szb_version(void) { return "sparkzstd-b200 0.1 (sm_100a)"; }
 const char *szb_strerror(int code) {
     switch (code) {
     case SZB_OK: return "ok";
+    case SZB_ERR_IO: return "read or write callback failed";
     case SZB_ERR_WRONG_MAGICNUMBER: return "Magicnum is not correct";
     case SZB_ERR_CORRUPT_SIZES: return "The sizes of literal and sequence section did not add up to blocksize";
     case SZB_ERR_OUT_OF_BLOCKS: return "No blocks left in frame";
@@ -249,11 +261,24 @@ void szb_ctx_destroy(szb_ctx *ctx) {
     if (ctx->s_lit) cudaStreamDestroy(ctx->s_lit);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    for (int i = 0; i < szb_ctx::kPinIn; i++) {
+        if (ctx->pin_in[i]) cudaFreeHost(ctx->pin_in[i]);
+        if (ctx->pin_in_ev[i]) cudaEventDestroy(ctx->pin_in_ev[i]);
+    }
+    for (int i = 0; i < szb_ctx::kPinOut; i++) {
+        if (ctx->pin_out[i]) cudaFreeHost(ctx->pin_out[i]);
+        if (ctx->pin_out_ev[i]) cudaEventDestroy(ctx->pin_out_ev[i]);
+    }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 void *szb_ctx_stream(szb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int szb_ctx_last_frame(szb_ctx *ctx, szb_frame_desc *out) {
+    if (!ctx || !out) return SZB_ERR_INVALID_ARGUMENT;
+    *out = ctx->last_frame;
+    return SZB_OK;
+}
 const char *szb_ctx_last_error(szb_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 uint64_t szb_launch_count(szb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
@@ -518,6 +543,8 @@ int szb_batch_create_from_tables(szb_ctx *ctx, size_t src_len, const szb_frame_d
             return SZB_ERR_INVALID_ARGUMENT;
         }
     }
+    // The scratch ranges (literal bytes, sequence rows) must ascend without overlapping, as the walkers hand them out:
+    // kernels of different blocks write them at the same time.
     uint64_t lit = 0, seq = 0;
     for (uint32_t i = 0; i < nblocks; i++) {
         const szb_block_desc &d = b->blocks[i];
@@ -527,10 +554,14 @@ int szb_batch_create_from_tables(szb_ctx *ctx, size_t src_len, const szb_frame_d
             bad = d.lit_type > 3 || (uint64_t)d.lit_hdr_bytes + d.lit_comp > d.block_size || d.lit_regen > 128 * 1024 ||
                   (uint64_t)d.seq_off + d.seq_hdr_bytes > d.block_size || d.seq_off != (uint32_t)d.lit_hdr_bytes + d.lit_comp ||
                   (d.lit_streams != 1 && d.lit_streams != 4);
+            // Raw literals are read from the payload (lit_regen bytes after the header), RLE literals are its one byte
+            if (!bad && d.lit_type == 0) bad = d.lit_comp != d.lit_regen;
+            if (!bad && d.lit_type == 1) bad = d.lit_comp != 1;
             if (!bad && d.lit_type >= 2) {
                 bad = d.huf_origin >= nblocks || d.huf_origin > i || b->blocks[d.huf_origin].type != 2 ||
-                      b->blocks[d.huf_origin].lit_type != 2;
-                lit = d.lit_buf_off + d.lit_regen > lit ? d.lit_buf_off + d.lit_regen : lit;
+                      b->blocks[d.huf_origin].lit_type != 2 || (d.lit_type == 2 && d.huf_origin != i) ||
+                      (d.lit_buf_off & 15) != 0 || d.lit_buf_off < lit || d.lit_buf_off > (1ull << 48);
+                lit = d.lit_buf_off + d.lit_regen;
             }
             if (!bad && d.nseq > 0) {
                 const uint32_t org[3] = {d.ll_origin, d.of_origin, d.ml_origin};
@@ -542,7 +573,9 @@ int szb_batch_create_from_tables(szb_ctx *ctx, size_t src_len, const szb_frame_d
                               field_mode(b->blocks[org[k]].seq_modes, kinds[k]) == 3;
                     }
                 }
-                seq = d.seq_buf_off + d.nseq > seq ? d.seq_buf_off + d.nseq : seq;
+                // k_decode_sequences stores rows 16 bytes at a time and stage 4 reads whole rounds: slices start at multiples of 32
+                if (!bad) bad = (d.seq_buf_off & 31) != 0 || d.seq_buf_off < seq || d.seq_buf_off > (1ull << 40);
+                seq = d.seq_buf_off + d.nseq;
             }
         }
         if (bad) {
@@ -854,6 +887,7 @@ static int collect_timing(szb_ctx *ctx) {
 
 int szb_batch_decode_entropy(szb_batch *b, const void *d_src) {
     if (!b || (!d_src && b->src_len)) return SZB_ERR_INVALID_ARGUMENT;
+    if (reinterpret_cast<uintptr_t>(d_src) & 15) return SZB_ERR_INVALID_ARGUMENT;  // szb200.h: device source buffers
     return launch_entropy(b, d_src);
 }
 
@@ -887,7 +921,7 @@ int szb_batch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t dst_c
 }
 
 int szb_batch_run(szb_batch *b, const void *d_src, void *d_dst, size_t dst_cap) {
-    if (!b) return SZB_ERR_INVALID_ARGUMENT;
+    if (!b || (reinterpret_cast<uintptr_t>(d_src) & 15)) return SZB_ERR_INVALID_ARGUMENT;  // szb200.h: device source buffers
     int rc = launch_entropy(b, d_src);
     if (rc) return rc;
     return launch_execute(b, d_src, d_dst, dst_cap);
@@ -980,10 +1014,155 @@ static int ensure_dev(szb_ctx *ctx, uint8_t **p, size_t *cap, size_t need) {
     return SZB_OK;
 }
 
+// ---- pinned staging ---------------------------------------------------------
+static int pin_rings(szb_ctx *ctx) {
+    for (int i = 0; i < szb_ctx::kPinIn; i++) {
+        if (!ctx->pin_in[i]) CUDA_TRY(ctx, cudaHostAlloc((void **)&ctx->pin_in[i], szb_ctx::kPinBytes, cudaHostAllocDefault));
+        if (!ctx->pin_in_ev[i]) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->pin_in_ev[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < szb_ctx::kPinOut; i++) {
+        if (!ctx->pin_out[i]) CUDA_TRY(ctx, cudaHostAlloc((void **)&ctx->pin_out[i], szb_ctx::kPinBytes, cudaHostAllocDefault));
+        if (!ctx->pin_out_ev[i]) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->pin_out_ev[i], cudaEventDisableTiming));
+    }
+    if (!ctx->s_h2d) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+    if (!ctx->s_d2h) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    return SZB_OK;
+}
+// Is p ordinary (pageable) host memory?  cudaMemcpyAsync from / to it is staged by the driver and does not overlap anything.
+static bool host_pageable(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return true;
+    }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+static unsigned host_threads() {
+    unsigned n = std::thread::hardware_concurrency();
+    n = n < 2 ? 1 : (n > 8 ? 8 : n - 1);
+    if (const char *wt = getenv("SZB_WALK_THREADS")) {
+        const unsigned cap = (unsigned)strtoul(wt, nullptr, 10);
+        if (cap >= 1 && cap < n) n = cap;
+    }
+    return n;
+}
+// memcpy on several threads: one core moves ~10 GB/s, the PCIe link five times that
+static void parallel_memcpy(uint8_t *dst, const uint8_t *src, size_t n) {
+    const size_t kMin = (size_t)4 << 20;
+    unsigned t = host_threads();
+    if (n < 2 * kMin || t < 2) {
+        memcpy(dst, src, n);
+        return;
+    }
+    if ((size_t)t > n / kMin) t = (unsigned)(n / kMin);
+    const size_t part = align_up(n / t, 4096);
+    std::vector<std::thread> th;
+    size_t done = 0;
+    try {
+        for (unsigned i = 0; i + 1 < t && done + part < n; i++, done += part) th.emplace_back(memcpy, dst + done, src + done, part);
+    } catch (...) {
+    }
+    memcpy(dst + done, src + done, n - done);
+    for (auto &x : th) x.join();
+}
+// Host -> device through the pinned ring (pageable callers): the host-side copy of piece k+1 runs while piece k is on the link.
+static int staged_h2d(szb_ctx *ctx, uint8_t *d, const uint8_t *h, size_t n, uint32_t *slot) {
+    for (size_t off = 0; off < n;) {
+        const size_t m = n - off < szb_ctx::kPinBytes ? n - off : szb_ctx::kPinBytes;
+        const int k = (int)((*slot)++ % szb_ctx::kPinIn);
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->pin_in_ev[k]));  // the slot's last copy has left it
+        parallel_memcpy(ctx->pin_in[k], h + off, m);
+        CUDA_TRY(ctx, cudaMemcpyAsync(d + off, ctx->pin_in[k], m, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->pin_in_ev[k], ctx->s_h2d));
+        off += m;
+    }
+    return SZB_OK;
+}
+// Device -> pageable host memory: a drain thread waits for each piece to land in its pinned slot and copies it out, so the
+// thread that submits work keeps running ahead by kPinOut pieces.
+struct Drain {
+    struct Job {
+        int slot;
+        uint8_t *dst;
+        size_t n;
+    };
+    szb_ctx *ctx;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Job> jobs;
+    bool free_slot[szb_ctx::kPinOut];
+    bool quit = false, failed = false;
+    std::thread th;
+    explicit Drain(szb_ctx *c) : ctx(c) {
+        for (bool &f : free_slot) f = true;
+        th = std::thread([this] { run(); });
+    }
+    void run() {
+        cudaSetDevice(ctx->device);
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [this] { return quit || !jobs.empty(); });
+                if (jobs.empty()) return;
+                j = jobs.front();
+                jobs.pop_front();
+            }
+            if (cudaEventSynchronize(ctx->pin_out_ev[j.slot]) != cudaSuccess) failed = true;
+            else parallel_memcpy(j.dst, ctx->pin_out[j.slot], j.n);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                free_slot[j.slot] = true;
+            }
+            cv.notify_all();
+        }
+    }
+    // d -> h on s_d2h (which the caller has made wait for the producer of d), piece by piece
+    int copy(const uint8_t *d, uint8_t *h, size_t n) {
+        for (size_t off = 0; off < n;) {
+            const size_t m = n - off < szb_ctx::kPinBytes ? n - off : szb_ctx::kPinBytes;
+            int k = -1;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] {
+                    for (int i = 0; i < szb_ctx::kPinOut; i++)
+                        if (free_slot[i]) {
+                            k = i;
+                            return true;
+                        }
+                    return false;
+                });
+                free_slot[k] = false;
+            }
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pin_out[k], d + off, m, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->pin_out_ev[k], ctx->s_d2h));
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                jobs.push_back(Job{k, h + off, m});
+            }
+            cv.notify_all();
+            off += m;
+        }
+        return SZB_OK;
+    }
+    // everything handed to copy() is in the caller's memory when this returns
+    bool finish() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit = true;
+        }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+        return !failed;
+    }
+    ~Drain() { finish(); }
+};
+
 static int decode_tables(szb_ctx *ctx, szb_batch *b, const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap,
                          uint64_t *out_off, uint64_t *out_len, int32_t *status, uint32_t flags) {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const void *d_src = src;
+    if ((flags & SZB_FLAG_SRC_DEVICE) && (reinterpret_cast<uintptr_t>(src) & 15)) return SZB_ERR_INVALID_ARGUMENT;  // szb200.h
     float h2d_ms = 0, d2h_ms = 0;
     if (!(flags & SZB_FLAG_SRC_DEVICE)) {
         int rc = ensure_dev(ctx, &ctx->d_src, &ctx->d_src_cap, src_len + 16);
@@ -1078,6 +1257,15 @@ static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_l
     if (rc) return rc;
     rc = ensure_dev(ctx, &ctx->d_dst, &ctx->d_dst_cap, (size_t)total + 16);
     if (rc) return rc;
+    // pageable caller memory goes through the context's pinned rings, so that the copies still overlap the kernels
+    const bool src_pg = host_pageable(src), dst_pg = host_pageable(dst);
+    if (src_pg || dst_pg) {
+        rc = pin_rings(ctx);
+        if (rc) return rc;
+    }
+    std::unique_ptr<Drain> drain;
+    if (dst_pg) drain.reset(new Drain(ctx));
+    uint32_t in_slot = 0;
 
     struct Chunk {
         uint32_t f0, f1;
@@ -1177,7 +1365,15 @@ static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_l
         CUDA_BRK(cudaEventCreateWithFlags(&c.up, cudaEventDisableTiming));
         CUDA_BRK(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
         // compressed bytes of this chunk: H2D on the copy stream
-        CUDA_BRK(cudaMemcpyAsync(ctx->d_src + c.src_lo, src + c.src_lo, (size_t)(c.src_hi - c.src_lo), cudaMemcpyHostToDevice, ctx->s_h2d));
+        if (src_pg) {
+            rc = staged_h2d(ctx, ctx->d_src + c.src_lo, src + c.src_lo, (size_t)(c.src_hi - c.src_lo), &in_slot);
+            if (rc) {
+                fail = rc;
+                break;
+            }
+        } else {
+            CUDA_BRK(cudaMemcpyAsync(ctx->d_src + c.src_lo, src + c.src_lo, (size_t)(c.src_hi - c.src_lo), cudaMemcpyHostToDevice, ctx->s_h2d));
+        }
         CUDA_BRK(cudaEventRecord(c.up, ctx->s_h2d));
         // descriptor tables of this chunk (walked by a worker), their upload, the kernels
         double t0 = now();
@@ -1212,7 +1408,15 @@ static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_l
         t_launch += now() - t0;
         // output of this chunk: D2H on the other copy stream
         CUDA_BRK(cudaStreamWaitEvent(ctx->s_d2h, c.done, 0));
-        if (c.dst_len) CUDA_BRK(cudaMemcpyAsync(dst + c.dst_lo, ctx->d_dst + c.dst_lo, (size_t)c.dst_len, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (c.dst_len && dst_pg) {
+            rc = drain->copy(ctx->d_dst + c.dst_lo, dst + c.dst_lo, (size_t)c.dst_len);
+            if (rc) {
+                fail = rc;
+                break;
+            }
+        } else if (c.dst_len) {
+            CUDA_BRK(cudaMemcpyAsync(dst + c.dst_lo, ctx->d_dst + c.dst_lo, (size_t)c.dst_len, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        }
     }
 #undef CUDA_BRK
     stop.store(true);
@@ -1221,6 +1425,7 @@ static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_l
     cudaStreamSynchronize(ctx->s_h2d);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->s_d2h);
+    if (drain && !drain->finish() && fail == SZB_OK) fail = SZB_ERR_CUDA;
     if (trace)
         fprintf(stderr, "[szb] pipelined: %zu chunks, submit loop %.1f ms (walk wait %.1f, tables %.1f, launches %.1f), drain %.1f ms\n",
                 chunks.size(), t_loop1 - t_loop0, t_wait, t_create, t_launch, now() - t_loop1);
@@ -1330,6 +1535,114 @@ int szb_decode_blocks(szb_ctx *ctx, const void *d_src, size_t src_len, const szb
                        SZB_FLAG_SRC_DEVICE | SZB_FLAG_DST_DEVICE);
     szb_batch_destroy(b);
     return rc;
+}
+
+// One frame from a reader to a writer (szb200.h).  Host side: the source is read piece by piece into pinned slots (and kept
+// in an ordinary buffer for the header walk); every piece goes H2D while the next is being read.  After the decode the output
+// comes back through the pinned out-slots, two pieces ahead of the one `write` is consuming.
+int szb_decompress_reader(szb_ctx *ctx, szb_read_fn read, void *read_user, szb_write_fn write, void *write_user,
+                          uint64_t *in_used, uint64_t *out_total, uint32_t flags) {
+    if (!ctx || !read || !write) return SZB_ERR_INVALID_ARGUMENT;
+    if (in_used) *in_used = 0;
+    if (out_total) *out_total = 0;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = pin_rings(ctx);
+    if (rc) return rc;
+    constexpr size_t kPiece = szb_ctx::kPinBytes;
+    std::vector<uint8_t> host;
+    size_t have = 0;
+    // ---- input: read -> pinned slot -> device, the device buffer growing by doubling (its content moves with it) ----
+    for (uint32_t k = 0;; k++) {
+        const int slot = (int)(k % szb_ctx::kPinIn);
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->pin_in_ev[slot]));
+        size_t got = 0;
+        bool eof = false;
+        while (got < kPiece) {  // a reader may return short counts: fill the piece
+            const int64_t n = read(read_user, ctx->pin_in[slot] + got, kPiece - got);
+            if (n < 0 || (uint64_t)n > kPiece - got) return SZB_ERR_IO;
+            if (n == 0) {
+                eof = true;
+                break;
+            }
+            got += (size_t)n;
+        }
+        if (got) {
+            try {
+                host.insert(host.end(), ctx->pin_in[slot], ctx->pin_in[slot] + got);
+            } catch (...) {
+                return SZB_ERR_NOMEM;
+            }
+            if (have + got + 16 > ctx->d_src_cap || !ctx->d_src) {
+                size_t want = ctx->d_src_cap ? ctx->d_src_cap : ((size_t)64 << 20);
+                while (want < have + got + 16) want *= 2;
+                uint8_t *bigger = nullptr;
+                CUDA_TRY(ctx, cudaMalloc((void **)&bigger, want));
+                if (have) CUDA_TRY(ctx, cudaMemcpyAsync(bigger, ctx->d_src, have, cudaMemcpyDeviceToDevice, ctx->s_h2d));
+                CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_h2d));
+                if (ctx->d_src) CUDA_TRY(ctx, cudaFree(ctx->d_src));
+                ctx->d_src = bigger;
+                ctx->d_src_cap = want;
+            }
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_src + have, ctx->pin_in[slot], got, cudaMemcpyHostToDevice, ctx->s_h2d));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->pin_in_ev[slot], ctx->s_h2d));
+            have += got;
+        }
+        if (eof) break;
+    }
+    // ---- the walk (host bytes), then the four stages once the last piece has arrived ----
+    uint64_t off = 0, len = have;
+    szb_batch *b = nullptr;
+    rc = szb_batch_create(ctx, host.data(), have, &off, &len, 1, &b);
+    if (rc) return rc;
+    if (in_used) *in_used = b->frames[0].src_len;
+    ctx->last_frame = b->frames[0];
+    cudaEvent_t up = nullptr;
+    uint64_t total = 0;
+    int32_t st = 0;
+    auto fail = [&](int code) {
+        if (up) cudaEventDestroy(up);
+        szb_batch_destroy(b);
+        return code;
+    };
+    if (cudaEventCreateWithFlags(&up, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(up, ctx->s_h2d) != cudaSuccess ||
+        cudaStreamWaitEvent(ctx->stream, up, 0) != cudaSuccess)
+        return fail(SZB_ERR_CUDA);
+    if (!ctx->d_src) {  // an empty source: the walk has reported the missing magic number already; nothing to run
+        rc = ensure_dev(ctx, &ctx->d_src, &ctx->d_src_cap, 16);
+        if (rc) return fail(rc);
+    }
+    rc = launch_entropy(b, ctx->d_src);
+    if (!rc) rc = szb_batch_sizes(b, &total, nullptr, nullptr);
+    if (!rc) rc = ensure_dev(ctx, &ctx->d_dst, &ctx->d_dst_cap, (size_t)total + 16);
+    if (!rc) rc = launch_execute(b, ctx->d_src, ctx->d_dst, (size_t)total);
+    if (!rc && (flags & SZB_FLAG_VERIFY_CHECKSUM)) rc = szb_batch_verify_checksums(b, ctx->d_dst);
+    if (!rc) rc = szb_batch_finish(b, &st);  // synchronises: the frame's verdict is known before a byte is handed out
+    if (rc) return fail(rc);
+    // ---- output: pieces through the pinned out-slots, kPinOut - 1 of them ahead of the writer ----
+    const uint64_t pieces = (total + kPiece - 1) / kPiece;
+    auto issue = [&](uint64_t p) -> bool {
+        const int slot = (int)(p % szb_ctx::kPinOut);
+        const size_t n = (size_t)(total - p * kPiece < kPiece ? total - p * kPiece : kPiece);
+        return cudaMemcpyAsync(ctx->pin_out[slot], ctx->d_dst + p * kPiece, n, cudaMemcpyDeviceToHost, ctx->s_d2h) == cudaSuccess &&
+               cudaEventRecord(ctx->pin_out_ev[slot], ctx->s_d2h) == cudaSuccess;
+    };
+    for (uint64_t p = 0; p < pieces && p + 1 < (uint64_t)szb_ctx::kPinOut; p++)
+        if (!issue(p)) return fail(SZB_ERR_CUDA);
+    for (uint64_t p = 0; p < pieces; p++) {
+        const int slot = (int)(p % szb_ctx::kPinOut);
+        const size_t n = (size_t)(total - p * kPiece < kPiece ? total - p * kPiece : kPiece);
+        // the slot of piece p + kPinOut - 1 is the one piece p - 1 has just been written out of
+        if (p + szb_ctx::kPinOut - 1 < pieces && !issue(p + szb_ctx::kPinOut - 1)) return fail(SZB_ERR_CUDA);
+        if (cudaEventSynchronize(ctx->pin_out_ev[slot]) != cudaSuccess) return fail(SZB_ERR_CUDA);
+        if (write(write_user, ctx->pin_out[slot], n) != 0) {
+            cudaStreamSynchronize(ctx->s_d2h);
+            return fail(SZB_ERR_IO);
+        }
+    }
+    if (out_total) *out_total = total;
+    cudaEventDestroy(up);
+    szb_batch_destroy(b);
+    return SZB_OK;
 }
 
 int szb_decompress_frame(szb_ctx *ctx, const uint8_t *src, size_t src_len, uint8_t **out, size_t *out_len,

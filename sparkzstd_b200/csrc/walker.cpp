@@ -5,7 +5,10 @@
 // :306-374) with structure/frame.go:23-127, structure/block.go:33-55, and the header halves
 // of structure/literals.go:67-204 and structure/sequences.go:228-269.  Nothing here touches
 // entropy-coded payload: that is the GPU's job.
+#include <algorithm>
 #include <cstdlib>
+#include <numeric>
+#include <queue>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -229,6 +232,33 @@ void walk_frame(szb_walk &w, const uint8_t *src, uint64_t off, uint64_t len, uin
 extern "C" {
 
 uint32_t szb_abi_layout(uint32_t *out, uint32_t cap) { return szb_abi_layout_impl(out, out ? cap : 0); }
+
+// Frames share no state (framedecompressor.go:42-61): multi-GPU decode is a partition of the frame list.  Greedy
+// longest-processing-time binning: frames by descending weight (ties: lower index first), each to the least loaded shard
+// (ties: lower shard first).  Deterministic, so every rank computes the same partition from the same weights.
+int szb_shard_frames(const uint64_t *weight, uint32_t nframes, uint32_t nshards, uint32_t *shard_of, uint64_t *shard_load) {
+    if (nshards == 0 || (nframes && (!weight || !shard_of))) return SZB_ERR_INVALID_ARGUMENT;
+    std::vector<uint64_t> load(nshards, 0);
+    if (nframes) {
+        std::vector<uint32_t> order(nframes);
+        std::iota(order.begin(), order.end(), 0u);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return weight[a] > weight[b]; });
+        typedef std::pair<uint64_t, uint32_t> Slot;  // (load, shard): the smallest pair is the least loaded, lowest shard
+        std::priority_queue<Slot, std::vector<Slot>, std::greater<Slot>> heap;
+        for (uint32_t r = 0; r < nshards; r++) heap.push(Slot(0, r));
+        for (uint32_t i : order) {
+            Slot s = heap.top();
+            heap.pop();
+            shard_of[i] = s.second;
+            s.first += weight[i];
+            load[s.second] = s.first;
+            heap.push(s);
+        }
+    }
+    if (shard_load)
+        for (uint32_t r = 0; r < nshards; r++) shard_load[r] = load[r];
+    return SZB_OK;
+}
 
 int szb_walk_create(const uint8_t *src, size_t src_len, const uint64_t *frame_off, const uint64_t *frame_len,
                     uint32_t nframes, szb_walk **out) {

@@ -201,6 +201,57 @@ class Context:
         return res, used.value
 
 
+    def decompress_reader(self, source, target, verify_checksum: bool = False, prefix: bytes = b"") -> Tuple[int, int, FrameDesc]:
+        """szb_decompress_reader: one frame from `source` (.read(n)) to `target` (.write(bytes)) with the transfers overlapped
+        -- input pieces go to the device while the next is being read, output pieces come back while `target` consumes the
+        one before.  `prefix`: bytes already taken from the source (an eager header check).  Returns (compressed bytes the
+        frame occupied, decoded bytes, the frame's header row)."""
+        pending = bytearray(prefix)  # bytes taken from the source but not handed to the library yet
+        err: List[BaseException] = []
+
+        def _read(_user, buf, cap):
+            try:
+                if pending:
+                    chunk = bytes(pending[:cap])
+                    del pending[:cap]
+                else:
+                    chunk = source.read(cap)
+                    if chunk and len(chunk) > cap:  # a reader that ignores n: keep the rest for the next call
+                        pending.extend(chunk[cap:])
+                        chunk = chunk[:cap]
+                if not chunk:
+                    return 0
+                C.memmove(buf, bytes(chunk), len(chunk))
+                return len(chunk)
+            except BaseException as e:  # noqa: BLE001 -- carried across the C frame and re-raised below
+                err.append(e)
+                return -1
+
+        def _write(_user, buf, n):
+            try:
+                target.write(C.string_at(buf, n))
+                return 0
+            except BaseException as e:  # noqa: BLE001
+                err.append(e)
+                return 1
+
+        rcb = _READ_FN(_read)
+        wcb = _WRITE_FN(_write)
+        used = C.c_uint64()
+        total = C.c_uint64()
+        rc = self._L.szb_decompress_reader(self._h, rcb, None, wcb, None, C.byref(used), C.byref(total), 4 if verify_checksum else 0)
+        if err:
+            raise err[0]
+        if rc != 0:
+            self._raise(rc)
+        fr = FrameDesc()
+        self._L.szb_ctx_last_frame(self._h, C.byref(fr))
+        return int(used.value), int(total.value), fr
+
+
+_READ_FN = C.CFUNCTYPE(C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t)
+_WRITE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
+
 _default_ctx = threading.local()
 
 
@@ -478,6 +529,17 @@ class FrameDecompressor:
 
     # framedecompressor.go:153-170
     def Decompress(self):
+        if self._data is None and self._out is None and hasattr(self._source, "read"):
+            # nothing read yet: source -> GPU -> target with the transfers overlapped (szb_decompress_reader), instead of
+            # read-all / decode / write-all.  Errors are the ones the step-by-step path raises.
+            ctx = self._ctx or default_context()
+            _, total, fr = ctx.decompress_reader(self._source, self._target)
+            self._frame = fr
+            self._written = total
+            self._out = b""
+            self.BlockCounter = int(fr.nblocks)
+            self.CurrentBlock.Header.LastBlock = True
+            return
         self.CheckMagicnum()
         self.DecodeFrameHeader()
         while not self.CurrentBlock.Header.LastBlock:
@@ -497,47 +559,128 @@ def NewFrameDecompressor(s, t, ctx: Optional[Context] = None) -> FrameDecompress
 
 
 class FrameReader:
-    """decompression.FrameReader (framereader.go:9-109): an io.Reader over one zstd frame."""
+    """decompression.FrameReader (framereader.go:9-109): an io.Reader over one zstd frame.
+
+    The reference hands out bytes as its window ring evicts them, while it is still reading input.  Here the first Read starts
+    szb_decompress_reader on a worker thread (input pieces travel to the device while the source is still being read; the
+    output comes back in pinned pieces) and Read returns as soon as the first piece has landed, the rest of the
+    device-to-host copy running behind it.  At most a few pieces are buffered (the queue is bounded)."""
+
+    _HEADER_MAX = 18  # magic 4 + descriptor 1 + window 1 + dictionary id 4 + content size 8 (frame.go:23-127)
 
     def __init__(self, source=None, ctx: Optional[Context] = None):
         self.PrintStatus = False
-        self._buffer = io.BytesIO()
-        self._fd = FrameDecompressor(source, self._buffer, ctx)
-        self._rpos = 0
-        self._done = False
-        self.readTotal = 0
-        if source is not None:  # framereader.go:22-31: eager magic + header check
-            self._fd.CheckMagicnum()
-            self._fd.DecodeFrameHeader()
+        self._ctx = ctx
+        self._fd = FrameDecompressor(None, None, ctx)
+        self.Reset(source)
+
+    def _eager_header_check(self, source) -> bytes:
+        """framereader.go:22-31: the magic number and the frame header are checked when the reader is made.  Only the header's
+        bytes are taken from the source; they are handed to the decoder in front of the rest."""
+        head = b""
+        while len(head) < self._HEADER_MAX:
+            more = source.read(self._HEADER_MAX - len(head))
+            if not more:
+                break
+            head += bytes(more)
+        if len(head) < 4:
+            raise ErrUnexpectedEOF()
+        if head[:4] != b"\x28\xb5\x2f\xfd":
+            raise ErrWrongMagicnumber()
+        if len(head) < 5:
+            raise ErrUnexpectedEOF()
+        fhd = head[4]
+        single = (fhd >> 5) & 1
+        fcs = (1 if single else 0, 2, 4, 8)[fhd >> 6]
+        need = 5 + (0 if single else 1) + (0, 1, 2, 4)[fhd & 3] + fcs
+        if len(head) < need:
+            raise ErrUnexpectedEOF()
+        return head
 
     # framereader.go:35-49
     def Reset(self, source):
-        self._buffer = io.BytesIO()
-        self._fd.Reset(source, self._buffer)
-        self._rpos = 0
-        self._done = False
+        self._stop_worker()
+        self._source = source
+        self._head = b""
+        self._q = None
+        self._worker = None
+        self._cur = memoryview(b"")
+        self._eof = source is None
+        self._err = None
         self.readTotal = 0
         if source is not None:
-            self._fd.CheckMagicnum()
-            self._fd.DecodeFrameHeader()
+            self._head = self._eager_header_check(source)
+
+    def _stop_worker(self):
+        w = getattr(self, "_worker", None)
+        if w is not None and w.is_alive():
+            self._abort = True
+            try:
+                while w.is_alive():
+                    self._q.get(timeout=0.05)  # unblock a producer waiting on the full queue
+            except Exception:
+                pass
+            w.join()
+        self._abort = False
+
+    def _start(self):
+        import queue
+
+        self._q = queue.Queue(maxsize=4)
+        self._abort = False
+        reader = self
+
+        class _Sink:
+            def write(self, b):
+                if reader._abort:
+                    raise RuntimeError("reader was reset")
+                reader._q.put(bytes(b))
+
+        def run():
+            try:
+                ctx = reader._ctx or default_context()
+                ctx.decompress_reader(reader._source, _Sink(), prefix=reader._head)
+                reader._q.put(None)
+            except BaseException as e:  # noqa: BLE001 -- handed to the thread that calls Read
+                reader._q.put(e)
+
+        self._worker = threading.Thread(target=run, daemon=True)
+        self._worker.start()
 
     # framereader.go:51-109.  Returns up to n bytes; b"" is io.EOF.
     def Read(self, n: int = -1) -> bytes:
-        if not self._done:
-            fd = self._fd
-            while not fd.CurrentBlock.Header.LastBlock:
-                fd.DecodeNextBlock()
-                fd.BlockCounter += 1
-            fd._flush()
-            self._done = True
-        data = self._buffer.getbuffer()
-        end = len(data) if n is None or n < 0 else min(len(data), self._rpos + n)
-        out = bytes(data[self._rpos : end])
-        self._rpos = end
+        if self._err is not None:
+            raise self._err
+        if self._worker is None and not self._eof:
+            self._start()
+        out = []
+        want = None if n is None or n < 0 else n
+        while want is None or want > 0:
+            if not len(self._cur):
+                if self._eof:
+                    break
+                item = self._q.get()
+                if item is None:
+                    self._eof = True
+                    break
+                if isinstance(item, BaseException):
+                    self._eof = True
+                    self._err = item
+                    if out:
+                        break
+                    raise item
+                self._cur = memoryview(item)
+            take = len(self._cur) if want is None else min(want, len(self._cur))
+            out.append(bytes(self._cur[:take]))
+            self._cur = self._cur[take:]
+            if want is not None:
+                want -= take
+                break  # a Read returns what is there: short reads are legal (io.Reader)
+        data = b"".join(out)
         if self.PrintStatus:
-            print(f"Read bytes: {self.readTotal + len(out)}")
-        self.readTotal += len(out)
-        return out
+            print(f"Read bytes: {self.readTotal + len(data)}")
+        self.readTotal += len(data)
+        return data
 
     read = Read
 
@@ -545,6 +688,17 @@ class FrameReader:
         chunk = self.Read(len(b))
         b[: len(chunk)] = chunk
         return len(chunk)
+
+    def close(self):
+        """Stops a decode whose output was not read to its end (the worker would otherwise wait on the full queue)."""
+        self._stop_worker()
+        self._eof = True
+
+    def __del__(self):
+        try:
+            self._stop_worker()
+        except Exception:
+            pass
 
 
 def NewFrameReader(source=None, ctx: Optional[Context] = None) -> FrameReader:

@@ -8,28 +8,26 @@ on the partition and to reduce timings.
 """
 from __future__ import annotations
 
-import heapq
 from typing import List, Sequence
 
 import numpy as np
 
 
 def shard_frames(weights: Sequence[int], world_size: int) -> List[np.ndarray]:
-    """Greedy longest-processing-time binning of frames by weight (decompressed size when the
-    header declares it, else compressed size).  Deterministic: every rank computes the same
+    """szb_shard_frames (include/szb200.h): greedy longest-processing-time binning of frames by weight (decompressed size
+    when the header declares it, else a multiple of the compressed size).  Deterministic: every rank computes the same
     partition from the same weights.  Returns world_size sorted index arrays."""
-    w = np.asarray(weights, dtype=np.int64)
+    from . import load
+
+    w = np.ascontiguousarray(np.asarray(weights, dtype=np.int64).astype(np.uint64))
     if world_size <= 1:
         return [np.arange(len(w), dtype=np.int64)]
-    order = np.argsort(-w, kind="stable")
-    heap = [(0, r) for r in range(world_size)]
-    heapq.heapify(heap)
-    bins: List[List[int]] = [[] for _ in range(world_size)]
-    for i in order:
-        load, r = heapq.heappop(heap)
-        bins[r].append(int(i))
-        heapq.heappush(heap, (load + int(w[i]), r))
-    return [np.array(sorted(b), dtype=np.int64) for b in bins]
+    shard = np.zeros(max(len(w), 1), dtype=np.uint32)
+    rc = load().szb_shard_frames(w.ctypes.data if len(w) else None, len(w), world_size, shard.ctypes.data, None)
+    if rc != 0:
+        raise ValueError(f"szb_shard_frames: {rc}")
+    shard = shard[: len(w)]
+    return [np.nonzero(shard == r)[0].astype(np.int64) for r in range(world_size)]
 
 
 def frame_weights(frames) -> np.ndarray:

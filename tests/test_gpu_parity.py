@@ -211,6 +211,83 @@ def test_pipelined_path_with_a_frame_that_lies_about_its_size(ctx):
     assert (got[ok] == c.raw_hash[ok]).all()
 
 
+def test_streamed_reader_hands_out_pieces_and_reads_in_pieces(ctx):
+    """szb_decompress_reader behind FrameReader.Read / FrameDecompressor.Decompress: a 96 MiB frame read from a
+    source that returns short counts; the output arrives in pieces (the first Read returns before everything was copied back)
+    and equals the generator's original."""
+    import hashlib as H
+
+    from sparkzstd_b200 import decompression as D
+
+    c = cg.config3_single_frame(96 << 20, 20)
+    frame = c.frame(0)
+
+    class Dribble(io.RawIOBase):  # a reader that never returns more than 1 MiB + 17 bytes
+        def __init__(self, data):
+            self.data, self.pos, self.calls = data, 0, 0
+
+        def read(self, n=-1):
+            self.calls += 1
+            n = len(self.data) - self.pos if n is None or n < 0 else n
+            n = min(n, (1 << 20) + 17)
+            out = self.data[self.pos : self.pos + n]
+            self.pos += len(out)
+            return out
+
+    src = Dribble(frame)
+    r = D.NewFrameReader(src, ctx)
+    assert src.pos <= 18  # only the frame header was taken eagerly (framereader.go:22-31)
+    h, total, reads = H.sha256(), 0, 0
+    first = r.Read(1 << 16)
+    assert 0 < len(first) <= (1 << 16)
+    h.update(first)
+    total += len(first)
+    while True:
+        chunk = r.Read(8 << 20)
+        if not chunk:
+            break
+        h.update(chunk)
+        total += len(chunk)
+        reads += 1
+    assert total == int(c.raw_size[0]) and reads >= 3 and src.calls > 20
+    target = io.BytesIO()
+    D.NewFrameDecompressor(Dribble(frame), target, ctx).Decompress()
+    assert H.sha256(target.getvalue()).digest() == h.digest()
+    got = cg.hash_frames(np.frombuffer(target.getvalue(), dtype=np.uint8), np.array([0], np.uint64), np.array([total], np.uint64))
+    assert got[0] == c.raw_hash[0]
+    # errors come through the same way: a truncated frame, a failing source, a failing target
+    with pytest.raises(D.SzbError):
+        D.NewFrameDecompressor(io.BytesIO(frame[: len(frame) // 2]), io.BytesIO(), ctx).Decompress()
+
+    class Boom(io.RawIOBase):
+        def read(self, n=-1):
+            raise OSError("source went away")
+
+        def write(self, b):
+            raise OSError("disk full")
+
+    with pytest.raises(OSError, match="source went away"):
+        D.NewFrameDecompressor(Boom(), io.BytesIO(), ctx).Decompress()
+    with pytest.raises(OSError, match="disk full"):
+        D.NewFrameDecompressor(io.BytesIO(frame), Boom(), ctx).Decompress()
+    # a reader that is dropped half way must not wedge the context
+    r = D.NewFrameReader(io.BytesIO(frame), ctx)
+    assert len(r.Read(1000)) > 0
+    r.close()
+    assert ctx.decode_batch([frame[: len(frame)]])[0][:16] == target.getvalue()[:16]
+
+
+def test_pageable_host_buffers_go_through_the_pinned_rings(ctx):
+    """szb_decode_batch with ordinary (pageable) numpy buffers and > 192 MB of input: the chunked path stages both directions
+    through the context's pinned slots; same bytes as with the caller's memory pinned."""
+    c = cg.config2_text_frames(10000)
+    src = np.array(c.src, copy=True)  # plain malloc'd memory
+    dst = np.empty(c.decompressed_bytes + 64, dtype=np.uint8)
+    out_off, out_len, status = ctx.decode_batch_into(src, c.frame_off, c.frame_len, dst)
+    assert not status.any() and (out_len == c.raw_size).all()
+    assert (cg.hash_frames(dst, out_off, out_len) == c.raw_hash).all()
+
+
 # ---- edge cases and error behaviour --------------------------------------------------------------------
 def test_empty_batch_and_empty_frames(ctx, corpus):
     assert ctx.decode_batch([]) == []

@@ -196,9 +196,9 @@ def golden_frames():
     return out
 
 
-def config5_mixed(total_bytes: int = 16 << 30, seed: int = BASE_SEED + 30_000_000, with_golden: bool = True, **kw) -> Corpus:
-    """configs[4]: seeded mix of frame kinds (Raw / RLE / Compressed blocks, predefined + custom tables,
-    Treeless literals in multi-block frames) plus the replicated decodecorpus frames."""
+def config5_plan(total_bytes: int = 16 << 30, seed: int = BASE_SEED + 30_000_000):
+    """The frame list of configs[4] without generating a byte: (kinds, seeds, sizes) of the synthetic frames.  Every rank of a
+    frame-sharded run computes the same plan and generates only the frames of its shard."""
     rng = np.random.default_rng(seed)
     kinds, sizes = [], []
     acc = 0
@@ -219,22 +219,41 @@ def config5_mixed(total_bytes: int = 16 << 30, seed: int = BASE_SEED + 30_000_00
         sizes.append(menu[k][1])
         acc += menu[k][1]
     n = len(kinds)
-    c = generate("mixed", np.array(kinds, np.int32), seed + np.arange(n, dtype=np.uint64), np.array(sizes, np.uint64), **kw)
+    return np.array(kinds, np.int32), seed + np.arange(n, dtype=np.uint64), np.array(sizes, np.uint64)
+
+
+def config5_mixed(total_bytes: int = 16 << 30, seed: int = BASE_SEED + 30_000_000, with_golden: bool = True, shard=None, **kw) -> Corpus:
+    """configs[4]: seeded mix of frame kinds (Raw / RLE / Compressed blocks, predefined + custom tables,
+    Treeless literals in multi-block frames) plus the replicated decodecorpus frames.
+    shard = (rank, world): only the frames szb_shard_frames gives this rank (by decompressed size) are generated; the golden
+    replicas are dealt out round robin.  meta["shard"] records the split."""
+    kinds, seeds, sizes = config5_plan(total_bytes, seed)
+    mine = None
+    if shard is not None:
+        from sparkzstd_b200.sharding import shard_frames
+
+        rank, world = shard
+        parts = shard_frames(sizes, world)
+        mine = parts[rank]
+        loads = [int(sizes[p].sum()) for p in parts]
+        kinds, seeds, sizes = kinds[mine], seeds[mine], sizes[mine]
+    c = generate("mixed", kinds, seeds, sizes, **kw)
+    if shard is not None:
+        c.meta["shard"] = {"rank": int(shard[0]), "world": int(shard[1]), "frames": int(len(mine)), "shard_bytes": loads}
     if with_golden:
         gold = golden_frames()
         reps = max(1, min(64, (total_bytes // 100) // max(1, sum(g[2] for g in gold))))
+        my_reps = reps if shard is None else len(range(shard[0], reps, shard[1]))
         extra = b"".join(g[1] for g in gold)
         base = len(c.src)
-        arena = np.concatenate([c.src, np.frombuffer(extra * reps, dtype=np.uint8), np.zeros(16, np.uint8)])
+        arena = np.concatenate([c.src, np.frombuffer(extra * my_reps, dtype=np.uint8), np.zeros(16, np.uint8)])
         offs, lens, raws, hashes = [], [], [], []
         p = base
-        import hashlib  # noqa: F401
-
         one = []
         for name, data, osz, _ in gold:
             one.append((len(data), osz))
         # hashes of the golden originals are not stored (only sha256 in the manifest): use 0 = "check via oracle"
-        for _ in range(reps):
+        for _ in range(my_reps):
             for ln_, osz in one:
                 offs.append(p)
                 lens.append(ln_)
@@ -245,7 +264,7 @@ def config5_mixed(total_bytes: int = 16 << 30, seed: int = BASE_SEED + 30_000_00
                    np.concatenate([c.frame_len, np.array(lens, np.uint64)]),
                    np.concatenate([c.raw_size, np.array(raws, np.uint64)]),
                    np.concatenate([c.raw_hash, np.array(hashes, np.uint64)]), dict(c.meta))
-        c.meta["golden_reps"] = int(reps)
+        c.meta["golden_reps"] = int(my_reps)
     c.meta.update(workload=f"mixed corpus ~{total_bytes} B, {c.nframes} frames", seed=seed)
     return c
 
