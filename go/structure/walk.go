@@ -187,7 +187,13 @@ func WalkFrame(src []byte) (*Walk, error) {
 				break
 			}
 			if err := parseCompressed(&d, src[pos:pos+int(size)], self, &carryHuf, &carryLL, &carryOF, &carryML, &litBytes, &seqs); err != nil {
-				w.Err = err
+				var he *headerError
+				if errors.As(err, &he) { // the block's literals are still decoded: it is the frame's last row
+					w.Blocks = append(w.Blocks, d)
+					w.Err = he.Err
+				} else {
+					w.Err = err
+				}
 				break
 			}
 			pos += int(size)

@@ -96,71 +96,84 @@ func parseCompressed(d *szb200.BlockDesc, b []byte, self uint32, carryHuf, carry
 		return io.ErrUnexpectedEOF
 	}
 	d.SeqOff = uint32(litTotal)
-	s := b[litTotal:]
-	if len(s) < 1 {
-		return io.ErrUnexpectedEOF
-	}
-	nb := 1
-	if s[0] >= 128 {
-		nb = 2
-	}
-	if s[0] == 255 {
-		nb = 3
-	}
-	if len(s) < nb {
-		return io.ErrUnexpectedEOF
-	}
-	var nseq uint32
-	switch {
-	case s[0] < 128:
-		nseq = uint32(s[0])
-	case s[0] < 255:
-		nseq = uint32(s[0]-128)<<8 + uint32(s[1])
-	default:
-		nseq = uint32(s[1]) + uint32(s[2])<<8 + 0x7F00
-	}
-	if s[0] == 0 {
-		d.SeqHdrBytes = 1
-		if litTotal+1 != len(b) {
-			return ErrCorruptSizes
-		}
-	} else if nseq == 0 {
-		// A two- or three-byte count that says zero (0x80 0x00): the reference (sequences.go:395-400 short-circuits on the
-		// first byte only) goes on to decode tables and a stream of no sequences.  Both walkers agree on ONE answer instead:
-		// the section is not the single zero byte, so the sizes do not add up (walker.cpp; DESIGN.md section 2).  The carry
-		// origins are left alone: a block without sequences defines no tables.
-		return ErrCorruptSizes
-	} else {
-		if len(s) < nb+1 {
+	// From here on the reference has already decoded the block's literals (DecodeNextBlockContent,
+	// framedecompressor.go:93-126: literals first, then the sequences header): an error in this header must not hide an error
+	// in the literals.  The block stays in the table -- without sequences, the error in HdrStatus -- so that the device decodes
+	// its literals and the first error wins; the caller ends the walk (walker.cpp does the same).
+	seqHeader := func() error {
+		s := b[litTotal:]
+		if len(s) < 1 {
 			return io.ErrUnexpectedEOF
 		}
-		d.NSeq = uint32(nseq)
-		d.SeqModes = uint8(s[nb])
-		d.SeqHdrBytes = uint8(nb + 1)
-		modes := s[nb]
-		pick := func(mode byte, carry *uint32, missing error) (uint32, error) {
-			if mode == 3 {
-				if *carry == none {
-					return 0, missing
-				}
-				return *carry, nil
+		nb := 1
+		if s[0] >= 128 {
+			nb = 2
+		}
+		if s[0] == 255 {
+			nb = 3
+		}
+		if len(s) < nb {
+			return io.ErrUnexpectedEOF
+		}
+		var nseq uint32
+		switch {
+		case s[0] < 128:
+			nseq = uint32(s[0])
+		case s[0] < 255:
+			nseq = uint32(s[0]-128)<<8 + uint32(s[1])
+		default:
+			nseq = uint32(s[1]) + uint32(s[2])<<8 + 0x7F00
+		}
+		if s[0] == 0 {
+			d.SeqHdrBytes = 1
+			if litTotal+1 != len(b) {
+				return ErrCorruptSizes
 			}
-			return self, nil
+		} else if nseq == 0 {
+			// A two- or three-byte count that says zero (0x80 0x00): the reference (sequences.go:395-400 short-circuits on the
+			// first byte only) goes on to decode tables and a stream of no sequences.  Both walkers agree on ONE answer instead:
+			// the section is not the single zero byte, so the sizes do not add up (walker.cpp; DESIGN.md section 2).  The carry
+			// origins are left alone: a block without sequences defines no tables.
+			return ErrCorruptSizes
+		} else {
+			if len(s) < nb+1 {
+				return io.ErrUnexpectedEOF
+			}
+			d.NSeq = uint32(nseq)
+			d.SeqModes = uint8(s[nb])
+			d.SeqHdrBytes = uint8(nb + 1)
+			modes := s[nb]
+			pick := func(mode byte, carry *uint32, missing error) (uint32, error) {
+				if mode == 3 {
+					if *carry == none {
+						return 0, missing
+					}
+					return *carry, nil
+				}
+				return self, nil
+			}
+			ll, err := pick(modes>>6, carryLL, ErrNoLLTableToCarryOver)
+			if err != nil {
+				return err
+			}
+			of, err := pick((modes>>4)&3, carryOF, ErrNoOFTableToCarryOver)
+			if err != nil {
+				return err
+			}
+			ml, err := pick((modes>>2)&3, carryML, ErrNoMLTableToCarryOver)
+			if err != nil {
+				return err
+			}
+			d.LLOrigin, d.OFOrigin, d.MLOrigin = uint32(ll), uint32(of), uint32(ml)
+			*carryLL, *carryOF, *carryML = ll, of, ml
 		}
-		ll, err := pick(modes>>6, carryLL, ErrNoLLTableToCarryOver)
-		if err != nil {
-			return err
-		}
-		of, err := pick((modes>>4)&3, carryOF, ErrNoOFTableToCarryOver)
-		if err != nil {
-			return err
-		}
-		ml, err := pick((modes>>2)&3, carryML, ErrNoMLTableToCarryOver)
-		if err != nil {
-			return err
-		}
-		d.LLOrigin, d.OFOrigin, d.MLOrigin = uint32(ll), uint32(of), uint32(ml)
-		*carryLL, *carryOF, *carryML = ll, of, ml
+		return nil
+	}
+	var hdrErr error
+	if hdrErr = seqHeader(); hdrErr != nil {
+		d.HdrStatus = CodeForError(hdrErr)
+		d.NSeq, d.SeqHdrBytes, d.SeqModes = 0, 0, 0
+		d.LLOrigin, d.OFOrigin, d.MLOrigin = none, none, none
 	}
 	if litType >= 2 {
 		*carryHuf = uint32(d.HufOrigin)
@@ -169,5 +182,41 @@ func parseCompressed(d *szb200.BlockDesc, b []byte, self uint32, carryHuf, carry
 	}
 	d.SeqBufOff = uint64(*seqs)
 	*seqs += (uint64(d.NSeq) + 31) &^ 31
+	if hdrErr != nil {
+		return &headerError{hdrErr}
+	}
 	return nil
+}
+
+// headerError: the block belongs in the table (its literals are decoded), the walk ends with Err.
+type headerError struct{ Err error }
+
+func (e *headerError) Error() string { return e.Err.Error() }
+func (e *headerError) Unwrap() error { return e.Err }
+
+// CodeForError is the szb200 status code of the errors a walk can end with (the inverse of ErrorForCode).
+func CodeForError(err error) int32 {
+	switch err {
+	case ErrIllegalBlockType:
+		return -7
+	case ErrIllegalBlockSize:
+		return -8
+	case ErrNoHuffTableToCarryOver:
+		return -14
+	case ErrNoLLTableToCarryOver:
+		return -21
+	case ErrNoMLTableToCarryOver:
+		return -22
+	case ErrNoOFTableToCarryOver:
+		return -23
+	case ErrCorruptSizes:
+		return -2
+	case ErrWrongMagicnumber:
+		return -1
+	case io.ErrUnexpectedEOF, io.EOF:
+		return -32
+	case errPanic:
+		return -33
+	}
+	return -33
 }

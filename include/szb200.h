@@ -126,13 +126,16 @@ typedef struct szb_block_desc {
     uint8_t seq_hdr_bytes; /* bytes of the sequence count (1..3) plus the modes byte when nseq > 0 */
     uint8_t seq_modes;     /* raw Symbol_Compression_Modes byte (sequences.go:228-232) */
     uint8_t _pad;
-    uint32_t _pad2;
+    int32_t hdr_status;    /* 0, or the error the walk hit in THIS block's sequences-section header (count, modes, a Repeat mode
+                              with nothing to repeat, sizes that do not add up).  The reference decodes a block's literals before
+                              it looks at that header (framedecompressor.go:93-126), so the device still decodes the literals of
+                              such a block and an error in them wins; the block is the last of its frame's rows and nseq is 0 */
 } szb_block_desc;
 
 /* The layout of the two structs above, for bindings that mirror them instead of including this header (the Go structs of
  * go/szb200, the ctypes mirror): sizeof(szb_frame_desc), the offset of each of its fields in declaration order (src_off ..
- * checksum_valid), sizeof(szb_block_desc), the offset of each of its fields (src_off .. seq_modes; the padding is not
- * listed).  Writes at most cap values, returns how many there are (36).  A binding compares them with its own when it loads. */
+ * checksum_valid), sizeof(szb_block_desc), the offset of each of its fields (src_off .. seq_modes, hdr_status; the padding
+ * byte is not listed).  Writes at most cap values, returns how many there are (37).  A binding compares them with its own when it loads. */
 uint32_t szb_abi_layout(uint32_t *out, uint32_t cap);
 
 /* Multi-GPU host split: frames are independent, so G GPUs decode a partition of the frame list, one process

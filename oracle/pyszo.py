@@ -234,14 +234,20 @@ class FrameTrace:
     bytes_consumed: int
 
 
-def decode_frame(data: bytes, want_trace: bool = False):
-    """Decode one frame.  Returns bytes, or (bytes, FrameTrace) when want_trace."""
+def decode_frame(data: bytes, want_trace: bool = False, dictionary: bytes = None):
+    """Decode one frame.  Returns bytes, or (bytes, FrameTrace) when want_trace.  dictionary (raw content or formatted): NOT a
+    reference behaviour -- the oracle's restatement of RFC 8878 section 5 (szo_decode_frame_dict)."""
     L = lib()
     out = C.c_void_p()
     n = C.c_size_t()
     tr = _Trace() if want_trace else None
     buf = (C.c_uint8 * max(len(data), 1)).from_buffer_copy(data.ljust(1, b"\0")) if True else None
-    rc = L.szo_decode_frame(buf, len(data), C.byref(out), C.byref(n), C.byref(tr) if want_trace else None)
+    if dictionary:
+        L.szo_decode_frame_dict.restype = C.c_int
+        L.szo_decode_frame_dict.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p]
+        rc = L.szo_decode_frame_dict(buf, len(data), dictionary, len(dictionary), C.byref(out), C.byref(n), C.byref(tr) if want_trace else None)
+    else:
+        rc = L.szo_decode_frame(buf, len(data), C.byref(out), C.byref(n), C.byref(tr) if want_trace else None)
     if rc != 0:
         if want_trace:
             L.szo_trace_free(C.byref(tr))

@@ -1193,10 +1193,89 @@ static int execute_sequences(frame_state *fs, lit_section *ls, int nseq, outbuf 
  * DecodeFrameHeader :306-374, decodeAllBlocks :246-267, DecodeNextBlock :198-244,
  * DecodeNextBlockHeader :270-303 + Block.DecodeHeader (block.go:33-55),
  * DecodeNextBlockContent :93-126. */
+/* ------------------------------------------------------------------------- */
+/* Dictionaries.  NOT in the reference (Readme.md:59-61 lists them as missing; frame.go:38-47 parses the
+ * Dictionary_ID and ignores it): this part restates the zstd format specification (RFC 8878 section 5, "Dictionary Format"):
+ *   raw-content dictionary:  any bytes; they are the history in front of the frame (matches may reach into them);
+ *   formatted dictionary:    magic 0xEC30A437 | Dictionary_ID (4, LE) | Huffman tree description for literals |
+ *                            FSE table descriptions for offsets, match lengths, literal lengths (that order) |
+ *                            three repeat offsets (4 bytes LE each) | content.
+ * The tables act as the "previous block" of the frame's first block (Treeless literals, Repeat modes), the repeat offsets
+ * replace 1, 4, 8.  Pinned by frames libzstd 1.5.5 compressed WITH the dictionary (tools/corpusgen.c: ZSTD_compress_usingDict,
+ * ZDICT_trainFromBuffer): the oracle must give back the original bytes (tests/test_dictionary.py). */
+static int load_dictionary(frame_state *fs, const uint8_t *dict, size_t dlen, const uint8_t **content, size_t *content_len,
+                           uint32_t *dict_id) {
+    *content = dict;
+    *content_len = dlen;
+    *dict_id = 0;
+    if (dlen < 8 || !(dict[0] == 0x37 && dict[1] == 0xA4 && dict[2] == 0x30 && dict[3] == 0xEC)) return SZO_OK; /* raw content */
+    *dict_id = (uint32_t)dict[4] | ((uint32_t)dict[5] << 8) | ((uint32_t)dict[6] << 16) | ((uint32_t)dict[7] << 24);
+    size_t pos = 8;
+    {   /* Huffman tree description, as in a Compressed literals section (literals.go:254-267) */
+        uint8_t weights[4096];
+        int nweights = 0, tree_bytes = 0;
+        int e = szo_huf_decode_tree_desc(dict + pos, dlen - pos, weights, &nweights, &tree_bytes);
+        if (e) return e;
+        pos += (size_t)tree_bytes;
+        szo_huf_table *table = (szo_huf_table *)calloc(1, sizeof(*table));
+        if (!table) return SZO_ERR_NOMEM;
+        if (own(fs, table, 1)) {
+            free(table);
+            return SZO_ERR_NOMEM;
+        }
+        e = szo_huf_build(weights, nweights, table);
+        if (e) return e;
+        fs->prev_huf = table;
+    }
+    for (int k = 0; k < 3; k++) { /* offsets, match lengths, literal lengths */
+        int used = 0, e;
+        szo_fse_table *t = new_fse(fs);
+        if (!t) return SZO_ERR_NOMEM;
+        e = szo_fse_read_table_description(t, dict + pos, dlen - pos, &used);
+        if (e) return e;
+        pos += (size_t)used;
+        if (k == 0) {
+            e = szo_fse_build_decoding_table(t, NULL, 0, NULL, 0);
+            fs->prev_of = t;
+        } else if (k == 1) {
+            e = szo_fse_build_decoding_table(t, szo_ml_base, 53, szo_ml_extra, 53);
+            fs->prev_ml = t;
+        } else {
+            e = szo_fse_build_decoding_table(t, szo_ll_base, 36, szo_ll_extra, 36);
+            fs->prev_ll = t;
+        }
+        if (e) return e;
+    }
+    if (dlen - pos < 12) return SZO_ERR_UNEXPECTED_EOF;
+    for (int k = 0; k < 3; k++) {
+        uint32_t r = (uint32_t)dict[pos] | ((uint32_t)dict[pos + 1] << 8) | ((uint32_t)dict[pos + 2] << 16) | ((uint32_t)dict[pos + 3] << 24);
+        pos += 4;
+        fs->offset_history[k] = r;
+    }
+    for (int k = 0; k < 3; k++) /* a repeat offset of the dictionary points into its content */
+        if (fs->offset_history[k] == 0 || (uint64_t)fs->offset_history[k] > dlen - pos) return SZO_ERR_CANT_REPEAT_BYTES;
+    *content = dict + pos;
+    *content_len = dlen - pos;
+    return SZO_OK;
+}
+
+static int decode_frame_impl(const uint8_t *src, size_t len, const uint8_t *dict, size_t dict_len, uint8_t **out, size_t *out_len,
+                             szo_trace *tr);
+
 int szo_decode_frame(const uint8_t *src, size_t len, uint8_t **out, size_t *out_len, szo_trace *tr) {
+    return decode_frame_impl(src, len, NULL, 0, out, out_len, tr);
+}
+int szo_decode_frame_dict(const uint8_t *src, size_t len, const uint8_t *dict, size_t dict_len, uint8_t **out, size_t *out_len,
+                          szo_trace *tr) {
+    return decode_frame_impl(src, len, dict, dict_len, out, out_len, tr);
+}
+
+static int decode_frame_impl(const uint8_t *src, size_t len, const uint8_t *dict, size_t dict_len, uint8_t **out, size_t *out_len,
+                             szo_trace *tr) {
     frame_state fs;
     outbuf o = {NULL, 0, 0};
     size_t pos = 0;
+    size_t prefix = 0; /* dictionary content in front of the frame's output */
     int rc = SZO_OK;
     memset(&fs, 0, sizeof(fs));
     if (tr) memset(tr, 0, sizeof(*tr));
@@ -1205,14 +1284,41 @@ int szo_decode_frame(const uint8_t *src, size_t len, uint8_t **out, size_t *out_
     fs.offset_history[0] = 1; /* framedecompressor.go:48,59 */
     fs.offset_history[1] = 4;
     fs.offset_history[2] = 8;
+    if (dict && dict_len) {
+        const uint8_t *content;
+        size_t clen;
+        uint32_t id;
+        rc = load_dictionary(&fs, dict, dict_len, &content, &clen, &id);
+        if (rc) {
+            frame_state_free(&fs);
+            return rc;
+        }
+        if (clen) {
+            if (out_reserve(&o, clen)) {
+                frame_state_free(&fs);
+                return SZO_ERR_NOMEM;
+            }
+            memcpy(o.buf, content, clen);
+            o.len = prefix = clen;
+        }
+    }
 
     /* CheckMagicnum */
-    if (len < 4) return SZO_ERR_UNEXPECTED_EOF;
-    if (!(src[0] == 0x28 && src[1] == 0xB5 && src[2] == 0x2F && src[3] == 0xFD)) return SZO_ERR_WRONG_MAGICNUMBER;
+    if (len < 4) {
+        rc = SZO_ERR_UNEXPECTED_EOF;
+        goto done;
+    }
+    if (!(src[0] == 0x28 && src[1] == 0xB5 && src[2] == 0x2F && src[3] == 0xFD)) {
+        rc = SZO_ERR_WRONG_MAGICNUMBER;
+        goto done;
+    }
     pos = 4;
 
     /* DecodeFrameHeader + frame.go getters */
-    if (pos >= len) return SZO_ERR_UNEXPECTED_EOF;
+    if (pos >= len) {
+        rc = SZO_ERR_UNEXPECTED_EOF;
+        goto done;
+    }
     uint8_t fhd = src[pos++];
     int single_segment = (fhd >> 5) & 1;                   /* frame.go:101-103 */
     int dict_flag = fhd & 3;                               /* frame.go:113-127 */
@@ -1220,7 +1326,10 @@ int szo_decode_frame(const uint8_t *src, size_t len, uint8_t **out, size_t *out_
     int fcs_flag = fhd >> 6;                               /* frame.go:79-98 */
     int fcs_size = fcs_flag == 0 ? (single_segment ? 1 : 0) : (fcs_flag == 1 ? 2 : (fcs_flag == 2 ? 4 : 8));
     int header_size = (single_segment ? 0 : 1) + dict_size + fcs_size;
-    if (len - pos < (size_t)header_size) return SZO_ERR_UNEXPECTED_EOF;
+    if (len - pos < (size_t)header_size) {
+        rc = SZO_ERR_UNEXPECTED_EOF;
+        goto done;
+    }
     uint64_t window_size = 0, fcs = 0;
     if (!single_segment) { /* frame.go:28-36 */
         uint8_t wd = src[pos++];
@@ -1243,7 +1352,7 @@ int szo_decode_frame(const uint8_t *src, size_t len, uint8_t **out, size_t *out_
         tr->single_segment = single_segment;
     }
     if (fcs_size > 0 && fcs < ((uint64_t)1 << 40)) {
-        if (out_reserve(&o, (size_t)fcs + 1)) {
+        if (out_reserve(&o, (size_t)fcs + 1)) { /* room beyond what is there already (the dictionary's content) */
             rc = SZO_ERR_NOMEM;
             goto done;
         }
@@ -1285,7 +1394,7 @@ int szo_decode_frame(const uint8_t *src, size_t len, uint8_t **out, size_t *out_
             bt->type = btype;
             bt->last = last_block;
             bt->block_size = (uint32_t)bsize;
-            bt->out_off = o.len;
+            bt->out_off = o.len - prefix;
         }
         if (btype == 0) { /* Raw: framedecompressor.go:211-215 */
             if (len - pos < bsize) {
@@ -1353,7 +1462,7 @@ int szo_decode_frame(const uint8_t *src, size_t len, uint8_t **out, size_t *out_
             pos += (size_t)bsize;
         }
         if (bt) {
-            bt->out_len = o.len - bt->out_off;
+            bt->out_len = o.len - prefix - bt->out_off;
             bt->hist_after[0] = fs.offset_history[0];
             bt->hist_after[1] = fs.offset_history[1];
             bt->hist_after[2] = fs.offset_history[2];
@@ -1367,8 +1476,9 @@ done:
         return rc;
     }
     if (!o.buf) o.buf = (uint8_t *)malloc(1);
+    if (prefix) memmove(o.buf, o.buf + prefix, o.len - prefix); /* the frame's own bytes */
     *out = o.buf;
-    *out_len = o.len;
+    *out_len = o.len - prefix;
     return SZO_OK;
 }
 

@@ -198,6 +198,10 @@ void szo_trace_free(szo_trace *t);
 /* Decode ONE frame starting at src[0].  *out is malloc'ed (caller frees).  Mirrors
  * FrameDecompressor.Decompress (framedecompressor.go:153-170). */
 int szo_decode_frame(const uint8_t *src, size_t len, uint8_t **out, size_t *out_len, szo_trace *trace);
+/* The same with a dictionary (raw content, or formatted: magic 0xEC30A437).  NOT a reference behaviour (the reference has no
+ * dictionary support): restates RFC 8878 section 5; pinned against frames libzstd compressed with the dictionary. */
+int szo_decode_frame_dict(const uint8_t *src, size_t len, const uint8_t *dict, size_t dict_len, uint8_t **out, size_t *out_len,
+                          szo_trace *trace);
 
 /* Convenience for the CPU baseline: decode nframes independent frames with nthreads
  * POSIX threads (one decoder per thread, as BASELINE.md section 3 prescribes).  dst may be NULL

@@ -53,7 +53,7 @@ class BlockDesc(C.Structure):
         ("seq_hdr_bytes", C.c_uint8),
         ("seq_modes", C.c_uint8),
         ("_pad", C.c_uint8),
-        ("_pad2", C.c_uint32),
+        ("hdr_status", C.c_int32),
     ]
 
 

@@ -98,6 +98,7 @@ struct szb_batch {
     uint64_t *d_out_size = nullptr, *d_out_off = nullptr, *d_total = nullptr, *d_frame_out_off = nullptr,
              *d_frame_out_len = nullptr;
     int32_t *d_lit_status = nullptr, *d_seq_status = nullptr, *d_frame_status = nullptr;
+    uint32_t *d_frame_nexec = nullptr;
     size_t status_bytes = 0;
     uint8_t *d_litbuf = nullptr;
     uint32_t *d_seq = nullptr;  // ll | ml | of
@@ -357,10 +358,16 @@ static int batch_upload_tables(szb_batch *b) {
         b->long_jump = n_long > 0 && !(mode && strcmp(mode, "pair") == 0);
         b->lt.clear();
         if (b->long_jump) {
-            // SZB_LONG_SLICE (sequences, rounded up to whole rounds; default 0 = one warp per block): k_long_hist and k_long_emit
+            // SZB_LONG_SLICE (sequences, rounded up to whole rounds; 0 = one warp per block): k_long_hist and k_long_emit
             // run one warp per slice -- more, shorter warps for frames of few blocks -- at the price of cells that are only
-            // resolved inside a slice when they leave k_long_emit.  Not measured yet.
-            const uint32_t slice = getenv("SZB_LONG_SLICE") ? (uint32_t)((strtoul(getenv("SZB_LONG_SLICE"), nullptr, 10) + 31) / 32 * 32) : 0;
+            // resolved inside a slice when they leave k_long_emit.
+            // Measured (profiles/README.md, r02a / r02j; one frame): 64 MiB 14.9 -> 27.5 GB/s and 256 MiB 39 -> 53 GB/s with slices of
+            // 512, 1 GiB 58.7 -> 64.5 GB/s with 1 024 (61.4 with 4 096).  Few blocks want many short warps; beyond 16 384 blocks
+            // (2 GiB) the whole-block default stays (not measured with slices).
+            uint64_t long_blocks = 0;
+            for (uint32_t k = 0; k < n_long; k++) long_blocks += b->frames[b->exec_list[k]].nblocks;
+            const uint32_t auto_slice = long_blocks <= 4096 ? 512u : (long_blocks <= 16384 ? 1024u : 0u);
+            const uint32_t slice = getenv("SZB_LONG_SLICE") ? (uint32_t)((strtoul(getenv("SZB_LONG_SLICE"), nullptr, 10) + 31) / 32 * 32) : auto_slice;
             b->long_slice = slice;
             build_long_tables(b->frames.data(), b->blocks.data(), b->exec_list.data(), n_long, slice, kJumpTile, b->lt);
             const uint64_t cells = b->lt.long_dbase.back();
@@ -494,7 +501,8 @@ static int batch_upload_tables(szb_batch *b) {
     size_t s_fst = s_seqs + 4 * (size_t)nb;
     size_t s_pst = s_fst + 4 * (size_t)nf;
     b->status_bytes = 4 * (2 * (size_t)nb + 2 * (size_t)nf);
-    size_t s_end = align_up(s_pst + 4 * (size_t)nf, 256) + 256;
+    size_t s_nexec = s_pst + 4 * (size_t)nf;
+    size_t s_end = align_up(s_nexec + 4 * (size_t)nf, 256) + 256;
     CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_state, s_end));
     CUDA_TRY(ctx, cudaMemsetAsync(b->d_state, 0, s_end, ctx->stream));
     base = (uint8_t *)b->d_state;
@@ -507,6 +515,7 @@ static int batch_upload_tables(szb_batch *b) {
     b->d_seq_status = (int32_t *)(base + s_seqs);
     b->d_frame_status = (int32_t *)(base + s_fst);
     b->d_place_state = (int32_t *)(base + s_pst);
+    b->d_frame_nexec = (uint32_t *)(base + s_nexec);
     // scratch arenas
     CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_litbuf, (size_t)b->literal_bytes + 256));
     CUDA_TRY(ctx, pool_alloc(ctx, (void **)&b->d_seq, (size_t)(b->sequences * 3 + 64) * 4));
@@ -674,6 +683,7 @@ static DeviceBatch make_args(szb_batch *b, const void *d_src, void *d_dst, size_
     a.frame_out_off = b->d_frame_out_off;
     a.frame_out_len = b->d_frame_out_len;
     a.frame_status = b->d_frame_status;
+    a.frame_nexec = b->d_frame_nexec;
     a.exec_list = b->d_exec_list;
     a.body_list = b->d_body_list;
     a.n_body = (uint32_t)b->body_list.size();

@@ -55,6 +55,10 @@ struct DeviceBatch {
     uint64_t dst_cap;
     uint64_t *frame_out_off, *frame_out_len;
     int32_t *frame_status;
+    uint32_t *frame_nexec;      // per frame: how many of its leading blocks stage 4 executes -- all of them when the frame is fine;
+                                // the blocks in front of the first one that failed in stages 1-3 otherwise (the reference would have
+                                // executed those before it met the failing block: an error in THEIR execution comes first); 0 when
+                                // nothing may be written (destination too small)
     const uint32_t *exec_list;  // frames in the order k_execute starts them (most sequences first)
     const uint32_t *body_list;  // Raw / RLE / zero-sequence blocks: output independent of earlier output
     uint32_t n_body;

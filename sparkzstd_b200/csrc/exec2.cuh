@@ -113,6 +113,8 @@ __device__ __forceinline__ void x2_step(X2Smem &sm, X2State &st, uint32_t lo, ui
         const uint32_t rel = (c << 5) + lane;
         if (kWhole || (rel >= lo && rel < hi)) out[c << 5] = (uint8_t)v[c];
     }
+    __syncwarp();                // every lane has read the line's bitmap words (the votes above converge the warp, but they
+                                 // are no memory fence: racecheck, profiles/r02j_racecheck.txt)
     if (lane < 4) bw[lane] = 0;  // the bitmap is a ring: leave it clean for the next lap
     __syncwarp();
 }
@@ -165,7 +167,7 @@ __device__ __forceinline__ void x2_seek(X2State &st, uint32_t q) {
 // One frame (status OK, taken by x2_takes), one warp: blocks in order, 32 sequences per round (sequence_execution.go:14-63).
 __device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Smem &sm, uint32_t lane) {
     const szb_frame_desc fr = a.frames[f];
-    const uint32_t b0 = fr.first_block, nb = fr.nblocks;
+    const uint32_t b0 = fr.first_block, nb = a.frame_nexec ? a.frame_nexec[f] : fr.nblocks;  // k_frame_verdict
     if (nb == 0) return;
     int err = SZB_OK;
     const uint64_t frame_base = a.out_off[b0];
@@ -428,7 +430,7 @@ __global__ void __launch_bounds__(kX2Warps * 32, SZB_EXEC2_MIN_CTAS) k_execute2(
     const uint32_t slot = blockIdx.x * kX2Warps + (threadIdx.x >> 5);
     if (slot >= n_slots) return;
     const uint32_t f = a.exec_list[first_slot + slot];
-    if (a.frame_status[f] != SZB_OK) return;  // k_frame_verdict
+    if (a.frame_nexec ? a.frame_nexec[f] == 0 : a.frame_status[f] != SZB_OK) return;  // k_frame_verdict
     if (!x2_takes(a, f)) return;              // k_execute's
     X2Smem &sm = smem[threadIdx.x >> 5];
     for (uint32_t wd = lane; wd < kX2Bits / 32; wd += 32) sm.bits[wd] = 0;

@@ -353,25 +353,37 @@ __global__ void k_frame_verdict(DeviceBatch a) {
     const szb_frame_desc fr = a.frames[f];
     const uint32_t b0 = fr.first_block, nb = fr.nblocks;
     int err = SZB_OK;
+    uint32_t nexec = nb;  // leading blocks that are fine as far as stages 1-3 and the header walk can tell
     // k_resolve walked the frame in order (place.cuh): its verdict covers the blocks' entropy stages and the execution
     const int ps = a.place_state ? a.place_state[f] : 1;
     if (ps <= 0) {
         err = ps;
+        nexec = ps == 0 ? nb : 0;  // 0: k_place executes the whole frame; < 0: the error k_resolve found
     } else {
         for (uint32_t i0 = 0; i0 < nb; i0 += 32) {
             int e = SZB_OK;
             if (i0 + lane < nb) {
                 const int ls = a.lit_status[b0 + i0 + lane], ss = a.seq_status[b0 + i0 + lane];
-                if ((ls | ss) != 0) e = ls ? ls : ss;
+                const int hs = a.blocks[b0 + i0 + lane].hdr_status;  // the walk's verdict on this block's sequences header
+                if ((ls | ss | hs) != 0) e = ls ? ls : (ss ? ss : hs);
             }
-            err = warp_first_error(e);
-            if (err != SZB_OK) break;
+            const uint32_t bad = __ballot_sync(kFull, e != 0);
+            if (bad) {
+                const uint32_t first = (uint32_t)__ffs(bad) - 1;
+                err = __shfl_sync(kFull, e, first);
+                nexec = i0 + first;
+                break;
+            }
         }
     }
     if (lane != 0) return;
     if (err == SZB_OK) err = fr.status;  // blocks after a failing header are absent from the table
-    if (err == SZB_OK && a.total[0] > a.dst_cap) err = SZB_ERR_DST_TOO_SMALL;
+    if (a.total[0] > a.dst_cap) {
+        if (err == SZB_OK) err = SZB_ERR_DST_TOO_SMALL;
+        nexec = 0;
+    }
     const uint64_t frame_base = nb ? a.out_off[b0] : 0;
+    if (a.frame_nexec) a.frame_nexec[f] = nexec;
     a.frame_status[f] = err;
     a.frame_out_off[f] = frame_base;
     a.frame_out_len[f] = (nb && err == SZB_OK) ? a.out_off[b0 + nb - 1] + a.out_size[b0 + nb - 1] - frame_base : 0;
@@ -387,7 +399,7 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute_bodies(DeviceBatch a) {
     if (w >= a.n_body) return;
     const uint32_t b = a.body_list[w];
     const szb_block_desc d = a.blocks[b];
-    if (a.frame_status[d.frame] != SZB_OK) return;
+    if (a.frame_nexec ? b - a.frames[d.frame].first_block >= a.frame_nexec[d.frame] : a.frame_status[d.frame] != SZB_OK) return;
     uint8_t *out = a.dst + a.out_off[b];
     const uint8_t *payload = a.src + d.src_off;
     if (d.type == 0) {
@@ -406,7 +418,7 @@ __global__ void __launch_bounds__(kCtaThreads) k_execute_bodies(DeviceBatch a) {
 template <class Sink>
 __device__ __forceinline__ void produce_frame(const DeviceBatch &a, uint32_t f, ExecSmem &sm, Sink &sink, uint32_t lane) {
     const szb_frame_desc fr = a.frames[f];
-    const uint32_t b0 = fr.first_block, nb = fr.nblocks;
+    const uint32_t b0 = fr.first_block, nb = a.frame_nexec ? a.frame_nexec[f] : fr.nblocks;  // k_frame_verdict
     uint8_t *const dst = a.dst;
     int err = SZB_OK;
     const uint64_t frame_base = nb ? a.out_off[b0] : 0;
@@ -655,7 +667,7 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
     const uint32_t slot = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     if (slot >= n_slots) return;
     const uint32_t f = a.exec_list[first_slot + slot];
-    if (a.frame_status[f] != SZB_OK) return;  // k_frame_verdict
+    if (a.frame_nexec ? a.frame_nexec[f] == 0 : a.frame_status[f] != SZB_OK) return;  // k_frame_verdict
     if (a.place_state && a.place_state[f] != 1) return;  // k_place executes it (place.cuh)
     if (x2_takes(a, f)) return;                          // k_execute2 executes it (exec2.cuh)
     ExecSmem &sm = smem[threadIdx.x >> 5];

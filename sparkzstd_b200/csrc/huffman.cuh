@@ -29,22 +29,22 @@ SZB_HD int fse_decode_weights(const uint32_t *table, uint32_t al, const uint8_t 
     uint32_t n = 0;
     for (;;) {  // fse.go:341-388
         uint32_t e = table[s1];
-        if (n >= kMaxHufWeights) return SZB_ERR_CORRUPTED_HUFF_TREE;
+        if (n >= kMaxHufWeights) return SZB_ERR_UNSUPPORTED;  // more weights than byte values: beyond the format (the reference goes on)
         weights[n++] = (uint8_t)fse_code(e);
         rev_refill(r);
         s1 = fse_baseline(e) + rev_read(r, fse_nb(e));
         if (r.remaining < 0) {  // fse.go:362: stream over-read -> flush the other state's symbol
-            if (n >= kMaxHufWeights) return SZB_ERR_CORRUPTED_HUFF_TREE;
+            if (n >= kMaxHufWeights) return SZB_ERR_UNSUPPORTED;  // more weights than byte values: beyond the format (the reference goes on)
             weights[n++] = (uint8_t)fse_code(table[s2]);
             break;
         }
         e = table[s2];
-        if (n >= kMaxHufWeights) return SZB_ERR_CORRUPTED_HUFF_TREE;
+        if (n >= kMaxHufWeights) return SZB_ERR_UNSUPPORTED;  // more weights than byte values: beyond the format (the reference goes on)
         weights[n++] = (uint8_t)fse_code(e);
         rev_refill(r);
         s2 = fse_baseline(e) + rev_read(r, fse_nb(e));
         if (r.remaining < 0) {
-            if (n >= kMaxHufWeights) return SZB_ERR_CORRUPTED_HUFF_TREE;
+            if (n >= kMaxHufWeights) return SZB_ERR_UNSUPPORTED;  // more weights than byte values: beyond the format (the reference goes on)
             weights[n++] = (uint8_t)fse_code(table[s1]);
             break;
         }

@@ -509,16 +509,26 @@ __global__ void __launch_bounds__(kCtaThreads) k_decode_literals(DeviceBatch a) 
                         const uint32_t s1 = jt[0] | (jt[1] << 8), s2 = jt[2] | (jt[3] << 8), s3 = jt[4] | (jt[5] << 8);
                         const uint32_t normal = (regen + 3) / 4;  // literals.go:306-311
                         const int32_t last = (int32_t)regen - 3 * (int32_t)normal;
-                        if (s1 + s2 + s3 > (uint32_t)comp) {
-                            my_rc = SZB_ERR_CORRUPTED_JUMPTABLE;  // literals.go:54-56 (the reference drops this error and re-slices)
-                        } else if (last < 0) {
+                        // The reference decodes the streams one after the other and checks every stream's extent right before it
+                        // decodes it (literals.go:313-359): stream k's extent error comes AFTER the decode errors of the streams
+                        // before it.  Every lane applies the checks of its own stream; the first failing stream decides (below).
+                        const uint32_t end1 = s1, end2 = s1 + s2, end3 = s1 + s2 + s3;
+                        const uint32_t s4 = (uint32_t)(uint16_t)((uint32_t)comp - (uint32_t)(uint16_t)end3);  // CalcStreamsize4: uint16 arithmetic
+                        const uint32_t my_end = my_k == 0 ? end1 : (my_k == 1 ? end2 : (my_k == 2 ? end3 : end3 + s4));
+                        const uint32_t before = my_k == 0 ? 0 : (my_k == 1 ? end1 : (my_k == 2 ? end2 : end3));
+                        if (last < 0) {
                             my_rc = SZB_ERR_PANIC;  // literals.go:311 inverted slice
+                        } else if (before > (uint32_t)comp) {
+                            my_rc = SZB_ERR_CORRUPTED_JUMPTABLE;  // an earlier stream reports it first; never decoded from here
+                        } else if (my_k == 2 && my_end > regen) {
+                            my_rc = SZB_ERR_PANIC;  // literals.go:339-342 panic("Corrupt stream sizes")
+                        } else if (my_k < 3 && my_end > (uint32_t)comp) {
+                            my_rc = SZB_ERR_CORRUPTED_JUMPTABLE;  // literals.go:54-56 (the reference re-slices into stale capacity)
+                        } else if (my_k == 3 && my_end != (uint32_t)comp) {
+                            my_rc = SZB_ERR_PANIC;  // literals.go:356-359
                         } else {
-                            const uint32_t s4 = (uint32_t)comp - (s1 + s2 + s3);
-                            const uint32_t start = my_k == 0 ? 0 : (my_k == 1 ? s1 : (my_k == 2 ? s1 + s2 : s1 + s2 + s3));
-                            const uint32_t len = my_k == 0 ? s1 : (my_k == 1 ? s2 : (my_k == 2 ? s3 : s4));
                             const uint32_t expected = my_k < 3 ? normal : (uint32_t)last;
-                            my_rc = huf_decode_stream_vec(tabs + my_off, bits, jt + 6 + start, len, out + my_k * normal, expected, my_ring);
+                            my_rc = huf_decode_stream_vec(tabs + my_off, bits, jt + 6 + before, my_end - before, out + my_k * normal, expected, my_ring);
                         }
                     }
                 }

@@ -227,9 +227,9 @@ __device__ __forceinline__ void resolve_next_block(const DeviceBatch &a, Resolve
             return;
         }
         const uint32_t b = s.b++;
-        const int ls = a.lit_status[b], ss = a.seq_status[b];
-        if ((ls | ss) != 0) {
-            s.err = ls ? ls : ss;
+        const int ls = a.lit_status[b], ss = a.seq_status[b], hs = a.blocks[b].hdr_status;
+        if ((ls | ss | hs) != 0) {
+            s.err = ls ? ls : (ss ? ss : hs);
             s.active = false;
             return;
         }

@@ -190,14 +190,32 @@ void walk_frame(szb_walk &w, const uint8_t *src, uint64_t off, uint64_t len, uin
                 uint64_t lit_total = (uint64_t)d.lit_hdr_bytes + d.lit_comp;
                 if (lit_total > d.block_size) { rc = SZB_ERR_UNEXPECTED_EOF; break; }
                 d.seq_off = (uint32_t)lit_total;
-                rc = parse_sequences_header(bp + lit_total, d.block_size - lit_total, d);
-                if (rc) break;
-                if (d.nseq == 0 && lit_total + 1 != d.block_size) { rc = SZB_ERR_CORRUPT_SIZES; break; }  // framedecompressor.go:114-123
-                if (d.nseq > 0) {                       // DecodeTables order LL, OF, ML (sequences.go:275-369)
+                // From here on the reference has already decoded the block's literals (DecodeNextBlockContent,
+                // framedecompressor.go:93-126: literals section first, then the sequences header): an error in this header
+                // does not hide an error in the literals.  The block stays in the table -- without sequences, with the
+                // error in hdr_status -- so that the device decodes its literals and the first error wins; the walk ends.
+                int hs = parse_sequences_header(bp + lit_total, d.block_size - lit_total, d);
+                if (!hs && d.nseq == 0 && lit_total + 1 != d.block_size) hs = SZB_ERR_CORRUPT_SIZES;  // framedecompressor.go:114-123
+                if (!hs && d.nseq > 0) {                // DecodeTables order LL, OF, ML (sequences.go:275-369)
                     uint32_t llm = d.seq_modes >> 6, ofm = (d.seq_modes >> 4) & 3, mlm = (d.seq_modes >> 2) & 3;
-                    if (llm == 3) { if (carry.ll == SZB_NONE) { rc = SZB_ERR_NO_LL_TABLE_TO_CARRY_OVER; break; } d.ll_origin = carry.ll; } else d.ll_origin = self;
-                    if (ofm == 3) { if (carry.of == SZB_NONE) { rc = SZB_ERR_NO_OF_TABLE_TO_CARRY_OVER; break; } d.of_origin = carry.of; } else d.of_origin = self;
-                    if (mlm == 3) { if (carry.ml == SZB_NONE) { rc = SZB_ERR_NO_ML_TABLE_TO_CARRY_OVER; break; } d.ml_origin = carry.ml; } else d.ml_origin = self;
+                    if (llm == 3) { if (carry.ll == SZB_NONE) hs = SZB_ERR_NO_LL_TABLE_TO_CARRY_OVER; else d.ll_origin = carry.ll; } else d.ll_origin = self;
+                    if (!hs) { if (ofm == 3) { if (carry.of == SZB_NONE) hs = SZB_ERR_NO_OF_TABLE_TO_CARRY_OVER; else d.of_origin = carry.of; } else d.of_origin = self; }
+                    if (!hs) { if (mlm == 3) { if (carry.ml == SZB_NONE) hs = SZB_ERR_NO_ML_TABLE_TO_CARRY_OVER; else d.ml_origin = carry.ml; } else d.ml_origin = self; }
+                }
+                if (hs) {
+                    d.hdr_status = hs;
+                    d.nseq = 0;
+                    d.seq_hdr_bytes = 0;
+                    d.seq_modes = 0;
+                    d.ll_origin = d.of_origin = d.ml_origin = SZB_NONE;
+                    if (d.lit_type >= 2) {
+                        d.lit_buf_off = w.literal_bytes;
+                        w.literal_bytes += ((uint64_t)d.lit_regen + 15) & ~15ull;
+                    }
+                    d.seq_buf_off = w.sequences;
+                    w.blocks.push_back(d);
+                    rc = hs;
+                    break;
                 }
                 // carry rules, framedecompressor.go:283-294
                 if (d.lit_type >= 2) carry.huf = d.huf_origin;

@@ -377,6 +377,8 @@ int hostsim_stage4_at(const uint8_t *src, size_t len, uint8_t *out, size_t cap, 
     a.frame_out_off = frame_out_off.data();
     a.frame_out_len = frame_out_len.data();
     a.frame_status = frame_status.data();
+    std::vector<uint32_t> frame_nexec(copies, 0xDEADu);
+    a.frame_nexec = frame_nexec.data();
     a.exec_list = exec_list.data();
     a.body_list = body_list.data();
     a.n_body = (uint32_t)body_list.size();

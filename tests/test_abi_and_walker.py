@@ -46,7 +46,7 @@ def test_struct_layouts_match_the_header():
     ff = [f[0] for f in FrameDesc._fields_]
     bf = [f[0] for f in BlockDesc._fields_ if not f[0].startswith("_pad")]
     want = [C.sizeof(FrameDesc)] + [getattr(FrameDesc, f).offset for f in ff] + [C.sizeof(BlockDesc)] + [getattr(BlockDesc, f).offset for f in bf]
-    assert n == len(want) == 36 and got == want
+    assert n == len(want) == 37 and got == want
     # ... and so must the Go mirror (go/szb200/szb200.go: plain structs with exported fields, same order, same widths; Go
     # aligns every field naturally, as the C compiler does): recompute its layout from the declaration
     import os

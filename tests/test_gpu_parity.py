@@ -256,7 +256,7 @@ def test_streamed_reader_hands_out_pieces_and_reads_in_pieces(ctx):
     got = cg.hash_frames(np.frombuffer(target.getvalue(), dtype=np.uint8), np.array([0], np.uint64), np.array([total], np.uint64))
     assert got[0] == c.raw_hash[0]
     # errors come through the same way: a truncated frame, a failing source, a failing target
-    with pytest.raises(D.SzbError):
+    with pytest.raises(D.ErrUnexpectedEOF):
         D.NewFrameDecompressor(io.BytesIO(frame[: len(frame) // 2]), io.BytesIO(), ctx).Decompress()
 
     class Boom(io.RawIOBase):

@@ -48,6 +48,12 @@ def lib():
         L.cg_compress_stream.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int]
         L.cg_zstd_decompress.restype = C.c_size_t
         L.cg_zstd_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.cg_compress_dict.restype = C.c_size_t
+        L.cg_compress_dict.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
+        L.cg_zstd_decompress_dict.restype = C.c_size_t
+        L.cg_zstd_decompress_dict.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.cg_train_dictionary.restype = C.c_size_t
+        L.cg_train_dictionary.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint]
         L.cg_zstd_decompress_batch_mt.restype = C.c_uint32
         L.cg_zstd_decompress_batch_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]
         L.cg_generate_frames.restype = C.c_uint64
@@ -267,6 +273,58 @@ def config5_mixed(total_bytes: int = 16 << 30, seed: int = BASE_SEED + 30_000_00
         c.meta["golden_reps"] = int(my_reps)
     c.meta.update(workload=f"mixed corpus ~{total_bytes} B, {c.nframes} frames", seed=seed)
     return c
+
+
+# ---- dictionaries ---------------------------------------------------------------
+def train_dictionary(samples, size: int = 16 << 10) -> bytes:
+    """A formatted zstd dictionary (ZDICT_trainFromBuffer) from a list of byte strings."""
+    L = lib()
+    blob = np.frombuffer(b"".join(samples), dtype=np.uint8)
+    sizes = np.array([len(x) for x in samples], dtype=np.uint64)  # size_t
+    out = np.empty(size, dtype=np.uint8)
+    n = L.cg_train_dictionary(out.ctypes.data, size, blob.ctypes.data, sizes.ctypes.data, len(samples))
+    if n == 0:
+        raise RuntimeError("ZDICT_trainFromBuffer failed (too few / too uniform samples?)")
+    return out[: int(n)].tobytes()
+
+
+def compress_with_dict(data: bytes, dictionary: bytes, level: int = 3) -> bytes:
+    L = lib()
+    src = np.frombuffer(data, dtype=np.uint8) if data else np.zeros(1, np.uint8)
+    d = np.frombuffer(dictionary, dtype=np.uint8)
+    cap = int(L.cg_compress_bound(len(data))) + 64
+    dst = np.empty(cap, dtype=np.uint8)
+    n = L.cg_compress_dict(src.ctypes.data, len(data), d.ctypes.data, len(dictionary), dst.ctypes.data, cap, level)
+    if n == 0:
+        raise RuntimeError("ZSTD_compress_usingDict failed")
+    return dst[: int(n)].tobytes()
+
+
+def zstd_decompress_with_dict(frame: bytes, dictionary: bytes, cap: int) -> bytes:
+    L = lib()
+    src = np.frombuffer(frame, dtype=np.uint8)
+    d = np.frombuffer(dictionary, dtype=np.uint8)
+    dst = np.empty(max(cap, 1), dtype=np.uint8)
+    n = L.cg_zstd_decompress_dict(src.ctypes.data, len(frame), d.ctypes.data, len(dictionary), dst.ctypes.data, cap)
+    if n == (1 << 64) - 1:
+        raise RuntimeError("ZSTD_decompress_usingDict failed")
+    return dst[: int(n)].tobytes()
+
+
+def dictionary_messages(n: int = 200, seed: int = 77):
+    """Small JSON-like records with a shared vocabulary: the classic dictionary workload (many small frames whose matches
+    point into the dictionary).  Deterministic."""
+    rng = np.random.default_rng(seed)
+    keys = ["user_id", "session", "timestamp", "event_type", "payload", "region", "device", "latency_ms", "status", "trace"]
+    vals = ["click", "view", "purchase", "eu-west-1", "us-east-2", "ap-south-1", "android", "ios", "desktop", "ok", "retry", "timeout"]
+    out = []
+    for i in range(n):
+        parts = []
+        for k in rng.permutation(len(keys))[: int(rng.integers(4, len(keys)))]:
+            v = vals[int(rng.integers(len(vals)))] if rng.random() < 0.6 else str(int(rng.integers(1 << 30)))
+            parts.append('"%s": "%s"' % (keys[int(k)], v))
+        out.append(("{" + ", ".join(parts) + ', "seq": %d}' % i).encode() * int(rng.integers(1, 4)))
+    return out
 
 
 def algorithmic_bytes(c: Corpus, match_bytes: int) -> int:

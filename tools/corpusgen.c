@@ -202,6 +202,12 @@ static struct {
     size_t (*compressStream2)(void *, zout_t *, zin_t *, int);
     size_t (*decompress)(void *, size_t, const void *, size_t);
     unsigned (*versionNumber)(void);
+    size_t (*compressUsingDict)(void *, void *, size_t, const void *, size_t, const void *, size_t, int);
+    size_t (*decompressUsingDict)(void *, void *, size_t, const void *, size_t, const void *, size_t);
+    void *(*createDCtx)(void);
+    size_t (*freeDCtx)(void *);
+    size_t (*trainFromBuffer)(void *, size_t, const void *, const size_t *, unsigned);
+    unsigned (*zdictIsError)(size_t);
 } Z;
 static pthread_once_t z_once = PTHREAD_ONCE_INIT;
 static void z_init(void) {
@@ -216,6 +222,12 @@ static void z_init(void) {
     Z.compressStream2 = dlsym(Z.h, "ZSTD_compressStream2");
     Z.decompress = dlsym(Z.h, "ZSTD_decompress");
     Z.versionNumber = dlsym(Z.h, "ZSTD_versionNumber");
+    Z.compressUsingDict = dlsym(Z.h, "ZSTD_compress_usingDict");
+    Z.decompressUsingDict = dlsym(Z.h, "ZSTD_decompress_usingDict");
+    Z.createDCtx = dlsym(Z.h, "ZSTD_createDCtx");
+    Z.freeDCtx = dlsym(Z.h, "ZSTD_freeDCtx");
+    Z.trainFromBuffer = dlsym(Z.h, "ZDICT_trainFromBuffer");
+    Z.zdictIsError = dlsym(Z.h, "ZDICT_isError");
 }
 int cg_zstd_available(void) {
     pthread_once(&z_once, z_init);
@@ -268,6 +280,31 @@ size_t cg_compress_stream(const uint8_t *src, size_t n, uint8_t *dst, size_t cap
     }
     Z.freeCCtx(c);
     return ok ? o.pos : 0;
+}
+
+/* ---- dictionaries: inputs for the dictionary tests only ---- */
+/* One-shot compress WITH a dictionary (raw content, or a formatted one from cg_train_dictionary).  Returns size or 0. */
+size_t cg_compress_dict(const uint8_t *src, size_t n, const uint8_t *dict, size_t dict_len, uint8_t *dst, size_t cap, int level) {
+    if (!cg_zstd_available() || !Z.compressUsingDict) return 0;
+    void *c = Z.createCCtx();
+    size_t r = Z.compressUsingDict(c, dst, cap, src, n, dict, dict_len, level);
+    Z.freeCCtx(c);
+    return Z.isError(r) ? 0 : r;
+}
+/* libzstd's own decoder with the dictionary: the known answer the oracle's dictionary extension is pinned with. */
+size_t cg_zstd_decompress_dict(const uint8_t *src, size_t n, const uint8_t *dict, size_t dict_len, uint8_t *dst, size_t cap) {
+    if (!cg_zstd_available() || !Z.decompressUsingDict) return (size_t)-1;
+    void *d = Z.createDCtx();
+    size_t r = Z.decompressUsingDict(d, dst, cap, src, n, dict, dict_len);
+    Z.freeDCtx(d);
+    return Z.isError(r) ? (size_t)-1 : r;
+}
+/* ZDICT_trainFromBuffer: a FORMATTED dictionary (magic, id, entropy tables, repeat offsets, content) from samples laid out
+ * back to back.  Returns its size or 0. */
+size_t cg_train_dictionary(uint8_t *dict, size_t cap, const uint8_t *samples, const size_t *sizes, unsigned nsamples) {
+    if (!cg_zstd_available() || !Z.trainFromBuffer) return 0;
+    size_t r = Z.trainFromBuffer(dict, cap, samples, sizes, nsamples);
+    return Z.zdictIsError(r) ? 0 : r;
 }
 
 size_t cg_zstd_decompress(const uint8_t *src, size_t n, uint8_t *dst, size_t cap) {
