@@ -70,7 +70,7 @@ type BlockDesc struct {
 	LitHdrBytes uint8
 	SeqHdrBytes uint8
 	SeqModes    uint8
-	Pad         uint8
+	Flags       uint8 // BlockTablesOnly: a dictionary's table-only row
 	HdrStatus   int32 // the error the walk hit in this block's sequences-section header (the literals are still decoded first)
 }
 
@@ -95,7 +95,8 @@ func layout() []uint32 {
 		uint32(unsafe.Offsetof(b.HufOrigin)), uint32(unsafe.Offsetof(b.LLOrigin)), uint32(unsafe.Offsetof(b.OFOrigin)),
 		uint32(unsafe.Offsetof(b.MLOrigin)), uint32(unsafe.Offsetof(b.Type)), uint32(unsafe.Offsetof(b.Last)),
 		uint32(unsafe.Offsetof(b.LitType)), uint32(unsafe.Offsetof(b.LitStreams)), uint32(unsafe.Offsetof(b.LitHdrBytes)),
-		uint32(unsafe.Offsetof(b.SeqHdrBytes)), uint32(unsafe.Offsetof(b.SeqModes)), uint32(unsafe.Offsetof(b.HdrStatus)),
+		uint32(unsafe.Offsetof(b.SeqHdrBytes)), uint32(unsafe.Offsetof(b.SeqModes)), uint32(unsafe.Offsetof(b.Flags)),
+		uint32(unsafe.Offsetof(b.HdrStatus)),
 	}
 }
 

@@ -67,7 +67,8 @@ enum {
     SZB_ERR_INVALID_ARGUMENT = -66,
     SZB_ERR_NO_DEVICE = -67,
     SZB_ERR_CHECKSUM_MISMATCH = -68, /* only when SZB_FLAG_VERIFY_CHECKSUM is set (not a reference behaviour) */
-    SZB_ERR_IO = -69                 /* a read / write callback of szb_decompress_reader failed */
+    SZB_ERR_IO = -69,                /* a read / write callback of szb_decompress_reader failed */
+    SZB_ERR_WRONG_DICTIONARY = -70   /* the frame names another Dictionary_ID than the dictionary given (szb_decode_batch_dict) */
 };
 
 /* replaces: the Go `error` values' Error() strings */
@@ -81,6 +82,7 @@ const char *szb_strerror(int code);
  * walk and emits these two tables; szb_walk_* is the C++ twin of that walker. */
 
 #define SZB_NONE 0xFFFFFFFFu
+#define SZB_BLOCK_TABLES_ONLY 1u
 #define SZB_CONTENT_SIZE_UNKNOWN 0xFFFFFFFFFFFFFFFFull
 
 typedef struct szb_frame_desc {
@@ -125,7 +127,8 @@ typedef struct szb_block_desc {
     uint8_t lit_hdr_bytes; /* 1..5 (literals.go:162-204) */
     uint8_t seq_hdr_bytes; /* bytes of the sequence count (1..3) plus the modes byte when nseq > 0 */
     uint8_t seq_modes;     /* raw Symbol_Compression_Modes byte (sequences.go:228-232) */
-    uint8_t _pad;
+    uint8_t flags;         /* SZB_BLOCK_TABLES_ONLY: the block only carries entropy tables (a dictionary's, szb_dict_create):
+                              stage 1 builds them, nothing is decoded from it and it regenerates nothing */
     int32_t hdr_status;    /* 0, or the error the walk hit in THIS block's sequences-section header (count, modes, a Repeat mode
                               with nothing to repeat, sizes that do not add up).  The reference decodes a block's literals before
                               it looks at that header (framedecompressor.go:93-126), so the device still decodes the literals of
@@ -134,8 +137,8 @@ typedef struct szb_block_desc {
 
 /* The layout of the two structs above, for bindings that mirror them instead of including this header (the Go structs of
  * go/szb200, the ctypes mirror): sizeof(szb_frame_desc), the offset of each of its fields in declaration order (src_off ..
- * checksum_valid), sizeof(szb_block_desc), the offset of each of its fields (src_off .. seq_modes, hdr_status; the padding
- * byte is not listed).  Writes at most cap values, returns how many there are (37).  A binding compares them with its own when it loads. */
+ * checksum_valid), sizeof(szb_block_desc), the offset of each of its fields (src_off .. seq_modes, flags,
+ * hdr_status).  Writes at most cap values, returns how many there are (38).  A binding compares them with its own when it loads. */
 uint32_t szb_abi_layout(uint32_t *out, uint32_t cap);
 
 /* Multi-GPU host split: frames are independent, so G GPUs decode a partition of the frame list, one process
@@ -157,6 +160,11 @@ typedef struct szb_walk szb_walk;
  * DecodeNextLiteralsSection / DecodeNextSequenceSection. */
 int szb_walk_create(const uint8_t *src, size_t src_len, const uint64_t *frame_off, const uint64_t *frame_len,
                     uint32_t nframes, szb_walk **out);
+/* The same for a batch decoded with a dictionary: dict_block (NULL for a raw-content dictionary) becomes row 0 of the block
+ * table, owned by a pseudo frame appended after the caller's frames (szb_walk_nframes counts it; it has no blocks and a
+ * non-zero status); a frame naming another Dictionary_ID than dict_id ends with SZB_ERR_WRONG_DICTIONARY. */
+int szb_walk_create_dict(const uint8_t *src, size_t src_len, const uint64_t *frame_off, const uint64_t *frame_len,
+                         uint32_t nframes, const szb_block_desc *dict_block, uint32_t dict_id, szb_walk **out);
 void szb_walk_destroy(szb_walk *w);
 uint32_t szb_walk_nframes(const szb_walk *w);
 uint32_t szb_walk_nblocks(const szb_walk *w);
@@ -234,6 +242,22 @@ int szb_decompress_reader(szb_ctx *ctx, szb_read_fn read, void *read_user, szb_w
 /* The header row (window size, content size, number of blocks, walk status ...) of the frame szb_decompress_reader decoded
  * last on this context: what FrameDecompressor.BlockCounter and the reference's frame-header fields are filled from. */
 int szb_ctx_last_frame(szb_ctx *ctx, szb_frame_desc *out);
+
+/* ---- dictionaries (NOT a reference behaviour: the reference parses Dictionary_ID and ignores it, frame.go:38-47,
+ * and lists dictionaries as missing, Readme.md:59-61).  RFC 8878 section 5: a raw-content dictionary is history in front of the
+ * frame; a formatted one (magic 0xEC30A437) also brings a Huffman table, three FSE tables and three repeat offsets that act
+ * as the "previous block" of the frame's first block.  szb_dict_create parses the dictionary on the host and keeps its content
+ * and its tables' descriptions in device memory; the tables enter a batch as one table-only row of the block table
+ * (SZB_BLOCK_TABLES_ONLY) that Treeless literals and Repeat modes of first blocks name as their origin. */
+typedef struct szb_dict szb_dict;
+int szb_dict_create(szb_ctx *ctx, const uint8_t *dict, size_t len, szb_dict **out);
+void szb_dict_destroy(szb_dict *d);
+uint32_t szb_dict_id(const szb_dict *d); /* 0 for a raw-content dictionary */
+/* szb_decode_batch with a dictionary: every frame whose header names the dictionary's id, or none, is decoded with it; a frame
+ * that names another id ends with SZB_ERR_WRONG_DICTIONARY.  Host buffers only (no SZB_FLAG_SRC_DEVICE / _DST_DEVICE). */
+int szb_decode_batch_dict(szb_ctx *ctx, const szb_dict *dict, const uint8_t *src, size_t src_len, const uint64_t *frame_off,
+                          const uint64_t *frame_len, uint32_t nframes, uint8_t *dst, size_t dst_cap, uint64_t *out_off,
+                          uint64_t *out_len, int32_t *status, uint32_t flags);
 
 /* ---- staged batch object (size-then-decode, resident inputs, timing) ------------------ */
 typedef struct szb_batch szb_batch;

@@ -52,7 +52,7 @@ class BlockDesc(C.Structure):
         ("lit_hdr_bytes", C.c_uint8),
         ("seq_hdr_bytes", C.c_uint8),
         ("seq_modes", C.c_uint8),
-        ("_pad", C.c_uint8),
+        ("flags", C.c_uint8),
         ("hdr_status", C.c_int32),
     ]
 
@@ -62,6 +62,7 @@ _P = C.c_void_p
 SYMBOLS = [
     ("szb_strerror", C.c_char_p, [C.c_int]),
     ("szb_walk_create", C.c_int, [_P, C.c_size_t, _P, _P, C.c_uint32, C.POINTER(_P)]),
+    ("szb_walk_create_dict", C.c_int, [_P, C.c_size_t, _P, _P, C.c_uint32, _P, C.c_uint32, C.POINTER(_P)]),
     ("szb_walk_destroy", None, [_P]),
     ("szb_walk_nframes", C.c_uint32, [_P]),
     ("szb_walk_nblocks", C.c_uint32, [_P]),
@@ -80,6 +81,10 @@ SYMBOLS = [
     ("szb_decode_stream", C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t, _P, _P, _P, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_uint32]),
     ("szb_ctx_last_frame", C.c_int, [_P, _P]),
     ("szb_decompress_reader", C.c_int, [_P, _P, _P, _P, _P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint32]),
+    ("szb_dict_create", C.c_int, [_P, _P, C.c_size_t, C.POINTER(_P)]),
+    ("szb_dict_destroy", None, [_P]),
+    ("szb_dict_id", C.c_uint32, [_P]),
+    ("szb_decode_batch_dict", C.c_int, [_P, _P, _P, C.c_size_t, _P, _P, C.c_uint32, _P, C.c_size_t, _P, _P, _P, C.c_uint32]),
     ("szb_decode_blocks", C.c_int, [_P, _P, C.c_size_t, _P, C.c_uint32, _P, C.c_uint32, _P, C.c_size_t, _P, _P, _P]),
     ("szb_batch_create", C.c_int, [_P, _P, C.c_size_t, _P, _P, C.c_uint32, C.POINTER(_P)]),
     ("szb_batch_create_from_tables", C.c_int, [_P, C.c_size_t, _P, C.c_uint32, _P, C.c_uint32, C.POINTER(_P)]),

@@ -13,7 +13,7 @@
 #define SZB_BLOCK_FIELDS(X)                                                                                         \
     X(src_off) X(lit_buf_off) X(seq_buf_off) X(block_size) X(frame) X(lit_regen) X(lit_comp) X(nseq) X(seq_off) \
     X(huf_origin) X(ll_origin) X(of_origin) X(ml_origin) X(type) X(last) X(lit_type) X(lit_streams)            \
-    X(lit_hdr_bytes) X(seq_hdr_bytes) X(seq_modes) X(hdr_status)
+    X(lit_hdr_bytes) X(seq_hdr_bytes) X(seq_modes) X(flags) X(hdr_status)
 
 // what every binding assumes (go/szb200/szb200.go, sparkzstd_b200/_lib.py)
 static_assert(sizeof(szb_frame_desc) == 64, "szb_frame_desc is 64 bytes");
@@ -36,7 +36,7 @@ static_assert(offsetof(szb_block_desc, src_off) == 0 && offsetof(szb_block_desc,
                   offsetof(szb_block_desc, last) == 65 && offsetof(szb_block_desc, lit_type) == 66 &&
                   offsetof(szb_block_desc, lit_streams) == 67 && offsetof(szb_block_desc, lit_hdr_bytes) == 68 &&
                   offsetof(szb_block_desc, seq_hdr_bytes) == 69 && offsetof(szb_block_desc, seq_modes) == 70 &&
-                  offsetof(szb_block_desc, hdr_status) == 72,
+                  offsetof(szb_block_desc, flags) == 71 && offsetof(szb_block_desc, hdr_status) == 72,
               "szb_block_desc field offsets");
 
 static inline uint32_t szb_abi_layout_impl(uint32_t *out, uint32_t cap) {

@@ -54,6 +54,22 @@ struct szb_ctx {
     cudaEvent_t pin_in_ev[kPinIn] = {}, pin_out_ev[kPinOut] = {};
 };
 
+// A dictionary (szb200.h): parsed once on the host.  `payload` is a synthetic Compressed block that carries the dictionary's
+// entropy tables in the places a real block keeps them -- a literals section with the Huffman tree description and no streams,
+// a sequences section whose three FSE table descriptions follow the modes byte in the block order LL, OF, ML (the dictionary
+// stores them OF, ML, LL) -- so that the table builders, and the Repeat / Treeless rules of the blocks that name it as their
+// origin, work on it unchanged.  `blk` is its row of the block table (src_off is filled in per batch).
+struct szb_dict {
+    szb_ctx *ctx = nullptr;
+    uint32_t id = 0;
+    bool has_tables = false;
+    uint32_t rep[3] = {1, 4, 8};
+    std::vector<uint8_t> payload;
+    szb_block_desc blk = {};
+    uint8_t *d_content = nullptr;  // the dictionary's content (history in front of a frame), + 16 readable bytes
+    uint32_t content_len = 0;
+};
+
 static cudaError_t pool_alloc(szb_ctx *ctx, void **p, size_t bytes);
 static void pool_free(szb_ctx *ctx, void *p);
 
@@ -107,6 +123,8 @@ struct szb_batch {
     // frames one warp executes (place.cuh)
     bool place = false;
     bool exec2 = false;      // k_execute2 (exec2.cuh) for the frames one warp executes
+    const szb_dict *dict = nullptr;  // the batch is decoded with this dictionary (szb_decode_batch_dict)
+    uint8_t *d_frame_dict = nullptr; // per frame: decoded with the dictionary
     std::vector<uint64_t> rec_off;
     uint64_t rec_entries = 0, bm_bound = 0, bm_words = 0;
     uint64_t *d_rec_off = nullptr;
@@ -132,6 +150,7 @@ const char *szb_strerror(int code) {
     switch (code) {
     case SZB_OK: return "ok";
     case SZB_ERR_IO: return "read or write callback failed";
+    case SZB_ERR_WRONG_DICTIONARY: return "the frame names another dictionary than the one given";
     case SZB_ERR_WRONG_MAGICNUMBER: return "Magicnum is not correct";
     case SZB_ERR_CORRUPT_SIZES: return "The sizes of literal and sequence section did not add up to blocksize";
     case SZB_ERR_OUT_OF_BLOCKS: return "No blocks left in frame";
@@ -350,6 +369,7 @@ static int batch_upload_tables(szb_batch *b) {
         const uint64_t long_seqs = getenv("SZB_LONG_SEQS") ? strtoull(getenv("SZB_LONG_SEQS"), nullptr, 10) : kLongFrameSequences;
         uint32_t n_long = 0;
         while (n_long < nf && n_long < kMaxLongFrames && work[b->exec_list[n_long]] >= long_seqs && work[b->exec_list[n_long]] > 0) n_long++;
+        if (b->dict) n_long = 0;  // dictionary batches are k_execute2's (below)
         b->n_long = n_long;
         // The block-parallel path (execute_long.cuh) wants every block of the long frames, and one distance cell per
         // output byte: the host knows an upper bound (a Raw/RLE block regenerates Block_Size bytes, a compressed one at
@@ -408,6 +428,10 @@ static int batch_upload_tables(szb_batch *b) {
         b->place = want_place && nf > b->n_noplace;
         // SZB_EXEC=legacy: k_execute for every frame; exec2 (the default): k_execute2, k_execute for frames of 2 GiB and more
         b->exec2 = !b->place && !(em && strcmp(em, "legacy") == 0);
+        if (b->dict) {  // only k_execute2 reaches into a dictionary's content: no long-frame paths, no k_place
+            b->place = false;
+            b->exec2 = true;
+        }
         b->rec_off.assign(nb ? nb : 1, 0);
         uint64_t entries = 0, bound = 0;
         if (b->place) {
@@ -527,13 +551,20 @@ static int batch_upload_tables(szb_batch *b) {
     return SZB_OK;
 }
 
+static int batch_create_from_tables_impl(szb_ctx *ctx, size_t src_len, const szb_frame_desc *frames, uint32_t nframes,
+                                         const szb_block_desc *blocks, uint32_t nblocks, const szb_dict *dict, szb_batch **out);
 int szb_batch_create_from_tables(szb_ctx *ctx, size_t src_len, const szb_frame_desc *frames, uint32_t nframes,
                                  const szb_block_desc *blocks, uint32_t nblocks, szb_batch **out) {
+    return batch_create_from_tables_impl(ctx, src_len, frames, nframes, blocks, nblocks, nullptr, out);
+}
+static int batch_create_from_tables_impl(szb_ctx *ctx, size_t src_len, const szb_frame_desc *frames, uint32_t nframes,
+                                         const szb_block_desc *blocks, uint32_t nblocks, const szb_dict *dict, szb_batch **out) {
     if (!ctx || !out || (nframes && !frames) || (nblocks && !blocks)) return SZB_ERR_INVALID_ARGUMENT;
     *out = nullptr;
     szb_batch *b = new (std::nothrow) szb_batch();
     if (!b) return SZB_ERR_NOMEM;
     b->ctx = ctx;
+    b->dict = dict;
     b->nframes = nframes;
     b->nblocks = nblocks;
     b->src_len = src_len;
@@ -642,6 +673,7 @@ void szb_batch_destroy(szb_batch *b) {
     pool_free(b->ctx, b->d_huf_info);
     pool_free(b->ctx, b->d_long);
     pool_free(b->ctx, b->d_place);
+    pool_free(b->ctx, b->d_frame_dict);
     delete b;
 }
 
@@ -712,6 +744,10 @@ static DeviceBatch make_args(szb_batch *b, const void *d_src, void *d_dst, size_
     a.place_state = a.rec ? b->d_place_state : nullptr;
     a.n_noplace = b->n_noplace;
     a.exec2 = b->exec2 ? 1u : 0u;
+    a.dict_content = b->dict ? b->dict->d_content : nullptr;
+    a.dict_len = b->dict ? b->dict->content_len : 0;
+    for (int k = 0; k < 3; k++) a.dict_rep[k] = b->dict ? b->dict->rep[k] : (k == 0 ? 1u : (k == 1 ? 4u : 8u));
+    a.frame_dict = b->dict ? b->d_frame_dict : nullptr;
     return a;
 }
 
@@ -1501,6 +1537,165 @@ int szb_decode_batch(szb_ctx *ctx, const uint8_t *src, size_t src_len, const uin
     rc = decode_tables(ctx, b, src, src_len, dst, dst_cap, out_off, out_len, status, flags);
     szb_batch_destroy(b);
     return rc;
+}
+
+// ---- dictionaries (szb200.h) ----------------------------------------------------
+int szb_dict_create(szb_ctx *ctx, const uint8_t *dict, size_t len, szb_dict **out) {
+    if (!ctx || !out || (!dict && len) || len > 0x7FFF0000u) return SZB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    szb_dict *d = new (std::nothrow) szb_dict();
+    if (!d) return SZB_ERR_NOMEM;
+    d->ctx = ctx;
+    const uint8_t *content = dict;
+    size_t content_len = len;
+    int rc = SZB_OK;
+    if (len >= 8 && dict[0] == 0x37 && dict[1] == 0xA4 && dict[2] == 0x30 && dict[3] == 0xEC) {  // formatted (RFC 8878 section 5)
+        d->id = (uint32_t)dict[4] | ((uint32_t)dict[5] << 8) | ((uint32_t)dict[6] << 16) | ((uint32_t)dict[7] << 24);
+        size_t pos = 8;
+        // Huffman tree description: header byte, then FSE-compressed (< 128: that many bytes) or direct 4-bit weights (huffman.go:40-104)
+        size_t tree_len = 0;
+        if (pos >= len) {
+            rc = SZB_ERR_UNEXPECTED_EOF;
+        } else {
+            const uint32_t hb = dict[pos];
+            tree_len = hb < 128 ? 1 + (size_t)hb : 1 + ((size_t)(hb - 127) + 1) / 2;
+            if (tree_len > len - pos) rc = SZB_ERR_UNEXPECTED_EOF;
+        }
+        const size_t tree_at = pos;
+        pos += tree_len;
+        // FSE table descriptions in the dictionary's order: offsets, match lengths, literal lengths
+        size_t at[3] = {0, 0, 0}, sz[3] = {0, 0, 0};
+        const uint32_t max_al[3] = {kMaxALOF, kMaxALML, kMaxALLL};
+        for (int k = 0; k < 3 && !rc; k++) {
+            int16_t norm[kMaxFseSymbols];
+            uint32_t nsym = 0, al = 0, used = 0;
+            rc = fse_read_description(dict + pos, (uint32_t)(len - pos < 0x10000 ? len - pos : 0x10000), max_al[k], norm, &nsym, &al, &used);
+            at[k] = pos;
+            sz[k] = used;
+            pos += used;
+        }
+        if (!rc && len - pos < 12) rc = SZB_ERR_UNEXPECTED_EOF;
+        if (!rc) {
+            for (int k = 0; k < 3; k++) {
+                d->rep[k] = (uint32_t)dict[pos] | ((uint32_t)dict[pos + 1] << 8) | ((uint32_t)dict[pos + 2] << 16) | ((uint32_t)dict[pos + 3] << 24);
+                pos += 4;
+            }
+            content = dict + pos;
+            content_len = len - pos;
+            for (int k = 0; k < 3; k++)
+                if (d->rep[k] == 0 || d->rep[k] > content_len) rc = SZB_ERR_CANT_REPEAT_BYTES;  // points outside the content
+        }
+        if (!rc) {
+            // the synthetic block: [literals header: Compressed, 1 stream, regenerates 0, "compressed size" = the tree][tree]
+            //                      [1 sequence][modes FSE FSE FSE][LL][OF][ML][one byte of bitstream that nobody decodes]
+            std::vector<uint8_t> &p = d->payload;
+            const uint32_t v = 2u | (0u << 2) | (0u << 4) | ((uint32_t)tree_len << 14);
+            p.push_back((uint8_t)v);
+            p.push_back((uint8_t)(v >> 8));
+            p.push_back((uint8_t)(v >> 16));
+            p.insert(p.end(), dict + tree_at, dict + tree_at + tree_len);
+            const uint32_t seq_off = (uint32_t)p.size();
+            p.push_back(1);
+            p.push_back(0xA8);
+            const int order[3] = {2, 0, 1};  // LL, OF, ML out of OF, ML, LL
+            for (int k : order) p.insert(p.end(), dict + at[k], dict + at[k] + sz[k]);
+            p.push_back(1);
+            szb_block_desc &b = d->blk;
+            memset(&b, 0, sizeof(b));
+            b.block_size = (uint32_t)p.size();
+            b.type = 2;
+            b.lit_type = 2;
+            b.lit_streams = 1;
+            b.lit_hdr_bytes = 3;
+            b.lit_regen = 0;
+            b.lit_comp = (uint32_t)tree_len;
+            b.nseq = 1;
+            b.seq_off = seq_off;
+            b.seq_hdr_bytes = 2;
+            b.seq_modes = 0xA8;
+            b.huf_origin = b.ll_origin = b.of_origin = b.ml_origin = 0;  // itself: row 0 of the block table
+            b.flags = SZB_BLOCK_TABLES_ONLY;
+            d->has_tables = true;
+        }
+    }
+    if (rc) {
+        delete d;
+        return rc;
+    }
+    d->content_len = (uint32_t)content_len;
+    cudaSetDevice(ctx->device);
+    if (cudaMalloc((void **)&d->d_content, content_len + 16) != cudaSuccess ||
+        (content_len && cudaMemcpy(d->d_content, content, content_len, cudaMemcpyHostToDevice) != cudaSuccess)) {
+        (void)cudaGetLastError();
+        if (d->d_content) cudaFree(d->d_content);
+        delete d;
+        return SZB_ERR_CUDA;
+    }
+    *out = d;
+    return SZB_OK;
+}
+
+void szb_dict_destroy(szb_dict *d) {
+    if (!d) return;
+    cudaSetDevice(d->ctx->device);
+    cudaStreamSynchronize(d->ctx->stream);
+    if (d->d_content) cudaFree(d->d_content);
+    delete d;
+}
+
+uint32_t szb_dict_id(const szb_dict *d) { return d ? d->id : 0; }
+
+int szb_decode_batch_dict(szb_ctx *ctx, const szb_dict *dict, const uint8_t *src, size_t src_len, const uint64_t *frame_off,
+                          const uint64_t *frame_len, uint32_t nframes, uint8_t *dst, size_t dst_cap, uint64_t *out_off,
+                          uint64_t *out_len, int32_t *status, uint32_t flags) {
+    if (!ctx || !dict || dict->ctx != ctx || (!src && src_len) || (!dst && dst_cap) || !frame_off || !frame_len)
+        return SZB_ERR_INVALID_ARGUMENT;
+    if (flags & (SZB_FLAG_SRC_DEVICE | SZB_FLAG_DST_DEVICE)) return SZB_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    // the dictionary's table-only block lives behind the caller's bytes in the device copy of src
+    const size_t at = align_up(src_len + 16, 16);
+    const size_t ext_len = at + dict->payload.size();
+    szb_block_desc blk = dict->blk;
+    blk.src_off = at;
+    szb_walk *w = nullptr;
+    int rc = szb_walk_create_dict(src, src_len, frame_off, frame_len, nframes, dict->has_tables ? &blk : nullptr, dict->id, &w);
+    if (rc) return rc;
+    const uint32_t nf = szb_walk_nframes(w);  // nframes, + the pseudo frame of the table-only block
+    szb_batch *b = nullptr;
+    rc = batch_create_from_tables_impl(ctx, ext_len, szb_walk_frames(w), nf, szb_walk_blocks(w), szb_walk_nblocks(w), dict, &b);
+    szb_walk_destroy(w);
+    if (rc) return rc;
+    auto fail = [&](int code) {
+        szb_batch_destroy(b);
+        return code;
+    };
+    {   // which frames are decoded with the dictionary: the caller's (a wrong Dictionary_ID has failed in the walk), not the pseudo frame
+        std::vector<uint8_t> use(nf ? nf : 1, 0);
+        for (uint32_t f = 0; f < nframes && f < nf; f++) use[f] = 1;
+        if (pool_alloc(ctx, (void **)&b->d_frame_dict, use.size()) != cudaSuccess ||
+            cudaMemcpyAsync(b->d_frame_dict, use.data(), use.size(), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+            return fail(SZB_ERR_CUDA);
+    }
+    rc = ensure_dev(ctx, &ctx->d_src, &ctx->d_src_cap, ext_len + 16);
+    if (rc) return fail(rc);
+    if ((src_len && cudaMemcpyAsync(ctx->d_src, src, src_len, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) ||
+        (!dict->payload.empty() &&
+         cudaMemcpyAsync(ctx->d_src + at, dict->payload.data(), dict->payload.size(), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess))
+        return fail(SZB_ERR_CUDA);
+    std::vector<uint64_t> off(nf ? nf : 1), len(nf ? nf : 1);
+    std::vector<int32_t> st(nf ? nf : 1, 0);
+    rc = decode_tables(ctx, b, ctx->d_src, ext_len, dst, dst_cap, off.data(), len.data(), st.data(), flags | SZB_FLAG_SRC_DEVICE);
+    int first = SZB_OK;
+    for (uint32_t f = 0; f < nframes && f < nf; f++) {
+        if (out_off) out_off[f] = off[f];
+        if (out_len) out_len[f] = len[f];
+        if (status) status[f] = st[f];
+        if (first == SZB_OK && st[f] != SZB_OK) first = st[f];
+    }
+    szb_batch_destroy(b);
+    if (rc == SZB_ERR_CUDA || rc == SZB_ERR_NOMEM) return rc;
+    return first;  // (decode_tables' own verdict also counts the pseudo frame, whose status is never 0)
 }
 
 int szb_decode_stream(szb_ctx *ctx, const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap, uint64_t *out_off,

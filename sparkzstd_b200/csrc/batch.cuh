@@ -83,6 +83,11 @@ struct DeviceBatch {
     uint32_t *long_hist;            // per lb_block entry: the history the block starts with (3 entries)
     unsigned long long *long_ticket;  // k_long_jump hands out its tiles in address order
     unsigned long long *long_err;   // per long frame: the first error found while emitting (block << 40 | round << 8 | -code)
+    // dictionary (szb_decode_batch_dict): history in front of every frame that uses it, and the repeat offsets it starts with
+    const uint8_t *dict_content;    // nullptr: no dictionary
+    uint32_t dict_len;
+    uint32_t dict_rep[3];           // 1, 4, 8 for a raw-content dictionary
+    const uint8_t *frame_dict;      // per frame: non-zero = decoded with the dictionary
     uint32_t exec2;                 // non-zero: k_execute2 (exec2.cuh) executes the frames one warp executes; 0: k_execute
     // frames one warp executes (place.cuh): k_resolve -> k_place; nullptr: k_execute takes them all
     uint32_t *rec;                  // per block with sequences, at rec_off[block]: one entry per segment (literal run or match) in

@@ -187,6 +187,10 @@ __device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Sme
     uint32_t nseg = 0;    // segments appended so far
 
     History hist{1, 4, 8};  // framedecompressor.go:48,59
+    // With a dictionary (not a reference behaviour; RFC 8878 section 5) the frame starts with the dictionary's repeat offsets
+    // and its content is history in front of the frame: a match may reach up to dlen bytes in front of position 0.
+    const uint32_t dlen = (a.frame_dict && a.frame_dict[f]) ? a.dict_len : 0;
+    if (a.frame_dict && a.frame_dict[f]) hist = History{a.dict_rep[0], a.dict_rep[1], a.dict_rep[2]};
     for (uint32_t bi = 0; bi < nb && err == SZB_OK; bi++) {
         const uint32_t b = b0 + bi;
         const szb_block_desc d = a.blocks[b];
@@ -298,12 +302,15 @@ __device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Sme
                 // every match must lie inside the frame (ringbuffer.go:203-214); a match length of 0 cannot come out of
                 // stage 3 (ML codes start at 3, predefined.go:36-50) and would break the segment count below
                 const uint32_t fb = qpos - mis;  // frame bytes in front of the round
-                const bool bad = off > fb + excl_tot + ll;
+                const bool bad = off > fb + excl_tot + ll + dlen;
                 if (__any_sync(kFull, act && (bad || off == 0 || ml == 0))) {
                     err = SZB_ERR_CANT_REPEAT_BYTES;
                     break;
                 }
             }
+            // a match that starts in the dictionary's content is copied by the whole warp, one sequence at a time (below)
+            const bool reach = dlen != 0 && act && off > (qpos - mis) + excl_tot + ll;
+            const bool any_reach = dlen != 0 && __any_sync(kFull, reach);
 
             // --- the round's segments go to the ring, as many sequences at a time as the bitmap holds (normally all) ---
             uint32_t start = 0;
@@ -316,10 +323,10 @@ __device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Sme
                 }
                 const uint32_t my_rel = out_rel + excl_tot;  // my literal run, relative to the line being consumed
                 uint32_t nfit;
-                if (start == 0 && !lit_rle && out_rel + round_tot <= kX2Span) {
+                if (start == 0 && !lit_rle && !any_reach && out_rel + round_tot <= kX2Span) {
                     nfit = cnt;  // the usual case: the whole round fits the ring
                 } else {
-                    const bool fits = my_rel + tot <= kX2Span && !(lit_rle && ll > kX2ConstRun);
+                    const bool fits = my_rel + tot <= kX2Span && !(lit_rle && ll > kX2ConstRun) && !reach;
                     const uint32_t fitmask = __ballot_sync(kFull, fits && lane < cnt) >> start;
                     nfit = fitmask == (0xFFFFFFFFu >> start) ? 32 - start : __ffs(~fitmask) - 1;  // leading fits
                 }
@@ -337,7 +344,18 @@ __device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Sme
                     __syncwarp();
                     uint8_t *MD = D + L;
                     const uint8_t *MS = MD - OFF;
-                    if (OFF >= 32) {
+                    const uint32_t mpos = Dq + L - mis;  // the match's first byte, counted from the frame's
+                    if (OFF > mpos) {
+                        // The match starts in the dictionary: byte k repeats history byte (mpos + k - OFF); from k = OFF on that
+                        // is a byte of this match, i.e. byte k % OFF of its first OFF bytes.  All sources lie in front of the
+                        // match (dictionary content or output already in memory): no order among the lanes is needed.
+                        const uint8_t *dict_end = a.dict_content + dlen;  // "frame position 0" of the dictionary's content
+                        const uint8_t *frame0 = st.qb + mis;
+                        for (uint32_t k = lane; k < ML; k += 32) {
+                            const int32_t sp = (int32_t)(mpos + (k < OFF ? k : k % OFF)) - (int32_t)OFF;
+                            MD[k] = sp < 0 ? dict_end[sp] : frame0[sp];
+                        }
+                    } else if (OFF >= 32) {
                         for (uint32_t k0 = 0; k0 < ML; k0 += 32) {
                             const uint32_t k = k0 + lane;
                             if (k < ML) MD[k] = MS[k];

@@ -670,6 +670,13 @@ __global__ void __launch_bounds__(kCtaThreads, SZB_EXEC_MIN_CTAS) k_execute(Devi
     if (a.frame_nexec ? a.frame_nexec[f] == 0 : a.frame_status[f] != SZB_OK) return;  // k_frame_verdict
     if (a.place_state && a.place_state[f] != 1) return;  // k_place executes it (place.cuh)
     if (x2_takes(a, f)) return;                          // k_execute2 executes it (exec2.cuh)
+    if (a.frame_dict && a.frame_dict[f]) {               // only k_execute2 knows dictionaries (frames of 2 GiB and more: not with one)
+        if (lane == 0) {
+            a.frame_status[f] = SZB_ERR_UNSUPPORTED;
+            a.frame_out_len[f] = 0;
+        }
+        return;
+    }
     ExecSmem &sm = smem[threadIdx.x >> 5];
     for (uint32_t wd = lane; wd < kRingBits / 32; wd += 32) sm.bits[wd] = 0;
     __syncwarp();

@@ -366,7 +366,7 @@ __device__ __forceinline__ void hring_skip(HufBits &r, uint32_t n) {
 // huf_decode_stream (huffman.cuh) with the symbols buffered 16 deep in registers so they leave as
 // aligned 16-byte stores, and one refill check per two symbols (2 x 11 bits <= the 32 guaranteed).
 __device__ __forceinline__ int huf_decode_stream_vec(const uint16_t *table, uint32_t max_bits, const uint8_t *p, uint32_t len,
-                                                     uint8_t *out, uint32_t expected, uint8_t *ring) {
+                                                     uint8_t *out, uint32_t expected, uint8_t *ring, bool one_of_four) {
     HufBits r;
     if (!hring_init(r, p, (int32_t)len, ring)) return SZB_ERR_BAD_PADDING;
     {   // skip padding: zero bits then the first 1 bit, at most 8 (huffman.go:227-238)
@@ -374,6 +374,11 @@ __device__ __forceinline__ int huf_decode_stream_vec(const uint16_t *table, uint
         if (top == 0) return SZB_ERR_BAD_PADDING;
         hring_skip(r, (uint32_t)__clz(top) - 24 + 1);
     }
+    // The reference decodes symbols while bits remain and then looks at how the stream ended (huffman.go:248-261): exactly
+    // used up -> fine (too few symbols is the caller's ErrStreamDidntDecodeToRightLength), overrun -> ErrDidntUseAllBits.  Here
+    // `expected` symbols are decoded whatever the stream holds; `clean` remembers whether the bits ever ran out exactly at a
+    // symbol boundary, which is where the reference would have stopped.
+    bool clean = r.remaining == 0;
     uint32_t n = 0;
     uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15)) & 15;
     if (head > expected) head = expected;
@@ -383,6 +388,7 @@ __device__ __forceinline__ int huf_decode_stream_vec(const uint16_t *table, uint
         const uint32_t e = table[hring_peek(r, max_bits)];
         out[n] = (uint8_t)e;
         hring_skip(r, e >> 8);
+        clean |= r.remaining == 0;
     }
     hring_fill(r);
     while (n + 16 <= expected) {
@@ -400,6 +406,7 @@ __device__ __forceinline__ int huf_decode_stream_vec(const uint16_t *table, uint
                 const uint32_t e = table[hring_peek(r, max_bits)];
                 acc |= (e & 0xFF) << (8 * t);
                 hring_skip(r, e >> 8);
+                clean |= r.remaining == 0;
             }
             wv[q] = acc;
         }
@@ -412,9 +419,12 @@ __device__ __forceinline__ int huf_decode_stream_vec(const uint16_t *table, uint
         const uint32_t e = table[hring_peek(r, max_bits)];
         out[n] = (uint8_t)e;
         hring_skip(r, e >> 8);
+        clean |= r.remaining == 0;
     }
-    if (r.remaining > 0) return SZB_ERR_STREAM_DIDNT_DECODE_TO_RIGHT_LENGTH;  // more symbols than its slot holds
-    if (r.remaining < 0) return SZB_ERR_DIDNT_USE_ALL_BITS_TO_DECODE_HUFFMAN;
+    if (r.remaining > 0) return SZB_ERR_PANIC;  // more symbols than its slot holds: the reference indexes past its output slice
+    // ended early but on a symbol boundary: the caller of a 4-stream block compares the count (literals.go:320,332,349); for a
+    // single stream the reference does not (it goes on with what its reused buffer held): the engine's documented -19
+    if (r.remaining < 0) return clean && one_of_four ? SZB_ERR_STREAM_DIDNT_DECODE_TO_RIGHT_LENGTH : SZB_ERR_DIDNT_USE_ALL_BITS_TO_DECODE_HUFFMAN;
     return SZB_OK;
 }
 
@@ -487,6 +497,8 @@ __global__ void __launch_bounds__(kCtaThreads) k_decode_literals(DeviceBatch a) 
             const szb_block_desc d = a.blocks[b];
             if (rc0 != SZB_OK) {
                 my_rc = rc0;
+            } else if (d.flags & SZB_BLOCK_TABLES_ONLY) {
+                my_rc = SZB_OK;  // a dictionary's row: its tree was built, it has no literals
             } else {
                 // --- this block's streams (literals.go:270-371) ---
                 const uint8_t *payload = a.src + d.src_off;
@@ -499,7 +511,7 @@ __global__ void __launch_bounds__(kCtaThreads) k_decode_literals(DeviceBatch a) 
                     if (comp < 0)
                         my_rc = SZB_ERR_PANIC;
                     else if (my_k == 0)
-                        my_rc = huf_decode_stream_vec(tabs + my_off, bits, payload + skip, (uint32_t)comp, out, regen, my_ring);
+                        my_rc = huf_decode_stream_vec(tabs + my_off, bits, payload + skip, (uint32_t)comp, out, regen, my_ring, false);
                 } else {
                     comp -= 6;
                     if (comp < 0) {
@@ -528,7 +540,9 @@ __global__ void __launch_bounds__(kCtaThreads) k_decode_literals(DeviceBatch a) 
                             my_rc = SZB_ERR_PANIC;  // literals.go:356-359
                         } else {
                             const uint32_t expected = my_k < 3 ? normal : (uint32_t)last;
-                            my_rc = huf_decode_stream_vec(tabs + my_off, bits, jt + 6 + before, my_end - before, out + my_k * normal, expected, my_ring);
+                            my_rc = huf_decode_stream_vec(tabs + my_off, bits, jt + 6 + before, my_end - before, out + my_k * normal, expected, my_ring, true);
+                            // the fourth stream's count is only checked through the sum of all four: a panic (literals.go:366-369)
+                            if (my_k == 3 && my_rc == SZB_ERR_STREAM_DIDNT_DECODE_TO_RIGHT_LENGTH) my_rc = SZB_ERR_PANIC;
                         }
                     }
                 }
@@ -837,6 +851,10 @@ __global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
     const uint32_t b = a.seq_list[w];
     if (a.seq_status[b] != SZB_OK) return;  // its tables failed to build
     const szb_block_desc d = a.blocks[b];
+    if (d.flags & SZB_BLOCK_TABLES_ONLY) {  // a dictionary's row: its tables were built, it has no sequences to decode
+        a.out_size[b] = 0;
+        return;
+    }
     const SeqInfo info = a.seq_info[w];
     const uint16_t *tll = tabs + lane * kTabSlotWords, *tml = tll + 512, *tof = tll + 1024;
     const uint32_t al_ll = info.al_ll, al_ml = info.al_ml, al_of = info.al_of;

@@ -21,6 +21,10 @@ struct szb_walk {
     std::vector<szb_block_desc> blocks;
     uint64_t literal_bytes = 0;
     uint64_t sequences = 0;
+    // a dictionary's table-only row (szb_walk_create_dict): what a frame's first block carries over from "the previous block"
+    uint32_t dict_huf = SZB_NONE, dict_seq = SZB_NONE;
+    bool dict = false;
+    uint32_t dict_id = 0;
 };
 
 namespace {
@@ -117,6 +121,8 @@ void walk_frame(szb_walk &w, const uint8_t *src, uint64_t off, uint64_t len, uin
     Cursor c{src + off, len, 0};
     int rc = SZB_OK;
     Carry carry;
+    carry.huf = w.dict_huf;  // SZB_NONE without a dictionary (framedecompressor.go:42-52: a frame starts with nothing to carry over)
+    carry.ll = carry.of = carry.ml = w.dict_seq;
     uint32_t frame_idx = (uint32_t)w.frames.size();
 
     do {
@@ -238,6 +244,8 @@ void walk_frame(szb_walk &w, const uint8_t *src, uint64_t off, uint64_t len, uin
         }
     } while (false);
 
+    // with a dictionary: a frame that names ANOTHER dictionary is not decoded with this one (RFC 8878 3.1.1.1.3)
+    if (rc == SZB_OK && w.dict && f.dictionary_id != 0 && f.dictionary_id != w.dict_id) rc = SZB_ERR_WRONG_DICTIONARY;
     f.status = rc;
     f.src_len = c.pos;
     f.nblocks = (uint32_t)w.blocks.size() - f.first_block;
@@ -278,12 +286,42 @@ int szb_shard_frames(const uint64_t *weight, uint32_t nframes, uint32_t nshards,
     return SZB_OK;
 }
 
+static int walk_create_impl(const uint8_t *src, size_t src_len, const uint64_t *frame_off, const uint64_t *frame_len,
+                            uint32_t nframes, const szb_block_desc *dict_block, uint32_t dict_id, bool dict, szb_walk **out);
+
 int szb_walk_create(const uint8_t *src, size_t src_len, const uint64_t *frame_off, const uint64_t *frame_len,
                     uint32_t nframes, szb_walk **out) {
+    return walk_create_impl(src, src_len, frame_off, frame_len, nframes, nullptr, 0, false, out);
+}
+
+// The walk for a batch that is decoded with a dictionary (szb200.h, dictionaries).  dict_block (may be NULL: raw-content
+// dictionary) becomes row 0 of the block table: the origin of Treeless literals and Repeat modes in every frame's first
+// blocks.  It belongs to a pseudo frame appended AFTER the caller's frames (no blocks of its own, status
+// SZB_ERR_INVALID_ARGUMENT): szb_walk_nframes counts it.
+int szb_walk_create_dict(const uint8_t *src, size_t src_len, const uint64_t *frame_off, const uint64_t *frame_len,
+                         uint32_t nframes, const szb_block_desc *dict_block, uint32_t dict_id, szb_walk **out) {
+    return walk_create_impl(src, src_len, frame_off, frame_len, nframes, dict_block, dict_id, true, out);
+}
+
+static int walk_create_impl(const uint8_t *src, size_t src_len, const uint64_t *frame_off, const uint64_t *frame_len,
+                            uint32_t nframes, const szb_block_desc *dict_block, uint32_t dict_id, bool dict, szb_walk **out) {
     if (!out || (!src && src_len)) return SZB_ERR_INVALID_ARGUMENT;
     szb_walk *w = new (std::nothrow) szb_walk();
     if (!w) return SZB_ERR_NOMEM;
     try {
+        w->dict = dict;
+        w->dict_id = dict_id;
+        if (dict_block) {
+            szb_block_desc d = *dict_block;
+            d.flags |= SZB_BLOCK_TABLES_ONLY;
+            d.lit_buf_off = 0;
+            d.seq_buf_off = 0;
+            w->literal_bytes = ((uint64_t)d.lit_regen + 15) & ~15ull;
+            w->sequences = ((uint64_t)d.nseq + 31) & ~31ull;
+            if (d.lit_type == 2) w->dict_huf = 0;
+            if (d.nseq) w->dict_seq = 0;
+            w->blocks.push_back(d);
+        }
         if (frame_off) {
             w->frames.reserve(nframes);
             w->blocks.reserve(nframes);
@@ -313,6 +351,14 @@ int szb_walk_create(const uint8_t *src, size_t src_len, const uint64_t *frame_of
                 if (w->frames.back().status != SZB_OK || used == 0) break;
                 pos += used;
             }
+        }
+        if (dict_block) {  // the pseudo frame the table-only row belongs to: after the caller's frames, no blocks to execute
+            szb_frame_desc f;
+            std::memset(&f, 0, sizeof(f));
+            f.content_size = SZB_CONTENT_SIZE_UNKNOWN;
+            f.status = SZB_ERR_INVALID_ARGUMENT;
+            w->blocks[0].frame = (uint32_t)w->frames.size();
+            w->frames.push_back(f);
         }
     } catch (const std::bad_alloc &) {
         delete w;

@@ -155,6 +155,38 @@ class Context:
             self._raise(rc)
         return dst[: total.value].tobytes()
 
+    def decode_batch_dict(self, frames: Sequence[bytes], dictionary: bytes, capacity: Optional[int] = None) -> List[bytes]:
+        """szb_decode_batch_dict: independent frames that were compressed with `dictionary` (raw content, or a formatted zstd
+        dictionary).  Not a reference behaviour (the reference has no dictionary support); raises the first frame's error."""
+        if not frames:
+            return []
+        d = C.c_void_p()
+        dbuf = np.frombuffer(dictionary, dtype=np.uint8) if dictionary else np.zeros(1, np.uint8)
+        rc = self._L.szb_dict_create(self._h, dbuf.ctypes.data, len(dictionary), C.byref(d))
+        if rc != 0:
+            self._raise(rc)
+        try:
+            lens = np.array([len(f) for f in frames], dtype=np.uint64)
+            offs = np.zeros(len(frames), dtype=np.uint64)
+            offs[1:] = np.cumsum(lens)[:-1]
+            src = np.frombuffer(b"".join(frames) + b"\0" * 16, dtype=np.uint8)
+            cap = capacity if capacity is not None else max(64, int(lens.sum()) * 24 + (1 << 20))
+            dst = np.empty(cap, dtype=np.uint8)
+            out_off = np.zeros(len(frames), dtype=np.uint64)
+            out_len = np.zeros(len(frames), dtype=np.uint64)
+            status = np.zeros(len(frames), dtype=np.int32)
+            rc = self._L.szb_decode_batch_dict(self._h, d, src.ctypes.data, int(lens.sum()), offs.ctypes.data, lens.ctypes.data, len(frames),
+                                               dst.ctypes.data, dst.nbytes, out_off.ctypes.data, out_len.ctypes.data, status.ctypes.data, 0)
+            if rc in (-65, -66, -34):
+                self._raise(rc)
+            self.last_status = status
+            bad = np.nonzero(status)[0]
+            if len(bad):
+                self._raise(int(status[bad[0]]))
+            return [dst[int(o) : int(o) + int(n)].tobytes() for o, n in zip(out_off, out_len)]
+        finally:
+            self._L.szb_dict_destroy(d)
+
     def decode_batch(self, frames: Sequence[bytes], capacity: Optional[int] = None) -> List[bytes]:
         """Decodes independent frames; raises the first frame's error (like a loop of Decompress())."""
         if not frames:

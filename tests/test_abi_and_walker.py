@@ -46,7 +46,7 @@ def test_struct_layouts_match_the_header():
     ff = [f[0] for f in FrameDesc._fields_]
     bf = [f[0] for f in BlockDesc._fields_ if not f[0].startswith("_pad")]
     want = [C.sizeof(FrameDesc)] + [getattr(FrameDesc, f).offset for f in ff] + [C.sizeof(BlockDesc)] + [getattr(BlockDesc, f).offset for f in bf]
-    assert n == len(want) == 37 and got == want
+    assert n == len(want) == 38 and got == want
     # ... and so must the Go mirror (go/szb200/szb200.go: plain structs with exported fields, same order, same widths; Go
     # aligns every field naturally, as the C compiler does): recompute its layout from the declaration
     import os
@@ -72,6 +72,7 @@ def test_struct_layouts_match_the_header():
     fsize, foffs = go_layout("FrameDesc")
     bsize, boffs = go_layout("BlockDesc")
     boffs = [o for o in boffs if not o[0].startswith("Pad")]
+    assert "Flags" in [n_ for n_, _ in boffs]
     assert [fsize] + [o for _, o in foffs] + [bsize] + [o for _, o in boffs] == got
     # same field order by name (snake_case <-> CamelCase)
     camel = lambda s: "".join(p.upper() if p in ("ll", "of", "ml", "id") else p.capitalize() for p in s.split("_"))

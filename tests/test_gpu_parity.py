@@ -288,6 +288,34 @@ def test_pageable_host_buffers_go_through_the_pinned_rings(ctx):
     assert (cg.hash_frames(dst, out_off, out_len) == c.raw_hash).all()
 
 
+def test_dictionaries_formatted_and_raw(ctx):
+    """SURVEY 8f-4 (not in the reference, which ignores Dictionary_ID): frames libzstd compressed with a dictionary, decoded in one
+    batch with szb_decode_batch_dict, equal the originals and the oracle's dictionary extension; matches reach into the
+    dictionary's content, first blocks use its Huffman / FSE tables and its repeat offsets."""
+    from sparkzstd_b200 import decompression as D
+
+    msgs = cg.dictionary_messages(400)
+    formatted = cg.train_dictionary(msgs[:300], 8 << 10)
+    raw = b"".join(msgs[:40])
+    bigger = [bytes(cg.fill(cg.KIND_TEXT, 4242 + i, 30000 + 977 * i, 0)) for i in range(3)]
+    originals = msgs[300:400] + bigger + [b"", b"x"]
+    for d in (formatted, raw):
+        frames = [cg.compress_with_dict(m, d) for m in originals]
+        outs = ctx.decode_batch_dict(frames, d)
+        assert outs == originals
+        assert outs == [pyszo.decode_frame(f, dictionary=d) for f in frames]
+    # a frame that names another dictionary id, and a frame decoded without its dictionary
+    frames = [cg.compress_with_dict(m, formatted) for m in originals[:8]]
+    other = bytearray(formatted)
+    other[4] ^= 0x55  # another Dictionary_ID
+    with pytest.raises(D.SzbError) as e:
+        ctx.decode_batch_dict(frames, bytes(other))
+    assert e.value.code == -70
+    # plain frames decode with a dictionary given, too (they name no dictionary and never reach in front of themselves)
+    plain = [c for c in (cg.config2_text_frames(3).frame(i) for i in range(3))]
+    assert ctx.decode_batch_dict(plain, raw) == [pyszo.decode_frame(f) for f in plain]
+
+
 # ---- edge cases and error behaviour --------------------------------------------------------------------
 def test_empty_batch_and_empty_frames(ctx, corpus):
     assert ctx.decode_batch([]) == []
