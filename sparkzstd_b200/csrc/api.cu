@@ -893,10 +893,13 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
                 static bool once = false;
                 if (!once) {
                     once = true;
-                    cudaFuncSetAttribute(k_execute2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+                    cudaFuncSetAttribute(k_execute2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
                 }
             }
-            k_execute2<<<(n_rest + kX2Warps - 1) / kX2Warps, kX2Warps * 32, pad, s>>>(a, n_long, n_rest);
+            if (b->dict)
+                k_execute2<true><<<(n_rest + kX2Warps - 1) / kX2Warps, kX2Warps * 32, 0, s>>>(a, n_long, n_rest);
+            else
+                k_execute2<false><<<(n_rest + kX2Warps - 1) / kX2Warps, kX2Warps * 32, pad, s>>>(a, n_long, n_rest);
             ctx->launches++;
         }
         if (n_rest) {  // with k_place or k_execute2 on: only the frames they could not take (place_on, x2_takes)

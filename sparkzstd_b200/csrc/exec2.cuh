@@ -165,6 +165,8 @@ __device__ __forceinline__ void x2_seek(X2State &st, uint32_t q) {
 }
 
 // One frame (status OK, taken by x2_takes), one warp: blocks in order, 32 sequences per round (sequence_execution.go:14-63).
+// kDict: the batch is decoded with a dictionary (its own instantiation: the plain one pays nothing for it).
+template <bool kDict>
 __device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Smem &sm, uint32_t lane) {
     const szb_frame_desc fr = a.frames[f];
     const uint32_t b0 = fr.first_block, nb = a.frame_nexec ? a.frame_nexec[f] : fr.nblocks;  // k_frame_verdict
@@ -189,8 +191,8 @@ __device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Sme
     History hist{1, 4, 8};  // framedecompressor.go:48,59
     // With a dictionary (not a reference behaviour; RFC 8878 section 5) the frame starts with the dictionary's repeat offsets
     // and its content is history in front of the frame: a match may reach up to dlen bytes in front of position 0.
-    const uint32_t dlen = (a.frame_dict && a.frame_dict[f]) ? a.dict_len : 0;
-    if (a.frame_dict && a.frame_dict[f]) hist = History{a.dict_rep[0], a.dict_rep[1], a.dict_rep[2]};
+    const uint32_t dlen = (kDict && a.frame_dict && a.frame_dict[f]) ? a.dict_len : 0;
+    if (kDict && a.frame_dict && a.frame_dict[f]) hist = History{a.dict_rep[0], a.dict_rep[1], a.dict_rep[2]};
     for (uint32_t bi = 0; bi < nb && err == SZB_OK; bi++) {
         const uint32_t b = b0 + bi;
         const szb_block_desc d = a.blocks[b];
@@ -309,8 +311,8 @@ __device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Sme
                 }
             }
             // a match that starts in the dictionary's content is copied by the whole warp, one sequence at a time (below)
-            const bool reach = dlen != 0 && act && off > (qpos - mis) + excl_tot + ll;
-            const bool any_reach = dlen != 0 && __any_sync(kFull, reach);
+            const bool reach = kDict && dlen != 0 && act && off > (qpos - mis) + excl_tot + ll;
+            const bool any_reach = kDict && dlen != 0 && __any_sync(kFull, reach);
 
             // --- the round's segments go to the ring, as many sequences at a time as the bitmap holds (normally all) ---
             uint32_t start = 0;
@@ -345,7 +347,7 @@ __device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Sme
                     uint8_t *MD = D + L;
                     const uint8_t *MS = MD - OFF;
                     const uint32_t mpos = Dq + L - mis;  // the match's first byte, counted from the frame's
-                    if (OFF > mpos) {
+                    if (kDict && OFF > mpos) {
                         // The match starts in the dictionary: byte k repeats history byte (mpos + k - OFF); from k = OFF on that
                         // is a byte of this match, i.e. byte k % OFF of its first OFF bytes.  All sources lie in front of the
                         // match (dictionary content or output already in memory): no order among the lanes is needed.
@@ -442,6 +444,7 @@ __device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Sme
 #define SZB_EXEC2_MIN_CTAS 32
 #endif
 constexpr int kX2Warps = SZB_EXEC2_WARPS;
+template <bool kDict>
 __global__ void __launch_bounds__(kX2Warps * 32, SZB_EXEC2_MIN_CTAS) k_execute2(DeviceBatch a, uint32_t first_slot, uint32_t n_slots) {
     __shared__ X2Smem smem[kX2Warps];
     const uint32_t lane = threadIdx.x & 31;
@@ -453,5 +456,5 @@ __global__ void __launch_bounds__(kX2Warps * 32, SZB_EXEC2_MIN_CTAS) k_execute2(
     X2Smem &sm = smem[threadIdx.x >> 5];
     for (uint32_t wd = lane; wd < kX2Bits / 32; wd += 32) sm.bits[wd] = 0;
     __syncwarp();
-    x2_frame(a, f, sm, lane);
+    x2_frame<kDict>(a, f, sm, lane);
 }

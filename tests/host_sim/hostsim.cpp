@@ -458,7 +458,7 @@ int hostsim_stage4_at(const uint8_t *src, size_t len, uint8_t *out, size_t cap, 
         warpsim::launch((copies + kPlaceWarps - 1) / kPlaceWarps, kPlaceWarps * 32, [&] { k_place(a, 0, copies); });
         warpsim::launch((copies + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, [&] { k_execute(a, 0, copies); });
     } else if (path == 5) {  // k_execute2 (exec2.cuh), with k_execute launched behind it for the frames it does not take
-        warpsim::launch((copies + kX2Warps - 1) / kX2Warps, kX2Warps * 32, [&] { k_execute2(a, 0, copies); });
+        warpsim::launch((copies + kX2Warps - 1) / kX2Warps, kX2Warps * 32, [&] { k_execute2<false>(a, 0, copies); });
         warpsim::launch((copies + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, [&] { k_execute(a, 0, copies); });
     } else if (path == 0) {
         warpsim::launch((copies + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, [&] { k_execute(a, 0, copies); });
