@@ -220,7 +220,10 @@ int szb_decode_stream(szb_ctx *ctx, const uint8_t *src, size_t src_len, uint8_t 
 /* DEVICE SOURCE BUFFERS (d_src here, in szb_batch_decode_entropy / szb_batch_execute / szb_batch_run, and src with
  * SZB_FLAG_SRC_DEVICE): the bit readers fetch whole aligned 16-byte chunks, so d_src must be 16-byte aligned and at least 16
  * bytes past src_len must be readable (their content does not matter).  A misaligned pointer is SZB_ERR_INVALID_ARGUMENT; the
- * padding cannot be checked and is the caller's to provide (cudaMalloc'd buffers of src_len + 16 bytes satisfy both). */
+ * padding cannot be checked and is the caller's to provide (cudaMalloc'd buffers of src_len + 16 bytes satisfy both).
+ * DEVICE DESTINATION BUFFERS (d_dst, and dst with SZB_FLAG_DST_DEVICE): stage 4 re-reads earlier output in whole aligned
+ * 16-byte chunks, so d_dst should be 16-byte aligned with 16 readable bytes behind dst_cap (any cudaMalloc'd buffer has them:
+ * allocations are padded to 256 bytes). */
 int szb_decode_blocks(szb_ctx *ctx, const void *d_src, size_t src_len, const szb_frame_desc *frames, uint32_t nframes,
                       const szb_block_desc *blocks, uint32_t nblocks, void *d_dst, size_t dst_cap, uint64_t *out_off,
                       uint64_t *out_len, int32_t *status);

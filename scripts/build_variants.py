@@ -10,10 +10,16 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sparkzstd_b200 import build as b  # noqa: E402
 
 VARIANTS = {
-    # k_execute2 (exec2.cuh): warps per CTA x CTAs per SM the register allocation aims at (launch bounds); the default is 1 x 32
-    "x2w4": ("SZB_EXEC2_WARPS=4", "SZB_EXEC2_MIN_CTAS=8"),
-    "x2w2": ("SZB_EXEC2_WARPS=2", "SZB_EXEC2_MIN_CTAS=16"),
-    "x2w1c24": ("SZB_EXEC2_WARPS=1", "SZB_EXEC2_MIN_CTAS=24"),   # 85 registers
+    # k_decode_sequences: blocks (state chains) per warp; shared memory then fits 228 KB / (lanes x 2.7 KB) one-warp CTAs per SM
+    "sq10": ("SZB_SEQ_LANES=10",),   # 8 CTAs per SM: two warps per scheduler, half the lanes busy
+    "sq14": ("SZB_SEQ_LANES=14",),   # 6 CTAs per SM
+    "sq16": ("SZB_SEQ_LANES=16",),   # 5 CTAs per SM
+    "sq28": ("SZB_SEQ_LANES=28",),   # 3 CTAs per SM
+    # k_execute2 (exec2.cuh): rounds of short sequences staged in shared memory, one lane per sequence
+    "x2st": ("SZB_X2_STAGED=1",),
+    # more than 32 warps per SM need CTAs of two warps (32 CTAs per SM is the limit) and fewer registers per thread
+    "x2w2c24": ("SZB_EXEC2_WARPS=2", "SZB_EXEC2_MIN_CTAS=24"),   # 48 warps per SM, 42 registers
+    "x2w2c20": ("SZB_EXEC2_WARPS=2", "SZB_EXEC2_MIN_CTAS=20"),   # 40 warps per SM, 51 registers
 }
 
 if __name__ == "__main__":

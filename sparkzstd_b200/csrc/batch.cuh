@@ -11,7 +11,10 @@ constexpr int kWarpsPerCta = 4;
 constexpr int kCtaThreads = kWarpsPerCta * 32;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 
-constexpr int kSeqLanes = 21;             // blocks per warp in k_decode_sequences: 21 x 2.6 KB (tables + bit ring), 4 warps per SM
+#ifndef SZB_SEQ_LANES
+#define SZB_SEQ_LANES 21
+#endif
+constexpr int kSeqLanes = SZB_SEQ_LANES;  // blocks per warp in k_decode_sequences: 21 x 2.6 KB (tables + bit ring), 4 warps per SM
 constexpr uint32_t kTabSlotWords = 1280;  // LL 512 | ML 512 | OF 256
 
 struct SeqInfo {

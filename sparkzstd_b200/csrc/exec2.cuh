@@ -35,6 +35,24 @@ struct X2Smem {
     __align__(16) uint32_t bits[kX2Bits / 32];     // bit q % kX2Bits set: a segment starts at q
 };
 
+// Staged rounds (x2_round_staged below): the output of one round of 32 short sequences is assembled in shared memory by one
+// LANE per sequence and leaves as whole 16-byte units.
+#ifndef SZB_X2_STAGED
+#define SZB_X2_STAGED 0  // measured (profiles/r02q_*): 13.1 ms against 8.97 ms on configs[1] -- 9.75 G warp instructions, not fewer
+#endif
+constexpr uint32_t kS2Cap = 1280;     // output bytes of a round that is staged (32 sequences of text: ~350)
+constexpr uint32_t kS2Lit = 16;       // a lane copies its own literal run up to this length ...
+constexpr uint32_t kS2Ml = 17;        // ... and its own match up to this length: what two aligned 16-byte loads cover at any alignment
+#ifndef SZB_S2_MAX_DEFERRED
+#define SZB_S2_MAX_DEFERRED 12
+#endif
+constexpr uint32_t kS2MaxDeferred = SZB_S2_MAX_DEFERRED;  // with more sequences than this left to the whole warp, the segment path is cheaper
+constexpr uint32_t kS2ScrStride = 80;  // 2 x 16 literal bytes + 2 x 16 match-source bytes (+ 16: rows start in different banks)
+struct X2Stage {
+    __align__(16) uint8_t stg[kS2Cap + 48];        // [16 * u, 16 * u + 16) = the round's output unit u, counted from qpos & ~15
+    __align__(16) uint8_t scr[32 * kS2ScrStride];  // per lane: the aligned 16-byte chunks that hold its literals and its match's source
+};
+
 struct X2State {
     uint8_t *qb;         // q position 0
     const uint8_t *lit;  // the literals of the block being executed
@@ -164,10 +182,116 @@ __device__ __forceinline__ void x2_seek(X2State &st, uint32_t q) {
     st.head = q & 127u;
 }
 
+// One round of 32 sequences whose output fits the staging buffer, everything below qpos in memory (flushed).
+//
+// The per-byte gather of x2_step costs ~16 warp instructions per byte slot however long a segment is, and text at zstd
+// level 3 has 8-byte segments.  Here one LANE executes one sequence: its literal run (<= kS2Lit bytes) byte by byte from the
+// block's literals, its match (<= kS2Ml bytes, source entirely below the round: two aligned 16-byte loads into the lane's
+// scratch, then byte moves inside shared memory).  Sequences that do not fit that -- a source inside the round's own output
+// (it is not in memory yet), longer runs -- are left to the whole warp afterwards, one at a time in sequence order, reading
+// staged bytes or memory byte by byte.  The staged bytes then leave as 16-byte units, 512 contiguous bytes per warp store.
+// Returns false (nothing touched) when too many sequences would be left to the warp.
+__device__ __forceinline__ bool x2_round_staged(X2Stage &S, const X2State &st, const uint8_t *lit_at, uint32_t qpos, uint32_t round_tot,
+                                                bool act, uint32_t ll, uint32_t ml, uint32_t off, uint32_t excl_tot, uint32_t incl_tot,
+                                                uint32_t excl_ll, uint32_t lane) {
+    const bool lit_small = ll <= kS2Lit;
+    const bool m_self = off >= incl_tot && ml <= kS2Ml;  // the source ends at or below the round's first byte, and is short
+    const uint32_t deferred = __ballot_sync(kFull, act && !(lit_small && m_self));
+    if ((uint32_t)__popc(deferred) > kS2MaxDeferred) return false;
+    const uint32_t base16 = qpos & ~15u;
+    const uint32_t s_lit = qpos + excl_tot - base16;  // staging index of my literal run; my match follows it
+    // --- all loads of the round leave together: per lane the two aligned 16-byte chunks that hold its literal run and the two
+    // that hold its match's source; they are parked in the lane's scratch and moved to their place byte by byte in shared
+    // memory (a load per byte would expose the memory latency once per byte) ---
+    const uint32_t n_lit = (act && lit_small) ? ll : 0u;
+    const bool m1 = act && m_self;
+    const uint32_t n_m = m1 ? ml : 0u;
+    const uint8_t *lsrc = lit_at + excl_ll;
+    const uint32_t lo_ = (uint32_t)(reinterpret_cast<uintptr_t>(lsrc) & 15);
+    const uint8_t *msrc = st.qb + (qpos + excl_tot + ll - off);
+    const uint32_t mo_ = (uint32_t)(reinterpret_cast<uintptr_t>(msrc) & 15);
+    uint4 l0 = make_uint4(0, 0, 0, 0), l1 = l0, m0 = l0, m1v = l0;
+    if (n_lit) {
+        const uint4 *c = reinterpret_cast<const uint4 *>(lsrc - lo_);
+        l0 = c[0];
+        if (lo_ + n_lit > 16) l1 = c[1];
+    }
+    if (m1) {
+        const uint4 *c = reinterpret_cast<const uint4 *>(msrc - mo_);
+        m0 = c[0];
+        if (mo_ + n_m > 16) m1v = c[1];
+    }
+    uint8_t *my = S.scr + lane * kS2ScrStride;
+    *reinterpret_cast<uint4 *>(my) = l0;
+    *reinterpret_cast<uint4 *>(my + 16) = l1;
+    *reinterpret_cast<uint4 *>(my + 32) = m0;
+    *reinterpret_cast<uint4 *>(my + 48) = m1v;
+    {
+        const uint32_t lmax = __reduce_max_sync(kFull, n_lit);
+        const uint8_t *from = my + lo_;
+        uint8_t *sp = S.stg + s_lit;
+        for (uint32_t k = 0; k < lmax; k++)
+            if (k < n_lit) sp[k] = from[k];
+        const uint32_t mmax = __reduce_max_sync(kFull, n_m);
+        const uint8_t *mfrom = my + 32 + mo_;
+        uint8_t *dp = S.stg + s_lit + ll;
+        for (uint32_t k = 0; k < mmax; k++)
+            if (k < n_m) dp[k] = mfrom[k];
+    }
+    __syncwarp();
+    // --- what is left, the whole warp on one sequence at a time, in order ---
+    for (uint32_t D = deferred; D; D &= D - 1) {
+        const uint32_t j = (uint32_t)__ffs(D) - 1;
+        const uint32_t LL = __shfl_sync(kFull, ll, j), ML = __shfl_sync(kFull, ml, j), OFF = __shfl_sync(kFull, off, j);
+        const uint32_t SL = __shfl_sync(kFull, s_lit, j), EL = __shfl_sync(kFull, excl_ll, j);
+        const bool done = __shfl_sync(kFull, (uint32_t)m_self, j) != 0;  // its match was short and independent: done above
+        if (LL > kS2Lit)
+            for (uint32_t k = lane; k < LL; k += 32) S.stg[SL + k] = lit_at[EL + k];
+        if (!done) {
+            const uint32_t sm0 = SL + LL;         // staging index of the match's first byte
+            const uint32_t qm = base16 + sm0;     // its q position
+            __syncwarp();                         // earlier sequences' bytes are staged
+            if (OFF >= ML || OFF >= 32) {
+                for (uint32_t k0 = 0; k0 < ML; k0 += 32) {
+                    const uint32_t k = k0 + lane;
+                    if (k < ML) {
+                        const uint32_t sq = qm + k - OFF;
+                        S.stg[sm0 + k] = sq >= qpos ? S.stg[sq - base16] : st.qb[sq];
+                    }
+                    if (OFF < ML) __syncwarp();   // the next 32 bytes may repeat these
+                }
+            } else {  // overlapping with a period below 32: byte k repeats byte k % OFF of the OFF bytes in front of the match
+                for (uint32_t k = lane; k < ML; k += 32) {
+                    const uint32_t sq = qm - OFF + k % OFF;
+                    S.stg[sm0 + k] = sq >= qpos ? S.stg[sq - base16] : st.qb[sq];
+                }
+            }
+        }
+        __syncwarp();
+    }
+    // --- out: [qpos, qpos + round_tot) as 16-byte units, single bytes at both ends ---
+    {
+        const uint32_t hi = qpos + round_tot;
+        const uint32_t first_full = (qpos + 15) & ~15u, last_full = hi & ~15u;  // full units: [first_full, last_full)
+        if (first_full < last_full) {
+            for (uint32_t q = first_full + 16 * lane; q < last_full; q += 512)
+                *reinterpret_cast<uint4 *>(st.qb + q) = *reinterpret_cast<const uint4 *>(S.stg + (q - base16));
+            const uint32_t head = first_full - qpos;  // < 16
+            if (lane < head) st.qb[qpos + lane] = S.stg[qpos - base16 + lane];
+            const uint32_t tail = hi - last_full;  // < 16
+            if (lane >= 16 && lane - 16 < tail) st.qb[last_full + lane - 16] = S.stg[last_full - base16 + lane - 16];
+        } else {  // no full unit: at most 30 bytes
+            if (lane < round_tot) st.qb[qpos + lane] = S.stg[qpos - base16 + lane];
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
 // One frame (status OK, taken by x2_takes), one warp: blocks in order, 32 sequences per round (sequence_execution.go:14-63).
 // kDict: the batch is decoded with a dictionary (its own instantiation: the plain one pays nothing for it).
 template <bool kDict>
-__device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Smem &sm, uint32_t lane) {
+__device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Smem &sm, X2Stage &stage, uint32_t lane) {
     const szb_frame_desc fr = a.frames[f];
     const uint32_t b0 = fr.first_block, nb = a.frame_nexec ? a.frame_nexec[f] : fr.nblocks;  // k_frame_verdict
     if (nb == 0) return;
@@ -314,6 +438,17 @@ __device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Sme
             const bool reach = kDict && dlen != 0 && act && off > (qpos - mis) + excl_tot + ll;
             const bool any_reach = kDict && dlen != 0 && __any_sync(kFull, reach);
 
+            // --- rounds of short sequences are staged in shared memory, one lane per sequence (x2_round_staged) ---
+            if (SZB_X2_STAGED && !lit_rle && !any_reach && round_tot <= kS2Cap) {
+                if (prod != st.line + st.head) st = x2_flush_cold(sm, st, prod, lane, le_mask);  // segments still in the ring
+                if (x2_round_staged(stage, st, lit + lit_pos, qpos, round_tot, act, ll, ml, off, excl_tot, incl_tot, excl_ll, lane)) {
+                    qpos += round_tot;
+                    lit_pos += round_ll;
+                    prod = qpos;
+                    x2_seek(st, prod);
+                    continue;
+                }
+            }
             // --- the round's segments go to the ring, as many sequences at a time as the bitmap holds (normally all) ---
             uint32_t start = 0;
             while (start < cnt) {
@@ -447,6 +582,7 @@ constexpr int kX2Warps = SZB_EXEC2_WARPS;
 template <bool kDict>
 __global__ void __launch_bounds__(kX2Warps * 32, SZB_EXEC2_MIN_CTAS) k_execute2(DeviceBatch a, uint32_t first_slot, uint32_t n_slots) {
     __shared__ X2Smem smem[kX2Warps];
+    __shared__ X2Stage stages[SZB_X2_STAGED ? kX2Warps : 1];  // (one unused slot when the staged path is compiled out)
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t slot = blockIdx.x * kX2Warps + (threadIdx.x >> 5);
     if (slot >= n_slots) return;
@@ -456,5 +592,5 @@ __global__ void __launch_bounds__(kX2Warps * 32, SZB_EXEC2_MIN_CTAS) k_execute2(
     X2Smem &sm = smem[threadIdx.x >> 5];
     for (uint32_t wd = lane; wd < kX2Bits / 32; wd += 32) sm.bits[wd] = 0;
     __syncwarp();
-    x2_frame<kDict>(a, f, sm, lane);
+    x2_frame<kDict>(a, f, sm, stages[SZB_X2_STAGED ? (threadIdx.x >> 5) : 0], lane);
 }
