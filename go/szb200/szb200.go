@@ -209,3 +209,95 @@ func (c *Ctx) DecodeBlocks(dSrc unsafe.Pointer, srcLen int, frames []FrameDesc, 
 	}
 	return outOff, outLen, status, nil
 }
+
+// DecodeStream decodes a `.zst` stream as the zstd tools write it -- frames back to back, skippable frames in between --
+// into dst and returns the number of bytes of content (szb_decode_stream; not a reference behaviour).
+func (c *Ctx) DecodeStream(src, dst []byte, flags uint32) (int, error) {
+	if len(src) == 0 {
+		return 0, nil
+	}
+	var dp *C.uint8_t
+	if len(dst) > 0 {
+		dp = (*C.uint8_t)(unsafe.Pointer(&dst[0]))
+	}
+	var found C.uint32_t
+	var total C.uint64_t
+	rc := C.szb_decode_stream(c.p, (*C.uint8_t)(unsafe.Pointer(&src[0])), C.size_t(len(src)), dp, C.size_t(len(dst)),
+		nil, nil, nil, 0, &found, &total, C.uint32_t(flags))
+	if rc != 0 {
+		return int(total), Error(rc)
+	}
+	return int(total), nil
+}
+
+// ShardFrames is the multi-GPU split (szb_shard_frames): frames are independent, so G GPUs decode a partition of the frame
+// list, one process (one Ctx) per GPU.  shardOf[i] is the GPU of frame i; deterministic for equal weights on every rank.
+func ShardFrames(weight []uint64, shards int) (shardOf []uint32, load []uint64, err error) {
+	shardOf = make([]uint32, len(weight))
+	load = make([]uint64, shards)
+	if shards <= 0 {
+		return nil, nil, errors.New("szb200: shards must be positive")
+	}
+	var wp *C.uint64_t
+	var sp *C.uint32_t
+	if len(weight) > 0 {
+		wp = (*C.uint64_t)(unsafe.Pointer(&weight[0]))
+		sp = (*C.uint32_t)(unsafe.Pointer(&shardOf[0]))
+	}
+	if rc := C.szb_shard_frames(wp, C.uint32_t(len(weight)), C.uint32_t(shards), sp, (*C.uint64_t)(unsafe.Pointer(&load[0]))); rc != 0 {
+		return nil, nil, Error(rc)
+	}
+	return shardOf, load, nil
+}
+
+// Dict is a zstd dictionary (raw content, or formatted: magic 0xEC30A437) parsed and resident on the context's GPU.
+// Not a reference behaviour: the reference parses Dictionary_ID and ignores it (structure/frame.go:38-47).
+type Dict struct{ p *C.szb_dict }
+
+func (c *Ctx) NewDict(dict []byte) (*Dict, error) {
+	var p *C.szb_dict
+	var dp *C.uint8_t
+	if len(dict) > 0 {
+		dp = (*C.uint8_t)(unsafe.Pointer(&dict[0]))
+	}
+	if rc := C.szb_dict_create(c.p, dp, C.size_t(len(dict)), &p); rc != 0 {
+		return nil, Error(rc)
+	}
+	return &Dict{p: p}, nil
+}
+
+func (d *Dict) ID() uint32 { return uint32(C.szb_dict_id(d.p)) }
+
+func (d *Dict) Close() {
+	if d.p != nil {
+		C.szb_dict_destroy(d.p)
+		d.p = nil
+	}
+}
+
+// DecodeBatchDict is DecodeBatch for frames that were compressed with the dictionary.
+func (c *Ctx) DecodeBatchDict(d *Dict, src []byte, off, length []uint64, dst []byte, flags uint32) (outOff, outLen []uint64, status []int32, err error) {
+	n := len(off)
+	if n == 0 {
+		return nil, nil, nil, nil
+	}
+	if len(length) != n || len(src) == 0 || d == nil || d.p == nil {
+		return nil, nil, nil, errors.New("szb200: bad batch arguments")
+	}
+	outOff = make([]uint64, n)
+	outLen = make([]uint64, n)
+	status = make([]int32, n)
+	var dp *C.uint8_t
+	if len(dst) > 0 {
+		dp = (*C.uint8_t)(unsafe.Pointer(&dst[0]))
+	}
+	rc := C.szb_decode_batch_dict(c.p, d.p, (*C.uint8_t)(unsafe.Pointer(&src[0])), C.size_t(len(src)),
+		(*C.uint64_t)(unsafe.Pointer(&off[0])), (*C.uint64_t)(unsafe.Pointer(&length[0])), C.uint32_t(n),
+		dp, C.size_t(len(dst)),
+		(*C.uint64_t)(unsafe.Pointer(&outOff[0])), (*C.uint64_t)(unsafe.Pointer(&outLen[0])),
+		(*C.int32_t)(unsafe.Pointer(&status[0])), C.uint32_t(flags))
+	if rc == C.SZB_ERR_CUDA || rc == C.SZB_ERR_INVALID_ARGUMENT || rc == C.SZB_ERR_NOMEM {
+		return nil, nil, nil, Error(rc)
+	}
+	return outOff, outLen, status, nil
+}

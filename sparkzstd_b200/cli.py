@@ -22,6 +22,8 @@ def main(argv=None) -> int:
     ap.add_argument("files", nargs="+", help="X.zst files; X is used as the expected output when present")
     ap.add_argument("--verify-checksum", action="store_true", help="also verify the content checksum (not done by the reference)")
     ap.add_argument("-o", "--output-dir", help="write decoded files here")
+    ap.add_argument("--dict", dest="dictionary", help="a zstd dictionary file (raw content or formatted) the files were compressed with "
+                    "(szb_decode_batch_dict; the reference has no dictionary support)")
     ap.add_argument("--stream", action="store_true", help="treat every file as a zstd stream: concatenated frames, skippable frames "
                     "(szb_decode_stream; the reference decodes exactly one frame per file)")
     args = ap.parse_args(argv)
@@ -36,7 +38,10 @@ def main(argv=None) -> int:
     for path in args.files:
         t0 = time.perf_counter()
         try:
-            if args.stream:
+            if args.dictionary:
+                with open(args.dictionary, "rb") as df, open(path, "rb") as f:
+                    out = ctx.decode_batch_dict([f.read()], df.read())[0]
+            elif args.stream:
                 with open(path, "rb") as f:
                     out = ctx.decode_stream(f.read(), verify_checksum=args.verify_checksum)
             else:
