@@ -32,7 +32,7 @@ def main():
 
     kernels = {}
     for r in rows[2:]:
-        name = r[hdr.index("Kernel Name")].split("(")[0]
+        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").split("<")[0].strip()  # "void k_execute2<0>(...)" -> k_execute2
         if name in kernels:  # the first launch of every kernel
             continue
         kernels[name] = {"dram_read": val(r, "dram__bytes_read.sum"), "dram_write": val(r, "dram__bytes_write.sum"),

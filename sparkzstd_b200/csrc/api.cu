@@ -382,11 +382,11 @@ static int batch_upload_tables(szb_batch *b) {
             // run one warp per slice -- more, shorter warps for frames of few blocks -- at the price of cells that are only
             // resolved inside a slice when they leave k_long_emit.
             // Measured (profiles/README.md, r02a / r02j; one frame): 64 MiB 14.9 -> 27.5 GB/s and 256 MiB 39 -> 53 GB/s with slices of
-            // 512, 1 GiB 58.7 -> 64.5 GB/s with 1 024 (61.4 with 4 096).  Few blocks want many short warps; beyond 16 384 blocks
-            // (2 GiB) the whole-block default stays (not measured with slices).
+            // 512, 1 GiB 58.7 -> 64.5 GB/s with 1 024 (61.4 with 4 096), 4 GiB 61.4 -> 64.9 GB/s with 1 024 (r02s).  Few blocks want
+            // many short warps.
             uint64_t long_blocks = 0;
             for (uint32_t k = 0; k < n_long; k++) long_blocks += b->frames[b->exec_list[k]].nblocks;
-            const uint32_t auto_slice = long_blocks <= 4096 ? 512u : (long_blocks <= 16384 ? 1024u : 0u);
+            const uint32_t auto_slice = long_blocks <= 4096 ? 512u : 1024u;
             const uint32_t slice = getenv("SZB_LONG_SLICE") ? (uint32_t)((strtoul(getenv("SZB_LONG_SLICE"), nullptr, 10) + 31) / 32 * 32) : auto_slice;
             b->long_slice = slice;
             build_long_tables(b->frames.data(), b->blocks.data(), b->exec_list.data(), n_long, slice, kJumpTile, b->lt);
