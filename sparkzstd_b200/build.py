@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libszb200.so")
 SOURCES = ["api.cu", "walker.cpp"]
-HEADERS = ["bits.cuh", "fse.cuh", "huffman.cuh", "sequences.cuh", "batch.cuh", "kernels.cuh", "execute.cuh", "execute_long.cuh", "place.cuh", "exec2.cuh", "long_tables.h", "abi_layout.h", "../../include/szb200.h"]
+HEADERS = ["bits.cuh", "fse.cuh", "huffman.cuh", "sequences.cuh", "batch.cuh", "kernels.cuh", "execute.cuh", "execute_long.cuh", "place.cuh", "exec2.cuh", "sequences3.cuh", "long_tables.h", "abi_layout.h", "../../include/szb200.h"]
 
 NVCC_FLAGS = [
     "-gencode",

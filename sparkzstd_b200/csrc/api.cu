@@ -327,6 +327,9 @@ constexpr uint64_t kPlaceMaxSeqs = 16384;  // per frame, for k_resolve / k_place
 #define SZB_DEFAULT_EXEC_PLACE 0
 #endif
 constexpr bool kDefaultExecPlace = SZB_DEFAULT_EXEC_PLACE != 0;
+#ifndef SZB_DEFAULT_SEQ
+#define SZB_DEFAULT_SEQ 1
+#endif
 
 static int batch_upload_tables(szb_batch *b) {
     szb_ctx *ctx = b->ctx;
@@ -777,7 +780,12 @@ static int launch_entropy(szb_batch *b, const void *d_src) {
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[7], s));
     if (a.n_seq) {
-        k_decode_sequences<<<(a.n_seq + kSeqLanes - 1) / kSeqLanes, 32, kSeqDecodeSmemBytes, s>>>(a);
+        // SZB_SEQ=1: one lane per block (k_decode_sequences); 3: three lanes per block, one per FSE state (sequences3.cuh)
+        static const int seq_mode = getenv("SZB_SEQ") ? atoi(getenv("SZB_SEQ")) : SZB_DEFAULT_SEQ;
+        if (seq_mode == 3)
+            k_decode_sequences3<<<(a.n_seq + kSeq3Chains - 1) / kSeq3Chains, 32, kSeq3SmemBytes, s>>>(a);
+        else
+            k_decode_sequences<<<(a.n_seq + kSeqLanes - 1) / kSeqLanes, 32, kSeqDecodeSmemBytes, s>>>(a);
         ctx->launches++;
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));

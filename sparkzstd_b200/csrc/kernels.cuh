@@ -961,6 +961,7 @@ __global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
     a.out_size[b] = (uint64_t)d.lit_regen + ml_sum;
 }
 
+#include "sequences3.cuh"
 #include "execute.cuh"
 
 }  // namespace szb
