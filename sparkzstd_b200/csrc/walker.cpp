@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <numeric>
 #include <queue>
+#include <thread>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -323,16 +324,102 @@ static int walk_create_impl(const uint8_t *src, size_t src_len, const uint64_t *
             w->blocks.push_back(d);
         }
         if (frame_off) {
-            w->frames.reserve(nframes);
-            w->blocks.reserve(nframes);
             for (uint32_t i = 0; i < nframes; i++) {
-                uint64_t off = frame_off[i];
-                uint64_t len = frame_len ? frame_len[i] : (off <= src_len ? src_len - off : 0);
+                const uint64_t off = frame_off[i];
+                const uint64_t len = frame_len ? frame_len[i] : (off <= src_len ? src_len - off : 0);
                 if (off > src_len || len > src_len - off) {
                     delete w;
                     return SZB_ERR_INVALID_ARGUMENT;
                 }
-                walk_frame(*w, src, off, len, nullptr);
+            }
+            // Frames with given extents are independent: with many of them the walk runs on several threads, each over a
+            // contiguous range of frames into tables of its own, which are appended in frame order with their block indices
+            // (a frame's first block, the origins of Treeless / Repeat tables) and scratch offsets moved to their final place.
+            // The result is the table a single thread makes.  SZB_WALK_THREADS caps the threads (one process per GPU).
+            unsigned nthreads = std::thread::hardware_concurrency();
+            nthreads = nthreads < 2 ? 1 : (nthreads > 8 ? 8 : nthreads);
+            if (const char *wt = getenv("SZB_WALK_THREADS")) {
+                const unsigned cap = (unsigned)strtoul(wt, nullptr, 10);
+                if (cap >= 1 && cap < nthreads) nthreads = cap;
+            }
+            if (nframes < 4096) nthreads = 1;
+            auto walk_range = [&](szb_walk &part, uint32_t lo, uint32_t hi) {
+                part.frames.reserve(hi - lo);
+                part.blocks.reserve(hi - lo);
+                for (uint32_t i = lo; i < hi; i++) {
+                    const uint64_t off = frame_off[i];
+                    walk_frame(part, src, off, frame_len ? frame_len[i] : src_len - off, nullptr);
+                }
+            };
+            if (nthreads == 1) {
+                w->frames.reserve(w->frames.size() + nframes);
+                w->blocks.reserve(w->blocks.size() + nframes);
+                walk_range(*w, 0, nframes);
+            } else {
+                std::vector<szb_walk> parts(nthreads);
+                std::vector<std::thread> th;
+                std::vector<int> failed(nthreads, 0);
+                const uint32_t per = (nframes + nthreads - 1) / nthreads;
+                for (unsigned t = 0; t < nthreads; t++) {
+                    szb_walk &part = parts[t];
+                    part.dict = w->dict;
+                    part.dict_id = w->dict_id;
+                    // what every frame starts with is the same in every part: the dictionary's row of the FINAL table.  Bit 31
+                    // marks such an origin as absolute; the part's own origins are relative to its first block (below)
+                    part.dict_huf = w->dict_huf == SZB_NONE ? SZB_NONE : (w->dict_huf | 0x80000000u);
+                    part.dict_seq = w->dict_seq == SZB_NONE ? SZB_NONE : (w->dict_seq | 0x80000000u);
+                    const uint32_t lo = t * per < nframes ? t * per : nframes, hi = lo + per < nframes ? lo + per : nframes;
+                    auto job = [&, t, lo, hi]() {
+                        try {
+                            walk_range(parts[t], lo, hi);
+                        } catch (...) {
+                            failed[t] = 1;
+                        }
+                    };
+                    bool started = false;
+                    if (t + 1 < nthreads) {
+                        try {
+                            th.emplace_back(job);
+                            started = true;
+                        } catch (...) {
+                        }
+                    }
+                    if (!started) job();  // the last range, or no thread to be had: right here
+                }
+                for (auto &x : th) x.join();
+                for (unsigned t = 0; t < nthreads; t++)
+                    if (failed[t]) throw std::bad_alloc();
+                for (unsigned t = 0; t < nthreads; t++) {
+                    const szb_walk &part = parts[t];
+                    const uint32_t fbase = (uint32_t)w->frames.size(), bbase = (uint32_t)w->blocks.size();
+                    const uint64_t lbase = w->literal_bytes, sbase = w->sequences;
+                    for (szb_frame_desc f : part.frames) {
+                        f.first_block += bbase;
+                        w->frames.push_back(f);
+                    }
+                    for (szb_block_desc d : part.blocks) {
+                        d.frame += fbase;
+                        w->blocks.push_back(d);
+                    }
+                    for (size_t k = bbase; k < w->blocks.size(); k++) {
+                        szb_block_desc &d = w->blocks[k];
+                        auto move = [&](uint32_t &o) {
+                            if (o == SZB_NONE) return;
+                            if (o & 0x80000000u)
+                                o &= 0x7FFFFFFFu;  // the dictionary's row: an absolute index
+                            else
+                                o += bbase;
+                        };
+                        move(d.huf_origin);
+                        move(d.ll_origin);
+                        move(d.of_origin);
+                        move(d.ml_origin);
+                        if (d.type == 2 && d.lit_type >= 2) d.lit_buf_off += lbase;
+                        if (d.type == 2) d.seq_buf_off += sbase;
+                    }
+                    w->literal_bytes += part.literal_bytes;
+                    w->sequences += part.sequences;
+                }
             }
         } else {
             // concatenated frames: discover boundaries (not a reference behaviour)

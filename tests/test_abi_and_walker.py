@@ -243,3 +243,42 @@ def test_walker_reports_the_content_checksum(corpus):
         assert fr.checksum == _xxh64(pyszo.decode_frame(data)) & 0xFFFFFFFF, name
         checked += 1
     assert checked > 40
+
+
+def test_parallel_walk_makes_the_same_tables(monkeypatch):
+    """Batches of >= 4096 frames with given extents are walked on several threads (SZB_WALK_THREADS caps them); the merged
+    tables -- first blocks, table origins, scratch offsets, a dictionary's row as origin -- equal the single-threaded ones."""
+    import sparkzstd_b200
+    from sparkzstd_b200._lib import BlockDesc, FrameDesc
+
+    L = sparkzstd_b200.load()
+    L.szb_walk_literal_bytes.restype = C.c_uint64
+    L.szb_walk_sequences.restype = C.c_uint64
+    from tools import corpus as cg
+
+    text = cg.config2_text_frames(3000, 6000)
+    mixed = cg.config5_mixed(96 << 20)  # multi-block frames with Treeless literals and Repeat modes, the golden frames
+    # 3000 + ~900 frames are not 4096 yet: the same frames twice
+    src = np.concatenate([text.src[: text.compressed_bytes], mixed.src])
+    off = np.concatenate([text.frame_off, mixed.frame_off + np.uint64(text.compressed_bytes)] * 2)
+    ln = np.concatenate([text.frame_len, mixed.frame_len] * 2)
+    assert len(off) >= 4096
+
+    def walk(threads, dict_blk=None):
+        monkeypatch.setenv("SZB_WALK_THREADS", str(threads))
+        h = C.c_void_p()
+        if dict_blk is None:
+            rc = L.szb_walk_create(src.ctypes.data, src.nbytes, off.ctypes.data, ln.ctypes.data, len(off), C.byref(h))
+        else:
+            rc = L.szb_walk_create_dict(src.ctypes.data, src.nbytes, off.ctypes.data, ln.ctypes.data, len(off), C.byref(dict_blk), 0, C.byref(h))
+        assert rc == 0
+        nf, nb = L.szb_walk_nframes(h), L.szb_walk_nblocks(h)
+        out = (C.string_at(L.szb_walk_frames(h), nf * C.sizeof(FrameDesc)), C.string_at(L.szb_walk_blocks(h), nb * C.sizeof(BlockDesc)),
+               L.szb_walk_literal_bytes(h), L.szb_walk_sequences(h))
+        L.szb_walk_destroy(h)
+        return out
+
+    assert walk(1) == walk(5) == walk(8)
+    blk = BlockDesc()
+    blk.type, blk.lit_type, blk.nseq, blk.block_size, blk.lit_streams, blk.lit_hdr_bytes, blk.seq_hdr_bytes, blk.seq_modes = 2, 2, 1, 10, 1, 3, 2, 0xA8
+    assert walk(1, blk) == walk(7, blk)
