@@ -329,7 +329,14 @@ def main():
                 cov["of_modes"][(b.seq_modes >> 4) & 3] += 1
                 cov["ml_modes"][(b.seq_modes >> 2) & 3] += 1
     cov["legend"] = "block types Raw/RLE/Compressed; literal types Raw/RLE/Compressed/Treeless; modes Predefined/RLE/FSE/Repeat"
-    if args.workload == "mixed" and args.scaling == "weak":
+    if args.workload == "mixed" and args.scaling == "strong" and world > 1:
+        # a shard may miss a format path; the corpus as a whole must not: sum the counts over the ranks
+        flat = [x for k in ("block_types", "literal_types", "ll_modes", "of_modes", "ml_modes") for x in cov[k]]
+        tot_cov = torch.tensor(flat, dtype=torch.int64, device=f"cuda:{local_rank}")
+        dist.all_reduce(tot_cov)
+        assert bool((tot_cov > 0).all()), f"the sharded mixed corpus misses a format path: {tot_cov.tolist()}"
+        cov["all_ranks"] = tot_cov.tolist()
+    if args.workload == "mixed" and (args.scaling == "weak" or world == 1):
         assert all(cov["block_types"]) and all(cov["literal_types"]) and all(cov["ll_modes"]) and all(cov["of_modes"]) and \
             all(cov["ml_modes"]), f"the mixed corpus misses a format path: {cov}"
 

@@ -668,7 +668,9 @@ constexpr uint32_t kSeqRingBytes = 128;
 constexpr uint32_t kSeqRingStride = kSeqRingBytes + 16;           // per lane: the ring + a mirror of its first 16 B
 constexpr uint32_t kSeqRingOff = kSeqTabBytes;                    // byte offset of the rings
 constexpr uint32_t kSeqLutWord = (kSeqRingOff + kSeqLanes * kSeqRingStride) / 4;  // ll[64] | ml[64]: base | extra << 24
-constexpr uint32_t kSeqDecodeSmemBytes = (kSeqLutWord + 128) * 4;
+constexpr uint32_t kSeqBarWord = kSeqLutWord + 128;                // the table load's mbarrier (8 bytes, 8-byte aligned)
+static_assert(kSeqBarWord % 2 == 0, "the mbarrier is a 64-bit object");
+constexpr uint32_t kSeqDecodeSmemBytes = (kSeqBarWord + 2) * 4;
 // A group of four window reads consumes at most 4 x 57 bits = 28.5 bytes and a window reaches 10
 // bytes below the byte of its top bit: a group touches nothing below (top - kSeqGroupReach).
 // The top-up of group g requests chunks down to the one holding (top - kSeqRingAhead); what it
@@ -831,19 +833,32 @@ __global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
     const uint32_t n_here = a.n_seq - first < (uint32_t)kSeqLanes ? a.n_seq - first : (uint32_t)kSeqLanes;
     uint16_t *tabs = reinterpret_cast<uint16_t *>(sw);
 
-    // tables: HBM arena -> shared memory, 2560 contiguous bytes per block, all copies in flight at once
+    // tables: HBM arena -> shared memory, 2560 contiguous bytes per block.  One bulk copy per block (cp.async.bulk, the copy engine
+    // of sm_90+: one instruction per lane instead of 160 16-byte cp.async's), all in flight at once, their bytes counted by an
+    // mbarrier the warp then waits on.
     {
         const uint32_t tabs_saddr = (uint32_t)__cvta_generic_to_shared(tabs);
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(sw + kSeqBarWord);
         const uint8_t *arena = reinterpret_cast<const uint8_t *>(a.seq_tabs + (size_t)first * kTabSlotWords);
-        const uint32_t chunks = n_here * (kTabSlotWords * 2 / 16);
-        for (uint32_t c = lane; c < chunks; c += 32) cp_async16(tabs_saddr + c * 16, arena + (size_t)c * 16);
-        asm volatile("cp.async.commit_group;");
+        constexpr uint32_t kSlotBytes = kTabSlotWords * 2;
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n_here * kSlotBytes) : "memory");
+        }
+        __syncwarp();
+        if (lane < n_here)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tabs_saddr + lane * kSlotBytes),
+                         "l"(arena + (size_t)lane * kSlotBytes), "r"(kSlotBytes), "r"(bar)
+                         : "memory");
+        for (uint32_t i = lane; i < 64; i += 32) {
+            sw[kSeqLutWord + i] = kLLBaseDev[i] | ((uint32_t)kLLExtraDev[i] << 24);
+            sw[kSeqLutWord + 64 + i] = kMLBaseDev[i] | ((uint32_t)kMLExtraDev[i] << 24);
+        }
+        uint32_t landed = 0;
+        while (!landed)  // phase 0 completes when the expected bytes have arrived (try_wait sleeps in hardware, it does not spin)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(landed) : "r"(bar) : "memory");
     }
-    for (uint32_t i = lane; i < 64; i += 32) {
-        sw[kSeqLutWord + i] = kLLBaseDev[i] | ((uint32_t)kLLExtraDev[i] << 24);
-        sw[kSeqLutWord + 64 + i] = kMLBaseDev[i] | ((uint32_t)kMLExtraDev[i] << 24);
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     if (lane >= n_here) return;
 
