@@ -1315,7 +1315,10 @@ static int decode_batch_pipelined(szb_ctx *ctx, const uint8_t *src, size_t src_l
     rc = ensure_dev(ctx, &ctx->d_dst, &ctx->d_dst_cap, (size_t)total + 16);
     if (rc) return rc;
     // pageable caller memory goes through the context's pinned rings, so that the copies still overlap the kernels
-    const bool src_pg = host_pageable(src), dst_pg = host_pageable(dst);
+    // (SZB_NO_STAGING=1, measurements only: hand pageable pointers to cudaMemcpyAsync as they are -- the driver then stages them
+    // itself, synchronously)
+    static const bool no_staging = getenv("SZB_NO_STAGING") != nullptr;
+    const bool src_pg = !no_staging && host_pageable(src), dst_pg = !no_staging && host_pageable(dst);
     if (src_pg || dst_pg) {
         rc = pin_rings(ctx);
         if (rc) return rc;
