@@ -45,6 +45,10 @@ struct szb_ctx {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaStream_t s_lit = nullptr;          // the literal chain runs beside the sequence chain (they meet at stage 4)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // overlap mode (szb_overlap): stage 4 runs on its own low-priority stream behind the entropy stages of the same batch, so that
+    // the entropy stages of the NEXT batch (high priority, a capped number of CTAs per SM) run beside it
+    cudaStream_t s_exec = nullptr;
+    cudaEvent_t ev_ent = nullptr, ev_exec = nullptr;
     // Pinned staging for callers whose buffers are pageable (a Go slice, a Python bytes object): the copy engines only run
     // asynchronously from / to page-locked memory.  Two rings of kPinBytes slots, allocated on first use.
     static constexpr int kPinIn = 2, kPinOut = 3;
@@ -213,7 +217,7 @@ int szb_ctx_create(int device, void *stream, szb_ctx **out) {
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
     } else {
-        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        if (stream_create(&ctx->stream, true)) {
             delete ctx;
             return SZB_ERR_CUDA;
         }
@@ -279,6 +283,12 @@ void szb_ctx_destroy(szb_ctx *ctx) {
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     if (ctx->s_lit) cudaStreamDestroy(ctx->s_lit);
+    if (ctx->s_exec) {
+        cudaStreamSynchronize(ctx->s_exec);
+        cudaStreamDestroy(ctx->s_exec);
+    }
+    if (ctx->ev_ent) cudaEventDestroy(ctx->ev_ent);
+    if (ctx->ev_exec) cudaEventDestroy(ctx->ev_exec);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     for (int i = 0; i < szb_ctx::kPinIn; i++) {
@@ -747,11 +757,27 @@ static DeviceBatch make_args(szb_batch *b, const void *d_src, void *d_dst, size_
     a.place_state = a.rec ? b->d_place_state : nullptr;
     a.n_noplace = b->n_noplace;
     a.exec2 = b->exec2 ? 1u : 0u;
+    // SZB_PAIR2=0: the long frames that do not take the block-parallel path stay on k_execute_pair (round 1's producer / consumer)
+    static const bool pair2 = !(getenv("SZB_PAIR2") && atoi(getenv("SZB_PAIR2")) == 0);
+    a.pair2 = b->exec2 && !b->dict && pair2 ? 1u : 0u;
     a.dict_content = b->dict ? b->dict->d_content : nullptr;
     a.dict_len = b->dict ? b->dict->content_len : 0;
     for (int k = 0; k < 3; k++) a.dict_rep[k] = b->dict ? b->dict->rep[k] : (k == 0 ? 1u : (k == 1 ? 4u : 8u));
     a.frame_dict = b->dict ? b->d_frame_dict : nullptr;
     return a;
+}
+
+// SZB_SPLIT=1 (experiment): stage 4 on its own stream (see szb_ctx::s_exec); SZB_SEQ_CTAS_PER_SM=n caps k_decode_sequences' grid at
+// n CTAs per SM (a CTA then walks several groups), which leaves shared memory and CTA slots to the stage 4 of another batch.
+static bool szb_overlap() {
+    static const bool on = getenv("SZB_SPLIT") && atoi(getenv("SZB_SPLIT")) != 0;
+    return on;
+}
+static int stream_create(cudaStream_t *s, bool high) {
+    int least = 0, greatest = 0;
+    if (!szb_overlap() || cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess)
+        return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) == cudaSuccess ? 0 : 1;
+    return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, high ? greatest : least) == cudaSuccess ? 0 : 1;
 }
 
 static int launch_entropy(szb_batch *b, const void *d_src) {
@@ -760,7 +786,7 @@ static int launch_entropy(szb_batch *b, const void *d_src) {
     cudaStream_t s = ctx->stream;
     DeviceBatch a = make_args(b, d_src, nullptr, 0);
     if (!ctx->s_lit) {
-        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_lit, cudaStreamNonBlocking));
+        if (stream_create(&ctx->s_lit, true)) return SZB_ERR_CUDA;
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     }
@@ -785,7 +811,12 @@ static int launch_entropy(szb_batch *b, const void *d_src) {
         if (seq_mode == 3)
             k_decode_sequences3<<<(a.n_seq + kSeq3Chains - 1) / kSeq3Chains, 32, kSeq3SmemBytes, s>>>(a);
         else
-            k_decode_sequences<<<(a.n_seq + kSeqLanes - 1) / kSeqLanes, 32, kSeqDecodeSmemBytes, s>>>(a);
+        {
+            static const int cap = getenv("SZB_SEQ_CTAS_PER_SM") ? atoi(getenv("SZB_SEQ_CTAS_PER_SM")) : 0;
+            uint32_t grid = (a.n_seq + kSeqLanes - 1) / kSeqLanes;
+            if (cap > 0 && grid > (uint32_t)(cap * ctx->sm_count)) grid = (uint32_t)(cap * ctx->sm_count);
+            k_decode_sequences<<<grid, 32, kSeqDecodeSmemBytes, s>>>(a);
+        }
         ctx->launches++;
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
@@ -814,6 +845,16 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
     szb_ctx *ctx = b->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
+    if (szb_overlap()) {
+        if (!ctx->s_exec) {
+            if (stream_create(&ctx->s_exec, false)) return SZB_ERR_CUDA;
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_ent, cudaEventDisableTiming));
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_exec, cudaEventDisableTiming));
+        }
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_ent, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_exec, ctx->ev_ent, 0));
+        s = ctx->s_exec;
+    }
     DeviceBatch a = make_args(b, d_src, d_dst, dst_cap);
     if (a.nframes && a.rec) {  // place.cuh: every frame k_place will execute, walked in order by one lane
         k_place_zero<<<ctx->sm_count * 8, 256, 0, s>>>(a);
@@ -868,7 +909,12 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
             }
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, s));
             CUDA_TRY(ctx, cudaStreamWaitEvent(sl, ctx->ev_fork, 0));
-            k_execute_pair<<<n_long, 64, 0, sl>>>(a, 0, n_long);  // the frames the block-parallel path does not take
+            // the frames the block-parallel path does not take: k_execute_pair2, and k_execute_pair for those of 2 GiB and more
+            if (a.pair2) {
+                k_execute_pair2<<<n_long, 64, 0, sl>>>(a, 0, n_long);
+                ctx->launches++;
+            }
+            k_execute_pair<<<n_long, 64, 0, sl>>>(a, 0, n_long);
             ctx->launches++;
             if (b->long_jump) {
                 const uint32_t g_lb = (a.n_lb + kWarpsPerCta - 1) / kWarpsPerCta, g_ls = (a.n_ls + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -917,6 +963,7 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
         if (n_long) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
+    if (s != ctx->stream) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_exec, s));
     CUDA_TRY(ctx, cudaGetLastError());
     return SZB_OK;
 }
@@ -1001,6 +1048,7 @@ int szb_batch_finish(szb_batch *b, int32_t *status) {
     szb_ctx *ctx = b->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     std::vector<int32_t> st(b->nframes ? b->nframes : 1, 0);
+    if (ctx->s_exec) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_exec));
     if (b->nframes)
         CUDA_TRY(ctx, cudaMemcpyAsync(st.data(), b->d_frame_status, 4 * (size_t)b->nframes, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

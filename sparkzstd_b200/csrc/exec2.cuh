@@ -191,7 +191,7 @@ __device__ __forceinline__ void x2_seek(X2State &st, uint32_t q) {
 // (it is not in memory yet), longer runs -- are left to the whole warp afterwards, one at a time in sequence order, reading
 // staged bytes or memory byte by byte.  The staged bytes then leave as 16-byte units, 512 contiguous bytes per warp store.
 // Returns false (nothing touched) when too many sequences would be left to the warp.
-__device__ __forceinline__ bool x2_round_staged(X2Stage &S, const X2State &st, const uint8_t *lit_at, uint32_t qpos, uint32_t round_tot,
+__device__ __forceinline__ bool x2_round_staged(X2Stage &S, uint8_t *qb, const uint8_t *lit_at, uint32_t qpos, uint32_t round_tot,
                                                 bool act, uint32_t ll, uint32_t ml, uint32_t off, uint32_t excl_tot, uint32_t incl_tot,
                                                 uint32_t excl_ll, uint32_t lane) {
     const bool lit_small = ll <= kS2Lit;
@@ -208,7 +208,7 @@ __device__ __forceinline__ bool x2_round_staged(X2Stage &S, const X2State &st, c
     const uint32_t n_m = m1 ? ml : 0u;
     const uint8_t *lsrc = lit_at + excl_ll;
     const uint32_t lo_ = (uint32_t)(reinterpret_cast<uintptr_t>(lsrc) & 15);
-    const uint8_t *msrc = st.qb + (qpos + excl_tot + ll - off);
+    const uint8_t *msrc = qb + (qpos + excl_tot + ll - off);
     const uint32_t mo_ = (uint32_t)(reinterpret_cast<uintptr_t>(msrc) & 15);
     uint4 l0 = make_uint4(0, 0, 0, 0), l1 = l0, m0 = l0, m1v = l0;
     if (n_lit) {
@@ -256,14 +256,14 @@ __device__ __forceinline__ bool x2_round_staged(X2Stage &S, const X2State &st, c
                     const uint32_t k = k0 + lane;
                     if (k < ML) {
                         const uint32_t sq = qm + k - OFF;
-                        S.stg[sm0 + k] = sq >= qpos ? S.stg[sq - base16] : st.qb[sq];
+                        S.stg[sm0 + k] = sq >= qpos ? S.stg[sq - base16] : qb[sq];
                     }
                     if (OFF < ML) __syncwarp();   // the next 32 bytes may repeat these
                 }
             } else {  // overlapping with a period below 32: byte k repeats byte k % OFF of the OFF bytes in front of the match
                 for (uint32_t k = lane; k < ML; k += 32) {
                     const uint32_t sq = qm - OFF + k % OFF;
-                    S.stg[sm0 + k] = sq >= qpos ? S.stg[sq - base16] : st.qb[sq];
+                    S.stg[sm0 + k] = sq >= qpos ? S.stg[sq - base16] : qb[sq];
                 }
             }
         }
@@ -275,13 +275,13 @@ __device__ __forceinline__ bool x2_round_staged(X2Stage &S, const X2State &st, c
         const uint32_t first_full = (qpos + 15) & ~15u, last_full = hi & ~15u;  // full units: [first_full, last_full)
         if (first_full < last_full) {
             for (uint32_t q = first_full + 16 * lane; q < last_full; q += 512)
-                *reinterpret_cast<uint4 *>(st.qb + q) = *reinterpret_cast<const uint4 *>(S.stg + (q - base16));
+                *reinterpret_cast<uint4 *>(qb + q) = *reinterpret_cast<const uint4 *>(S.stg + (q - base16));
             const uint32_t head = first_full - qpos;  // < 16
-            if (lane < head) st.qb[qpos + lane] = S.stg[qpos - base16 + lane];
+            if (lane < head) qb[qpos + lane] = S.stg[qpos - base16 + lane];
             const uint32_t tail = hi - last_full;  // < 16
-            if (lane >= 16 && lane - 16 < tail) st.qb[last_full + lane - 16] = S.stg[last_full - base16 + lane - 16];
+            if (lane >= 16 && lane - 16 < tail) qb[last_full + lane - 16] = S.stg[last_full - base16 + lane - 16];
         } else {  // no full unit: at most 30 bytes
-            if (lane < round_tot) st.qb[qpos + lane] = S.stg[qpos - base16 + lane];
+            if (lane < round_tot) qb[qpos + lane] = S.stg[qpos - base16 + lane];
         }
     }
     __syncwarp();
@@ -289,26 +289,89 @@ __device__ __forceinline__ bool x2_round_staged(X2Stage &S, const X2State &st, c
 }
 
 // One frame (status OK, taken by x2_takes), one warp: blocks in order, 32 sequences per round (sequence_execution.go:14-63).
+// the consumer's state at the frame's first byte
+__device__ __forceinline__ void x2_frame_start(const DeviceBatch &a, uint32_t f, X2State &st) {
+    const szb_frame_desc fr = a.frames[f];
+    uint8_t *first = a.dst + (fr.nblocks ? a.out_off[fr.first_block] : 0);
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 127);
+    st.qb = first - mis;
+    st.lit = nullptr;
+    st.seen = 0;
+    x2_seek(st, mis);
+}
+
+// Where the producer's segments go, and who makes the lines.
+// X2Inline: the producing warp is the consumer too; it stays one append behind, so that the prefetches it issued for the
+// match sources have time to land.
+struct X2Inline {
+    static constexpr bool kInline = true;
+    X2Smem &sm;
+    X2State st;
+    uint32_t lane, le_mask;
+    __device__ __forceinline__ uint32_t line() const { return st.line; }
+    __device__ __forceinline__ bool idle(uint32_t prod) const { return prod == st.line + st.head; }  // nothing left in the ring
+    __device__ __forceinline__ void set_lit(const uint8_t *lit) { st.lit = lit; }
+    __device__ __forceinline__ void seek(uint32_t q) { x2_seek(st, q); }
+    __device__ __forceinline__ void flush(uint32_t prod) { st = x2_flush_cold(sm, st, prod, lane, le_mask); }
+    __device__ __forceinline__ void drain_to(uint32_t prod) { st = x2_drain_cold(sm, st, prod, lane, le_mask); }
+    __device__ __forceinline__ void appended(uint32_t prev_prod, uint32_t) { x2_drain(sm, st, prev_prod, lane, le_mask); }
+    __device__ __forceinline__ void finish(uint32_t prod) { st = x2_flush_cold(sm, st, prod, lane, le_mask); }
+};
+
+// X2Pair: a second warp of the CTA consumes (k_execute_pair2), for the frames that are far longer than the rest and run almost
+// alone at the end: the two warps meet at one __syncthreads per command, and a command is executed by the consumer while the
+// producer works on the next round.  The producer only ever needs a LOWER bound of the consumer's line.
+enum : uint32_t { kX2cNop = 0, kX2cDrain = 1, kX2cFlush = 2, kX2cSeek = 3, kX2cLit = 4, kX2cExit = 5 };
+struct X2PairShared {
+    unsigned long long arg[2];  // a q position, or the literals' address
+    uint32_t cmd[2];
+    uint32_t line[2];           // the consumer's st.line after command i, in slot i & 1
+};
+struct X2Pair {
+    static constexpr bool kInline = false;
+    X2PairShared &sh;
+    uint32_t lane, it;
+    uint32_t seen_line;  // what the consumer had reached one command ago
+    __device__ __forceinline__ void hand(uint32_t cmd, unsigned long long arg) {
+        if (lane == 0) {
+            sh.cmd[it & 1] = cmd;
+            sh.arg[it & 1] = arg;
+        }
+        __syncthreads();  // command `it` starts; command it-1 is complete and has published its line before this barrier
+        if (it) seen_line = sh.line[(it - 1) & 1];
+        it++;
+    }
+    __device__ __forceinline__ uint32_t line() const { return seen_line; }
+    __device__ __forceinline__ bool idle(uint32_t) const { return false; }
+    __device__ __forceinline__ void set_lit(const uint8_t *lit) { hand(kX2cLit, reinterpret_cast<uintptr_t>(lit)); }
+    __device__ __forceinline__ void seek(uint32_t q) {
+        hand(kX2cSeek, q);
+        seen_line = q & ~127u;
+    }
+    __device__ __forceinline__ void flush(uint32_t prod) {  // returns when everything below prod is in memory
+        hand(kX2cFlush, prod);
+        hand(kX2cNop, 0);
+    }
+    __device__ __forceinline__ void drain_to(uint32_t prod) { hand(kX2cDrain, prod); }
+    __device__ __forceinline__ void appended(uint32_t, uint32_t prod) { hand(kX2cDrain, prod); }
+    __device__ __forceinline__ void finish(uint32_t prod) {
+        hand(kX2cFlush, prod);
+        hand(kX2cExit, 0);
+    }
+};
+
 // kDict: the batch is decoded with a dictionary (its own instantiation: the plain one pays nothing for it).
-template <bool kDict>
-__device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Smem &sm, X2Stage &stage, uint32_t lane) {
+template <bool kDict, class Sink>
+__device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Smem &sm, X2Stage &stage, Sink &sink, uint32_t lane) {
     const szb_frame_desc fr = a.frames[f];
     const uint32_t b0 = fr.first_block, nb = a.frame_nexec ? a.frame_nexec[f] : fr.nblocks;  // k_frame_verdict
     if (nb == 0) return;
     int err = SZB_OK;
     const uint64_t frame_base = a.out_off[b0];
-    const uint32_t le_mask = 0xFFFFFFFFu >> (31 - lane);  // bits 0..lane
-    const uint32_t lt_mask = le_mask >> 1;                // bits 0..lane-1
-    X2State st;
-    uint32_t mis;  // q position of the frame's first byte
-    {
-        uint8_t *first = a.dst + frame_base;
-        mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 127);
-        st.qb = first - mis;
-        st.lit = nullptr;
-        st.seen = 0;
-        x2_seek(st, mis);
-    }
+    const uint32_t lt_mask = 0x7FFFFFFFu >> (31 - lane);  // bits 0..lane-1
+    uint8_t *const first = a.dst + frame_base;
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 127);  // q position of the frame's first byte
+    uint8_t *const qb = first - mis;                                             // q position 0 (x2_frame_start gave the sink the same)
     uint32_t prod = mis;  // segments cover the output up to this q position
     uint32_t nseg = 0;    // segments appended so far
 
@@ -325,9 +388,9 @@ __device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Sme
         uint32_t qpos = mis + (uint32_t)(a.out_off[b] - frame_base);
         // the consumer is brought up to date at every block start: the literals' base address changes, and blocks in between
         // may have been written elsewhere
-        st = x2_flush_cold(sm, st, prod, lane, le_mask);
+        sink.flush(prod);
         if (qpos != prod) {
-            x2_seek(st, qpos);
+            sink.seek(qpos);
             prod = qpos;
         }
         // Compressed: ExecuteSequences (sequence_execution.go:14-63)
@@ -335,7 +398,7 @@ __device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Sme
         // RLE literals: every literal byte is payload[lit_hdr_bytes]; runs read it from that byte's row of the fill table
         const uint8_t *lit = lit_rle ? a.bytefill + 256 * (uint32_t)payload[d.lit_hdr_bytes]
                                      : (d.lit_type == 0 ? payload + d.lit_hdr_bytes : a.litbuf + d.lit_buf_off);
-        st.lit = lit;
+        sink.set_lit(lit);
         const uint32_t nseq = d.nseq;
         uint32_t lit_pos = 0;
         const uint32_t *const seqp = a.seq_ll + d.seq_buf_off;
@@ -439,24 +502,24 @@ __device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Sme
             const bool any_reach = kDict && dlen != 0 && __any_sync(kFull, reach);
 
             // --- rounds of short sequences are staged in shared memory, one lane per sequence (x2_round_staged) ---
-            if (SZB_X2_STAGED && !lit_rle && !any_reach && round_tot <= kS2Cap) {
-                if (prod != st.line + st.head) st = x2_flush_cold(sm, st, prod, lane, le_mask);  // segments still in the ring
-                if (x2_round_staged(stage, st, lit + lit_pos, qpos, round_tot, act, ll, ml, off, excl_tot, incl_tot, excl_ll, lane)) {
+            if (SZB_X2_STAGED && Sink::kInline && !lit_rle && !any_reach && round_tot <= kS2Cap) {
+                if (!sink.idle(prod)) sink.flush(prod);  // segments still in the ring
+                if (x2_round_staged(stage, qb, lit + lit_pos, qpos, round_tot, act, ll, ml, off, excl_tot, incl_tot, excl_ll, lane)) {
                     qpos += round_tot;
                     lit_pos += round_ll;
                     prod = qpos;
-                    x2_seek(st, prod);
+                    sink.seek(prod);
                     continue;
                 }
             }
             // --- the round's segments go to the ring, as many sequences at a time as the bitmap holds (normally all) ---
             uint32_t start = 0;
             while (start < cnt) {
-                uint32_t out_rel = qpos - st.line;
-                if (out_rel + round_tot > kX2Span && prod - st.line >= 128) {
+                uint32_t out_rel = qpos - sink.line();
+                if (out_rel + round_tot > kX2Span && prod - sink.line() >= 128) {
                     // rounds of long sequences: the consumer catches up before the round is cut into pieces
-                    st = x2_drain_cold(sm, st, prod, lane, le_mask);
-                    out_rel = qpos - st.line;
+                    if (Sink::kInline) sink.drain_to(prod); else sink.flush(prod);
+                    out_rel = qpos - sink.line();
                 }
                 const uint32_t my_rel = out_rel + excl_tot;  // my literal run, relative to the line being consumed
                 uint32_t nfit;
@@ -469,11 +532,11 @@ __device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Sme
                 }
                 if (nfit == 0) {
                     // one sequence longer than the ring: the whole warp on its literals, then on its match
-                    st = x2_flush_cold(sm, st, prod, lane, le_mask);
+                    sink.flush(prod);
                     const uint32_t L = __shfl_sync(kFull, ll, start), ML = __shfl_sync(kFull, ml, start);
                     const uint32_t OFF = __shfl_sync(kFull, off, start);
                     const uint32_t Dq = qpos + __shfl_sync(kFull, excl_tot, start);
-                    uint8_t *D = st.qb + Dq;
+                    uint8_t *D = qb + Dq;
                     if (lit_rle)
                         warp_memset(D, lit[0], L, lane);
                     else
@@ -487,7 +550,7 @@ __device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Sme
                         // is a byte of this match, i.e. byte k % OFF of its first OFF bytes.  All sources lie in front of the
                         // match (dictionary content or output already in memory): no order among the lanes is needed.
                         const uint8_t *dict_end = a.dict_content + dlen;  // "frame position 0" of the dictionary's content
-                        const uint8_t *frame0 = st.qb + mis;
+                        const uint8_t *frame0 = qb + mis;
                         for (uint32_t k = lane; k < ML; k += 32) {
                             const int32_t sp = (int32_t)(mpos + (k < OFF ? k : k % OFF)) - (int32_t)OFF;
                             MD[k] = sp < 0 ? dict_end[sp] : frame0[sp];
@@ -503,7 +566,7 @@ __device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Sme
                     }
                     __syncwarp();
                     prod = Dq + L + ML;
-                    x2_seek(st, prod);
+                    sink.seek(prod);
                     start++;
                     continue;
                 }
@@ -524,14 +587,14 @@ __device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Sme
                         sm.seg[ord & (kX2Ring - 1)] = off;
                         atomicOr(&sm.bits[(q_m >> 5) & (kX2Bits / 32 - 1)], 1u << (q_m & 31));
                         // the consumer gets here about a round later: have the source on its way to L1
-                        SZB_PREFETCH_L1(st.qb + (q_m - off));
+                        SZB_PREFETCH_L1(qb + (q_m - off));
                     }
                 }
                 nseg += 2 * nfit - __popc(no_lit);
                 const uint32_t prev_prod = prod;
-                prod = st.line + __shfl_sync(kFull, my_rel + tot, end - 1);
+                prod = qpos + __shfl_sync(kFull, excl_tot + tot, end - 1);
                 __syncwarp();
-                x2_drain(sm, st, prev_prod, lane, le_mask);  // one append behind: the prefetches have time to land
+                sink.appended(prev_prod, prod);  // inline: one append behind, so that the prefetches have time to land
                 start = end;
             }
             qpos += round_tot;
@@ -540,7 +603,7 @@ __device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Sme
         if (err != SZB_OK) break;
         // trailing literals (sequence_execution.go:55-60, literals.go:411-420): one more segment, or a bulk copy
         const uint32_t rest = d.lit_regen - lit_pos;
-        if (rest && (prod - st.line) + rest <= kX2Span && !(lit_rle && rest > kX2ConstRun)) {
+        if (rest && (prod - sink.line()) + rest <= kX2Span && !(lit_rle && rest > kX2ConstRun)) {
             if (lane == 0) {
                 sm.seg[nseg & (kX2Ring - 1)] = kX2Lit | (qpos - (lit_rle ? 0u : lit_pos));
                 atomicOr(&sm.bits[(prod >> 5) & (kX2Bits / 32 - 1)], 1u << (prod & 31));
@@ -548,20 +611,20 @@ __device__ __forceinline__ void x2_frame(const DeviceBatch &a, uint32_t f, X2Sme
             nseg++;
             prod += rest;
             __syncwarp();
-            st = x2_drain_cold(sm, st, prod, lane, le_mask);
+            sink.drain_to(prod);
         } else if (rest) {
-            st = x2_flush_cold(sm, st, prod, lane, le_mask);
+            sink.flush(prod);
             if (lit_rle)
-                warp_memset(st.qb + qpos, lit[0], rest, lane);
+                warp_memset(qb + qpos, lit[0], rest, lane);
             else
-                warp_memcpy(st.qb + qpos, lit + lit_pos, rest, lane);
+                warp_memcpy(qb + qpos, lit + lit_pos, rest, lane);
             __syncwarp();
             prod = qpos + rest;
-            x2_seek(st, prod);
+            sink.seek(prod);
         }
     }
     // On an error the frame's output is void; what the ring still holds is written anyway (it is within the frame's range).
-    st = x2_flush_cold(sm, st, prod, lane, le_mask);
+    sink.finish(prod);
     if (lane == 0 && err != SZB_OK) {  // failed while executing (bad offset, literals ran dry)
         a.frame_status[f] = err;
         a.frame_out_len[f] = 0;
@@ -592,5 +655,49 @@ __global__ void __launch_bounds__(kX2Warps * 32, SZB_EXEC2_MIN_CTAS) k_execute2(
     X2Smem &sm = smem[threadIdx.x >> 5];
     for (uint32_t wd = lane; wd < kX2Bits / 32; wd += 32) sm.bits[wd] = 0;
     __syncwarp();
-    x2_frame<kDict>(a, f, sm, stages[SZB_X2_STAGED ? (threadIdx.x >> 5) : 0], lane);
+    X2Inline sink{sm, X2State{}, lane, 0xFFFFFFFFu >> (31 - lane)};
+    x2_frame_start(a, f, sink.st);
+    x2_frame<kDict>(a, f, sm, stages[SZB_X2_STAGED ? (threadIdx.x >> 5) : 0], sink, lane);
+}
+
+// The frames with the most sequences (exec_list[first_slot, ...): >= 65 536 sequences, those the block-parallel path does not
+// take) finish last and then run almost alone: two warps per frame, one producing segments, one making the lines.  Stage 4 of
+// the mixed corpus is the time ONE such frame takes.  Same producer, same step as k_execute2.
+__global__ void __launch_bounds__(64) k_execute_pair2(DeviceBatch a, uint32_t first_slot, uint32_t n_slots) {
+    __shared__ X2Smem sm;
+    __shared__ X2Stage stage_unused[1];
+    __shared__ X2PairShared sh;
+    const uint32_t lane = threadIdx.x & 31;
+    if (blockIdx.x >= n_slots) return;
+    const uint32_t f = a.exec_list[first_slot + blockIdx.x];
+    if (a.frame_status[f] != SZB_OK) return;                // k_frame_verdict; both warps agree
+    if (long_jump_ok(a, first_slot + blockIdx.x)) return;   // taken by the block-parallel path (execute_long.cuh)
+    if (!(a.pair2 && x2_takes(a, f))) return;               // 2 GiB and more: k_execute_pair's
+    if ((a.frame_nexec ? a.frame_nexec[f] : a.frames[f].nblocks) == 0) return;  // x2_frame would leave before its first command
+    for (uint32_t wd = threadIdx.x; wd < kX2Bits / 32; wd += 64) sm.bits[wd] = 0;
+    __syncthreads();
+    X2State st0;
+    x2_frame_start(a, f, st0);
+    if (threadIdx.x < 32) {
+        X2Pair sink{sh, lane, 0, st0.line};
+        x2_frame<false>(a, f, sm, stage_unused[0], sink, lane);
+    } else {
+        const uint32_t le_mask = 0xFFFFFFFFu >> (31 - lane);
+        X2State st = st0;
+        for (uint32_t it = 0;; it++) {
+            __syncthreads();
+            const uint32_t cmd = sh.cmd[it & 1];
+            const unsigned long long arg = sh.arg[it & 1];
+            if (cmd == kX2cExit) break;
+            if (cmd == kX2cDrain)
+                x2_drain(sm, st, (uint32_t)arg, lane, le_mask);
+            else if (cmd == kX2cFlush)
+                x2_flush(sm, st, (uint32_t)arg, lane, le_mask);
+            else if (cmd == kX2cSeek)
+                x2_seek(st, (uint32_t)arg);
+            else if (cmd == kX2cLit)
+                st.lit = reinterpret_cast<const uint8_t *>((uintptr_t)arg);
+            if (lane == 0) sh.line[it & 1] = st.line;
+        }
+    }
 }

@@ -698,6 +698,7 @@ __global__ void __launch_bounds__(64) k_execute_pair(DeviceBatch a, uint32_t fir
     const uint32_t f = a.exec_list[first_slot + blockIdx.x];
     if (a.frame_status[f] != SZB_OK) return;  // k_frame_verdict; both warps agree
     if (long_jump_ok(a, first_slot + blockIdx.x)) return;  // taken by the block-parallel path (execute_long.cuh)
+    if (a.pair2 && x2_takes(a, f)) return;                 // k_execute_pair2's (exec2.cuh)
     const szb_frame_desc fr = a.frames[f];
     const uint64_t frame_base = fr.nblocks ? a.out_off[fr.first_block] : 0;
     for (uint32_t wd = threadIdx.x; wd < kRingBits / 32; wd += 64) sm.bits[wd] = 0;

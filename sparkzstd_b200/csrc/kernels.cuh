@@ -826,10 +826,9 @@ __device__ __noinline__ void slow_step(const uint32_t *sw, const uint16_t *tll, 
     }
 }
 
-__global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
-    extern __shared__ __align__(16) uint32_t sw[];
-    const uint32_t lane = threadIdx.x;
-    const uint32_t first = blockIdx.x * kSeqLanes;
+// One group of kSeqLanes blocks on one warp.  `use` counts the groups this CTA has decoded: the table load's mbarrier is
+// initialised once per CTA and completes one phase per group.
+__device__ __forceinline__ void seq_decode_group(const DeviceBatch &a, uint32_t *sw, uint32_t first, uint32_t use, uint32_t lane) {
     const uint32_t n_here = a.n_seq - first < (uint32_t)kSeqLanes ? a.n_seq - first : (uint32_t)kSeqLanes;
     uint16_t *tabs = reinterpret_cast<uint16_t *>(sw);
 
@@ -842,8 +841,13 @@ __global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
         const uint8_t *arena = reinterpret_cast<const uint8_t *>(a.seq_tabs + (size_t)first * kTabSlotWords);
         constexpr uint32_t kSlotBytes = kTabSlotWords * 2;
         if (lane == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            if (use == 0) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            } else {
+                // the previous group's cells were read through the generic proxy; the copy engine writes through the async proxy
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n_here * kSlotBytes) : "memory");
         }
         __syncwarp();
@@ -851,13 +855,14 @@ __global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tabs_saddr + lane * kSlotBytes),
                          "l"(arena + (size_t)lane * kSlotBytes), "r"(kSlotBytes), "r"(bar)
                          : "memory");
-        for (uint32_t i = lane; i < 64; i += 32) {
-            sw[kSeqLutWord + i] = kLLBaseDev[i] | ((uint32_t)kLLExtraDev[i] << 24);
-            sw[kSeqLutWord + 64 + i] = kMLBaseDev[i] | ((uint32_t)kMLExtraDev[i] << 24);
-        }
+        if (use == 0)
+            for (uint32_t i = lane; i < 64; i += 32) {
+                sw[kSeqLutWord + i] = kLLBaseDev[i] | ((uint32_t)kLLExtraDev[i] << 24);
+                sw[kSeqLutWord + 64 + i] = kMLBaseDev[i] | ((uint32_t)kMLExtraDev[i] << 24);
+            }
         uint32_t landed = 0;
-        while (!landed)  // phase 0 completes when the expected bytes have arrived (try_wait sleeps in hardware, it does not spin)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(landed) : "r"(bar) : "memory");
+        while (!landed)  // the phase completes when the expected bytes have arrived (try_wait sleeps in hardware, it does not spin)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(landed) : "r"(bar), "r"(use & 1) : "memory");
     }
     __syncwarp();
     if (lane >= n_here) return;
@@ -974,6 +979,19 @@ __global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
     // the stream must be consumed exactly (sequences.go:197-204)
     a.seq_status[b] = L.pos == 0 ? SZB_OK : SZB_ERR_NOT_ALL_BITS_USED;
     a.out_size[b] = (uint64_t)d.lit_regen + ml_sum;
+}
+
+// One group per CTA when the grid covers all groups (the default launch); with a smaller grid (launch_entropy: a cap on the
+// CTAs an SM holds, so that stage 4 of another batch fits beside this kernel) a CTA walks the groups blockIdx.x, + gridDim.x, ...
+__global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
+    extern __shared__ __align__(16) uint32_t sw[];
+    const uint32_t lane = threadIdx.x;
+    const uint32_t ngroups = (a.n_seq + kSeqLanes - 1) / kSeqLanes;
+    uint32_t use = 0;
+    for (uint32_t g = blockIdx.x; g < ngroups; g += gridDim.x, use++) {
+        seq_decode_group(a, sw, g * kSeqLanes, use, lane);
+        __syncwarp();  // every lane is done with the group's cells and rings
+    }
 }
 
 #include "sequences3.cuh"

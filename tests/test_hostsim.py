@@ -220,20 +220,23 @@ def test_place_kernels_report_the_oracles_errors(sim, corpus):
 
 # ---- k_execute2 (exec2.cuh): 32-bit positions and entries, lines of memory, four 32-byte rows per line ----
 K_EXECUTE2 = 5
+K_EXECUTE_PAIR2 = 6
 
 
-def test_execute2_decodes_golden_frames(sim, corpus):
+@pytest.mark.parametrize("x2path", [K_EXECUTE2, K_EXECUTE_PAIR2])
+def test_execute2_decodes_golden_frames(sim, corpus, x2path):
     done = 0
     for k, (name, data, size, sha) in enumerate(corpus):
         if size > 60_000:
             continue
-        rc, out = _stage4_at(sim, data, size, K_EXECUTE2, k % 2, 1, (k * 37) % 128)
+        rc, out = _stage4_at(sim, data, size, x2path, k % 2, 1, (k * 37) % 128)
         assert rc == 0 and len(out) == size and hashlib.sha256(out).hexdigest() == sha, name
         done += 1
     assert done >= 20
 
 
-def test_execute2_on_crafted_and_synthetic_frames(sim):
+@pytest.mark.parametrize("x2path", [K_EXECUTE2, K_EXECUTE_PAIR2])
+def test_execute2_on_crafted_and_synthetic_frames(sim, x2path):
     import sys
 
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -241,10 +244,10 @@ def test_execute2_on_crafted_and_synthetic_frames(sim):
 
     for k, (name, (frame, expected)) in enumerate(sorted(crafted.cases().items())):
         for mis in (0, 1 + (k * 29) % 127):
-            rc, out = _stage4_at(sim, frame, len(expected), K_EXECUTE2, k % 2, 0, mis)
+            rc, out = _stage4_at(sim, frame, len(expected), x2path, k % 2, 0, mis)
             assert rc == 0 and out == expected, (name, mis)
     big, expected = crafted.oversize_block_case()
-    rc, out = _stage4_at(sim, big, len(expected), K_EXECUTE2, 0, 0, 5)
+    rc, out = _stage4_at(sim, big, len(expected), x2path, 0, 0, 5)
     assert rc == 0 and out == expected
     for c in (cg.config2_text_frames(3), cg.config3_single_frame(1 << 19, 20), cg.config5_mixed(1 << 20, with_golden=False)):
         for i in range(min(c.nframes, 4)):
@@ -252,7 +255,7 @@ def test_execute2_on_crafted_and_synthetic_frames(sim):
             want = pyszo.decode_frame(f)
             if len(want) > 600_000:
                 continue
-            rc, out = _stage4_at(sim, f, len(want), K_EXECUTE2, i % 2, 0, (i * 53) % 128)
+            rc, out = _stage4_at(sim, f, len(want), x2path, i % 2, 0, (i * 53) % 128)
             assert rc == 0 and out == want, (c.name, i)
 
 
@@ -277,8 +280,12 @@ def test_execute2_agrees_with_execute_on_corrupted_frames(sim, corpus):
         a = _stage4_at(sim, frame, cap, K_EXECUTE, k % 2, 0, (k * 7) % 128)
         b = _stage4_at(sim, frame, cap, K_EXECUTE2, k % 2, 0, (k * 7) % 128)
         assert a[0] == b[0], (name, k, a[0], b[0])
+        # the two-warp kernels: k_execute_pair2 must end like k_execute_pair
+        p1 = _stage4_at(sim, frame, cap, K_EXECUTE_PAIR, k % 2, 0, (k * 7) % 128)
+        p2 = _stage4_at(sim, frame, cap, K_EXECUTE_PAIR2, k % 2, 0, (k * 7) % 128)
+        assert p1[0] == p2[0] and (p1[0] != 0 or p1[1] == p2[1]), (name, k, p1[0], p2[0])
         if a[0] == 0:
-            assert a[1] == b[1], (name, k)
+            assert a[1] == b[1] == p2[1], (name, k)
             if want is not None:
                 assert b[1] == want, (name, k)
                 ok += 1
