@@ -75,6 +75,19 @@ struct szb_dict {
 };
 
 static cudaError_t pool_alloc(szb_ctx *ctx, void **p, size_t bytes);
+// SZB_SPLIT=1 (experiment): stage 4 on its own stream (see szb_ctx::s_exec); SZB_SEQ_CTAS_PER_SM=n caps k_decode_sequences' grid at
+// n CTAs per SM (a CTA then walks several groups), which leaves shared memory and CTA slots to the stage 4 of another batch.
+static bool szb_overlap() {
+    static const bool on = getenv("SZB_SPLIT") && atoi(getenv("SZB_SPLIT")) != 0;
+    return on;
+}
+static int stream_create(cudaStream_t *s, bool high) {
+    int least = 0, greatest = 0;
+    if (!szb_overlap() || cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess)
+        return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) == cudaSuccess ? 0 : 1;
+    return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, high ? greatest : least) == cudaSuccess ? 0 : 1;
+}
+
 static void pool_free(szb_ctx *ctx, void *p);
 
 #define CUDA_TRY(ctx, expr)                                                                          \
@@ -265,6 +278,17 @@ int szb_ctx_create(int device, void *stream, szb_ctx **out) {
     cudaFuncSetAttribute(k_build_huf_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(HufSmem) * kWarpsPerCta));
     cudaFuncSetAttribute(k_build_seq_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SeqSmem) * kWarpsPerCta));
     cudaFuncSetAttribute(k_decode_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeqDecodeSmemBytes);
+    if (getenv("SZB_X2_CARVEOUT")) {  // experiment: an SM only changes its L1 / shared-memory split when it is idle, so kernels that are to
+                                      // run beside k_decode_sequences (222 KB of shared memory) must ask for the same split
+        const int pct = atoi(getenv("SZB_X2_CARVEOUT"));
+        cudaFuncSetAttribute(k_execute2<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_execute, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_execute_bodies, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_frame_verdict, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_scan_blocks, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_build_seq_tables, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_build_huf_tables, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
     cudaFuncSetAttribute(k_decode_literals, cudaFuncAttributePreferredSharedMemoryCarveout, 100);  // streams arrive by cp.async: L1 is not needed, resident warps are
     *out = ctx;
     return SZB_OK;
@@ -364,6 +388,28 @@ static int batch_upload_tables(szb_batch *b) {
                 b->hufo_list.push_back(i);
             }
         }
+        // k_decode_literals runs eight blocks (one lane per stream) per warp for as long as the longest stream takes: blocks
+        // that share a tree stay neighbours (they share one copy of the table), such families ordered by their longest stream,
+        // longest first (what scripts/lit_group_model.py measures on the mixed corpus: 33 % -> 43 % of the lanes busy)
+        auto stream_len = [&](uint32_t i) {
+            const szb_block_desc &d = b->blocks[i];
+            return d.lit_streams == 1 ? d.lit_regen : (d.lit_regen + 3) / 4;
+        };
+        std::vector<uint32_t> fam_len(b->hufo_list.size() + 1, 0);
+        auto fam_of = [&](uint32_t i) {
+            const uint32_t o = b->blocks[i].huf_origin;
+            const uint32_t sl = o < nb ? slot_of_block[o] : SZB_NONE;
+            return sl == SZB_NONE ? (uint32_t)b->hufo_list.size() : sl;
+        };
+        for (uint32_t i : b->huf_list) fam_len[fam_of(i)] = std::max(fam_len[fam_of(i)], stream_len(i));
+        static const bool lit_sort = !(getenv("SZB_LIT_SORT") && atoi(getenv("SZB_LIT_SORT")) == 0);
+        if (lit_sort)
+            std::stable_sort(b->huf_list.begin(), b->huf_list.end(), [&](uint32_t x, uint32_t y) {
+                const uint32_t fx = fam_of(x), fy = fam_of(y);
+                if (fam_len[fx] != fam_len[fy]) return fam_len[fx] > fam_len[fy];
+                if (fx != fy) return fx < fy;
+                return stream_len(x) > stream_len(y);
+            });
         for (uint32_t i : b->huf_list) b->huf_slot.push_back(slot_of_block[b->blocks[i].huf_origin]);
     }
     // k_decode_sequences runs kSeqLanes blocks per warp in lock step: neighbours should have similar
@@ -765,19 +811,6 @@ static DeviceBatch make_args(szb_batch *b, const void *d_src, void *d_dst, size_
     for (int k = 0; k < 3; k++) a.dict_rep[k] = b->dict ? b->dict->rep[k] : (k == 0 ? 1u : (k == 1 ? 4u : 8u));
     a.frame_dict = b->dict ? b->d_frame_dict : nullptr;
     return a;
-}
-
-// SZB_SPLIT=1 (experiment): stage 4 on its own stream (see szb_ctx::s_exec); SZB_SEQ_CTAS_PER_SM=n caps k_decode_sequences' grid at
-// n CTAs per SM (a CTA then walks several groups), which leaves shared memory and CTA slots to the stage 4 of another batch.
-static bool szb_overlap() {
-    static const bool on = getenv("SZB_SPLIT") && atoi(getenv("SZB_SPLIT")) != 0;
-    return on;
-}
-static int stream_create(cudaStream_t *s, bool high) {
-    int least = 0, greatest = 0;
-    if (!szb_overlap() || cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess)
-        return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) == cudaSuccess ? 0 : 1;
-    return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, high ? greatest : least) == cudaSuccess ? 0 : 1;
 }
 
 static int launch_entropy(szb_batch *b, const void *d_src) {
