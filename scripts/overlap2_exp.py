@@ -1,4 +1,5 @@
-"""Experiment: stage 4 of sub-batch k beside the entropy stages of sub-batch k+1 inside ONE context (SZB_SPLIT=1: stage 4 on a
+"""[historical: needs the SZB_SPLIT switch of commits f886271..f25ccb1; results in profiles/r03b-d_*]
+Experiment: stage 4 of sub-batch k beside the entropy stages of sub-batch k+1 inside ONE context (SZB_SPLIT=1: stage 4 on a
 low-priority stream of its own; SZB_SEQ_CTAS_PER_SM=n: k_decode_sequences capped at n CTAs per SM, so that stage 4's CTAs fit
 beside it).  usage: overlap2_exp.py FRAMES_PER_SUBBATCH [FIRST_SUBBATCH_FRAMES]"""
 import os, sys, time

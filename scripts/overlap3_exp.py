@@ -1,4 +1,5 @@
-"""Diagnostic: do the entropy stages of batch B run BESIDE stage 4 of batch A (SZB_SPLIT=1)?  Times entropy(B) alone, execute(A) alone
+"""[historical: needs the SZB_SPLIT switch of commits f886271..f25ccb1; results in profiles/r03b-d_*]
+Diagnostic: do the entropy stages of batch B run BESIDE stage 4 of batch A (SZB_SPLIT=1)?  Times entropy(B) alone, execute(A) alone
 and both launched together."""
 import os, sys, time
 sys.path.insert(0, '.')

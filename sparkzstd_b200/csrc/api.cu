@@ -45,10 +45,6 @@ struct szb_ctx {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaStream_t s_lit = nullptr;          // the literal chain runs beside the sequence chain (they meet at stage 4)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    // overlap mode (szb_overlap): stage 4 runs on its own low-priority stream behind the entropy stages of the same batch, so that
-    // the entropy stages of the NEXT batch (high priority, a capped number of CTAs per SM) run beside it
-    cudaStream_t s_exec = nullptr;
-    cudaEvent_t ev_ent = nullptr, ev_exec = nullptr;
     // Pinned staging for callers whose buffers are pageable (a Go slice, a Python bytes object): the copy engines only run
     // asynchronously from / to page-locked memory.  Two rings of kPinBytes slots, allocated on first use.
     static constexpr int kPinIn = 2, kPinOut = 3;
@@ -75,21 +71,6 @@ struct szb_dict {
 };
 
 static cudaError_t pool_alloc(szb_ctx *ctx, void **p, size_t bytes);
-// SZB_SPLIT=1 (experiment): stage 4 on its own stream (see szb_ctx::s_exec); SZB_SEQ_CTAS_PER_SM=n caps k_decode_sequences' grid at
-// n CTAs per SM (a CTA then walks several groups), which leaves shared memory and CTA slots to the stage 4 of another batch.
-static bool szb_overlap() {
-    static const bool on = getenv("SZB_SPLIT") && atoi(getenv("SZB_SPLIT")) != 0;
-    return on;
-}
-static int stream_create(cudaStream_t *s, bool high) {
-    int least = 0, greatest = 0;
-    if (!szb_overlap() || cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess)
-        return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) == cudaSuccess ? 0 : 1;
-    return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, high ? greatest : least) == cudaSuccess ? 0 : 1;
-}
-
-static void pool_free(szb_ctx *ctx, void *p);
-
 #define CUDA_TRY(ctx, expr)                                                                          \
     do {                                                                                             \
         cudaError_t e__ = (expr);                                                                    \
@@ -230,7 +211,7 @@ int szb_ctx_create(int device, void *stream, szb_ctx **out) {
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
     } else {
-        if (stream_create(&ctx->stream, true)) {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
             delete ctx;
             return SZB_ERR_CUDA;
         }
@@ -278,17 +259,6 @@ int szb_ctx_create(int device, void *stream, szb_ctx **out) {
     cudaFuncSetAttribute(k_build_huf_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(HufSmem) * kWarpsPerCta));
     cudaFuncSetAttribute(k_build_seq_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SeqSmem) * kWarpsPerCta));
     cudaFuncSetAttribute(k_decode_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeqDecodeSmemBytes);
-    if (getenv("SZB_X2_CARVEOUT")) {  // experiment: an SM only changes its L1 / shared-memory split when it is idle, so kernels that are to
-                                      // run beside k_decode_sequences (222 KB of shared memory) must ask for the same split
-        const int pct = atoi(getenv("SZB_X2_CARVEOUT"));
-        cudaFuncSetAttribute(k_execute2<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(k_execute, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(k_execute_bodies, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(k_frame_verdict, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(k_scan_blocks, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(k_build_seq_tables, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(k_build_huf_tables, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    }
     cudaFuncSetAttribute(k_decode_literals, cudaFuncAttributePreferredSharedMemoryCarveout, 100);  // streams arrive by cp.async: L1 is not needed, resident warps are
     *out = ctx;
     return SZB_OK;
@@ -307,12 +277,6 @@ void szb_ctx_destroy(szb_ctx *ctx) {
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     if (ctx->s_lit) cudaStreamDestroy(ctx->s_lit);
-    if (ctx->s_exec) {
-        cudaStreamSynchronize(ctx->s_exec);
-        cudaStreamDestroy(ctx->s_exec);
-    }
-    if (ctx->ev_ent) cudaEventDestroy(ctx->ev_ent);
-    if (ctx->ev_exec) cudaEventDestroy(ctx->ev_exec);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     for (int i = 0; i < szb_ctx::kPinIn; i++) {
@@ -819,7 +783,7 @@ static int launch_entropy(szb_batch *b, const void *d_src) {
     cudaStream_t s = ctx->stream;
     DeviceBatch a = make_args(b, d_src, nullptr, 0);
     if (!ctx->s_lit) {
-        if (stream_create(&ctx->s_lit, true)) return SZB_ERR_CUDA;
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_lit, cudaStreamNonBlocking));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     }
@@ -845,6 +809,7 @@ static int launch_entropy(szb_batch *b, const void *d_src) {
             k_decode_sequences3<<<(a.n_seq + kSeq3Chains - 1) / kSeq3Chains, 32, kSeq3SmemBytes, s>>>(a);
         else
         {
+            // SZB_SEQ_CTAS_PER_SM=n (experiments, tests): at most n CTAs per SM; a CTA then walks several groups
             static const int cap = getenv("SZB_SEQ_CTAS_PER_SM") ? atoi(getenv("SZB_SEQ_CTAS_PER_SM")) : 0;
             uint32_t grid = (a.n_seq + kSeqLanes - 1) / kSeqLanes;
             if (cap > 0 && grid > (uint32_t)(cap * ctx->sm_count)) grid = (uint32_t)(cap * ctx->sm_count);
@@ -878,16 +843,6 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
     szb_ctx *ctx = b->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    if (szb_overlap()) {
-        if (!ctx->s_exec) {
-            if (stream_create(&ctx->s_exec, false)) return SZB_ERR_CUDA;
-            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_ent, cudaEventDisableTiming));
-            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_exec, cudaEventDisableTiming));
-        }
-        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_ent, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_exec, ctx->ev_ent, 0));
-        s = ctx->s_exec;
-    }
     DeviceBatch a = make_args(b, d_src, d_dst, dst_cap);
     if (a.nframes && a.rec) {  // place.cuh: every frame k_place will execute, walked in order by one lane
         k_place_zero<<<ctx->sm_count * 8, 256, 0, s>>>(a);
@@ -996,7 +951,6 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
         if (n_long) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
-    if (s != ctx->stream) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_exec, s));
     CUDA_TRY(ctx, cudaGetLastError());
     return SZB_OK;
 }
@@ -1081,7 +1035,6 @@ int szb_batch_finish(szb_batch *b, int32_t *status) {
     szb_ctx *ctx = b->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     std::vector<int32_t> st(b->nframes ? b->nframes : 1, 0);
-    if (ctx->s_exec) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_exec));
     if (b->nframes)
         CUDA_TRY(ctx, cudaMemcpyAsync(st.data(), b->d_frame_status, 4 * (size_t)b->nframes, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

@@ -586,3 +586,40 @@ def test_long_frame_paths_on_every_frame(corpus, tmp_path, mode):
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300,
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert res.returncode == 0 and "long ok" in res.stdout, res.stdout + res.stderr
+
+
+def test_sequence_kernel_walks_several_groups_per_cta():
+    """k_decode_sequences with a capped grid (SZB_SEQ_CTAS_PER_SM=1: 148 CTAs, each walking the groups blockIdx.x, + gridDim.x, ...
+    through one mbarrier whose phase flips per group): same bytes as the oracle / the generator's hashes.  In a subprocess: the
+    switch is read once per process."""
+    import os
+    import subprocess
+    import sys
+    import textwrap
+
+    code = textwrap.dedent(
+        """
+        import hashlib, sys
+        import numpy as np
+        from tools import corpus as cg
+        from oracle import pyszo
+        from sparkzstd_b200.decompression import Context
+        ctx = Context(0)
+        gold = cg.golden_frames()
+        outs = ctx.decode_batch([d for _, d, _, _ in gold])
+        assert all(hashlib.sha256(o).hexdigest() == sha for o, (_, _, _, sha) in zip(outs, gold))
+        t = cg.config2_text_frames(7000)   # 334 groups of 21 blocks on 148 CTAs: two to three groups per CTA
+        for _ in range(2):
+            outs = ctx.decode_batch([t.frame(i) for i in range(t.nframes)])
+            assert all(cg.hash_bytes(np.frombuffer(o, dtype="uint8")) == int(t.raw_hash[i]) for i, o in enumerate(outs))
+        c = cg.config5_mixed(24 << 20)
+        frames = [c.frame(i) for i in range(c.nframes)]
+        outs = ctx.decode_batch(frames)
+        assert all(o == pyszo.decode_frame(f) for f, o in zip(frames, outs))
+        print("capped ok", ctx.launch_count())
+        """
+    )
+    env = dict(os.environ, SZB_SEQ_CTAS_PER_SM="1")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert res.returncode == 0 and "capped ok" in res.stdout, res.stdout + res.stderr
