@@ -20,6 +20,10 @@ VARIANTS = {
     # more than 32 warps per SM need CTAs of two warps (32 CTAs per SM is the limit) and fewer registers per thread
     "x2w2c24": ("SZB_EXEC2_WARPS=2", "SZB_EXEC2_MIN_CTAS=24"),   # 48 warps per SM, 42 registers
     "x2w2c20": ("SZB_EXEC2_WARPS=2", "SZB_EXEC2_MIN_CTAS=20"),   # 40 warps per SM, 51 registers
+    # k_execute_team (exec2.cuh): consumer warps per long frame (default 2); 11 CTAs per SM hold the mixed corpus' 1 630 long frames
+    "team4": ("SZB_X2_TEAM=4", "SZB_TEAM_MIN_CTAS=11"),   # 160 threads x 11 CTAs: 37 registers
+    "team4c8": ("SZB_X2_TEAM=4", "SZB_TEAM_MIN_CTAS=8"),  # 51 registers, 1 184 frames resident
+    "team1": ("SZB_X2_TEAM=1",),
 }
 
 if __name__ == "__main__":

@@ -767,9 +767,10 @@ static DeviceBatch make_args(szb_batch *b, const void *d_src, void *d_dst, size_
     a.place_state = a.rec ? b->d_place_state : nullptr;
     a.n_noplace = b->n_noplace;
     a.exec2 = b->exec2 ? 1u : 0u;
-    // SZB_PAIR2=0: the long frames that do not take the block-parallel path stay on k_execute_pair (round 1's producer / consumer)
-    static const bool pair2 = !(getenv("SZB_PAIR2") && atoi(getenv("SZB_PAIR2")) == 0);
-    a.pair2 = b->exec2 && !b->dict && pair2 ? 1u : 0u;
+    // The long frames that do not take the block-parallel path: SZB_PAIR2=1 (default) k_execute_pair2 (producer + one consumer
+    // warp), 2 k_execute_team (producer + a team of consumer warps: measured slower, profiles/r03g_*), 0 k_execute_pair (round 1's)
+    static const uint32_t pair2 = getenv("SZB_PAIR2") ? (uint32_t)atoi(getenv("SZB_PAIR2")) : 1u;
+    a.pair2 = b->exec2 && !b->dict ? (pair2 > 2 ? 2u : pair2) : 0u;
     a.dict_content = b->dict ? b->dict->d_content : nullptr;
     a.dict_len = b->dict ? b->dict->content_len : 0;
     for (int k = 0; k < 3; k++) a.dict_rep[k] = b->dict ? b->dict->rep[k] : (k == 0 ? 1u : (k == 1 ? 4u : 8u));
@@ -898,7 +899,10 @@ static int launch_execute(szb_batch *b, const void *d_src, void *d_dst, size_t d
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, s));
             CUDA_TRY(ctx, cudaStreamWaitEvent(sl, ctx->ev_fork, 0));
             // the frames the block-parallel path does not take: k_execute_pair2, and k_execute_pair for those of 2 GiB and more
-            if (a.pair2) {
+            if (a.pair2 == 2) {
+                k_execute_team<<<n_long, (kX2Team + 1) * 32, 0, sl>>>(a, 0, n_long);
+                ctx->launches++;
+            } else if (a.pair2) {
                 k_execute_pair2<<<n_long, 64, 0, sl>>>(a, 0, n_long);
                 ctx->launches++;
             }

@@ -92,7 +92,7 @@ struct DeviceBatch {
     uint32_t dict_rep[3];           // 1, 4, 8 for a raw-content dictionary
     const uint8_t *frame_dict;      // per frame: non-zero = decoded with the dictionary
     uint32_t exec2;                 // non-zero: k_execute2 (exec2.cuh) executes the frames one warp executes; 0: k_execute
-    uint32_t pair2;                 // non-zero: k_execute_pair2 (exec2.cuh) takes the long frames k_execute2 could take; 0: k_execute_pair
+    uint32_t pair2;                 // the long frames k_execute2 could take: 1 = k_execute_pair2, 2 = k_execute_team (exec2.cuh); 0: k_execute_pair
     // frames one warp executes (place.cuh): k_resolve -> k_place; nullptr: k_execute takes them all
     uint32_t *rec;                  // per block with sequences, at rec_off[block]: one entry per segment (literal run or match) in
                                     // output order: a match's offset (through the repeat history), or bit 31 | the match bytes

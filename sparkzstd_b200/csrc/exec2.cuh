@@ -672,7 +672,7 @@ __global__ void __launch_bounds__(64) k_execute_pair2(DeviceBatch a, uint32_t fi
     const uint32_t f = a.exec_list[first_slot + blockIdx.x];
     if (a.frame_status[f] != SZB_OK) return;                // k_frame_verdict; both warps agree
     if (long_jump_ok(a, first_slot + blockIdx.x)) return;   // taken by the block-parallel path (execute_long.cuh)
-    if (!(a.pair2 && x2_takes(a, f))) return;               // 2 GiB and more: k_execute_pair's
+    if (!(a.pair2 == 1 && x2_takes(a, f))) return;          // 2 GiB and more: k_execute_pair's; pair2 == 2: k_execute_team's
     if ((a.frame_nexec ? a.frame_nexec[f] : a.frames[f].nblocks) == 0) return;  // x2_frame would leave before its first command
     for (uint32_t wd = threadIdx.x; wd < kX2Bits / 32; wd += 64) sm.bits[wd] = 0;
     __syncthreads();
@@ -698,6 +698,204 @@ __global__ void __launch_bounds__(64) k_execute_pair2(DeviceBatch a, uint32_t fi
             else if (cmd == kX2cLit)
                 st.lit = reinterpret_cast<const uint8_t *>((uintptr_t)arg);
             if (lane == 0) sh.line[it & 1] = st.line;
+        }
+    }
+}
+
+// ---- k_execute_team: the consumer on several warps -------------------------------------------------------------------------
+// A long frame waits for ONE in-order instruction stream: its consumer (k_execute_pair2: ~190 instructions per 128-byte line on a
+// warp that runs almost alone, ~9 cycles each).  Here kTeam consumer warps make every line together, each the 32-byte chunks
+// w, w + kTeam, ... of it: the gather of a line is 4 / kTeam loads deep instead of four.  Bytes that repeat bytes of the same step
+// are exchanged through shared memory: every warp publishes the bytes it has, the others take them from there, chains of
+// in-line sources by pointer jumping over the published source positions.  The warps meet at a named barrier (bar.sync 1):
+// once per line for the vote "does any byte repeat a byte of this step", twice per exchange round, once after the stores (the
+// next line's loads may want them).  The producer (warp 0, x2_frame<X2Pair>) is not part of those; it hands its commands over
+// at __syncthreads like k_execute_pair2's.
+// MEASURED SLOWER (profiles/r03g_*, SZB_PAIR2=2; off by default): stage 4 of the mixed corpus 18.7 ms with two consumer warps,
+// 25.1 ms with four, 20.6 ms with one, against k_execute_pair2's 14.4 ms; one 64 MiB frame 272 ms against 244 ms.  A line's time
+// is not the gather's instruction count: it is one dependent trip bitmap -> entry -> source byte -> store per line, which the
+// team pays just the same, plus its barriers (the one-warp team, the same work as k_execute_pair2 with the exchange through
+// shared memory instead of shuffles, is 43 % slower).
+#ifndef SZB_X2_TEAM
+#define SZB_X2_TEAM 2
+#endif
+constexpr uint32_t kX2Team = SZB_X2_TEAM;          // consumer warps per frame: 1, 2 or 4
+constexpr uint32_t kX2TeamCpw = 4 / kX2Team;       // 32-byte chunks of a line per consumer warp
+static_assert(kX2Team == 1 || kX2Team == 2 || kX2Team == 4, "a line has four chunks");
+
+#if defined(SZB_WARPSIM)
+#define SZB_TEAM_SYNC() __named_barrier(1, kX2Team * 32)
+#else
+#define SZB_TEAM_SYNC() asm volatile("bar.sync 1, %0;" ::"n"(kX2Team * 32) : "memory")
+#endif
+
+struct X2TeamShared {
+    __align__(16) uint8_t lineb[128];  // the line's bytes as far as they are known
+    uint8_t srcpos[128];               // per byte that is not known yet: the place in the line of a byte with the same value
+    uint32_t have[4];                  // per chunk: lanes whose byte is in lineb
+    uint32_t vote[2][4];               // the team's votes (two in flight: a warp may be one vote ahead of another's read)
+};
+
+// true when `p` holds on any thread of the team; every warp of the team calls it the same number of times
+__device__ __forceinline__ bool x2t_any(X2TeamShared &T, uint32_t &phase, uint32_t w, uint32_t lane, bool p) {
+    const uint32_t b = __ballot_sync(kFull, p);
+    if (lane == 0) T.vote[phase][w] = b;
+    SZB_TEAM_SYNC();
+    uint32_t r = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kX2Team; k++) r |= T.vote[phase][k];
+    phase ^= 1;
+    return r != 0;
+}
+
+// The bytes [lo, hi) of the line at st.line, my chunks of it (x2_step for a team).
+template <bool kWhole>
+__device__ __forceinline__ void x2t_step(X2Smem &sm, X2TeamShared &T, X2State &st, uint32_t &phase, uint32_t lo, uint32_t hi, uint32_t w,
+                                         uint32_t lane, uint32_t le_mask) {
+    uint32_t *bw = &sm.bits[(st.line >> 5) & (kX2Bits / 32 - 1)];
+    const uint4 m4 = *reinterpret_cast<const uint4 *>(bw);
+    const uint32_t m[4] = {m4.x, m4.y, m4.z, m4.w};
+    const uint32_t cnt[4] = {(uint32_t)__popc(m[0]), (uint32_t)__popc(m[1]), (uint32_t)__popc(m[2]), (uint32_t)__popc(m[3])};
+    uint32_t v[kX2TeamCpw], so[kX2TeamCpw];
+    bool ing[kX2TeamCpw], live[kX2TeamCpw];
+    bool any_ing = false;
+#pragma unroll
+    for (uint32_t k = 0; k < kX2TeamCpw; k++) {
+        const uint32_t c = w + k * kX2Team;  // my k-th chunk of the line
+        const uint32_t rel = (c << 5) + lane;
+        uint32_t before = 0;  // segments that start in the chunks in front of this one
+#pragma unroll
+        for (uint32_t j = 0; j < 3; j++) before += j < c ? cnt[j] : 0u;
+        const uint32_t mc = c == 0 ? m[0] : (c == 1 ? m[1] : (c == 2 ? m[2] : m[3]));  // (no indexed register arrays)
+        const uint32_t ord = st.seen - 1 + before + __popc(mc & le_mask);  // the last segment that starts at or before my byte
+        const uint32_t e = sm.seg[ord & (kX2Ring - 1)];
+        live[k] = kWhole || (rel >= lo && rel < hi);
+        const uint32_t idx = st.line + rel - (e & ~kX2Lit);
+        ing[k] = live[k] && e <= rel - lo;  // a match whose source is a byte of this step: not in memory yet
+        so[k] = rel - e;
+        v[k] = 0;
+        if (live[k] && !ing[k]) v[k] = ((int32_t)e < 0 ? st.lit : st.qb)[idx];
+        any_ing |= ing[k];
+    }
+    st.seen += cnt[0] + cnt[1] + cnt[2] + cnt[3];
+    if (x2t_any(T, phase, w, lane, any_ing)) {
+        // publish what is known; a source position is >= lo and below its reader, i.e. a live byte of this step
+#pragma unroll
+        for (uint32_t k = 0; k < kX2TeamCpw; k++) {
+            const uint32_t c = w + k * kX2Team;
+            const uint32_t rel = (c << 5) + lane;
+            T.lineb[rel] = (uint8_t)v[k];
+            T.srcpos[rel] = (uint8_t)so[k];
+            const uint32_t known = __ballot_sync(kFull, !ing[k]);
+            if (lane == 0) T.have[c] = known;
+        }
+        SZB_TEAM_SYNC();
+        for (;;) {
+            // read: a known source gives its value; an unknown one gives ITS source (the same value, further down)
+            bool got[kX2TeamCpw];
+            bool open = false;
+#pragma unroll
+            for (uint32_t k = 0; k < kX2TeamCpw; k++) {
+                got[k] = false;
+                if (ing[k]) {
+                    if ((T.have[so[k] >> 5] >> (so[k] & 31)) & 1) {
+                        v[k] = T.lineb[so[k]];
+                        ing[k] = false;
+                        got[k] = true;
+                    } else {
+                        so[k] = T.srcpos[so[k]];
+                    }
+                }
+                open |= ing[k];
+            }
+            const bool more = x2t_any(T, phase, w, lane, open);  // its barrier: every read of the round is done
+#pragma unroll
+            for (uint32_t k = 0; k < kX2TeamCpw; k++) {
+                const uint32_t c = w + k * kX2Team;
+                const uint32_t rel = (c << 5) + lane;
+                if (got[k]) T.lineb[rel] = (uint8_t)v[k];
+                if (ing[k]) T.srcpos[rel] = (uint8_t)so[k];
+                const uint32_t newly = __ballot_sync(kFull, got[k]);
+                if (lane == 0 && newly) T.have[c] |= newly;
+            }
+            if (!more) break;
+            SZB_TEAM_SYNC();  // the round's writes are in place
+        }
+    }
+    uint8_t *out = st.qb + st.line + lane;
+#pragma unroll
+    for (uint32_t k = 0; k < kX2TeamCpw; k++)
+        if (live[k]) out[(w + k * kX2Team) << 5] = (uint8_t)v[k];
+    if (w == 0 && lane < 4) bw[lane] = 0;  // every warp read the words before the vote's barrier; the bitmap is a ring
+    SZB_TEAM_SYNC();  // the stores: the next step's loads (another warp's) may want these bytes
+}
+
+__device__ __forceinline__ void x2t_drain(X2Smem &sm, X2TeamShared &T, X2State &st, uint32_t &phase, uint32_t limit, uint32_t w, uint32_t lane,
+                                          uint32_t le_mask) {
+    uint32_t n = (limit - st.line) >> 7;
+    if (n == 0) return;
+    if (st.head) {  // the rest of a line that was flushed in part
+        x2t_step<false>(sm, T, st, phase, st.head, 128, w, lane, le_mask);
+        st.line += 128;
+        st.head = 0;
+        n--;
+    }
+    for (; n; n--) {
+        x2t_step<true>(sm, T, st, phase, 0, 128, w, lane, le_mask);
+        st.line += 128;
+    }
+}
+__device__ __forceinline__ void x2t_flush(X2Smem &sm, X2TeamShared &T, X2State &st, uint32_t &phase, uint32_t prod, uint32_t w, uint32_t lane,
+                                          uint32_t le_mask) {
+    x2t_drain(sm, T, st, phase, prod, w, lane, le_mask);
+    const uint32_t hi = prod - st.line;  // < 128
+    if (hi > st.head) {
+        x2t_step<false>(sm, T, st, phase, st.head, hi, w, lane, le_mask);
+        st.head = hi;
+    }
+}
+
+#ifndef SZB_TEAM_MIN_CTAS
+#define SZB_TEAM_MIN_CTAS 11
+#endif
+__global__ void __launch_bounds__((kX2Team + 1) * 32, SZB_TEAM_MIN_CTAS) k_execute_team(DeviceBatch a, uint32_t first_slot, uint32_t n_slots) {
+    __shared__ X2Smem sm;
+    __shared__ X2Stage stage_unused[1];
+    __shared__ X2PairShared sh;
+    __shared__ X2TeamShared T;
+    const uint32_t lane = threadIdx.x & 31;
+    if (blockIdx.x >= n_slots) return;
+    const uint32_t f = a.exec_list[first_slot + blockIdx.x];
+    if (a.frame_status[f] != SZB_OK) return;                // k_frame_verdict; every warp agrees
+    if (long_jump_ok(a, first_slot + blockIdx.x)) return;   // taken by the block-parallel path (execute_long.cuh)
+    if (!(a.pair2 == 2 && x2_takes(a, f))) return;          // 2 GiB and more: k_execute_pair's
+    if ((a.frame_nexec ? a.frame_nexec[f] : a.frames[f].nblocks) == 0) return;  // x2_frame would leave before its first command
+    for (uint32_t wd = threadIdx.x; wd < kX2Bits / 32; wd += (kX2Team + 1) * 32) sm.bits[wd] = 0;
+    __syncthreads();
+    X2State st0;
+    x2_frame_start(a, f, st0);
+    if (threadIdx.x < 32) {
+        X2Pair sink{sh, lane, 0, st0.line};
+        x2_frame<false>(a, f, sm, stage_unused[0], sink, lane);
+    } else {
+        const uint32_t w = (threadIdx.x >> 5) - 1;  // my place in the team
+        const uint32_t le_mask = 0xFFFFFFFFu >> (31 - lane);
+        X2State st = st0;  // every warp of the team keeps the same state
+        uint32_t phase = 0;
+        for (uint32_t it = 0;; it++) {
+            __syncthreads();
+            const uint32_t cmd = sh.cmd[it & 1];
+            const unsigned long long arg = sh.arg[it & 1];
+            if (cmd == kX2cExit) break;
+            if (cmd == kX2cDrain)
+                x2t_drain(sm, T, st, phase, (uint32_t)arg, w, lane, le_mask);
+            else if (cmd == kX2cFlush)
+                x2t_flush(sm, T, st, phase, (uint32_t)arg, w, lane, le_mask);
+            else if (cmd == kX2cSeek)
+                x2_seek(st, (uint32_t)arg);
+            else if (cmd == kX2cLit)
+                st.lit = reinterpret_cast<const uint8_t *>((uintptr_t)arg);
+            if (w == 0 && lane == 0) sh.line[it & 1] = st.line;
         }
     }
 }

@@ -258,6 +258,7 @@ int hostsim_decode_frame(const uint8_t *src, size_t len, uint8_t *out, size_t ca
 //   5: k_execute2 (exec2.cuh), with k_execute launched behind it as launch_execute does.
 //      (lines are aligned to memory, not to the output: callers also pass an `out` that is not 128-byte aligned)
 //   6: k_execute_pair2 (exec2.cuh: k_execute2's producer in one warp, its consumer in a second), with k_execute_pair behind it.
+//   7: k_execute_team (exec2.cuh: the consumer on kX2Team warps that meet at a named barrier), with k_execute_pair behind it.
 // order: 0 = CTAs in launch order, 1 = reversed (the worst case for k_long_jump), >= 2 = shuffled with that seed.
 // With two_frames the same frame is decoded twice in one batch and both copies must agree.
 // verify_checksum: 1 = also run k_verify_checksums; 2 = then flip an output byte and expect the mismatch (returns 3; 2 when the
@@ -384,8 +385,8 @@ int hostsim_stage4_at(const uint8_t *src, size_t len, uint8_t *out, size_t cap, 
     a.body_list = body_list.data();
     a.n_body = (uint32_t)body_list.size();
     a.n_long = (path == 0 || path == 5) ? 0 : copies;
-    a.exec2 = path == 5 || path == 6 ? 1 : 0;
-    a.pair2 = path == 6 ? 1 : 0;
+    a.exec2 = path == 5 || path == 6 || path == 7 ? 1 : 0;
+    a.pair2 = path == 6 ? 1 : (path == 7 ? 2 : 0);
     a.n_lb = n_lb;
     a.lb_block = lb_block.data();
     a.lb_slot = lb_slot.data();
@@ -462,6 +463,9 @@ int hostsim_stage4_at(const uint8_t *src, size_t len, uint8_t *out, size_t cap, 
     } else if (path == 5) {  // k_execute2 (exec2.cuh), with k_execute launched behind it for the frames it does not take
         warpsim::launch((copies + kX2Warps - 1) / kX2Warps, kX2Warps * 32, [&] { k_execute2<false>(a, 0, copies); });
         warpsim::launch((copies + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, [&] { k_execute(a, 0, copies); });
+    } else if (path == 7) {
+        warpsim::launch(copies, (kX2Team + 1) * 32, [&] { k_execute_team(a, 0, copies); });
+        warpsim::launch(copies, 64, [&] { k_execute_pair(a, 0, copies); });
     } else if (path == 6) {
         warpsim::launch(copies, 64, [&] { k_execute_pair2(a, 0, copies); });
         warpsim::launch(copies, 64, [&] { k_execute_pair(a, 0, copies); });

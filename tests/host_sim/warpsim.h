@@ -43,7 +43,7 @@ struct Dim3 {
 };
 inline Dim3 threadIdx, blockIdx, blockDim, gridDim;
 
-enum Op { OP_NONE, OP_SHFL, OP_SHFL_UP, OP_BALLOT, OP_REDUCE_MAX, OP_CTA_BARRIER };
+enum Op { OP_NONE, OP_SHFL, OP_SHFL_UP, OP_BALLOT, OP_REDUCE_MAX, OP_CTA_BARRIER, OP_NAMED_BARRIER };
 constexpr int kMaxThreads = 1024;
 struct Thread {
     ucontext_t ctx;
@@ -89,7 +89,7 @@ inline bool resolve_warp(int w) {
         if (op == OP_NONE) op = l[i].op;
         if (l[i].op != op || op == OP_NONE) die("lanes of a warp diverged at a full-mask collective");
     }
-    if (op == OP_NONE || op == OP_CTA_BARRIER) return false;
+    if (op == OP_NONE || op == OP_CTA_BARRIER || op == OP_NAMED_BARRIER) return false;
     collectives++;
     if (op == OP_BALLOT) {
         uint32_t m = 0;
@@ -141,11 +141,33 @@ inline void run_cta(unsigned nthreads) {
                 runnable[w] = resolve_warp(w);
             }
         }
-        // every warp is done or waits at the barrier
+        // every warp is done or waits at a barrier.  A named barrier (bar.sync id, nthreads: arg = id << 16 | nthreads) opens
+        // when that many threads wait at it; the warps at the CTA barrier stay where they are.
+        {
+            bool opened = false;
+            for (int w = 0; w < nwarps && !opened; w++) {
+                const Thread &t0 = threads[32 * w];
+                if (t0.done || t0.op != OP_NAMED_BARRIER) continue;
+                unsigned waiting = 0;
+                for (unsigned i = 0; i < nthreads; i++)
+                    if (!threads[i].done && threads[i].op == OP_NAMED_BARRIER && threads[i].arg == t0.arg) waiting++;
+                if (waiting > (t0.arg & 0xFFFF)) die("more threads at a named barrier than it was declared for");
+                if (waiting == (t0.arg & 0xFFFF)) {
+                    for (int v = 0; v < nwarps; v++)
+                        if (!threads[32 * v].done && threads[32 * v].op == OP_NAMED_BARRIER && threads[32 * v].arg == t0.arg) runnable[v] = 1;
+                    opened = true;
+                }
+            }
+            if (opened) {
+                collectives++;
+                continue;
+            }
+        }
         bool any_live = false;
         for (unsigned i = 0; i < nthreads; i++) {
             if (threads[i].done) continue;
             any_live = true;
+            if (threads[i].op == OP_NAMED_BARRIER) die("deadlock at a named barrier");
             if (threads[i].op != OP_CTA_BARRIER) die("a thread waits at a warp collective its warp cannot complete");
         }
         if (!any_live) return;
@@ -191,6 +213,8 @@ inline bool __any_sync(uint32_t, bool p) { return warpsim::collective(warpsim::O
 inline uint32_t __reduce_max_sync(uint32_t, uint32_t v) { return (uint32_t)warpsim::collective(warpsim::OP_REDUCE_MAX, v, 0); }
 inline void __syncwarp() { warpsim::collective(warpsim::OP_BALLOT, 0, 0); }
 inline void __syncthreads() { warpsim::collective(warpsim::OP_CTA_BARRIER, 0, 0); }
+// bar.sync id, nthreads: whole warps only (every lane of a warp arrives together)
+inline void __named_barrier(uint32_t id, uint32_t nthreads) { warpsim::collective(warpsim::OP_NAMED_BARRIER, 0, (id << 16) | nthreads); }
 inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
     const uint64_t t = ((uint64_t)b << 32) | a;
     uint32_t r = 0;

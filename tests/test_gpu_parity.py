@@ -512,10 +512,11 @@ def test_kernels_were_launched(ctx):
     assert t["total"] > 0
 
 
-@pytest.mark.parametrize("mode", ["jump", "pair", "pair1"])
+@pytest.mark.parametrize("mode", ["jump", "pair", "pair1", "team"])
 def test_long_frame_paths_on_every_frame(corpus, tmp_path, mode):
     """The stage-4 paths for LONG frames (normally frames with >= 65 536 sequences) forced onto every frame: the
-    block-parallel kernels of execute_long.cuh ("jump"), k_execute_pair2 ("pair") and k_execute_pair ("pair1": SZB_PAIR2=0).  Corpus, crafted frames, a text batch,
+    block-parallel kernels of execute_long.cuh ("jump"), k_execute_pair2 ("pair"), k_execute_pair ("pair1": SZB_PAIR2=0) and
+    k_execute_team ("team": SZB_PAIR2=2).  Corpus, crafted frames, a text batch,
     a streamed multi-block frame and the mixed corpus: same bytes; bit-flipped payloads: same statuses and bytes as the
     one-warp-per-frame path.  Run in a subprocess so that a hang cannot take the test session with it."""
     import os
@@ -582,7 +583,8 @@ def test_long_frame_paths_on_every_frame(corpus, tmp_path, mode):
         print("long ok", ctx.launch_count(), int((a[2] != 0).sum()), "of", len(frames), "fail")
         """
     )
-    env = dict(os.environ, SZB_LONG_SEQS="1", SZB_LONG_MODE="pair" if mode == "pair1" else mode, SZB_PAIR2="0" if mode == "pair1" else "1")
+    env = dict(os.environ, SZB_LONG_SEQS="1", SZB_LONG_MODE="jump" if mode == "jump" else "pair",
+               SZB_PAIR2={"pair1": "0", "team": "2"}.get(mode, "1"))
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300,
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert res.returncode == 0 and "long ok" in res.stdout, res.stdout + res.stderr

@@ -39,6 +39,17 @@ def sim_refill():
     return _build_sim("libhostsim_refill.so", ("SZB_JUMP_REFILL=1", "SZB_JUMP_CHAINS=4"))
 
 
+@pytest.fixture(scope="module")
+def sim_team4():
+    """The same with four consumer warps per frame in k_execute_team (the default build has two)."""
+    return _build_sim("libhostsim_team4.so", ("SZB_X2_TEAM=4",))
+
+
+@pytest.fixture(scope="module")
+def sim_team1():
+    return _build_sim("libhostsim_team1.so", ("SZB_X2_TEAM=1",))
+
+
 def _decode(L, data: bytes, cap: int):
     out = np.empty(cap + 16, dtype=np.uint8)
     n = C.c_size_t()
@@ -221,9 +232,10 @@ def test_place_kernels_report_the_oracles_errors(sim, corpus):
 # ---- k_execute2 (exec2.cuh): 32-bit positions and entries, lines of memory, four 32-byte rows per line ----
 K_EXECUTE2 = 5
 K_EXECUTE_PAIR2 = 6
+K_EXECUTE_TEAM = 7
 
 
-@pytest.mark.parametrize("x2path", [K_EXECUTE2, K_EXECUTE_PAIR2])
+@pytest.mark.parametrize("x2path", [K_EXECUTE2, K_EXECUTE_PAIR2, K_EXECUTE_TEAM])
 def test_execute2_decodes_golden_frames(sim, corpus, x2path):
     done = 0
     for k, (name, data, size, sha) in enumerate(corpus):
@@ -235,7 +247,7 @@ def test_execute2_decodes_golden_frames(sim, corpus, x2path):
     assert done >= 20
 
 
-@pytest.mark.parametrize("x2path", [K_EXECUTE2, K_EXECUTE_PAIR2])
+@pytest.mark.parametrize("x2path", [K_EXECUTE2, K_EXECUTE_PAIR2, K_EXECUTE_TEAM])
 def test_execute2_on_crafted_and_synthetic_frames(sim, x2path):
     import sys
 
@@ -284,6 +296,8 @@ def test_execute2_agrees_with_execute_on_corrupted_frames(sim, corpus):
         p1 = _stage4_at(sim, frame, cap, K_EXECUTE_PAIR, k % 2, 0, (k * 7) % 128)
         p2 = _stage4_at(sim, frame, cap, K_EXECUTE_PAIR2, k % 2, 0, (k * 7) % 128)
         assert p1[0] == p2[0] and (p1[0] != 0 or p1[1] == p2[1]), (name, k, p1[0], p2[0])
+        p3 = _stage4_at(sim, frame, cap, K_EXECUTE_TEAM, k % 2, 0, (k * 7) % 128)
+        assert p1[0] == p3[0] and (p1[0] != 0 or p1[1] == p3[1]), (name, k, p1[0], p3[0])
         if a[0] == 0:
             assert a[1] == b[1] == p2[1], (name, k)
             if want is not None:
@@ -439,3 +453,30 @@ def test_long_frame_kernels_with_sliced_blocks(sim, corpus, slice_seqs, monkeypa
         assert a == b, (name, k, a[0], b[0])
         errors += a[0] in (-28, -30, -33)
     assert errors >= 1
+
+
+@pytest.mark.parametrize("team", [1, 4])
+def test_execute_team_with_one_and_four_consumer_warps(sim_team1, sim_team4, corpus, team):
+    L = sim_team4 if team == 4 else sim_team1
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import crafted_frames as crafted
+
+    done = 0
+    for k, (name, data, size, sha) in enumerate(corpus):
+        if size > 40_000:
+            continue
+        rc, out = _stage4_at(L, data, size, K_EXECUTE_TEAM, k % 2, 1, (k * 37) % 128)
+        assert rc == 0 and len(out) == size and hashlib.sha256(out).hexdigest() == sha, name
+        done += 1
+    assert done >= 20
+    for k, (name, (frame, expected)) in enumerate(sorted(crafted.cases().items())):
+        rc, out = _stage4_at(L, frame, len(expected), K_EXECUTE_TEAM, k % 2, 0, 1 + (k * 29) % 127)
+        assert rc == 0 and out == expected, name
+    c = cg.config2_text_frames(2)
+    for i in range(c.nframes):
+        f = c.frame(i)
+        want = pyszo.decode_frame(f)
+        rc, out = _stage4_at(L, f, len(want), K_EXECUTE_TEAM, 0, 0, 77)
+        assert rc == 0 and out == want
