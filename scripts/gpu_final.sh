@@ -2,7 +2,7 @@
 # the round's closing run on one B200: every GPU test, the bench lines of all workloads, launch list, ncu --set full, sanitizers
 set -u
 mkdir -p gpurun_out
-TAG=${1:-r02s}
+TAG=${1:-r03z}
 echo "== pytest gpu"; timeout -s KILL 1500 python -m pytest tests -m gpu -q 2>&1 | tail -6 | cut -c1-400 | tee gpurun_out/${TAG}_pytest_gpu.log
 echo "== smoke"; timeout -s KILL 300 python __graft_entry__.py smoke 2>&1 | tail -2 | tee gpurun_out/${TAG}_smoke.log
 echo "== bench default"; timeout -s KILL 600 python bench.py > gpurun_out/${TAG}_bench_text.json 2> gpurun_out/${TAG}_bench_text.err
@@ -33,7 +33,13 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-fil
 python scripts/launch_shares.py gpurun_out/${TAG}_launches_text.csv | tee gpurun_out/${TAG}_launch_shares.txt
 ncu --set full --clock-control none --import-source on -k regex:"k_execute2|k_decode_sequences|k_decode_literals|k_build" -c 5 -o gpurun_out/${TAG}_full python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1
 ls -la gpurun_out/${TAG}_full.ncu-rep
+echo "== memcheck of the long-frame paths (subprocess tests: --target-processes all)"
+SZB_TEST_TIMEOUT=1500 timeout -s KILL 1500 compute-sanitizer --tool memcheck --target-processes all python -m pytest tests/test_gpu_parity.py -m gpu -q -k "(long_frame_paths or several_groups) and exec2" 2>&1 | grep -v "^=========     \|^$" | tail -12 | cut -c1-300 | tee gpurun_out/${TAG}_memcheck_long.txt
 echo "== memcheck"
 timeout -s KILL 1200 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -m gpu -q -k "(long_frame_paths or config2_text_frames_small or ragged or corrupted or decodecorpus_batch or dictionaries or concatenated or config5) and not place" 2>&1 | tail -8 | cut -c1-300 | tee gpurun_out/${TAG}_memcheck.txt
 echo "== racecheck"
 timeout -s KILL 900 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -m gpu -q -k "(config2_text_frames_small or decodecorpus_batch or dictionaries) and exec2" 2>&1 | tail -8 | cut -c1-300 | tee gpurun_out/${TAG}_racecheck.txt
+echo "== racecheck of the two-warp / team kernels (every frame forced onto them)"
+for p in 1 2; do
+  SZB_LONG_SEQS=1 SZB_LONG_MODE=pair SZB_PAIR2=$p timeout -s KILL 900 compute-sanitizer --tool racecheck python scripts/race_long.py 2>&1 | grep -v "^=========     \|^$" | tail -6 | cut -c1-300 | tee -a gpurun_out/${TAG}_racecheck_long.txt
+done

@@ -585,7 +585,7 @@ def test_long_frame_paths_on_every_frame(corpus, tmp_path, mode):
     )
     env = dict(os.environ, SZB_LONG_SEQS="1", SZB_LONG_MODE="jump" if mode == "jump" else "pair",
                SZB_PAIR2={"pair1": "0", "team": "2"}.get(mode, "1"))
-    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300,
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=int(os.environ.get("SZB_TEST_TIMEOUT", 300)),
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert res.returncode == 0 and "long ok" in res.stdout, res.stdout + res.stderr
 
@@ -622,6 +622,6 @@ def test_sequence_kernel_walks_several_groups_per_cta():
         """
     )
     env = dict(os.environ, SZB_SEQ_CTAS_PER_SM="1")
-    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300,
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=int(os.environ.get("SZB_TEST_TIMEOUT", 300)),
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert res.returncode == 0 and "capped ok" in res.stdout, res.stdout + res.stderr
