@@ -259,6 +259,7 @@ int szb_ctx_create(int device, void *stream, szb_ctx **out) {
     cudaFuncSetAttribute(k_build_huf_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(HufSmem) * kWarpsPerCta));
     cudaFuncSetAttribute(k_build_seq_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SeqSmem) * kWarpsPerCta));
     cudaFuncSetAttribute(k_decode_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeqDecodeSmemBytes);
+    cudaFuncSetAttribute(k_decode_sequences_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeqDecodeSmemBytes);
     cudaFuncSetAttribute(k_decode_literals, cudaFuncAttributePreferredSharedMemoryCarveout, 100);  // streams arrive by cp.async: L1 is not needed, resident warps are
     *out = ctx;
     return SZB_OK;
@@ -813,8 +814,10 @@ static int launch_entropy(szb_batch *b, const void *d_src) {
             // SZB_SEQ_CTAS_PER_SM=n (experiments, tests): at most n CTAs per SM; a CTA then walks several groups
             static const int cap = getenv("SZB_SEQ_CTAS_PER_SM") ? atoi(getenv("SZB_SEQ_CTAS_PER_SM")) : 0;
             uint32_t grid = (a.n_seq + kSeqLanes - 1) / kSeqLanes;
-            if (cap > 0 && grid > (uint32_t)(cap * ctx->sm_count)) grid = (uint32_t)(cap * ctx->sm_count);
-            k_decode_sequences<<<grid, 32, kSeqDecodeSmemBytes, s>>>(a);
+            if (cap > 0 && grid > (uint32_t)(cap * ctx->sm_count))
+                k_decode_sequences_multi<<<(uint32_t)(cap * ctx->sm_count), 32, kSeqDecodeSmemBytes, s>>>(a);
+            else
+                k_decode_sequences<<<grid, 32, kSeqDecodeSmemBytes, s>>>(a);
         }
         ctx->launches++;
     }

@@ -981,9 +981,15 @@ __device__ __forceinline__ void seq_decode_group(const DeviceBatch &a, uint32_t 
     a.out_size[b] = (uint64_t)d.lit_regen + ml_sum;
 }
 
-// One group per CTA when the grid covers all groups (the default launch); with a smaller grid (launch_entropy: a cap on the
-// CTAs an SM holds, so that stage 4 of another batch fits beside this kernel) a CTA walks the groups blockIdx.x, + gridDim.x, ...
+// One group per CTA: the default launch.
 __global__ void __launch_bounds__(32) k_decode_sequences(DeviceBatch a) {
+    extern __shared__ __align__(16) uint32_t sw[];
+    seq_decode_group(a, sw, blockIdx.x * kSeqLanes, 0, threadIdx.x);
+}
+
+// The same with a grid smaller than the number of groups (launch_entropy: SZB_SEQ_CTAS_PER_SM, a cap on the CTAs an SM holds --
+// experiments with other kernels beside this one, and tests): a CTA walks the groups blockIdx.x, + gridDim.x, ...
+__global__ void __launch_bounds__(32) k_decode_sequences_multi(DeviceBatch a) {
     extern __shared__ __align__(16) uint32_t sw[];
     const uint32_t lane = threadIdx.x;
     const uint32_t ngroups = (a.n_seq + kSeqLanes - 1) / kSeqLanes;
