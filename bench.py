@@ -448,7 +448,7 @@ def main():
         "stage4_path": os.environ.get("SZB_EXEC", "default"),
         "stages_note": "k_huffman_literals and k_sequences run side by side on two streams; each is measured from the start of the step; "
                        "k_execute is all of stage 4: (k_place_zero, k_resolve,) k_frame_verdict, k_execute_bodies, k_execute or k_place and, "
-                       "for frames with >= 65 536 sequences, k_execute_pair or the block-parallel kernels k_long_* (execute_long.cuh), "
+                       "for frames with >= 65 536 sequences, k_execute_pair2 (k_execute_pair from 2 GiB) or the block-parallel kernels k_long_* (execute_long.cuh), "
                        "whichever the host picked for the batch",
     }
 

@@ -12,9 +12,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STAGES = {
     "k_huffman_literals": ["k_build_huf_tables", "k_decode_literals"],
-    "k_sequences": ["k_build_seq_tables", "k_decode_sequences"],
+    "k_sequences": ["k_build_seq_tables", "k_decode_sequences", "k_decode_sequences_multi"],
     "k_scan_blocks": ["k_scan_blocks"],
-    "k_execute": ["k_place_zero", "k_resolve", "k_frame_verdict", "k_execute_bodies", "k_place", "k_execute2", "k_execute", "k_execute_pair", "k_long_hist",
+    "k_execute": ["k_place_zero", "k_resolve", "k_frame_verdict", "k_execute_bodies", "k_place", "k_execute2", "k_execute", "k_execute_pair", "k_execute_pair2", "k_execute_team", "k_long_hist",
                   "k_long_blockscan", "k_long_compose", "k_long_emit", "k_long_jump", "k_long_verdict"],
 }
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
