@@ -362,6 +362,40 @@ __device__ __forceinline__ void hring_skip(HufBits &r, uint32_t n) {
     r.remaining -= (int32_t)n;
 }
 
+// 16 symbols of one stream into one aligned 16-byte store (the body of huf_decode_stream_vec's main loop).
+template <bool kTrack>
+__device__ __forceinline__ void huf_group16(HufBits &r, uint32_t tb, uint32_t psh, uint8_t *dst, bool &clean) {
+    uint32_t wv[4];
+    uint32_t used = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if ((q & 1) == 0) {  // a group of eight symbols
+            hring_topup(r);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        }
+        uint32_t acc = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            if ((t & 1) == 0) hring_refill(r);
+            uint32_t e;
+            asm("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(tb + 2 * ((uint32_t)(r.win >> 32) >> psh)));
+            acc |= (e & 0xFF) << (8 * t);
+            const uint32_t nb = e >> 8;
+            r.win <<= nb;
+            r.avail -= (int32_t)nb;
+            if (kTrack) {
+                r.remaining -= (int32_t)nb;
+                clean |= r.remaining == 0;
+            } else {
+                used += nb;
+            }
+        }
+        wv[q] = acc;
+    }
+    if (!kTrack) r.remaining -= (int32_t)used;
+    *reinterpret_cast<uint4 *>(dst) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+}
+
 // HuffmanDecodingTable.DecodeStream (huffman.go:221-264) for one stream, one lane; same recurrence as
 // huf_decode_stream (huffman.cuh) with the symbols buffered 16 deep in registers so they leave as
 // aligned 16-byte stores, and one refill check per two symbols (2 x 11 bits <= the 32 guaranteed).
@@ -391,27 +425,22 @@ __device__ __forceinline__ int huf_decode_stream_vec(const uint16_t *table, uint
         clean |= r.remaining == 0;
     }
     hring_fill(r);
-    while (n + 16 <= expected) {
-        uint32_t wv[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            if ((q & 1) == 0) {  // a group of eight symbols
-                hring_topup(r);
-                asm volatile("cp.async.wait_group 1;" ::: "memory");
-            }
-            uint32_t acc = 0;
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                if ((t & 1) == 0) hring_refill(r);
-                const uint32_t e = table[hring_peek(r, max_bits)];
-                acc |= (e & 0xFF) << (8 * t);
-                hring_skip(r, e >> 8);
-                clean |= r.remaining == 0;
-            }
-            wv[q] = acc;
+    if (max_bits >= 1) {
+        // 16 symbols at a time.  Per symbol: the cell's index is the top max_bits bits of the window's high word (one shift: a
+        // refill leaves at least 32 valid bits there, and max_bits <= 11), one 16-bit load at a 32-bit shared-memory address, the
+        // skip.  Whether the bits run out exactly at a symbol boundary (`clean`) can only happen in a group that starts with
+        // less than 16 x max_bits bits left: only those groups look after every symbol.
+        const uint32_t tb = (uint32_t)__cvta_generic_to_shared(table);
+        const uint32_t psh = 32 - max_bits;
+        const int32_t near_end = (int32_t)(16 * max_bits);
+        while (n + 16 <= expected && r.remaining > near_end) {
+            huf_group16<false>(r, tb, psh, out + n, clean);
+            n += 16;
         }
-        *reinterpret_cast<uint4 *>(out + n) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-        n += 16;
+        while (n + 16 <= expected) {
+            huf_group16<true>(r, tb, psh, out + n, clean);
+            n += 16;
+        }
     }
     hring_fill(r);
     for (; n < expected; n++) {
