@@ -873,12 +873,14 @@ __device__ __forceinline__ void seq_decode_group(const DeviceBatch &a, uint32_t 
             if (use == 0) {
                 asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            } else {
-                // the previous group's cells were read through the generic proxy; the copy engine writes through the async proxy
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n_here * kSlotBytes) : "memory");
+            // the barrier's initialisation, and the previous group's reads of the cells (generic proxy), come before what the copy
+            // engine does to both (async proxy)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
+        __syncwarp();
+        if (lane == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n_here * kSlotBytes) : "memory");
         __syncwarp();
         if (lane < n_here)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tabs_saddr + lane * kSlotBytes),
